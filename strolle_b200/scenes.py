@@ -1,0 +1,192 @@
+"""Scene descriptions (input data) for the benchmark configurations.
+
+A scene is plain data: meshes, materials, instances, lights, sun, camera — the
+arguments a host application would pass through the Engine API
+(strolle/src/lib.rs:161-245).  `apply(engine, scene)` drives any object exposing
+that API (the CUDA engine in strolle_b200.engine, or the test oracle).
+"""
+import json
+import math
+import os
+
+import numpy as np
+
+_ASSETS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "assets")
+
+MODE_IMAGE, MODE_DI_DIFFUSE, MODE_DI_SPECULAR, MODE_GI_DIFFUSE, MODE_GI_SPECULAR, MODE_BVH_HEATMAP, MODE_REFERENCE = range(7)
+LIGHT_POINT, LIGHT_SPOT = 1, 2
+
+
+def blue_noise():
+    """256x256 RGBA8 blue-noise tile (strolle/assets/blue-noise.png as raw bytes)."""
+    return np.fromfile(os.path.join(_ASSETS, "blue_noise_256_rgba8.bin"), dtype=np.uint8).reshape(256, 256, 4)
+
+
+def perspective_infinite_reverse_rh(fov_y, aspect, near):
+    """glam Mat4::perspective_infinite_reverse_rh, column-major 16 floats (Bevy's default projection)."""
+    f = np.float32(1.0) / np.float32(math.tan(0.5 * fov_y))
+    m = np.zeros((4, 4), dtype=np.float32)  # m[col][row]
+    m[0][0] = f / np.float32(aspect)
+    m[1][1] = f
+    m[2][3] = -1.0
+    m[3][2] = near
+    return m.reshape(-1)
+
+
+def look_at_transform(eye, target, up=(0.0, 1.0, 0.0)):
+    """Bevy Transform::from_translation(eye).looking_at(target, up) as a column-major Mat4."""
+    eye = np.asarray(eye, dtype=np.float64)
+    fwd = np.asarray(target, dtype=np.float64) - eye
+    fwd /= np.linalg.norm(fwd)
+    back = -fwd
+    right = np.cross(np.asarray(up, dtype=np.float64), back)
+    right /= np.linalg.norm(right)
+    upv = np.cross(back, right)
+    m = np.zeros((4, 4), dtype=np.float32)
+    m[0][:3] = right
+    m[1][:3] = upv
+    m[2][:3] = back
+    m[3][:3] = eye
+    m[3][3] = 1.0
+    return m.reshape(-1)
+
+
+def material(base_color, emissive=(0, 0, 0, 0), perceptual_roughness=1.0, metallic=0.0, reflectance=0.5, ior=1.0):
+    return np.array(list(base_color) + list(emissive) + [perceptual_roughness, metallic, reflectance, ior], dtype=np.float32)
+
+
+def point_light(position, radius, color, rng):
+    return np.array(list(position) + [radius] + list(color) + [rng, 0, 0, 0, 0], dtype=np.float32)
+
+
+def tri36(positions, normals, uvs=None, tangents=None):
+    uvs = uvs if uvs is not None else [[0, 0]] * 3
+    tangents = tangents if tangents is not None else [[0, 0, 0, 0]] * 3
+    return np.concatenate([np.asarray(positions, np.float32).reshape(-1), np.asarray(normals, np.float32).reshape(-1),
+                           np.asarray(uvs, np.float32).reshape(-1), np.asarray(tangents, np.float32).reshape(-1)])
+
+
+def affine_from_colmajor4x4(m16):
+    m = np.asarray(m16, dtype=np.float32).reshape(4, 4)  # m[col][row]
+    return np.concatenate([m[0][:3], m[1][:3], m[2][:3], m[3][:3]]).astype(np.float32)
+
+
+IDENTITY_AFFINE = np.array([1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0], dtype=np.float32)
+
+
+def cornell(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, ref_depth=1):
+    """Config C1/C2/C4/C5: Cornell box, 32 triangles, one point light.
+
+    bevy-strolle/examples/cornell.rs:39-94: camera eye (0,1,3.2) -> (0,1,0), point light
+    (0,1.5,0.5) r=0.15 range 20 intensity 50, sun altitude -1.
+    """
+    doc = json.load(open(os.path.join(_ASSETS, "cornell.json")))
+    meshes, materials, instances = {}, {}, []
+    for i, m in enumerate(doc["materials"]):
+        materials[100 + i] = (material(m["base_color"], perceptual_roughness=m["perceptual_roughness"], metallic=m["metallic"]), False)
+    for i, m in enumerate(doc["meshes"]):
+        tris = np.stack([tri36(t["positions"], t["normals"]) for t in m["triangles"]])
+        meshes[200 + i] = tris
+        instances.append((300 + i, 200 + i, 100 + m["material"], affine_from_colmajor4x4(m["transform_colmajor"])))
+    intensity = 50.0 / (4.0 * math.pi)
+    lights = [(400, LIGHT_POINT, point_light((0.0, 1.5, 0.5), 0.15, (intensity,) * 3, 20.0))]
+    cam = dict(mode=mode, denoise=denoise, ref_depth=ref_depth, w=width, h=height,
+               transform=look_at_transform((0.0, 1.0, 3.2), (0.0, 1.0, 0.0)),
+               projection=perspective_infinite_reverse_rh(math.pi / 4.0, width / height, 0.1))
+    return dict(name="cornell", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(0.0, -1.0), camera=cam)
+
+
+def _box(lo, hi):
+    lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
+    c = [np.array([x, y, z], np.float32) for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])]
+    faces = [((0, 1, 3, 2), (-1, 0, 0)), ((4, 6, 7, 5), (1, 0, 0)), ((0, 4, 5, 1), (0, -1, 0)), ((2, 3, 7, 6), (0, 1, 0)),
+             ((0, 2, 6, 4), (0, 0, -1)), ((1, 5, 7, 3), (0, 0, 1))]
+    tris = []
+    for (a, b, cc, d), n in faces:
+        tris.append(tri36([c[a], c[b], c[cc]], [n] * 3, [[0, 0], [1, 0], [1, 1]]))
+        tris.append(tri36([c[a], c[cc], c[d]], [n] * 3, [[0, 0], [1, 1], [0, 1]]))
+    return tris
+
+
+def _torus(major=0.5, minor=0.25, nu=24, nv=12):
+    tris = []
+    def pt(i, j):
+        u, v = 2 * math.pi * i / nu, 2 * math.pi * j / nv
+        cx, cz = math.cos(u), math.sin(u)
+        p = np.array([(major + minor * math.cos(v)) * cx, minor * math.sin(v), (major + minor * math.cos(v)) * cz], np.float32)
+        n = np.array([math.cos(v) * cx, math.sin(v), math.cos(v) * cz], np.float32)
+        return p, n
+    for i in range(nu):
+        for j in range(nv):
+            (p00, n00), (p10, n10), (p01, n01), (p11, n11) = pt(i, j), pt(i + 1, j), pt(i, j + 1), pt(i + 1, j + 1)
+            tris.append(tri36([p00, p10, p11], [n00, n10, n11]))
+            tris.append(tri36([p00, p11, p01], [n00, n11, n01]))
+    return tris
+
+
+def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cells=14):
+    """Config C3 stand-in: a *synthetic* dungeon (BASELINE.json: "synthetic Cornell and dungeon scenes").
+
+    The reference's demo level (bevy-strolle/assets/demo.zip, 8,393 triangles + 3 emissive
+    tori, 6 point lights, sun az 3.0 / alt 0.35, bevy-strolle/examples/demo.rs:150-237) needs
+    the texture atlas (a "next" row); this generator builds an untextured level of
+    the same scale procedurally: a grid of rooms/corridors from boxes (floor, ceiling, walls,
+    pillars, crates), 3 emissive tori, 6 point lights, same sun, camera inside a corridor.
+    """
+    rng = np.random.RandomState(seed)
+    meshes, materials, instances, lights = {}, {}, [], []
+    palette = [(0.55, 0.5, 0.45, 1), (0.4, 0.38, 0.36, 1), (0.5, 0.3, 0.2, 1), (0.3, 0.35, 0.4, 1), (0.6, 0.55, 0.4, 1)]
+    for i, col in enumerate(palette):
+        materials[100 + i] = (material(col, perceptual_roughness=1.0, reflectance=0.0), False)
+    materials[150] = (material((0.9, 0.6, 0.3, 1), emissive=(9.0, 6.0, 3.0, 1.0), perceptual_roughness=1.0, reflectance=0.0), False)
+    nid = [0]
+    def add(tris, mat, xf=IDENTITY_AFFINE):
+        h = nid[0]; nid[0] += 1
+        meshes[1000 + h] = np.stack(tris)
+        instances.append((5000 + h, 1000 + h, mat, np.asarray(xf, np.float32)))
+    S = 4.0  # cell size
+    wall_h = 3.0
+    ox, oz = -cells * S / 2 - 5.75 + cells * S / 2, -17.0 - 3 * S
+    # floor + ceiling slabs per cell, walls on random cell borders, pillars and crates
+    for cx in range(cells):
+        for cz in range(cells):
+            x0, z0 = ox + (cx - cells / 2) * S, oz + (cz - cells / 2) * S + cells * S / 2
+            add(_box((x0, -0.2, z0), (x0 + S, 0.0, z0 + S)), 100 + (cx + cz) % 2)
+            add(_box((x0, wall_h, z0), (x0 + S, wall_h + 0.2, z0 + S)), 101)
+            if rng.rand() < 0.45:
+                add(_box((x0, 0.0, z0), (x0 + S, wall_h, z0 + 0.3)), 102 + rng.randint(0, 3))
+            if rng.rand() < 0.45:
+                add(_box((x0, 0.0, z0), (x0 + 0.3, wall_h, z0 + S)), 102 + rng.randint(0, 3))
+            for _ in range(rng.randint(0, 4)):
+                px, pz = x0 + rng.rand() * (S - 1) + 0.5, z0 + rng.rand() * (S - 1) + 0.5
+                hgt = 0.3 + rng.rand() * 1.2
+                add(_box((px - 0.25, 0.0, pz - 0.25), (px + 0.25, hgt, pz + 0.25)), 102 + rng.randint(0, 3))
+            if rng.rand() < 0.3:
+                px, pz = x0 + S / 2, z0 + S / 2
+                add(_box((px - 0.2, 0.0, pz - 0.2), (px + 0.2, wall_h, pz + 0.2)), 103)
+    torus = _torus()
+    for k, (tx, tz) in enumerate([(-5.75, -20.0), (-1.5, -22.0), (-9.5, -24.0)]):
+        xf = np.array([0.5, 0, 0, 0, 0.5, 0, 0, 0, 0.5, tx, 1.0, tz], np.float32)
+        add(torus, 150, xf)
+    inten = 5000.0 / (4.0 * math.pi)
+    for k, (lx, lz) in enumerate([(-5.75, -19.0), (-1.0, -23.0), (-10.0, -23.0), (-5.75, -28.0), (2.0, -18.0), (-13.0, -18.0)]):
+        lights.append((9000 + k, LIGHT_POINT, point_light((lx, 2.2, lz), 0.15, (inten,) * 3, 35.0)))
+    cam = dict(mode=mode, denoise=denoise, ref_depth=1, w=width, h=height,
+               transform=look_at_transform((-5.75, 0.5, -16.8), (-5.75, 0.5, -17.0)),
+               projection=perspective_infinite_reverse_rh(math.pi / 4.0, width / height, 0.1))
+    return dict(name="dungeon_synthetic", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(3.0, 0.35), camera=cam)
+
+
+def apply(engine, scene):
+    """Feed a scene through the Engine API in a fixed order; returns the camera handle."""
+    for h, tris in scene["meshes"].items():
+        engine.insert_mesh(h, tris)
+    for h, (params, alpha) in scene["materials"].items():
+        engine.insert_material(h, params, alpha)
+    for h, mesh, mat, xf in scene["instances"]:
+        engine.insert_instance(h, mesh, mat, xf)
+    for h, kind, params in scene["lights"]:
+        engine.insert_light(h, kind, params)
+    engine.update_sun(*scene["sun"])
+    c = scene["camera"]
+    return engine.create_camera(c["mode"], c["denoise"], c["ref_depth"], c["w"], c["h"], c["transform"], c["projection"])
