@@ -1,0 +1,166 @@
+/* strolle_b200 — C ABI of the B200-native Strolle hot path.
+ *
+ * Drop-in boundary for the per-pixel GI path of Patryk27/strolle: the functions
+ * below are what a Rust `extern "C"` shim behind `strolle::Engine<P>` binds in
+ * place of the wgpu compute dispatches (CameraComputePass::run,
+ * strolle/src/camera_controller/pass.rs:33-63) and buffer flushes
+ * (strolle/src/buffers/mapped_storage_buffer.rs:108-140).  Each entry point
+ * cites the reference method it replaces.  Plain pointers and sizes only; no
+ * torch / CUDA types.  See INTEGRATION.md for the reference-side binding.
+ *
+ * Conventions: every function returns ST_OK (0) or a negative error code and
+ * never aborts across the ABI; st_last_error() gives the message (the
+ * reference panics instead, e.g. strolle/src/triangles.rs:44-53).  Handles are
+ * caller-chosen opaque u64 (the reference's Params associated types,
+ * strolle/src/lib.rs:402-409).  Mutating calls are externally synchronised
+ * (single writer), like `ResMut<Engine>` in bevy-strolle.
+ */
+#ifndef STROLLE_B200_H
+#define STROLLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct st_engine st_engine;
+typedef uint64_t st_handle;
+typedef int32_t st_camera_handle;
+
+enum { ST_OK = 0, ST_ERR_CUDA = -1, ST_ERR_INVALID = -2, ST_ERR_NOT_FOUND = -3, ST_ERR_LIMIT = -4 };
+
+/* strolle::MeshTriangle (strolle/src/mesh_triangle.rs:7-12), object space */
+typedef struct st_mesh_triangle {
+    float positions[3][3];
+    float normals[3][3];
+    float uvs[3][2];
+    float tangents[3][4];
+} st_mesh_triangle;
+
+/* strolle::Material (strolle/src/material.rs:8-23); textures are a later row */
+typedef struct st_material {
+    float base_color[4];
+    float emissive[4];
+    float perceptual_roughness;
+    float metallic;
+    float reflectance;
+    float ior;
+    int32_t alpha_blend; /* AlphaMode::Blend != 0 (strolle/src/material.rs:76-91) */
+} st_material;
+
+/* strolle::Light::{Point,Spot} (strolle/src/light.rs:6-22) */
+enum { ST_LIGHT_POINT = 1, ST_LIGHT_SPOT = 2 };
+typedef struct st_light {
+    int32_t kind;
+    float position[3];
+    float radius;
+    float color[3];
+    float range;
+    float direction[3]; /* spot only */
+    float angle;        /* spot only */
+} st_light;
+
+/* strolle::CameraMode (strolle/src/camera.rs:83-105) */
+enum {
+    ST_MODE_IMAGE = 0, ST_MODE_DI_DIFFUSE = 1, ST_MODE_DI_SPECULAR = 2, ST_MODE_GI_DIFFUSE = 3,
+    ST_MODE_GI_SPECULAR = 4, ST_MODE_BVH_HEATMAP = 5, ST_MODE_REFERENCE = 6
+};
+/* strolle::Camera (strolle/src/camera.rs:8-14); matrices column-major like glam::Mat4 */
+typedef struct st_camera {
+    int32_t mode;
+    int32_t denoise;   /* CameraMode::*{denoise} */
+    int32_t ref_depth; /* CameraMode::Reference{depth} */
+    uint32_t width, height; /* CameraViewport::size */
+    float transform[16];
+    float projection[16];
+} st_camera;
+
+/* Output pixel formats for st_render_camera (the reference composes into the caller's
+ * TextureView of CameraViewport::format, strolle/src/camera.rs:170-185). */
+enum { ST_FORMAT_RGBA32F = 0, ST_FORMAT_RGBA8_SRGB = 1 };
+
+const char* st_last_error(void);
+
+/* Engine::new (strolle/src/lib.rs:132-158).  `device` = CUDA ordinal. */
+int st_engine_create(int device, st_engine** out);
+void st_engine_destroy(st_engine* e);
+
+/* Engine::insert_mesh / remove_mesh (lib.rs:161-171) */
+int st_insert_mesh(st_engine* e, st_handle mesh, const st_mesh_triangle* triangles, size_t count);
+int st_remove_mesh(st_engine* e, st_handle mesh);
+/* Engine::insert_material / has_material / remove_material (lib.rs:174-195) */
+int st_insert_material(st_engine* e, st_handle material, const st_material* m);
+int st_has_material(st_engine* e, st_handle material);
+int st_remove_material(st_engine* e, st_handle material);
+/* Engine::insert_instance / remove_instance (lib.rs:217-229); affine = glam::Affine3A as
+ * matrix3 columns x,y,z then translation (12 floats) */
+int st_insert_instance(st_engine* e, st_handle instance, st_handle mesh, st_handle material, const float affine[12]);
+int st_remove_instance(st_engine* e, st_handle instance);
+/* Engine::insert_light / remove_light (lib.rs:232-239) */
+int st_insert_light(st_engine* e, st_handle light, const st_light* l);
+int st_remove_light(st_engine* e, st_handle light);
+/* Engine::update_sun (lib.rs:242-245) */
+int st_update_sun(st_engine* e, float azimuth, float altitude);
+
+/* Engine::create_camera / update_camera / delete_camera (lib.rs:252-294) */
+int st_create_camera(st_engine* e, const st_camera* camera, st_camera_handle* out);
+int st_update_camera(st_engine* e, st_camera_handle camera, const st_camera* desc);
+int st_delete_camera(st_engine* e, st_camera_handle camera);
+
+/* Engine::tick (lib.rs:301-395): bakes dirty instances, rebuilds + uploads the BVH, lights,
+ * materials, world; must precede st_render_camera each frame. */
+int st_tick(st_engine* e);
+
+/* Engine::render_camera (lib.rs:279-286 -> CameraController::render,
+ * strolle/src/camera_controller.rs:87-174): runs the frame's pass schedule on the engine's
+ * stream.  If `host_out` is non-NULL the composed frame (width*height pixels of `format`) is
+ * copied to it and the call returns when the copy is done; with NULL the call only enqueues
+ * (use st_synchronize). */
+int st_render_camera(st_engine* e, st_camera_handle camera, void* host_out, int format);
+int st_synchronize(st_engine* e);
+
+/* ---- hooks that the reference does not have -------------------------------- */
+/* Explicit per-dispatch seeds: seed(frame f, dispatch k) = pcg(base ^ (f*64 + k)); the reference
+ * draws rand::thread_rng() per dispatch (camera_controller.rs:189-194) and is not reproducible. */
+int st_set_seed_base(st_engine* e, uint32_t base);
+/* 256x256 RGBA8 blue-noise tile (strolle/src/noise.rs:30-66 embeds a PNG; here the host passes bytes) */
+int st_set_blue_noise(st_engine* e, const uint8_t* rgba8_256x256);
+/* Copies a per-camera buffer (names = fields of CameraBuffers, strolle/src/camera_controller/
+ * buffers.rs:9-51; double-buffered ones take _a/_b) to host.  Returns #floats available via
+ * *count; copies min(cap, count). */
+int st_read_buffer(st_engine* e, st_camera_handle camera, const char* name, float* dst, size_t cap_floats, size_t* count);
+/* Scene buffers as uploaded: "triangles", "bvh", "materials", "lights", "world", "transmittance_lut",
+ * "scattering_lut", "sky_lut". */
+int st_read_scene(st_engine* e, const char* name, float* dst, size_t cap_floats, size_t* count);
+int st_bvh_depth(st_engine* e, int* depth);
+uint32_t st_frame(st_engine* e);
+/* Ray-stream entry points (the ref_tracing / *_spatial_resampling::trace shape): `rays` = n x 8
+ * host floats (origin.xyz, len, dir.xyz, pad).  closest: out = n x 12 floats (packed hit d0, d1
+ * as in strolle-gpu/src/hit.rs:112-120, then distance, triangle id bits, material id bits,
+ * used_memory).  any: out = n u32 flags.  `device_ms` (optional) receives kernel time. */
+int st_trace_closest(st_engine* e, const float* rays, size_t n, float* out, float* device_ms);
+int st_trace_any(st_engine* e, const float* rays, size_t n, uint32_t* out, float* device_ms);
+/* elementary functions as evaluated on the device (op: 0 sin, 1 cos, 2 acos, 3 atan2, 4 exp, 5 pow) */
+int st_device_math(st_engine* e, int op, const float* a, const float* b, float* out, size_t n);
+/* Per-pass device time (ms, CUDA events) accumulated since the last reset; `ms`/`launches`
+ * have ST_PASS_COUNT entries indexed by st_pass_name(). */
+#define ST_PASS_COUNT 26
+int st_enable_timing(st_engine* e, int enabled);
+int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset);
+const char* st_pass_name(int pass);
+/* Row-strip partition for multi-GPU runs: this engine computes rows [y0, y1) of the
+ * camera's frame; full-frame buffers stay addressable for halo rows. */
+int st_camera_set_strip(st_engine* e, st_camera_handle camera, int y0, int y1);
+/* Device pointer + byte size of a per-camera buffer (for NCCL halo exchange by the host runtime). */
+int st_buffer_device_ptr(st_engine* e, st_camera_handle camera, const char* name, void** ptr, size_t* bytes);
+/* Stage-wise rendering for strip-parallel runs: executes passes [first, last] of the frame
+ * schedule (indices into the schedule returned by st_frame_schedule). */
+int st_frame_schedule(st_engine* e, st_camera_handle camera, int* pass_ids, int cap, int* count);
+int st_render_range(st_engine* e, st_camera_handle camera, int first, int last);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STROLLE_B200_H */

@@ -1,0 +1,56 @@
+"""Builds libstrolle_b200.so (CUDA kernels + host engine + C ABI) in-tree with nvcc for sm_100a.
+
+    python -m strolle_b200.build [--force]
+
+Flags that matter for parity: -fmad=false (device) and -ffp-contract=off (host) keep every
+float operation a single IEEE-754 operation in source order.
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT_DIR = os.path.join(HERE, "_lib")
+LIB = os.path.join(OUT_DIR, "libstrolle_b200.so")
+SOURCES = ["kernels.cu", "engine.cu"]
+HEADERS = ["st_math.cuh", "st_device.cuh", "st_types.h", "kernels.h", os.path.join("..", "..", "include", "strolle_b200.h")]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
+         "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "-Xptxas", "-v"]
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build(force=False, verbose=False):
+    os.makedirs(OUT_DIR, exist_ok=True)
+    deps = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        objs.append(obj)
+        if force or _stale(obj, deps + [os.path.join(CSRC, src)]):
+            cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        with open(os.path.join(OUT_DIR, src + ".ptxas.log"), "w") as f:
+            f.write(out)
+        if p.returncode != 0:
+            sys.stderr.write(out)
+            raise RuntimeError("nvcc failed for " + src)
+        if verbose:
+            print(out)
+    if force or procs or _stale(LIB, objs):
+        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

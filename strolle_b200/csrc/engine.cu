@@ -1,0 +1,940 @@
+// strolle_b200 — host engine behind the C ABI (include/strolle_b200.h).
+//
+// Mirrors strolle::Engine (strolle/src/lib.rs:104-395): scene stores, world-space triangle
+// baking, binned-SAH BVH build + DFS serialisation, the light slot protocol, per-camera
+// buffers and the per-frame pass schedule of CameraController::render — with CUDA device
+// allocations, one stream and cudaMemcpyAsync uploads in place of wgpu buffers, bind groups
+// and queue.write_buffer.  Host float arithmetic is compiled with -ffp-contract=off.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <functional>
+#include <limits>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/strolle_b200.h"
+#include "kernels.h"
+
+namespace st {
+
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CK(call)                                                                                   \
+    do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(ST_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+// ---- small host vector maths (glam evaluation order) ----------------------------------------------
+struct H3 { float x, y, z; };
+static inline H3 h3(float x, float y, float z) { H3 r = {x, y, z}; return r; }
+static inline H3 operator+(H3 a, H3 b) { return h3(a.x + b.x, a.y + b.y, a.z + b.z); }
+static inline H3 operator-(H3 a, H3 b) { return h3(a.x - b.x, a.y - b.y, a.z - b.z); }
+static inline H3 operator*(H3 a, float s) { return h3(a.x * s, a.y * s, a.z * s); }
+static inline H3 operator*(H3 a, H3 b) { return h3(a.x * b.x, a.y * b.y, a.z * b.z); }
+static inline H3 operator/(H3 a, float s) { return h3(a.x / s, a.y / s, a.z / s); }
+static inline float hdot(H3 a, H3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
+static inline H3 hcross(H3 a, H3 b) { return h3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+static inline H3 hnorm(H3 a) { return a * (1.0f / std::sqrt(hdot(a, a))); }
+static inline float hmin(float a, float b) { return (a != a) ? b : ((b != b) ? a : (a < b ? a : b)); }
+static inline float hmax(float a, float b) { return (a != a) ? b : ((b != b) ? a : (a > b ? a : b)); }
+static inline uint32_t to_u32(float f) { if (!(f == f) || f <= 0.0f) return 0u; if (f >= 4294967296.0f) return 0xffffffffu; return (uint32_t)f; }
+static inline float bits2f(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline uint32_t f2bits(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static const float FMAX = std::numeric_limits<float>::max();
+
+struct Affine3 { H3 x, y, z, t; };
+static inline H3 aff_mat(const Affine3& a, H3 v) { return (a.x * v.x + a.y * v.y) + a.z * v.z; }
+static inline H3 aff_point(const Affine3& a, H3 p) { return aff_mat(a, p) + a.t; }
+static Affine3 aff_inverse(const Affine3& a) {   // glam Affine3A::inverse
+    H3 t0 = hcross(a.y, a.z), t1 = hcross(a.z, a.x), t2 = hcross(a.x, a.y);
+    float det = hdot(a.z, t2);
+    float inv = 1.0f / det;
+    H3 c0 = t0 * inv, c1 = t1 * inv, c2 = t2 * inv;
+    Affine3 r;
+    r.x = h3(c0.x, c1.x, c2.x); r.y = h3(c0.y, c1.y, c2.y); r.z = h3(c0.z, c1.z, c2.z);
+    H3 mt = aff_mat(r, a.t);
+    r.t = h3(-mt.x, -mt.y, -mt.z);
+    return r;
+}
+
+struct Box {   // strolle/src/utils/bounding_box.rs
+    H3 lo, hi;
+    Box() : lo(h3(FMAX, FMAX, FMAX)), hi(h3(-FMAX, -FMAX, -FMAX)) {}
+    void grow(H3 p) { lo = h3(hmin(lo.x, p.x), hmin(lo.y, p.y), hmin(lo.z, p.z)); hi = h3(hmax(hi.x, p.x), hmax(hi.y, p.y), hmax(hi.z, p.z)); }
+    void grow(const Box& b) { grow(b.lo); grow(b.hi); }
+    bool set() const { return lo.x != FMAX; }
+    float half_area() const { H3 e = hi - lo; return e.x * e.y + e.y * e.z + e.z * e.x; }
+};
+
+// 4x4 column-major helpers for Camera::serialize (strolle/src/camera.rs:50-66)
+struct HM4 { float m[16]; };
+static HM4 hm_mul(const HM4& a, const HM4& b) {
+    HM4 r;
+    for (int c = 0; c < 4; c++) {
+        float v0 = b.m[4 * c], v1 = b.m[4 * c + 1], v2 = b.m[4 * c + 2], v3 = b.m[4 * c + 3];
+        for (int k = 0; k < 4; k++) {
+            float acc = a.m[k] * v0;
+            acc = acc + a.m[4 + k] * v1;
+            acc = acc + a.m[8 + k] * v2;
+            acc = acc + a.m[12 + k] * v3;
+            r.m[4 * c + k] = acc;
+        }
+    }
+    return r;
+}
+static HM4 hm_inverse(const HM4& s) {   // cofactor expansion in glam's Mat4::inverse order
+    const float* m = s.m;
+    float m00 = m[0], m01 = m[1], m02 = m[2], m03 = m[3], m10 = m[4], m11 = m[5], m12 = m[6], m13 = m[7];
+    float m20 = m[8], m21 = m[9], m22 = m[10], m23 = m[11], m30 = m[12], m31 = m[13], m32 = m[14], m33 = m[15];
+    float c00 = m22 * m33 - m32 * m23, c02 = m12 * m33 - m32 * m13, c03 = m12 * m23 - m22 * m13;
+    float c04 = m21 * m33 - m31 * m23, c06 = m11 * m33 - m31 * m13, c07 = m11 * m23 - m21 * m13;
+    float c08 = m21 * m32 - m31 * m22, c10 = m11 * m32 - m31 * m12, c11 = m11 * m22 - m21 * m12;
+    float c12 = m20 * m33 - m30 * m23, c14 = m10 * m33 - m30 * m13, c15 = m10 * m23 - m20 * m13;
+    float c16 = m20 * m32 - m30 * m22, c18 = m10 * m32 - m30 * m12, c19 = m10 * m22 - m20 * m12;
+    float c20 = m20 * m31 - m30 * m21, c22 = m10 * m31 - m30 * m11, c23 = m10 * m21 - m20 * m11;
+    float f0[4] = {c00, c00, c02, c03}, f1[4] = {c04, c04, c06, c07}, f2[4] = {c08, c08, c10, c11};
+    float f3[4] = {c12, c12, c14, c15}, f4[4] = {c16, c16, c18, c19}, f5[4] = {c20, c20, c22, c23};
+    float v0[4] = {m10, m00, m00, m00}, v1[4] = {m11, m01, m01, m01}, v2[4] = {m12, m02, m02, m02}, v3[4] = {m13, m03, m03, m03};
+    float sa[4] = {1.f, -1.f, 1.f, -1.f}, sb[4] = {-1.f, 1.f, -1.f, 1.f};
+    HM4 r;
+    for (int k = 0; k < 4; k++) {
+        r.m[k] = ((v1[k] * f0[k] - v2[k] * f1[k]) + v3[k] * f2[k]) * sa[k];
+        r.m[4 + k] = ((v0[k] * f0[k] - v2[k] * f3[k]) + v3[k] * f4[k]) * sb[k];
+        r.m[8 + k] = ((v0[k] * f1[k] - v1[k] * f3[k]) + v3[k] * f5[k]) * sa[k];
+        r.m[12 + k] = ((v0[k] * f2[k] - v1[k] * f4[k]) + v2[k] * f5[k]) * sb[k];
+    }
+    float d0 = m[0] * r.m[0], d1 = m[1] * r.m[4], d2 = m[2] * r.m[8], d3 = m[3] * r.m[12];
+    float det = d0 + d1 + d2 + d3;
+    float rcp = 1.0f / det;
+    for (int k = 0; k < 16; k++) r.m[k] = r.m[k] * rcp;
+    return r;
+}
+// host powf(x, 2.0) == x*x exactly (Material::serialize, strolle/src/material.rs:39)
+
+// ---- first-fit slot allocator (strolle/src/utils/allocator.rs) ----------------------------------------
+struct SlotAllocator {
+    struct Slot { size_t b, e; };
+    std::vector<Slot> free_;
+    bool unsorted = false;
+    void give(size_t b, size_t e) { if (!free_.empty() && b <= free_.back().e) unsorted = true; free_.push_back({b, e}); }
+    bool take(size_t n, size_t* b, size_t* e) {
+        if (unsorted && !free_.empty()) {
+            std::stable_sort(free_.begin(), free_.end(), [](const Slot& p, const Slot& q) { return p.b < q.b; });
+            for (size_t i = 0; i + 1 < free_.size();) { if (free_[i].e == free_[i + 1].b) { free_[i].e = free_[i + 1].e; free_.erase(free_.begin() + i + 1); } else i++; }
+        }
+        unsorted = false;
+        for (size_t i = 0; i < free_.size(); i++) {
+            size_t len = free_[i].e - free_[i].b;
+            if (len < n) continue;
+            *b = free_[i].b; *e = free_[i].b + n;
+            if (len == n) free_.erase(free_.begin() + i); else free_[i].b += n;
+            return true;
+        }
+        return false;
+    }
+};
+
+// ---- BVH: binned SAH build + DFS flatten (strolle/src/bvh/builder.rs, serializer.rs) ---------------------
+struct Prim { uint32_t tri, mat; H3 center; Box box; };
+struct BvhOut { std::vector<float4> buf; int depth = 0; };
+class BvhBuild {
+public:
+    static const int kBins = 12;   // builder.rs:15
+    struct Node { Box box; uint32_t b, e; int32_t left, right; };
+    std::vector<Node> nodes;
+    std::vector<Prim> prims;
+
+    void build(const std::vector<Prim>& all) {
+        prims.clear();
+        for (const Prim& p : all) if (p.center.x != FMAX) prims.push_back(p);   // alive only (primitives.rs:58-61)
+        nodes.clear();
+        nodes.push_back(Node{Box(), 0u, (uint32_t)prims.size(), -1, -1});   // root bounds stay unset: SAH cost = +inf (quirk C-8)
+        std::deque<int> work; work.push_back(0);
+        while (!work.empty()) {
+            int id = work.front(); work.pop_front();
+            int axis; float at, cost;
+            if (!best_plane(id, &axis, &at, &cost)) continue;
+            float leaf_cost = (float)(nodes[id].e - nodes[id].b) * nodes[id].box.half_area();
+            if (!(cost < leaf_cost)) continue;
+            partition(id, axis, at);
+            work.push_back(nodes[id].left); work.push_back(nodes[id].right);
+        }
+    }
+    void flatten(const std::vector<uint8_t>& alpha_blend, BvhOut* out) const { out->buf.clear(); out->depth = 0; emit(0, 1, alpha_blend, out); }
+
+private:
+    static float comp(H3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
+    bool best_plane(int id, int* axis_out, float* at_out, float* cost_out) const {   // builder.rs:70-181
+        const Node& nd = nodes[id];
+        uint32_t n = nd.e - nd.b;
+        if (n <= 1) return false;
+        const Prim* p = prims.data() + nd.b;
+        Box cb;
+        for (uint32_t i = 0; i < n; i++) cb.grow(p[i].center);
+        H3 ext = cb.hi - cb.lo;
+        H3 scale = h3((float)kBins / ext.x, (float)kBins / ext.y, (float)kBins / ext.z);
+        Box bb[3][kBins]; uint32_t cnt[3][kBins] = {};
+        for (uint32_t i = 0; i < n; i++) {
+            H3 f = scale * (p[i].center - cb.lo);
+            uint32_t id3[3] = {std::min(to_u32(f.x), (uint32_t)kBins - 1), std::min(to_u32(f.y), (uint32_t)kBins - 1), std::min(to_u32(f.z), (uint32_t)kBins - 1)};
+            for (int a = 0; a < 3; a++) { cnt[a][id3[a]] += 1; bb[a][id3[a]].grow(p[i].box); }
+        }
+        float la[3][kBins - 1], ra[3][kBins - 1]; uint32_t lc[3][kBins - 1], rc[3][kBins - 1];
+        for (int a = 0; a < 3; a++) {
+            Box lb, rb; uint32_t ln = 0, rn = 0;
+            for (int i = 0; i < kBins - 1; i++) {
+                ln += cnt[a][i]; lc[a][i] = ln;
+                if (bb[a][i].set()) lb.grow(bb[a][i]);
+                la[a][i] = lb.half_area();
+                rn += cnt[a][kBins - 1 - i]; rc[a][kBins - 2 - i] = rn;
+                if (bb[a][kBins - 1 - i].set()) rb.grow(bb[a][kBins - 1 - i]);
+                ra[a][kBins - 2 - i] = rb.half_area();
+            }
+        }
+        bool any = false; float best = 0.f;
+        H3 step = h3(ext.x / (float)kBins, ext.y / (float)kBins, ext.z / (float)kBins);
+        for (int a = 0; a < 3; a++) for (int i = 0; i < kBins - 1; i++) {
+            float c = (float)lc[a][i] * la[a][i] + (float)rc[a][i] * ra[a][i];
+            if (!any || c <= best) {   // NaN costs stick once taken (quirk C-7)
+                any = true; best = c; *axis_out = a; *at_out = comp(cb.lo, a) + comp(step, a) * (float)(i + 1);
+            }
+        }
+        *cost_out = best;
+        return any;
+    }
+    void partition(int id, int axis, float at) {   // builder.rs:183-319 (fresh build: no subtree reuse)
+        uint32_t b = nodes[id].b, e = nodes[id].e;
+        Prim* d = prims.data() + b;
+        int l = 0, r = (int)(e - b) - 1;
+        Box lb, rb;
+        while (l <= r) {
+            Prim cur = d[l];
+            if (comp(cur.center, axis) < at) { l++; lb.grow(cur.box); }
+            else { std::swap(d[l], d[r]); r--; rb.grow(cur.box); }
+        }
+        uint32_t mid = b + (uint32_t)l;
+        int li = (int)nodes.size(); nodes.push_back(Node{lb, b, mid, -1, -1});
+        int ri = (int)nodes.size(); nodes.push_back(Node{rb, mid, e, -1, -1});
+        nodes[id].left = li; nodes[id].right = ri;
+    }
+    uint32_t emit(int id, int depth, const std::vector<uint8_t>& alpha, BvhOut* out) const {   // serializer.rs:20-110
+        uint32_t at = (uint32_t)out->buf.size();
+        if (depth > out->depth) out->depth = depth;
+        const Node& nd = nodes[id];
+        if (nd.left >= 0) {
+            out->buf.resize(out->buf.size() + 4, make_float4(0, 0, 0, 0));
+            emit(nd.left, depth + 1, alpha, out);
+            uint32_t rp = emit(nd.right, depth + 1, alpha, out);
+            const Box& lb = nodes[nd.left].box; const Box& rb = nodes[nd.right].box;
+            out->buf[at] = make_float4(lb.lo.x, lb.lo.y, lb.lo.z, bits2f(0u));
+            out->buf[at + 1] = make_float4(lb.hi.x, lb.hi.y, lb.hi.z, bits2f(rp));
+            out->buf[at + 2] = make_float4(rb.lo.x, rb.lo.y, rb.lo.z, 0.0f);
+            out->buf[at + 3] = make_float4(rb.hi.x, rb.hi.y, rb.hi.z, 0.0f);
+        } else {
+            uint32_t n = nd.e - nd.b;
+            for (uint32_t i = 0; i < n; i++) {
+                const Prim& p = prims[nd.b + i];
+                uint32_t flags = (i + 1 < n ? 1u : 0u) | ((alpha[p.mat] ? 1u : 0u) << 1);
+                out->buf.push_back(make_float4(bits2f(flags), bits2f(p.tri), bits2f(p.mat), bits2f(1u)));
+            }
+        }
+        return at;
+    }
+};
+
+// ---- device buffer helper ------------------------------------------------------------------------------
+struct DevMem {
+    void* p = nullptr; size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return ST_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = std::max<size_t>(bytes, 256);
+        CK(cudaMalloc(&p, want));
+        CK(cudaMemset(p, 0, want));
+        cap = want;
+        return ST_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+static const char* kPassNames[P_COUNT] = {
+    "prim_gbuffer", "di_sampling", "di_temporal_resampling", "di_spatial_resampling_pick", "di_spatial_resampling_trace", "di_spatial_resampling_sample",
+    "di_resolving", "gi_reprojection", "gi_sampling_a", "gi_sampling_b", "gi_temporal_resampling", "gi_spatial_resampling_pick",
+    "gi_spatial_resampling_trace", "gi_spatial_resampling_sample", "gi_preview_resampling", "gi_resolving", "frame_reprojection",
+    "frame_denoising_reproject", "frame_denoising_estimate_variance", "frame_denoising_wavelet", "frame_composition", "ref_tracing",
+    "ref_shading", "bvh_heatmap", "atmosphere", "trace_stream"};
+
+static uint32_t dispatch_seed(uint32_t base, uint32_t frame, uint32_t k) {
+    uint32_t s = base ^ (frame * 64u + k);
+    s = s * 747796405u + 2891336453u;
+    uint32_t w = ((s >> ((s >> 28) + 4u)) ^ s) * 277803737u;
+    return (w >> 22) ^ w;
+}
+
+struct CameraSlot {
+    bool alive = false;
+    st_camera desc;
+    uint32_t frame = 0;
+    CameraDev dev;
+    std::vector<std::pair<std::string, float4**>> named;   // buffer name -> pointer slot in `dev`
+    std::vector<std::pair<std::string, size_t>> sizes;      // float4 count per named buffer
+    DevMem arena;
+    DevMem rgba8;
+};
+
+struct Step { int pass; std::function<void(cudaStream_t)> run; };
+
+}  // namespace st
+
+using namespace st;
+
+struct st_engine {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // meshes / materials / instances / triangles -------------------------------------------------
+    std::unordered_map<st_handle, std::vector<st_mesh_triangle>> meshes;
+    std::vector<st_material> materials; std::vector<st_handle> material_handles; bool materials_dirty = false;
+    struct Inst { st_handle handle, mesh, material; Affine3 xf, xf_inv, prev_xf; bool dirty; };
+    std::vector<Inst> instances; bool instances_dirty = false;
+    struct Range { st_handle handle; size_t b, e; };
+    std::vector<Range> tri_ranges; SlotAllocator tri_alloc;
+    std::vector<float4> h_triangles; std::vector<Prim> prims; bool triangles_dirty = false;
+    BvhBuild bvh; BvhOut bvh_out; bool bvh_dirty = false;
+    std::vector<GpuMaterial> h_materials;
+    // lights (strolle/src/lights.rs): slot 0 is the sun ------------------------------------------
+    static const st_handle kSun = ~(st_handle)0;
+    std::vector<GpuLight> h_lights; std::vector<std::pair<st_handle, uint32_t>> light_slots;
+    std::vector<st_handle> lights_created, lights_updated; std::vector<std::pair<st_handle, uint32_t>> lights_remapped; std::vector<uint32_t> lights_killed;
+    uint32_t next_light = 1; bool lights_dirty = true;
+    float sun_azimuth = 0.0f, sun_altitude = 0.35f; bool sun_dirty = true;
+    GpuWorld world;
+    uint32_t frame = 1, seed_base = 0xC0FFEEu;
+    // device scene ------------------------------------------------------------------------------
+    DevMem d_triangles, d_bvh, d_materials, d_lights, d_noise, d_tlut, d_slut, d_skylut, d_scratch;
+    bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
+    std::vector<CameraSlot*> cameras;
+    // timing ---------------------------------------------------------------------------------------
+    bool timing = false;
+    float pass_ms[P_COUNT] = {}; uint32_t pass_launches[P_COUNT] = {};
+    struct Timed { int pass; cudaEvent_t a, b; };
+    std::vector<Timed> pending; std::vector<cudaEvent_t> event_pool;
+
+    SceneDev scene() const {
+        SceneDev s;
+        s.triangles = (const float4*)d_triangles.p; s.bvh = (const float4*)d_bvh.p; s.materials = (const GpuMaterial*)d_materials.p;
+        s.lights = (const GpuLight*)d_lights.p; s.blue_noise = (const uchar4*)d_noise.p;
+        s.transmittance_lut = (const float4*)d_tlut.p; s.scattering_lut = (const float4*)d_slut.p; s.sky_lut = (const float4*)d_skylut.p;
+        s.world = world;
+        return s;
+    }
+    uint32_t* light_slot(st_handle h) { for (auto& p : light_slots) if (p.first == h) return &p.second; return nullptr; }
+    cudaEvent_t get_event() { if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
+    void run_timed(int pass, const std::function<void(cudaStream_t)>& fn) {
+        if (!timing) { fn(stream); pass_launches[pass]++; return; }
+        Timed t; t.pass = pass; t.a = get_event(); t.b = get_event();
+        cudaEventRecord(t.a, stream); fn(stream); cudaEventRecord(t.b, stream);
+        pending.push_back(t); pass_launches[pass]++;
+    }
+    void collect_timing() {
+        for (Timed& t : pending) { cudaEventSynchronize(t.b); float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b); pass_ms[t.pass] += ms; event_pool.push_back(t.a); event_pool.push_back(t.b); }
+        pending.clear();
+    }
+};
+
+namespace st {
+
+static GpuLight make_sun(float4 d0, float4 d1) {   // strolle-gpu/src/light.rs:49-65
+    GpuLight l; std::memset(&l, 0, sizeof l); l.d0 = d0; l.d1 = d1; l.d2 = make_float4(bits2f(1u), 0, 0, 0); return l;
+}
+static void uniq_add(std::vector<st_handle>& v, st_handle h) { if (std::find(v.begin(), v.end(), h) == v.end()) v.push_back(h); }
+static void uniq_del(std::vector<st_handle>& v, st_handle h) { v.erase(std::remove(v.begin(), v.end(), h), v.end()); }
+
+static void light_overwrite(st_engine* e, uint32_t slot, st_handle h, GpuLight nl) {   // Lights::update (lights.rs:168-182)
+    const GpuLight& old = e->h_lights[slot];
+    nl.prev_d0 = old.d0; nl.prev_d1 = old.d1; nl.prev_d2 = old.d2;
+    uniq_add(e->lights_updated, h);
+    e->h_lights[slot] = nl; e->lights_dirty = true;
+}
+
+static float2 oct_encode_host(H3 n) {   // strolle-gpu/src/normal.rs:9-23 (spot light direction)
+    float s = std::fabs(n.x) + std::fabs(n.y) + std::fabs(n.z);
+    n = n / s;
+    float2 r;
+    if (n.z >= 0.0f) r = make_float2(n.x, n.y);
+    else r = make_float2(std::copysign(1.0f - std::fabs(n.y), n.x), std::copysign(1.0f - std::fabs(n.x), n.y));
+    return make_float2(r.x * 0.5f + 0.5f, r.y * 0.5f + 0.5f);
+}
+
+// world-space bake of one mesh triangle (strolle/src/mesh_triangle.rs:47-86) + serialisation
+// (strolle/src/triangle.rs:16-38)
+static void bake_triangle(const st_mesh_triangle& t, const Affine3& xf, const Affine3& inv, float4* out9, Prim* prim) {
+    Affine3 nt;   // transpose of inv's 3x3
+    nt.x = h3(inv.x.x, inv.y.x, inv.z.x); nt.y = h3(inv.x.y, inv.y.y, inv.z.y); nt.z = h3(inv.x.z, inv.y.z, inv.z.z); nt.t = h3(0, 0, 0);
+    float det = hdot(xf.z, hcross(xf.x, xf.y));
+    float sign = (f2bits(det) >> 31) ? -1.0f : 1.0f;
+    H3 pos[3];
+    for (int k = 0; k < 3; k++) {
+        pos[k] = aff_point(xf, h3(t.positions[k][0], t.positions[k][1], t.positions[k][2]));
+        H3 n = hnorm(aff_mat(nt, h3(t.normals[k][0], t.normals[k][1], t.normals[k][2])));
+        H3 tg = hnorm(aff_mat(xf, h3(t.tangents[k][0], t.tangents[k][1], t.tangents[k][2])));
+        out9[3 * k] = make_float4(pos[k].x, pos[k].y, pos[k].z, t.uvs[k][0]);
+        out9[3 * k + 1] = make_float4(n.x, n.y, n.z, t.uvs[k][1]);
+        out9[3 * k + 2] = make_float4(tg.x, tg.y, tg.z, t.tangents[k][3] * sign);
+    }
+    prim->center = (((h3(0, 0, 0) + pos[0]) + pos[1]) + pos[2]) / 3.0f;
+    prim->box = Box();
+    for (int k = 0; k < 3; k++) prim->box.grow(pos[k]);
+}
+
+static void release_range(st_engine* e, st_handle inst) {   // Triangles::remove (triangles.rs:157-171)
+    for (size_t i = 0; i < e->tri_ranges.size(); i++) if (e->tri_ranges[i].handle == inst) {
+        e->tri_alloc.give(e->tri_ranges[i].b, e->tri_ranges[i].e);
+        for (size_t t = e->tri_ranges[i].b; t < e->tri_ranges[i].e; t++) e->prims[t].center = h3(FMAX, FMAX, FMAX);
+        e->tri_ranges.erase(e->tri_ranges.begin() + i);
+        return;
+    }
+}
+
+// Instances::refresh (instances.rs:69-139) in instance-insertion order
+static bool refresh_instances(st_engine* e) {
+    if (!e->instances_dirty) return false;
+    e->instances_dirty = false;
+    for (auto& in : e->instances) {
+        if (!in.dirty) continue;
+        in.dirty = false;
+        auto mesh = e->meshes.find(in.mesh);
+        auto mat = std::find(e->material_handles.begin(), e->material_handles.end(), in.material);
+        if (mesh == e->meshes.end() || mat == e->material_handles.end()) { in.dirty = true; e->instances_dirty = true; continue; }   // retried next tick
+        uint32_t mat_id = (uint32_t)(mat - e->material_handles.begin());
+        const std::vector<st_mesh_triangle>& tris = mesh->second;
+        st_engine::Range* have = nullptr;
+        for (auto& r : e->tri_ranges) if (r.handle == in.handle) have = &r;
+        size_t b, en;
+        if (have && have->e - have->b == tris.size()) { b = have->b; en = have->e; }
+        else {
+            if (have) release_range(e, in.handle);
+            if (!e->tri_alloc.take(tris.size(), &b, &en)) {
+                b = e->h_triangles.size() / 9; en = b + tris.size();
+                e->h_triangles.resize(9 * en, make_float4(0, 0, 0, 0));
+                e->prims.resize(en);
+            }
+            e->tri_ranges.push_back({in.handle, b, en});
+        }
+        for (size_t i = 0; i < tris.size(); i++) {
+            Prim& p = e->prims[b + i];
+            p.tri = (uint32_t)(b + i); p.mat = mat_id;
+            bake_triangle(tris[i], in.xf, in.xf_inv, &e->h_triangles[9 * (b + i)], &p);
+        }
+        e->triangles_dirty = true;
+    }
+    return true;
+}
+
+static int upload(st_engine* e, DevMem& d, const void* src, size_t bytes) {
+    int rc = d.ensure(bytes); if (rc) return rc;
+    if (bytes) CK(cudaMemcpyAsync(d.p, src, bytes, cudaMemcpyHostToDevice, e->stream));
+    return ST_OK;
+}
+
+static int ensure_luts(st_engine* e) {   // AtmospherePass::run (passes/atmosphere.rs:67-111)
+    int rc;
+    if (!e->luts_static_ready) {
+        if ((rc = e->d_tlut.ensure(256 * 64 * 16))) return rc;
+        if ((rc = e->d_slut.ensure(32 * 32 * 16))) return rc;
+        if ((rc = e->d_skylut.ensure(256 * 256 * 16))) return rc;
+        e->run_timed(P_ATMOSPHERE, [&](cudaStream_t s) { launch_atm_transmittance((float4*)e->d_tlut.p, s); launch_atm_scattering((const float4*)e->d_tlut.p, (float4*)e->d_slut.p, s); });
+        e->luts_static_ready = true;
+    }
+    if (!e->sky_ready || e->sky_for_altitude != e->sun_altitude) {
+        float alt = e->world.sun_altitude;
+        e->run_timed(P_ATMOSPHERE, [&](cudaStream_t s) { launch_atm_sky((const float4*)e->d_tlut.p, (const float4*)e->d_slut.p, alt, (float4*)e->d_skylut.p, s); });
+        e->sky_ready = true; e->sky_for_altitude = e->sun_altitude;
+    }
+    return ST_OK;
+}
+
+static GpuCamera serialize_camera(const st_camera& c) {   // Camera::serialize (strolle/src/camera.rs:50-66)
+    HM4 t, p; std::memcpy(t.m, c.transform, 64); std::memcpy(p.m, c.projection, 64);
+    HM4 pv = hm_mul(p, hm_inverse(t)), n2w = hm_mul(t, hm_inverse(p));
+    GpuCamera g;
+    std::memcpy(g.projection_view, pv.m, 64); std::memcpy(g.ndc_to_world, n2w.m, 64);
+    g.origin = make_float4(c.transform[12], c.transform[13], c.transform[14], 0.0f);
+    g.screen = make_float4((float)c.width, (float)c.height, 0.0f, 0.0f);
+    return g;
+}
+
+// CameraBuffers::new (strolle/src/camera_controller/buffers.rs:53-339): one zero-filled arena
+static int allocate_camera(st_engine* e, CameraSlot* cs) {
+    CameraDev& d = cs->dev;
+    size_t n = (size_t)cs->desc.width * cs->desc.height;
+    cs->named.clear(); cs->sizes.clear();
+    auto reg = [&](const char* name, float4** slot, size_t count) { cs->named.push_back({name, slot}); cs->sizes.push_back({name, count}); };
+    reg("prim_gbuffer_d0_a", &d.prim_gbuffer_d0[0], n); reg("prim_gbuffer_d0_b", &d.prim_gbuffer_d0[1], n);
+    reg("prim_gbuffer_d1_a", &d.prim_gbuffer_d1[0], n); reg("prim_gbuffer_d1_b", &d.prim_gbuffer_d1[1], n);
+    reg("prim_surface_map_a", &d.prim_surface_map[0], n); reg("prim_surface_map_b", &d.prim_surface_map[1], n);
+    reg("reprojection_map", &d.reprojection_map, n); reg("velocity_map", &d.velocity_map, n);
+    reg("di_reservoirs_0", &d.di_reservoirs[0], 2 * n); reg("di_reservoirs_1", &d.di_reservoirs[1], 2 * n); reg("di_reservoirs_2", &d.di_reservoirs[2], 2 * n);
+    reg("di_diff_samples", &d.di_diff_samples, n); reg("di_diff_prev_colors", &d.di_diff_prev_colors, n); reg("di_diff_curr_colors", &d.di_diff_curr_colors, n);
+    reg("di_diff_moments_a", &d.di_diff_moments[0], n); reg("di_diff_moments_b", &d.di_diff_moments[1], n); reg("di_diff_stash", &d.di_diff_stash, n);
+    reg("di_spec_samples", &d.di_spec_samples, n);
+    reg("gi_d0", &d.gi_d0, n); reg("gi_d1", &d.gi_d1, n); reg("gi_d2", &d.gi_d2, n);
+    reg("gi_reservoirs_0", &d.gi_reservoirs[0], 4 * n); reg("gi_reservoirs_1", &d.gi_reservoirs[1], 4 * n);
+    reg("gi_reservoirs_2", &d.gi_reservoirs[2], 4 * n); reg("gi_reservoirs_3", &d.gi_reservoirs[3], 4 * n);
+    reg("gi_diff_samples", &d.gi_diff_samples, n); reg("gi_diff_prev_colors", &d.gi_diff_prev_colors, n); reg("gi_diff_curr_colors", &d.gi_diff_curr_colors, n);
+    reg("gi_diff_moments_a", &d.gi_diff_moments[0], n); reg("gi_diff_moments_b", &d.gi_diff_moments[1], n); reg("gi_diff_stash", &d.gi_diff_stash, n);
+    reg("gi_spec_samples", &d.gi_spec_samples, n);
+    reg("ref_hits", &d.ref_hits, 2 * n); reg("ref_rays", &d.ref_rays, 3 * n); reg("ref_colors", &d.ref_colors, n);
+    reg("prim_triangle_ids", &d.prim_triangle_ids, n); reg("output", &d.output, n);
+    size_t total = 0;
+    for (auto& s : cs->sizes) total += (s.second * 16 + 255) / 256 * 256;
+    cs->arena.release();
+    int rc = cs->arena.ensure(total); if (rc) return rc;
+    CK(cudaMemsetAsync(cs->arena.p, 0, total, e->stream));
+    size_t off = 0;
+    for (size_t i = 0; i < cs->named.size(); i++) { *cs->named[i].second = (float4*)((char*)cs->arena.p + off); off += (cs->sizes[i].second * 16 + 255) / 256 * 256; }
+    d.w = (int)cs->desc.width; d.h = (int)cs->desc.height; d.y0 = 0; d.y1 = d.h;
+    return ST_OK;
+}
+
+// CameraController::render (strolle/src/camera_controller.rs:87-174) as an explicit step list
+static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* steps) {
+    const CameraDev cam = cs->dev;   // snapshot (pointers + cameras)
+    const SceneDev sc = e->scene();
+    const uint32_t f = cs->frame;
+    const int cur = (f % 2u) == 1u ? 1 : 0;   // is_alternate (camera_controller.rs:185-187)
+    const st_camera& d = cs->desc;
+    auto seed = [&](uint32_t k) { return dispatch_seed(e->seed_base, f, k); };
+    auto add = [&](int pass, std::function<void(cudaStream_t)> fn) { steps->push_back(Step{pass, std::move(fn)}); };
+    const float4* di_final = (d.denoise && (d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_DI_DIFFUSE)) ? cam.di_diff_curr_colors : cam.di_diff_samples;
+    const float4* gi_final = (d.denoise && (d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_GI_DIFFUSE)) ? cam.gi_diff_curr_colors : cam.gi_diff_samples;
+    if (d.mode == ST_MODE_BVH_HEATMAP) {
+        add(P_BVH_HEATMAP, [=](cudaStream_t s) { launch_bvh_heatmap(cam, sc, s); });
+        add(P_COMPOSITION, [=](cudaStream_t s) { launch_composition(cam, sc, cur, 5u, di_final, gi_final, s); });
+        return;
+    }
+    if (d.mode == ST_MODE_REFERENCE) {
+        for (uint32_t depth = 0; depth <= (uint32_t)d.ref_depth; depth++) {
+            uint32_t sd = seed(P_REF_SHADING_SEED + depth);
+            add(P_REF_TRACING, [=](cudaStream_t s) { launch_ref_tracing(cam, sc, depth, s); });
+            add(P_REF_SHADING, [=](cudaStream_t s) { launch_ref_shading(cam, sc, sd, depth, s); });
+        }
+        add(P_REF_SHADING, [=](cudaStream_t s) { launch_ref_shading(cam, sc, 0u, 255u, s); });
+        add(P_COMPOSITION, [=](cudaStream_t s) { launch_composition(cam, sc, cur, 6u, di_final, gi_final, s); });
+        return;
+    }
+    const bool needs_di = d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_DI_DIFFUSE || d.mode == ST_MODE_DI_SPECULAR;
+    const bool needs_gi = d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_GI_DIFFUSE || d.mode == ST_MODE_GI_SPECULAR;
+    add(P_PRIM_GBUFFER, [=](cudaStream_t s) { launch_prim_gbuffer(cam, sc, cur, s); });
+    if (!e->instances.empty()) {
+        add(P_FRAME_REPROJECTION, [=](cudaStream_t s) { launch_frame_reprojection(cam, sc, cur, s); });
+        if (needs_di) {
+            uint32_t s1 = seed(P_DI_SAMPLING), s2 = seed(P_DI_TEMPORAL), s3 = seed(P_DI_SPATIAL_PICK), s5 = seed(P_DI_SPATIAL_SAMPLE);
+            add(P_DI_SAMPLING, [=](cudaStream_t s) { launch_di_sampling(cam, sc, cur, s1, f, s); });
+            add(P_DI_TEMPORAL, [=](cudaStream_t s) { launch_di_temporal(cam, sc, cur, s2, s); });
+            add(P_DI_SPATIAL_PICK, [=](cudaStream_t s) { launch_di_spatial_pick(cam, sc, cur, s3, f, s); });
+            add(P_DI_SPATIAL_TRACE, [=](cudaStream_t s) { launch_spatial_trace(cam, sc, cam.di_diff_samples, cam.di_diff_curr_colors, cam.di_diff_stash, s); });
+            add(P_DI_SPATIAL_SAMPLE, [=](cudaStream_t s) { launch_di_spatial_sample(cam, sc, s5, f, s); });
+            add(P_DI_RESOLVING, [=](cudaStream_t s) { launch_di_resolving(cam, sc, cur, s); });
+        }
+        if (needs_gi) {
+            uint32_t sa = seed(P_GI_SAMPLING_A), sb = seed(P_GI_SAMPLING_B), st_ = seed(P_GI_TEMPORAL), sp = seed(P_GI_SPATIAL_PICK), ss = seed(P_GI_SPATIAL_SAMPLE), sv = seed(P_GI_PREVIEW);
+            uint32_t source;
+            add(P_GI_REPROJECTION, [=](cudaStream_t s) { launch_gi_reprojection(cam, sc, cur, s); });
+            auto sampling = [&]() {
+                add(P_GI_SAMPLING_A, [=](cudaStream_t s) { launch_gi_sampling_a(cam, sc, cur, sa, f, s); });
+                add(P_GI_SAMPLING_B, [=](cudaStream_t s) { launch_gi_sampling_b(cam, sc, cur, sb, f, s); });
+            };
+            if (f % 6u < 4u) {
+                if (f % 2u == 0u) sampling();
+                add(P_GI_TEMPORAL, [=](cudaStream_t s) { launch_gi_temporal(cam, sc, cur, st_, f, s); });
+                if (f % 2u == 1u) {
+                    add(P_GI_SPATIAL_PICK, [=](cudaStream_t s) { launch_gi_spatial_pick(cam, sc, cur, sp, f, s); });
+                    add(P_GI_SPATIAL_TRACE, [=](cudaStream_t s) { launch_spatial_trace(cam, sc, cam.gi_d0, cam.gi_d1, cam.gi_d2, s); });
+                    add(P_GI_SPATIAL_SAMPLE, [=](cudaStream_t s) { launch_gi_spatial_sample(cam, sc, ss, f, s); });
+                    source = 1;
+                } else source = 0;
+            } else {
+                sampling();
+                add(P_GI_TEMPORAL, [=](cudaStream_t s) { launch_gi_temporal(cam, sc, cur, st_, f, s); });
+                source = 0;
+            }
+            const float4* src0 = source == 0 ? cam.gi_reservoirs[1] : cam.gi_reservoirs[2];
+            add(P_GI_PREVIEW, [=](cudaStream_t s) { launch_gi_preview(cam, sc, cur, sv, 0u, src0, cam.gi_reservoirs[3], s); });
+            add(P_GI_PREVIEW, [=](cudaStream_t s) { launch_gi_preview(cam, sc, cur, sv, 1u, cam.gi_reservoirs[3], cam.gi_reservoirs[0], s); });
+            add(P_GI_RESOLVING, [=](cudaStream_t s) { launch_gi_resolving(cam, sc, cur, src0, s); });
+        }
+    }
+    if (d.denoise) {   // FrameDenoisingPass::run (passes/frame_denoising.rs:143-190)
+        add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.di_diff_prev_colors, cam.di_diff_moments[cur ^ 1], cam.di_diff_samples, cam.di_diff_curr_colors, cam.di_diff_moments[cur], s); });
+        add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.gi_diff_prev_colors, cam.gi_diff_moments[cur ^ 1], cam.gi_diff_samples, cam.gi_diff_curr_colors, cam.gi_diff_moments[cur], s); });
+        add(P_DENOISE_VARIANCE, [=](cudaStream_t s) { launch_denoise_variance(cam, sc, cur, s); });
+        float4* di_io[5][2] = {{cam.di_diff_stash, cam.di_diff_prev_colors}, {cam.di_diff_prev_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors},
+                               {cam.di_diff_curr_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors}};
+        float4* gi_io[5][2] = {{cam.gi_diff_stash, cam.gi_diff_prev_colors}, {cam.gi_diff_prev_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors},
+                               {cam.gi_diff_curr_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors}};
+        for (uint32_t nth = 0; nth < 5; nth++) {
+            float4 *a = di_io[nth][0], *b = di_io[nth][1], *c = gi_io[nth][0], *g = gi_io[nth][1];
+            add(P_DENOISE_WAVELET, [=](cudaStream_t s) { launch_denoise_wavelet(cam, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, s); });
+        }
+    }
+    uint32_t mode = (uint32_t)d.mode;
+    add(P_COMPOSITION, [=](cudaStream_t s) { launch_composition(cam, sc, cur, mode, di_final, gi_final, s); });
+}
+
+static CameraSlot* get_camera(st_engine* e, st_camera_handle h) { return (h >= 0 && (size_t)h < e->cameras.size() && e->cameras[h]->alive) ? e->cameras[h] : nullptr; }
+
+}  // namespace st
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+const char* st_last_error(void) { return g_err.c_str(); }
+const char* st_pass_name(int pass) { return (pass >= 0 && pass < P_COUNT) ? kPassNames[pass] : ""; }
+
+int st_engine_create(int device, st_engine** out) {
+    if (!out) return fail(ST_ERR_INVALID, "out is null");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0) return fail(ST_ERR_CUDA, "no CUDA device available: this library has no CPU fallback");
+    if (device < 0 || device >= count) return fail(ST_ERR_INVALID, "bad device ordinal");
+    CK(cudaSetDevice(device));
+    st_engine* e = new st_engine();
+    e->device = device;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    std::memset(&e->world, 0, sizeof e->world);
+    e->h_lights.push_back(make_sun(make_float4(0, 0, 0, 25.0f), make_float4(0, 0, 0, std::numeric_limits<float>::infinity())));   // Lights::new (lights.rs:33-50)
+    e->light_slots.push_back({st_engine::kSun, 0u});
+    int rc = e->d_noise.ensure(256 * 256 * 4); if (rc) { delete e; return rc; }
+    *out = e;
+    return ST_OK;
+}
+void st_engine_destroy(st_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); delete c; }
+    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch};
+    for (DevMem* d : all) d->release();
+    for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
+    for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+int st_insert_mesh(st_engine* e, st_handle mesh, const st_mesh_triangle* tris, size_t count) {
+    if (!e || (!tris && count)) return fail(ST_ERR_INVALID, "null argument");
+    e->meshes[mesh].assign(tris, tris + count);
+    return ST_OK;
+}
+int st_remove_mesh(st_engine* e, st_handle mesh) { if (!e) return fail(ST_ERR_INVALID, "null engine"); e->meshes.erase(mesh); return ST_OK; }
+
+int st_insert_material(st_engine* e, st_handle h, const st_material* m) {   // Materials::insert (materials.rs:36-55)
+    if (!e || !m) return fail(ST_ERR_INVALID, "null argument");
+    auto it = std::find(e->material_handles.begin(), e->material_handles.end(), h);
+    if (it != e->material_handles.end()) e->materials[it - e->material_handles.begin()] = *m;
+    else { e->material_handles.push_back(h); e->materials.push_back(*m); }
+    e->materials_dirty = true;
+    return ST_OK;
+}
+int st_has_material(st_engine* e, st_handle h) { return e && std::find(e->material_handles.begin(), e->material_handles.end(), h) != e->material_handles.end() ? 1 : 0; }
+int st_remove_material(st_engine* e, st_handle h) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    // Materials::remove only drops the handle: the slot is never reused (allocator.give(id..id) is an
+    // empty range, materials.rs:61-69), so ids of the other materials are stable.
+    auto it = std::find(e->material_handles.begin(), e->material_handles.end(), h);
+    if (it != e->material_handles.end()) *it = ~(st_handle)0 - 1;
+    e->materials_dirty = true;
+    return ST_OK;
+}
+
+int st_insert_instance(st_engine* e, st_handle h, st_handle mesh, st_handle material, const float a[12]) {   // Instances::insert (instances.rs:29-50)
+    if (!e || !a) return fail(ST_ERR_INVALID, "null argument");
+    Affine3 xf; xf.x = h3(a[0], a[1], a[2]); xf.y = h3(a[3], a[4], a[5]); xf.z = h3(a[6], a[7], a[8]); xf.t = h3(a[9], a[10], a[11]);
+    for (auto& in : e->instances) if (in.handle == h) { in.prev_xf = in.xf; in.mesh = mesh; in.material = material; in.xf = xf; in.xf_inv = aff_inverse(xf); in.dirty = true; e->instances_dirty = true; return ST_OK; }
+    st_engine::Inst in; in.handle = h; in.mesh = mesh; in.material = material; in.xf = xf; in.xf_inv = aff_inverse(xf); in.prev_xf = xf; in.dirty = true;
+    e->instances.push_back(in); e->instances_dirty = true;
+    return ST_OK;
+}
+int st_remove_instance(st_engine* e, st_handle h) {   // Engine::remove_instance (lib.rs:226-229)
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    size_t before = e->instances.size();
+    e->instances.erase(std::remove_if(e->instances.begin(), e->instances.end(), [&](const st_engine::Inst& i) { return i.handle == h; }), e->instances.end());
+    if (e->instances.size() != before) e->instances_dirty = true;
+    release_range(e, h);
+    return ST_OK;
+}
+
+int st_insert_light(st_engine* e, st_handle h, const st_light* l) {   // Lights::insert (lights.rs:54-82), Light::serialize (light.rs:25-79)
+    if (!e || !l) return fail(ST_ERR_INVALID, "null argument");
+    if (h == st_engine::kSun) return fail(ST_ERR_INVALID, "handle reserved for the sun");
+    GpuLight g; std::memset(&g, 0, sizeof g);
+    g.d0 = make_float4(l->position[0], l->position[1], l->position[2], l->radius);
+    g.d1 = make_float4(l->color[0], l->color[1], l->color[2], l->range);
+    if (l->kind == ST_LIGHT_POINT) g.d2 = make_float4(bits2f(1u), 0, 0, 0);
+    else if (l->kind == ST_LIGHT_SPOT) { float2 d = oct_encode_host(h3(l->direction[0], l->direction[1], l->direction[2])); g.d2 = make_float4(bits2f(2u), d.x, d.y, l->angle); }
+    else return fail(ST_ERR_INVALID, "unknown light kind");
+    if (uint32_t* slot = e->light_slot(h)) { light_overwrite(e, *slot, h, g); return ST_OK; }
+    uint32_t id;
+    if (e->next_light < e->h_lights.size()) { id = e->next_light; e->h_lights[id] = g; }
+    else { id = (uint32_t)e->h_lights.size(); e->h_lights.push_back(g); }
+    e->light_slots.push_back({h, id});
+    uniq_add(e->lights_created, h);
+    e->next_light += 1; e->lights_dirty = true;
+    return ST_OK;
+}
+int st_remove_light(st_engine* e, st_handle h) {   // Lights::remove (lights.rs:101-127)
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    uint32_t* sp = e->light_slot(h);
+    if (!sp) return ST_OK;
+    uint32_t id = *sp;
+    e->light_slots.erase(std::remove_if(e->light_slots.begin(), e->light_slots.end(), [&](const std::pair<st_handle, uint32_t>& p) { return p.first == h; }), e->light_slots.end());
+    e->h_lights.erase(e->h_lights.begin() + id);
+    GpuLight zero; std::memset(&zero, 0, sizeof zero); e->h_lights.push_back(zero);
+    uniq_del(e->lights_created, h); uniq_del(e->lights_updated, h);
+    e->lights_remapped.erase(std::remove_if(e->lights_remapped.begin(), e->lights_remapped.end(), [&](const std::pair<st_handle, uint32_t>& p) { return p.first == h; }), e->lights_remapped.end());
+    if (std::find(e->lights_killed.begin(), e->lights_killed.end(), id) == e->lights_killed.end()) e->lights_killed.push_back(id);
+    e->next_light -= 1;
+    for (auto& p : e->light_slots) if (p.second > id) {
+        bool seen = false; for (auto& r : e->lights_remapped) if (r.first == p.first) seen = true;
+        if (!seen) e->lights_remapped.push_back({p.first, p.second});
+        p.second -= 1;
+    }
+    e->lights_dirty = true;
+    return ST_OK;
+}
+int st_update_sun(st_engine* e, float az, float alt) { if (!e) return fail(ST_ERR_INVALID, "null engine"); e->sun_azimuth = az; e->sun_altitude = alt; e->sun_dirty = true; return ST_OK; }
+
+int st_set_seed_base(st_engine* e, uint32_t base) { if (!e) return fail(ST_ERR_INVALID, "null engine"); e->seed_base = base; return ST_OK; }
+int st_set_blue_noise(st_engine* e, const uint8_t* rgba) {
+    if (!e || !rgba) return fail(ST_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    CK(cudaMemcpyAsync(e->d_noise.p, rgba, 256 * 256 * 4, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return ST_OK;
+}
+uint32_t st_frame(st_engine* e) { return e ? e->frame : 0; }
+
+int st_create_camera(st_engine* e, const st_camera* c, st_camera_handle* out) {   // CameraController::new (camera_controller.rs:24-43)
+    if (!e || !c || !out) return fail(ST_ERR_INVALID, "null argument");
+    if (c->width == 0 || c->height == 0) return fail(ST_ERR_INVALID, "empty viewport");
+    CK(cudaSetDevice(e->device));
+    CameraSlot* cs = new CameraSlot();
+    cs->alive = true; cs->desc = *c;
+    int rc = allocate_camera(e, cs); if (rc) { delete cs; return rc; }
+    cs->dev.curr = serialize_camera(*c); cs->dev.prev = cs->dev.curr;
+    e->cameras.push_back(cs);
+    *out = (st_camera_handle)e->cameras.size() - 1;
+    return ST_OK;
+}
+int st_update_camera(st_engine* e, st_camera_handle h, const st_camera* c) {   // CameraController::update (camera_controller.rs:45-63)
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !c) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    CK(cudaSetDevice(e->device));
+    bool invalidated = cs->desc.mode != c->mode || cs->desc.denoise != c->denoise || cs->desc.ref_depth != c->ref_depth || cs->desc.width != c->width || cs->desc.height != c->height;
+    cs->desc = *c;
+    cs->dev.prev = cs->dev.curr;
+    cs->dev.curr = serialize_camera(*c);
+    if (invalidated) { GpuCamera a = cs->dev.curr, b = cs->dev.prev; CK(cudaStreamSynchronize(e->stream)); int rc = allocate_camera(e, cs); if (rc) return rc; cs->dev.curr = a; cs->dev.prev = b; }
+    return ST_OK;
+}
+int st_delete_camera(st_engine* e, st_camera_handle h) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    cs->alive = false; cs->arena.release(); cs->rgba8.release();
+    return ST_OK;
+}
+int st_camera_set_strip(st_engine* e, st_camera_handle h, int y0, int y1) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    if (y0 < 0 || y1 > (int)cs->desc.height || y0 >= y1) return fail(ST_ERR_INVALID, "bad strip");
+    cs->dev.y0 = y0; cs->dev.y1 = y1;
+    return ST_OK;
+}
+
+int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    int rc;
+    if (e->materials_dirty) {   // Materials::refresh + Material::serialize (materials.rs:79-85, material.rs:29-50)
+        e->materials_dirty = false;
+        e->h_materials.resize(e->materials.size());
+        for (size_t i = 0; i < e->materials.size(); i++) {
+            const st_material& m = e->materials[i];
+            GpuMaterial g; std::memset(&g, 0, sizeof g);
+            g.base_color = make_float4(m.base_color[0], m.base_color[1], m.base_color[2], m.base_color[3]);
+            g.emissive = make_float4(m.emissive[0], m.emissive[1], m.emissive[2], m.emissive[3]);
+            g.roughness = m.perceptual_roughness * m.perceptual_roughness; g.metallic = m.metallic; g.reflectance = m.reflectance; g.ior = m.ior;
+            e->h_materials[i] = g;
+        }
+        if ((rc = upload(e, e->d_materials, e->h_materials.data(), e->h_materials.size() * sizeof(GpuMaterial)))) return rc;
+    }
+    if (refresh_instances(e)) {   // Bvh::refresh (bvh.rs:48-70)
+        e->bvh.build(e->prims);
+        std::vector<uint8_t> alpha(e->materials.size());
+        for (size_t i = 0; i < alpha.size(); i++) alpha[i] = e->materials[i].alpha_blend ? 1 : 0;
+        e->bvh.flatten(alpha, &e->bvh_out);
+        if (e->bvh_out.depth - 1 > 24) return fail(ST_ERR_LIMIT, "BVH deeper than the 24-entry traversal stack (strolle-gpu/src/lib.rs:72-76)");
+        if ((rc = upload(e, e->d_bvh, e->bvh_out.buf.data(), e->bvh_out.buf.size() * 16))) return rc;
+    }
+    if (e->triangles_dirty) { e->triangles_dirty = false; if ((rc = upload(e, e->d_triangles, e->h_triangles.data(), e->h_triangles.size() * 16))) return rc; }
+    e->world.light_count = e->next_light; e->world.sun_azimuth = e->sun_azimuth; e->world.sun_altitude = e->sun_altitude;
+    if (e->sun_dirty) {   // Lights::update_sun (lights.rs:84-99); the transmittance integral runs on the device
+        e->sun_dirty = false;
+        if ((rc = e->d_scratch.ensure(64))) return rc;
+        launch_atm_sun_color((float4*)e->d_scratch.p, e->world, e->stream);
+        float4 sun[2];
+        CK(cudaMemcpyAsync(sun, e->d_scratch.p, 32, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        light_overwrite(e, 0, st_engine::kSun, make_sun(sun[0], sun[1]));
+    }
+    if (e->lights_dirty) {   // Lights::flush (lights.rs:133-162)
+        for (uint32_t id : e->lights_killed) e->h_lights[id].d3.x = bits2f(0xcafebabeu);
+        for (auto& r : e->lights_remapped) e->h_lights[r.second].d3.x = bits2f(*e->light_slot(r.first) + 1u);
+        if ((rc = upload(e, e->d_lights, e->h_lights.data(), e->h_lights.size() * sizeof(GpuLight)))) return rc;
+        CK(cudaStreamSynchronize(e->stream));   // the host mirror is edited right below
+        bool again = !e->lights_created.empty() || !e->lights_updated.empty() || !e->lights_killed.empty() || !e->lights_remapped.empty();
+        for (st_handle h : e->lights_created) { GpuLight& l = e->h_lights[*e->light_slot(h)]; l.prev_d0 = l.d0; l.prev_d1 = l.d1; l.prev_d2 = l.d2; }
+        for (st_handle h : e->lights_updated) { GpuLight& l = e->h_lights[*e->light_slot(h)]; l.prev_d0 = l.d0; l.prev_d1 = l.d1; l.prev_d2 = l.d2; }
+        for (uint32_t id : e->lights_killed) e->h_lights[id].d3.x = 0.0f;
+        for (auto& r : e->lights_remapped) e->h_lights[r.second].d3.x = 0.0f;
+        e->lights_created.clear(); e->lights_updated.clear(); e->lights_remapped.clear(); e->lights_killed.clear();
+        e->lights_dirty = again;   // commit()/clear_slot() re-dirty the mirror: uploaded on the next tick (mapped_storage_buffer.rs:167-168)
+    }
+    for (CameraSlot* c : e->cameras) if (c->alive) c->frame = e->frame;   // CameraController::flush (camera_controller.rs:81-85)
+    e->frame += 1;
+    return ST_OK;
+}
+
+int st_frame_schedule(st_engine* e, st_camera_handle h, int* pass_ids, int cap, int* count) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !count) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    std::vector<Step> steps; build_schedule(e, cs, &steps);
+    *count = (int)steps.size();
+    for (int i = 0; i < cap && i < *count; i++) pass_ids[i] = steps[i].pass;
+    return ST_OK;
+}
+int st_render_range(st_engine* e, st_camera_handle h, int first, int last) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    if (cs->frame == 0) return fail(ST_ERR_INVALID, "st_tick must precede st_render_camera");
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_luts(e); if (rc) return rc;
+    std::vector<Step> steps; build_schedule(e, cs, &steps);
+    if (last < 0 || last >= (int)steps.size()) last = (int)steps.size() - 1;
+    for (int i = std::max(first, 0); i <= last; i++) e->run_timed(steps[i].pass, steps[i].run);
+    CK(cudaGetLastError());
+    return ST_OK;
+}
+int st_render_camera(st_engine* e, st_camera_handle h, void* host_out, int format) {
+    int rc = st_render_range(e, h, 0, -1); if (rc) return rc;
+    if (host_out) {
+        CameraSlot* cs = get_camera(e, h);
+        size_t n = (size_t)cs->desc.width * cs->desc.height;
+        if (format == ST_FORMAT_RGBA32F) CK(cudaMemcpyAsync(host_out, cs->dev.output, n * 16, cudaMemcpyDeviceToHost, e->stream));
+        else return fail(ST_ERR_INVALID, "unsupported output format");
+        CK(cudaStreamSynchronize(e->stream));
+    }
+    return ST_OK;
+}
+int st_synchronize(st_engine* e) { if (!e) return fail(ST_ERR_INVALID, "null engine"); CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); return ST_OK; }
+
+int st_read_buffer(st_engine* e, st_camera_handle h, const char* name, float* dst, size_t cap, size_t* count) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !name || !count) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    CK(cudaSetDevice(e->device));
+    if (!std::strcmp(name, "curr_camera") || !std::strcmp(name, "prev_camera")) {
+        const GpuCamera& c = !std::strcmp(name, "curr_camera") ? cs->dev.curr : cs->dev.prev;
+        *count = 40; if (dst) std::memcpy(dst, &c, 4 * std::min<size_t>(cap, 40)); return ST_OK;
+    }
+    for (size_t i = 0; i < cs->named.size(); i++) if (cs->named[i].first == name) {
+        *count = cs->sizes[i].second * 4;
+        if (dst) { CK(cudaStreamSynchronize(e->stream)); CK(cudaMemcpy(dst, *cs->named[i].second, 4 * std::min(cap, *count), cudaMemcpyDeviceToHost)); }
+        return ST_OK;
+    }
+    return fail(ST_ERR_NOT_FOUND, std::string("unknown buffer ") + name);
+}
+int st_buffer_device_ptr(st_engine* e, st_camera_handle h, const char* name, void** ptr, size_t* bytes) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !name || !ptr || !bytes) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    for (size_t i = 0; i < cs->named.size(); i++) if (cs->named[i].first == name) { *ptr = *cs->named[i].second; *bytes = cs->sizes[i].second * 16; return ST_OK; }
+    return fail(ST_ERR_NOT_FOUND, std::string("unknown buffer ") + name);
+}
+int st_read_scene(st_engine* e, const char* name, float* dst, size_t cap, size_t* count) {
+    if (!e || !name || !count) return fail(ST_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    std::string s(name);
+    const void* dev = nullptr; size_t n = 0;
+    if (s == "world") { *count = 4; if (dst) std::memcpy(dst, &e->world, 4 * std::min<size_t>(cap, 4)); return ST_OK; }
+    if (s == "triangles") { dev = e->d_triangles.p; n = e->h_triangles.size() * 4; }
+    else if (s == "bvh") { dev = e->d_bvh.p; n = e->bvh_out.buf.size() * 4; }
+    else if (s == "materials") { dev = e->d_materials.p; n = e->h_materials.size() * 28; }
+    else if (s == "lights") { dev = e->d_lights.p; n = e->h_lights.size() * 28; }
+    else if (s == "transmittance_lut" || s == "scattering_lut" || s == "sky_lut") {
+        int rc = ensure_luts(e); if (rc) return rc;
+        if (s == "transmittance_lut") { dev = e->d_tlut.p; n = 256 * 64 * 4; } else if (s == "scattering_lut") { dev = e->d_slut.p; n = 32 * 32 * 4; } else { dev = e->d_skylut.p; n = 256 * 256 * 4; }
+    } else return fail(ST_ERR_NOT_FOUND, "unknown scene buffer " + s);
+    *count = n;
+    if (dst && n) { CK(cudaStreamSynchronize(e->stream)); CK(cudaMemcpy(dst, dev, 4 * std::min(cap, n), cudaMemcpyDeviceToHost)); }
+    return ST_OK;
+}
+int st_bvh_depth(st_engine* e, int* depth) { if (!e || !depth) return fail(ST_ERR_INVALID, "null argument"); *depth = e->bvh_out.depth; return ST_OK; }
+
+static int trace_stream(st_engine* e, const float* rays, size_t n, void* out, bool closest, float* device_ms) {
+    if (!e || !rays || !out) return fail(ST_ERR_INVALID, "null argument");
+    if (!e->d_bvh.p) return fail(ST_ERR_INVALID, "no scene uploaded: call st_tick first");
+    CK(cudaSetDevice(e->device));
+    size_t out_bytes = closest ? n * 48 : n * 4;
+    DevMem d_in, d_out; int rc;
+    if ((rc = d_in.ensure(n * 32)) || (rc = d_out.ensure(out_bytes))) { d_in.release(); d_out.release(); return rc; }
+    cudaEvent_t a = e->get_event(), b = e->get_event();
+    cudaMemcpyAsync(d_in.p, rays, n * 32, cudaMemcpyHostToDevice, e->stream);
+    SceneDev sc = e->scene();
+    cudaEventRecord(a, e->stream);
+    if (closest) launch_trace_stream_closest(sc, (const float4*)d_in.p, (long)n, (float4*)d_out.p, e->stream);
+    else launch_trace_stream_any(sc, (const float4*)d_in.p, (long)n, (uint32_t*)d_out.p, e->stream);
+    cudaEventRecord(b, e->stream);
+    cudaMemcpyAsync(out, d_out.p, out_bytes, cudaMemcpyDeviceToHost, e->stream);
+    cudaError_t ce = cudaStreamSynchronize(e->stream);
+    float ms = 0; cudaEventElapsedTime(&ms, a, b);
+    if (device_ms) *device_ms = ms;
+    e->pass_launches[P_TRACE_STREAM]++; e->pass_ms[P_TRACE_STREAM] += ms;
+    e->event_pool.push_back(a); e->event_pool.push_back(b);
+    d_in.release(); d_out.release();
+    if (ce != cudaSuccess) return fail(ST_ERR_CUDA, cudaGetErrorString(ce));
+    return ST_OK;
+}
+int st_trace_closest(st_engine* e, const float* rays, size_t n, float* out, float* ms) { return trace_stream(e, rays, n, out, true, ms); }
+int st_trace_any(st_engine* e, const float* rays, size_t n, uint32_t* out, float* ms) { return trace_stream(e, rays, n, out, false, ms); }
+
+int st_device_math(st_engine* e, int op, const float* a, const float* b, float* out, size_t n) {
+    if (!e || !a || !out) return fail(ST_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    DevMem da, db, dc; int rc;
+    if ((rc = da.ensure(n * 4)) || (rc = db.ensure(n * 4)) || (rc = dc.ensure(n * 4))) return rc;
+    CK(cudaMemcpyAsync(da.p, a, n * 4, cudaMemcpyHostToDevice, e->stream));
+    if (b) CK(cudaMemcpyAsync(db.p, b, n * 4, cudaMemcpyHostToDevice, e->stream));
+    launch_math(op, (const float*)da.p, (const float*)db.p, (float*)dc.p, (long)n, e->stream);
+    CK(cudaMemcpyAsync(out, dc.p, n * 4, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    da.release(); db.release(); dc.release();
+    return ST_OK;
+}
+
+int st_enable_timing(st_engine* e, int enabled) { if (!e) return fail(ST_ERR_INVALID, "null engine"); e->timing = enabled != 0; return ST_OK; }
+int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    e->collect_timing();
+    for (int i = 0; i < P_COUNT; i++) { if (ms) ms[i] = e->pass_ms[i]; if (launches) launches[i] = e->pass_launches[i]; }
+    if (reset) { std::memset(e->pass_ms, 0, sizeof e->pass_ms); std::memset(e->pass_launches, 0, sizeof e->pass_launches); }
+    return ST_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1054 @@
+// strolle_b200 — sm_100a kernels for the per-pixel GI hot path.
+//
+// One kernel per reference compute entry point (strolle-shaders/src/*.rs, K1–K22 in
+// SURVEY.md §2.2) plus the primary-visibility G-buffer kernel that replaces the rasteriser
+// and the composition kernel.  All kernels are HBM/latency-bound integer+f32 work: no tensor
+// cores.  Mapping: one thread per pixel, CTAs of 128 threads covering a 16x8 pixel tile so
+// that a warp reads two 256-byte row segments of every float4 texture (coalesced 16-byte
+// loads); BVH nodes / triangles go through the read-only path (ld.global.nc.v4.f32) and the
+// traversal stack lives in shared memory, one conflict-free column per thread.
+#include <cuda_fp16.h>
+#include "st_device.cuh"
+#include "kernels.h"
+
+namespace st {
+
+#define TILE_W 16
+#define TILE_H 8
+
+struct Px { u32 x, y; bool in; };
+ST_DEV Px pixel_full(const CameraDev& cam) {
+    Px p; p.x = blockIdx.x * TILE_W + (threadIdx.x % TILE_W); p.y = (u32)cam.y0 + blockIdx.y * TILE_H + (threadIdx.x / TILE_W);
+    p.in = p.x < (u32)cam.w && p.y < (u32)cam.y1;
+    return p;
+}
+// half-width checkerboard dispatch of the reference: gid.x < 8*(((W+7)/8)/2), gid.y < 8*((H+7)/8)
+ST_DEV int half_grid_w(int w) { return 8 * (((w + 7) / 8) / 2); }
+ST_DEV Px pixel_half(const CameraDev& cam) {
+    Px p; p.x = blockIdx.x * TILE_W + (threadIdx.x % TILE_W); p.y = (u32)cam.y0 + blockIdx.y * TILE_H + (threadIdx.x / TILE_W);
+    p.in = p.x < (u32)half_grid_w(cam.w) && p.y < (u32)cam.y1;
+    return p;
+}
+ST_DEV size_t pix(const CameraDev& cam, u32 x, u32 y) { return (size_t)y * (size_t)cam.w + x; }
+ST_DEV size_t screen_idx(const CameraDev& cam, u32 x, u32 y) { return (size_t)(y * to_u32_sat(cam.curr.screen.x) + x); }   // camera.rs:39-41 (u32 arithmetic)
+ST_DEV bool in_tex(const CameraDev& cam, u32 x, u32 y) { return x < (u32)cam.w && y < (u32)cam.h; }
+ST_DEV float4 tex_or_zero(const float4* __restrict__ t, const CameraDev& cam, u32 x, u32 y) { return in_tex(cam, x, y) ? t[pix(cam, x, y)] : f4zero(); }
+ST_DEV void tex_store(float4* __restrict__ t, const CameraDev& cam, u32 x, u32 y, float4 v) { if (in_tex(cam, x, y)) t[pix(cam, x, y)] = v; }
+ST_DEV Hit load_hit(const GpuCamera& c, const float4* __restrict__ d0, const float4* __restrict__ d1, const CameraDev& cam, u32 x, u32 y) {
+    return hit_make(cam_ray(c, x, y), gbuf_unpack(tex_or_zero(d0, cam, x, y), tex_or_zero(d1, cam, x, y)));
+}
+#define ST_TRACE_STACK()                                          \
+    __shared__ u32 s_stack[ST_BVH_STACK * ST_BLOCK];              \
+    TraceStack stk; stk.base = s_stack + threadIdx.x;
+
+#define KPARAMS const __grid_constant__ CameraDev cam, const __grid_constant__ SceneDev sc
+
+// ---------------------------------------------------------------------------------------------
+// Primary-visibility G-buffer (stands in for strolle-shaders/src/prim_raster.rs:41-128)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_BLOCK) k_prim_gbuffer(KPARAMS, int cur) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    Ray ray = cam_ray(cam.curr, p.x, p.y);
+    TriHit th = trace_closest(ray, sc, stk);
+    float4 g0 = f4zero(), g1 = f4zero(), surf = f4zero(), vel = f4zero(), tid = f4(bitsf(0xffffffffu), 0.f, 0.f, 0.f);
+    if (trihit_some(th)) {
+        const GpuMaterial m = sc.materials[th.material_id];
+        GBuf g;
+        g.base_color = mat_base_color(m, th.uv); g.normal = th.normal; g.metallic = m.metallic; g.emissive = mat_emissive(m, th.uv);
+        g.roughness = m.roughness; g.reflectance = m.reflectance; g.depth = dist(ray.o, th.point);
+        gbuf_pack(g, &g0, &g1);
+        float2 n = oct_encode(th.normal);
+        surf = f4(n.x, n.y, g.depth, m.roughness);
+        float2 v = cam_world_to_screen(cam.curr, th.point) - cam_world_to_screen(cam.prev, th.point);
+        if (len2(v) >= 0.001f) vel = f4(v.x, v.y, 0.f, 0.f);
+        tid.x = bitsf(th.triangle_id);
+    }
+    size_t i = pix(cam, p.x, p.y);
+    cam.prim_gbuffer_d0[cur][i] = g0; cam.prim_gbuffer_d1[cur][i] = g1; cam.prim_surface_map[cur][i] = surf;
+    cam.velocity_map[i] = vel; cam.prim_triangle_ids[i] = tid;
+}
+
+// K4 frame_reprojection::main (frame_reprojection.rs:7-95)
+__global__ void __launch_bounds__(ST_BLOCK) k_frame_reprojection(KPARAMS, int cur) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    const float4* sc_ = cam.prim_surface_map[cur]; const float4* sp_ = cam.prim_surface_map[cur ^ 1];
+    size_t i = pix(cam, p.x, p.y);
+    Reproj rp; rp.px = 0.f; rp.py = 0.f; rp.confidence = 0.f; rp.validity = 0u;
+    Surf surface = surf_decode(sc_[i]);
+    if (surface.depth == 0.0f) { cam.reprojection_map[i] = reproj_encode(rp); return; }
+    float4 vel = cam.velocity_map[i];
+    float2 prev = f2((float)p.x, (float)p.y) - f2(vel.x, vel.y);
+    float2 pr = f2(roundf(prev.x), roundf(prev.y));
+    if (cam_contains_f(cam.prev, pr)) {
+        Surf ps = surf_decode(tex_or_zero(sp_, cam, to_u32_sat(pr.x), to_u32_sat(pr.y)));
+        float conf = surf_similarity(ps, surface);
+        if (conf > 0.0f) { rp.px = prev.x; rp.py = prev.y; rp.confidence = conf; rp.validity = 0u; }
+    }
+    if (reproj_some(rp)) {
+        int x0 = to_i32_sat(floorf(rp.px)), x1 = to_i32_sat(ceilf(rp.px)), y0 = to_i32_sat(floorf(rp.py)), y1 = to_i32_sat(ceilf(rp.py));
+        int xs[4] = {x0, x1, x0, x1}, ys[4] = {y0, y0, y1, y1};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (!cam_contains_i(cam.curr, xs[k], ys[k])) continue;
+            if (surf_similarity(surf_decode(sp_[pix(cam, (u32)xs[k], (u32)ys[k])]), surface) >= 0.25f) rp.validity |= (1u << k);
+        }
+    }
+    cam.reprojection_map[i] = reproj_encode(rp);
+}
+
+// K5 di_sampling::main (di_sampling.rs:4-94)
+__global__ void __launch_bounds__(ST_BLOCK) k_di_sampling(KPARAMS, int cur, u32 seed, u32 frame) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    Rng rng = rng_make(seed, p.x, p.y);
+    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(hit)) return;
+    EphRes res = ephemeral_build(rng, sc, hit);
+    DiRes out = di_zero();
+    if (res.m > 0.0f) {
+        float4 bn = blue_noise(sc, p.x, p.y, frame);
+        Ray ray = light_ray_bnoise(light_load(sc, res.light_id), f2(bn.x, bn.y), hit.point);
+        bool occ = trace_any(ray, sc, stk);
+        if (occ) res.w = 0.0f;
+        out.pdf = 0.f; out.confidence = 0.f; out.light_id = res.light_id; out.light_point = ray.o; out.occluded = occ; out.m = 1.0f; out.w = res.w;
+    }
+    di_store(out, cam.di_reservoirs[1], screen_idx(cam, p.x, p.y));
+}
+
+// K6 di_temporal_resampling::main (di_temporal_resampling.rs:4-112)
+__global__ void __launch_bounds__(ST_BLOCK) k_di_temporal(KPARAMS, int cur, u32 seed) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t npx = (size_t)cam.w * cam.h;
+    size_t lhs_idx = screen_idx(cam, p.x, p.y);
+    Rng rng = rng_make(seed, p.x, p.y);
+    Hit lhs_hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(lhs_hit)) return;
+    DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
+    if (lhs.m != 0.0f) lhs.pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), lhs_hit);
+    DiRes rhs = di_zero();
+    Hit rhs_hit = hit_zero();
+    bool killed = false;
+    Reproj rp = reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)]);
+    if (reproj_some(rp)) {
+        uint2 rpos = reproj_round(rp);
+        size_t ridx = screen_idx(cam, rpos.x, rpos.y);
+        if (ridx < npx) rhs = di_load(cam.di_reservoirs[0], ridx);
+        rhs.m = rmin(rhs.m, 64.0f);
+        if (rhs.m != 0.0f) {
+            GpuLight rl = light_load(sc, rhs.light_id);
+            u32 slot = fbits(rl.d3.x);
+            if (slot == 0xcafebabeu) { rhs.w = 0.0f; killed = true; }
+            else if (slot > 0u) rhs.light_id = slot - 1u;
+            rhs_hit = load_hit(cam.prev, cam.prim_gbuffer_d0[cur ^ 1], cam.prim_gbuffer_d1[cur ^ 1], cam, rpos.x, rpos.y);
+        }
+    }
+    MisIn mi;
+    mi.lhs_m = lhs.m; mi.rhs_m = rhs.m; mi.rhs_jacobian = 1.0f; mi.lhs_lhs_pdf = lhs.pdf; mi.rhs_rhs_pdf = rhs.pdf;
+    mi.lhs_rhs_pdf = ((lhs.m > 0.0f) & hit_some(rhs_hit)) ? di_pdf_with(lhs, light_prev(light_load(sc, lhs.light_id)), rhs_hit) : 0.0f;
+    mi.rhs_lhs_pdf = ((rhs.m > 0.0f) & !killed) ? di_pdf_with(rhs, light_load(sc, rhs.light_id), lhs_hit) : 0.0f;
+    MisOut mo = mis_eval(mi);
+    DiRes main_ = di_zero();
+    float main_pdf = 0.0f;
+    if (di_update(main_, rng, lhs, mo.lhs_mis * mo.lhs_pdf * lhs.w)) main_pdf = mo.lhs_pdf;
+    if (di_update(main_, rng, rhs, mo.rhs_mis * mo.rhs_pdf * rhs.w)) main_pdf = mo.rhs_pdf;
+    main_.m = lhs.m + mo.m;
+    main_.pdf = main_pdf;
+    main_.confidence = killed ? 0.0f : 1.0f;
+    main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
+    di_store(main_, cam.di_reservoirs[1], lhs_idx);
+}
+
+// K7 di_spatial_resampling::pick (di_spatial_resampling.rs:4-147); scratch buf_d0 = di_diff_samples,
+// buf_d1 = di_diff_curr_colors (passes/di_spatial_resampling.rs:24-28).  Sky pixels clear buf_d1
+// (the reference leaves stale texels there and later reads out of bounds — SURVEY Appendix C-15).
+__global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
+    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
+    size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
+    Rng rng = rng_make(seed, lp.x, lp.y);
+    float4* buf_d0 = cam.di_diff_samples; float4* buf_d1 = cam.di_diff_curr_colors;
+    const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
+    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
+    Hit lhs_hit = load_hit(cam.curr, gd0, gd1, cam, lp.x, lp.y);
+    if (!hit_some(lhs_hit)) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
+    DiRes rhs = di_zero();
+    size_t rhs_idx = 0;
+    Hit rhs_hit = hit_zero();
+    float max_radius = 128.0f;
+    for (u32 nth = 0u; nth < 8u; nth++) {
+        float2 off = rng_disk(rng) * max_radius;
+        float2 fp = f2((float)lp.x, (float)lp.y) + off;
+        uint2 rpos = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
+        if (rpos.x == lp.x && rpos.y == lp.y) continue;
+        rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
+        if (!hit_some(rhs_hit)) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (fabs_(rhs_hit.g.depth - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (dot(rhs_hit.g.normal, lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        rhs_idx = screen_idx(cam, rpos.x, rpos.y);
+        rhs = di_load(cam.di_reservoirs[1], rhs_idx);
+        if (rhs.m != 0.0f) break;
+    }
+    if (rhs.m == 0.0f) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    float lhs_rhs_pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), rhs_hit);
+    float rhs_lhs_pdf = di_pdf_with(rhs, light_load(sc, rhs.light_id), lhs_hit);
+    Ray ra = (lhs_rhs_pdf > 0.0f) ? di_ray(lhs, rhs_hit.point) : ray_zero();
+    Ray rb = (rhs_lhs_pdf > 0.0f) ? di_ray(rhs, lhs_hit.point) : ray_zero();
+    float2 na = oct_encode(ra.d), nb = oct_encode(rb.d);
+    tex_store(buf_d0, cam, ax, g.y, f4(ra.o, ra.len));
+    tex_store(buf_d1, cam, ax, g.y, f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), 0.0f));
+    tex_store(buf_d0, cam, bx, g.y, f4(rb.o, rb.len));
+    tex_store(buf_d1, cam, bx, g.y, f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf));
+}
+
+// K8 / K16 *_spatial_resampling::trace (di_spatial_resampling.rs:150-209, gi_spatial_resampling.rs:163-222)
+__global__ void __launch_bounds__(ST_BLOCK) k_spatial_trace(KPARAMS, const float4* __restrict__ buf_d0, const float4* __restrict__ buf_d1, float4* __restrict__ buf_d2) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    float4 d0 = buf_d0[i], d1 = buf_d1[i];
+    if (all_zero(d1)) { buf_d2[i] = f4zero(); return; }
+    Ray ray = ray_make(xyz(d0), oct_decode(f2(d1.x, d1.y)), d0.w);
+    bool occ = trace_any(ray, sc, stk);
+    buf_d2[i] = f4(occ ? 0.0f : 1.0f, d1.z, d1.w, 0.0f);
+}
+
+// K9 di_spatial_resampling::sample (di_spatial_resampling.rs:212-297)
+__global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
+    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
+    size_t npx = (size_t)cam.w * cam.h;
+    size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
+    Rng rng = rng_make(seed, lp.x, lp.y);
+    const float4* in = cam.di_reservoirs[1]; float4* out = cam.di_reservoirs[2];
+    float4 d0 = tex_or_zero(cam.di_diff_stash, cam, g.x * 2u, g.y), d1 = tex_or_zero(cam.di_diff_stash, cam, g.x * 2u + 1u, g.y);
+    float lhs_rhs_vis = d0.x; u32 rhs_idx = fbits(d0.y);
+    float rhs_lhs_vis = d1.x, lhs_rhs_pdf = d1.y, rhs_lhs_pdf = d1.z;
+    DiRes lhs = di_load(in, lhs_idx);
+    if (rhs_idx > 0u && (size_t)rhs_idx - 1 < npx) {
+        DiRes rhs = di_load(in, (size_t)rhs_idx - 1);
+        MisIn mi;
+        mi.lhs_m = lhs.m; mi.rhs_m = rhs.m; mi.rhs_jacobian = 1.0f; mi.lhs_lhs_pdf = lhs.pdf;
+        mi.lhs_rhs_pdf = lhs_rhs_pdf * lhs_rhs_vis; mi.rhs_lhs_pdf = rhs_lhs_pdf * rhs_lhs_vis; mi.rhs_rhs_pdf = rhs.pdf;
+        MisOut mo = mis_eval(mi);
+        DiRes main_ = di_zero();
+        float main_pdf = 0.0f;
+        if (di_update(main_, rng, lhs, mo.lhs_mis * mo.lhs_pdf * lhs.w)) main_pdf = mo.lhs_pdf;
+        if (di_update(main_, rng, rhs, mo.rhs_mis * mo.rhs_pdf * rhs.w)) { main_pdf = mo.rhs_pdf; main_.occluded = lhs_rhs_vis == 0.0f; }
+        main_.m = lhs.m + mo.m;
+        main_.pdf = main_pdf;
+        main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
+        di_store(main_, out, lhs_idx);
+    } else di_store(lhs, out, lhs_idx);
+    uint2 op = checker(g.x, g.y, frame / 2u);
+    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); di_store(di_load(in, oi), out, oi); }
+}
+
+// K10 di_resolving::main (di_resolving.rs:4-119)
+__global__ void __launch_bounds__(ST_BLOCK) k_di_resolving(KPARAMS, int cur) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t idx = screen_idx(cam, p.x, p.y);
+    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    DiRes res = di_load(cam.di_reservoirs[2], idx);
+    float confidence;
+    LightRad rad;
+    if (hit_some(hit)) {
+        bool occ = trace_any(di_ray(res, hit.point), sc, stk);
+        confidence = (res.occluded == occ) ? res.confidence : 0.0f;
+        res.confidence = 1.0f;
+        res.occluded = occ;
+        if (occ) rad = lightrad_zero();
+        else { rad = light_radiance(light_load(sc, res.light_id), hit); rad.radiance = rad.radiance * res.w; }
+    } else {
+        confidence = 1.0f;
+        rad.radiance = atmosphere_sample(sc, world_sun_dir(sc.world), hit.dir);
+        rad.diff = f3s(1.0f); rad.spec = f3s(0.0f);
+    }
+    float diff_brdf = (1.0f - hit.g.metallic) / kPi;
+    size_t i = pix(cam, p.x, p.y);
+    cam.di_diff_samples[i] = f4(rad.radiance * diff_brdf, confidence);
+    cam.di_spec_samples[i] = f4(rad.radiance * rad.spec, confidence);
+    di_store(res, cam.di_reservoirs[0], idx);
+}
+
+// K11 gi_reprojection::main (gi_reprojection.rs:4-51)
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t npx = (size_t)cam.w * cam.h;
+    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(hit)) return;
+    Reproj rp = reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)]);
+    GiRes res = gi_zero();
+    if (reproj_some(rp)) {
+        uint2 rpos = reproj_round(rp);
+        size_t ridx = screen_idx(cam, rpos.x, rpos.y);
+        if (ridx < npx) res = gi_load(cam.gi_reservoirs[0], ridx);
+    }
+    res.confidence = 1.0f;
+    res.v1 = hit.point;
+    gi_store(res, cam.gi_reservoirs[2], screen_idx(cam, p.x, p.y));
+}
+
+// K12 gi_sampling_a::main (gi_sampling_a.rs:4-122)
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_a(KPARAMS, int cur, u32 seed, u32 frame) {
+    ST_TRACE_STACK();
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    bool tracing = gi_tracing_frame(frame);
+    uint2 sp = tracing ? checker(g.x, g.y, frame / 2u) : checker(g.x, g.y, frame);
+    if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
+    size_t idx = screen_idx(cam, sp.x, sp.y);
+    Ray gi_r; float gi_pdf_;
+    if (tracing) {
+        Rng rng = rng_make(seed, sp.x, sp.y);
+        Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
+        if (!hit_some(hit)) return;
+        BrdfS s = brdf_layered_sample(hit.g, rng, -hit.dir);
+        gi_r = ray_make(hit.point, s.dir);
+        gi_pdf_ = s.pdf;
+    } else {
+        GiRes res = gi_load(cam.gi_reservoirs[2], idx);
+        if (res.m == 0.0f) return;
+        gi_r = ray_make(res.v1, gi_dir(res, res.v1));
+        gi_pdf_ = 1.0f;
+    }
+    TriHit gh = trace_closest(gi_r, sc, stk);
+    GBuf gg = gbuf_zero();
+    if (trihit_some(gh)) {
+        GpuMaterial m = sc.materials[gh.material_id];
+        m.roughness = rmax(m.roughness, 0.75f * 0.75f);   // Material::regularize (material.rs:25-27)
+        gg.base_color = mat_base_color(m, gh.uv); gg.normal = gh.normal; gg.metallic = m.metallic; gg.emissive = mat_emissive(m, gh.uv);
+        gg.roughness = m.roughness; gg.reflectance = m.reflectance; gg.depth = dist(gi_r.o, gh.point);
+    }
+    float4 d1, d2; gbuf_pack(gg, &d1, &d2);
+    size_t gi = pix(cam, g.x, g.y);
+    cam.gi_d0[gi] = f4(gi_r.d, gi_pdf_); cam.gi_d1[gi] = d1; cam.gi_d2[gi] = d2;
+}
+
+// K13 gi_sampling_b::main (gi_sampling_b.rs:4-235)
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_b(KPARAMS, int cur, u32 seed, u32 frame) {
+    ST_TRACE_STACK();
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    bool tracing = gi_tracing_frame(frame);
+    uint2 sp = tracing ? checker(g.x, g.y, frame / 2u) : checker(g.x, g.y, frame);
+    if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
+    size_t idx = screen_idx(cam, sp.x, sp.y);
+    Hit prim = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
+    if (!hit_some(prim)) return;
+    size_t gi = pix(cam, g.x, g.y);
+    float4 d0 = cam.gi_d0[gi], d1 = cam.gi_d1[gi], d2 = cam.gi_d2[gi];
+    Rng rng; Hit gh; float gi_pdf_;
+    if (tracing) {
+        rng = rng_make(seed, sp.x, sp.y);
+        gh = hit_make(ray_make(prim.point, xyz(d0)), gbuf_unpack(d1, d2));
+        gi_pdf_ = d0.w;
+    } else {
+        GiRes res = gi_load(cam.gi_reservoirs[2], idx);
+        if (res.m == 0.0f) return;
+        rng.s = res.rng;
+        gh = hit_make(ray_make(res.v1, xyz(d0)), gbuf_unpack(d1, d2));
+        gi_pdf_ = 1.0f;
+    }
+    u32 rng_state = rng.s;
+    const u32 SKY = 0xffffffffu;
+    float3 sun_dir = world_sun_dir(sc.world);
+    u32 light_id; float light_pdf; float3 light_rad; float3 light_dir = f3s(0.f);
+    if (!hit_some(gh)) { light_id = SKY; light_pdf = 1.0f; light_rad = atmosphere_sample(sc, sun_dir, gh.dir); }
+    else {
+        float atm_pdf = (sc.world.sun_altitude <= -1.0f) ? 0.0f : 0.25f;
+        if (sc.world.light_count == 0u || rng_f(rng) < atm_pdf) {
+            light_id = SKY; light_pdf = atm_pdf;
+            light_dir = rng_hemisphere(rng, gh.g.normal);
+            light_rad = atmosphere_sample(sc, sun_dir, light_dir) * dot(gh.g.normal, light_dir);
+        } else {
+            EphRes er = ephemeral_build(rng, sc, gh);
+            if (er.w > 0.0f) { light_id = er.light_id; light_pdf = (1.0f / er.w) * (1.0f - atm_pdf); light_rad = er.rad.radiance * (f3s(1.0f) + er.rad.spec); }
+            else { light_id = 0u; light_pdf = 1.0f; light_rad = f3s(0.f); }
+        }
+    }
+    float3 radiance;
+    if (light_pdf > 0.0f) {
+        float vis;
+        if (hit_some(gh)) {
+            Ray r = (light_id == SKY) ? ray_make(gh.point, light_dir) : light_ray_wnoise(light_load(sc, light_id), rng, gh.point);
+            vis = trace_any(r, sc, stk) ? 0.0f : 1.0f;
+        } else vis = 1.0f;
+        radiance = light_rad * vis / light_pdf;
+    } else radiance = f3s(0.f);
+    if (hit_some(gh)) { radiance = radiance * (xyz(gh.g.base_color) / kPi); radiance = radiance + gh.g.emissive; }
+    GiRes res = gi_zero();
+    if (gi_pdf_ > 0.0f) {
+        res.rng = rng_state; res.radiance = radiance; res.v1 = prim.point;
+        if (hit_some(gh)) { res.v2 = gh.point; res.v2n = gh.g.normal; }
+        else { res.v2 = prim.point + gh.dir * 1000.0f; res.v2n = -gh.dir; }
+        res.m = 1.0f; res.w = 1.0f / gi_pdf_;
+        res.pdf = 0.0f;
+        res.pdf = gi_pdf(res, prim);
+    }
+    gi_store(res, cam.gi_reservoirs[1], idx);
+}
+
+// K14 gi_temporal_resampling::main (gi_temporal_resampling.rs:4-156)
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_temporal(KPARAMS, int cur, u32 seed, u32 frame) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    bool tracing = gi_tracing_frame(frame);
+    size_t lhs_idx = screen_idx(cam, p.x, p.y);
+    Rng rng = rng_make(seed, p.x, p.y);
+    Hit lhs_hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    float4* curr = cam.gi_reservoirs[1];
+    if (!hit_some(lhs_hit)) { gi_store(gi_zero(), curr, lhs_idx); return; }
+    bool got = tracing ? (frame % 2u == 0u && checker_at(p.x, p.y, frame / 2u)) : checker_at(p.x, p.y, frame);
+    GiRes lhs = got ? gi_load(curr, lhs_idx) : gi_zero();
+    GiRes rhs = gi_zero();
+    Hit rhs_hit = hit_zero();
+    Reproj rp = reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)]);
+    if (reproj_some(rp)) {
+        rhs = gi_load(cam.gi_reservoirs[2], lhs_idx);
+        rhs.confidence = 1.0f;
+        rhs.m = rmin(rhs.m, 128.0f);
+        if (!tracing && lhs.m != 0.0f && rhs.m != 0.0f && gi_exists(rhs)) {
+            if (dist(lhs.radiance, rhs.radiance) > 0.33f) rhs.confidence = 0.0f;
+            rhs.radiance = lhs.radiance; rhs.v2 = lhs.v2; rhs.v2n = lhs.v2n;
+        }
+        if (rhs.m != 0.0f) {
+            uint2 rpos = reproj_round(rp);
+            rhs_hit = load_hit(cam.prev, cam.prim_gbuffer_d0[cur ^ 1], cam.prim_gbuffer_d1[cur ^ 1], cam, rpos.x, rpos.y);
+        }
+    }
+    GiRes main_ = gi_zero();
+    float main_pdf = 0.0f;
+    if (tracing) {
+        MisIn mi;
+        mi.lhs_m = lhs.m; mi.rhs_m = rhs.m; mi.rhs_jacobian = 1.0f; mi.lhs_lhs_pdf = lhs.pdf; mi.rhs_rhs_pdf = rhs.pdf;
+        mi.lhs_rhs_pdf = ((lhs.m > 0.0f) & hit_some(rhs_hit)) ? gi_pdf(lhs, rhs_hit) : 0.0f;
+        mi.rhs_lhs_pdf = (rhs.m > 0.0f) ? gi_pdf(rhs, lhs_hit) : 0.0f;
+        MisOut mo = mis_eval(mi);
+        if (gi_update(main_, rng, lhs, mo.lhs_mis * mo.lhs_pdf * lhs.w)) main_pdf = mo.lhs_pdf;
+        if (gi_update(main_, rng, rhs, mo.rhs_mis * mo.rhs_pdf * rhs.w)) main_pdf = mo.rhs_pdf;
+        main_.m = lhs.m + mo.m;
+        main_.confidence = 1.0f;
+        main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
+    } else {
+        if (gi_merge(main_, rng, rhs, rhs.pdf)) main_pdf = rhs.pdf;
+        main_.confidence = rhs.confidence;
+        main_.w = res_norm(main_.w, main_pdf, 1.0f, main_.m);
+    }
+    main_.pdf = main_pdf;
+    main_.v1 = lhs_hit.point;
+    main_.w = rmin(main_.w, 5.0f);
+    gi_store(main_, curr, lhs_idx);
+}
+
+// K15 gi_spatial_resampling::pick (gi_spatial_resampling.rs:4-160); scratch = gi_d0, gi_d1
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
+    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
+    size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
+    Rng rng = rng_make(seed, lp.x, lp.y);
+    float4* buf_d0 = cam.gi_d0; float4* buf_d1 = cam.gi_d1;
+    const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
+    const float4* reservoirs = cam.gi_reservoirs[1];
+    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
+    Hit lhs_hit = load_hit(cam.curr, gd0, gd1, cam, lp.x, lp.y);
+    GiRes lhs = gi_load(reservoirs, lhs_idx);
+    if (!hit_some(lhs_hit) || lhs.m == 0.0f) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    GiRes rhs = gi_zero();
+    size_t rhs_idx = 0;
+    Hit rhs_hit = hit_zero();
+    float rhs_jac = 0.0f;
+    float max_radius = 128.0f;
+    for (u32 nth = 0u; nth < 8u; nth++) {
+        float2 off = rng_disk(rng) * max_radius;
+        float2 fp = f2((float)lp.x, (float)lp.y) + off;
+        uint2 rpos = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
+        if (rpos.x == lp.x && rpos.y == lp.y) continue;
+        rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
+        if (!hit_some(rhs_hit)) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (fabs_(rhs_hit.g.depth - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (dot(rhs_hit.g.normal, lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        rhs_idx = screen_idx(cam, rpos.x, rpos.y);
+        rhs = gi_load(reservoirs, rhs_idx);
+        if (rhs.m == 0.0f) continue;
+        rhs_jac = gi_jacobian(rhs, lhs_hit.point);
+        if (rhs_jac < 1.0f / 10.0f || rhs_jac > 10.0f) { rhs.m = 0.0f; continue; }
+        rhs_jac = rclamp(rhs_jac, 1.0f / 3.0f, 3.0f);
+        break;
+    }
+    if (rhs.m == 0.0f || !hit_some(rhs_hit)) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    float lhs_rhs_pdf = gi_pdf(lhs, rhs_hit);
+    float rhs_lhs_pdf = gi_pdf(rhs, lhs_hit);
+    Ray ra = (lhs_rhs_pdf > 0.0f) ? gi_ray(lhs, rhs_hit.point) : ray_zero();
+    Ray rb = (rhs_lhs_pdf > 0.0f) ? gi_ray(rhs, lhs_hit.point) : ray_zero();
+    float2 na = oct_encode(ra.d), nb = oct_encode(rb.d);
+    tex_store(buf_d0, cam, ax, g.y, f4(ra.o, ra.len));
+    tex_store(buf_d1, cam, ax, g.y, f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), rhs_jac));
+    tex_store(buf_d0, cam, bx, g.y, f4(rb.o, rb.len));
+    tex_store(buf_d1, cam, bx, g.y, f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf));
+}
+
+// K17 gi_spatial_resampling::sample (gi_spatial_resampling.rs:225-314)
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_sample(KPARAMS, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    uint2 sp = checker(g.x, g.y, frame / 2u + 1u);
+    if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
+    size_t npx = (size_t)cam.w * cam.h;
+    size_t idx = screen_idx(cam, sp.x, sp.y);
+    Rng rng = rng_make(seed, sp.x, sp.y);
+    const float4* in = cam.gi_reservoirs[1]; float4* out = cam.gi_reservoirs[2];
+    float4 d0 = tex_or_zero(cam.gi_d2, cam, g.x * 2u, g.y), d1 = tex_or_zero(cam.gi_d2, cam, g.x * 2u + 1u, g.y);
+    float lhs_rhs_vis = d0.x; u32 rhs_idx = fbits(d0.y); float rhs_jac = d0.z;
+    float rhs_lhs_vis = d1.x, lhs_rhs_pdf = d1.y, rhs_lhs_pdf = d1.z;
+    GiRes lhs = gi_load(in, idx);
+    if (rhs_idx > 0u && (size_t)rhs_idx - 1 < npx) {
+        GiRes rhs = gi_load(in, (size_t)rhs_idx - 1);
+        MisIn mi;
+        mi.lhs_m = lhs.m; mi.rhs_m = rhs.m; mi.rhs_jacobian = rhs_jac; mi.lhs_lhs_pdf = lhs.pdf;
+        mi.lhs_rhs_pdf = lhs_rhs_pdf * lhs_rhs_vis; mi.rhs_lhs_pdf = rhs_lhs_pdf * rhs_lhs_vis; mi.rhs_rhs_pdf = rhs.pdf;
+        MisOut mo = mis_eval(mi);
+        GiRes main_ = gi_zero();
+        float main_pdf = 0.0f;
+        if (gi_update(main_, rng, lhs, mo.lhs_mis * mo.lhs_pdf * lhs.w)) main_pdf = mo.lhs_pdf;
+        if (gi_update(main_, rng, rhs, mo.rhs_mis * mo.rhs_pdf * rhs.w * rhs_jac)) main_pdf = mo.rhs_pdf;
+        main_.m = lhs.m + mo.m;
+        main_.confidence = 1.0f;
+        main_.pdf = main_pdf;
+        main_.v1 = lhs.v1;
+        main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
+        main_.w = rmin(main_.w, 5.0f);
+        gi_store(main_, out, idx);
+    } else gi_store(lhs, out, idx);
+    uint2 op = checker(g.x, g.y, frame / 2u);
+    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); gi_store(gi_load(in, oi), out, oi); }
+}
+
+// K18 gi_preview_resampling::main (gi_preview_resampling.rs:4-138)
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_preview(KPARAMS, int cur, u32 seed, u32 nth, const float4* __restrict__ in, float4* __restrict__ out) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t cidx = screen_idx(cam, p.x, p.y);
+    Rng rng = rng_make(seed, p.x, p.y);
+    Hit chit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(chit)) { gi_store(gi_zero(), out, cidx); return; }
+    GiRes main_ = gi_zero();
+    float main_pdf = 0.0f;
+    GiRes center = gi_load(in, cidx);
+    if (gi_merge(main_, rng, center, center.pdf)) main_pdf = center.pdf;
+    u32 max_samples = to_u32_sat(lerpc(8.0f, 0.0f, main_.m / 8.0f));
+    float max_radius = (nth == 0u) ? 128.0f : 64.0f;
+    const float4* surf = cam.prim_surface_map[cur];
+    for (u32 k = 0u; k < max_samples; k++) {
+        float2 off = rng_disk(rng) * max_radius;
+        float2 fp = f2((float)p.x, (float)p.y) + off;
+        uint2 sp = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
+        if (sp.x == p.x && sp.y == p.y) return;   // quirk C-6: the kernel exits without writing
+        if (!cam_contains_u(cam.curr, sp.x, sp.y)) continue;
+        Surf ss = surf_decode(surf[pix(cam, sp.x, sp.y)]);
+        if (ss.depth == 0.0f) continue;
+        if (fabs_(ss.depth - chit.g.depth) > 0.25f * chit.g.depth) continue;
+        if (dot(ss.normal, chit.g.normal) < 0.5f) continue;
+        GiRes s = gi_load(in, screen_idx(cam, sp.x, sp.y));
+        if (s.m == 0.0f) continue;
+        float s_pdf = gi_pdf(s, chit);
+        float s_jac = gi_jacobian(s, chit.point);
+        if (s_jac < 1.0f / 10.0f || s_jac > 10.0f) continue;
+        s_jac = rclamp(s_jac, 1.0f / 3.0f, 3.0f);
+        if (gi_merge(main_, rng, s, s_pdf * s_jac)) main_pdf = s_pdf;
+    }
+    main_.confidence = center.confidence;
+    main_.pdf = main_pdf;
+    main_.v1 = center.v1;
+    main_.w = res_norm(main_.w, main_pdf, 1.0f, main_.m);
+    main_.w = rmin(main_.w, 5.0f);
+    gi_store(main_, out, cidx);
+}
+
+// K19 gi_resolving::main (gi_resolving.rs:4-67)
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_resolving(KPARAMS, int cur, const float4* __restrict__ in) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t idx = screen_idx(cam, p.x, p.y);
+    float4* out = cam.gi_reservoirs[0];
+    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    GiRes res = gi_load(out, idx);
+    float confidence; float3 radiance;
+    if (hit_some(hit)) { confidence = res.confidence; radiance = res.w * gi_cosine(res, hit) * res.radiance; }
+    else { confidence = 1.0f; radiance = f3s(0.f); }
+    float diff_brdf = (1.0f - hit.g.metallic) / kPi;
+    float3 spec = gi_spec(res, hit);
+    size_t i = pix(cam, p.x, p.y);
+    cam.gi_diff_samples[i] = f4(radiance * diff_brdf, confidence);
+    cam.gi_spec_samples[i] = f4(radiance * spec, confidence);
+    gi_store(gi_load(in, idx), out, idx);
+}
+
+// K20 frame_denoising::reproject (frame_denoising.rs:4-78)
+__global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject(KPARAMS, int cur, const float4* __restrict__ prev_colors, const float4* __restrict__ prev_moments,
+                                                                const float4* __restrict__ samples, float4* __restrict__ colors, float4* __restrict__ moments) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    float4 sample = samples[i];
+    if (cam.prim_surface_map[cur][i].z == 0.0f) { colors[i] = sample; return; }
+    float sl = luma(xyz(sample));
+    Reproj rp = reproj_decode(cam.reprojection_map[i]);
+    float3 color, moment;
+    if (reproj_some(rp) && sample.w > 0.0f) {
+        float4 pc = history_fetch(rp, prev_colors, cam.w, cam.h);
+        float4 pm = history_fetch(rp, prev_moments, cam.w, cam.h);
+        float hist = rmin(pm.x + 1.0f, 16.0f);
+        float alpha = 1.0f / hist;
+        color = lerpc(xyz(pc), xyz(sample), alpha);
+        moment = f3(hist, lerpc(pm.y, sl, alpha), lerpc(pm.z, sl * sl, alpha));
+    } else { color = xyz(sample); moment = f3(1.0f, sl, sl * sl); }
+    colors[i] = f4(color, 0.0f);
+    moments[i] = f4(moment, 0.0f);
+}
+
+// frame_denoising::sample_weight (frame_denoising.rs:363-392)
+ST_DEV float svgf_weight(float center_luma, float c_depth, float3 c_normal, float sample_luma, float s_depth, float3 s_normal, float luma_sigma, float depth_sigma) {
+    float lw = fabs_(sqrtf(center_luma) - sqrtf(sample_luma)) * luma_sigma;
+    float leeway = c_depth * depth_sigma;
+    float diff = fabs_(s_depth - c_depth);
+    float dw = (diff >= leeway) ? 0.0f : 1.0f - diff / leeway;
+    float nw = pow_det(rmax(dot(s_normal, c_normal), 0.0f), 64.0f);
+    return exp_det(-lw) * dw * nw;
+}
+
+// K21 frame_denoising::estimate_variance (frame_denoising.rs:81-217)
+__global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    const float4* surf = cam.prim_surface_map[cur];
+    const float4* di_colors = cam.di_diff_curr_colors; const float4* gi_colors = cam.gi_diff_curr_colors;
+    Surf cs = surf_decode(surf[i]);
+    float4 cdi = di_colors[i], cgi = gi_colors[i];
+    if (cs.depth == 0.0f) { cam.di_diff_stash[i] = cdi; cam.gi_diff_stash[i] = cgi; return; }
+    float4 mdi = cam.di_diff_moments[cur][i], mgi = cam.gi_diff_moments[cur][i];
+    float cdl = luma(xyz(cdi)), cgl = luma(xyz(cgi));
+    float di_var, gi_var;
+    if (mdi.x >= 4.0f) { di_var = mdi.z - sq(mdi.y); gi_var = mgi.z - sq(mgi.y); }
+    else {
+        float3 sdi = f3s(0.f), sgi = f3s(0.f);
+        int ox = -2, oy = -2;
+        for (;;) {   // quirk C-3: row -2 spans x in [-2,2], rows -1..2 span x in [-3,2]
+            int sx = (int)p.x + ox, sy = (int)p.y + oy;
+            if (cam_contains_i(cam.curr, sx, sy)) {
+                size_t si = pix(cam, (u32)sx, (u32)sy);
+                Surf ss = surf_decode(surf[si]);
+                if (ss.depth != 0.0f) {
+                    float sl = luma(xyz(di_colors[si]));
+                    float w = svgf_weight(cdl, cs.depth, cs.normal, sl, ss.depth, ss.normal, 1.0f, 0.2f);
+                    sdi = sdi + f3(sl, sl * sl, 1.0f) * f3s(w);
+                    float gl = luma(xyz(gi_colors[si]));
+                    float wg = svgf_weight(cgl, cs.depth, cs.normal, gl, ss.depth, ss.normal, 1.0f, 0.2f);
+                    sgi = sgi + f3(gl, gl * gl, 1.0f) * f3s(wg);
+                }
+            }
+            ox += 1;
+            if (ox == 3) { ox = -3; oy += 1; if (oy == 3) break; }
+        }
+        { float m1 = sdi.x / sdi.z, m2 = sdi.y / sdi.z; di_var = fabs_(m2 - m1 * m1) * 4.0f; }
+        { float m1 = sgi.x / sgi.z, m2 = sgi.y / sgi.z; gi_var = fabs_(m2 - m1 * m1) * 4.0f; }
+    }
+    di_var = rmax(di_var, 0.0f); gi_var = rmax(gi_var, 0.0f);
+    cam.di_diff_stash[i] = f4(xyz(cdi), di_var);
+    cam.gi_diff_stash[i] = f4(xyz(cgi), gi_var);
+}
+
+// K22 frame_denoising::wavelet (frame_denoising.rs:220-361): 3x3 à-trous, DI and GI together
+__global__ void __launch_bounds__(ST_BLOCK) k_denoise_wavelet(KPARAMS, int cur, u32 frame, u32 stride, float strength,
+                                                              const float4* __restrict__ di_in, float4* __restrict__ di_out,
+                                                              const float4* __restrict__ gi_in, float4* __restrict__ gi_out) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    const float4* surf = cam.prim_surface_map[cur];
+    float4 bn = blue_noise(sc, p.x, p.y, frame);
+    Surf cs = surf_decode(surf[i]);
+    float4 cdi = di_in[i];
+    float3 cdc = xyz(cdi); float cdv = cdi.w; float cdl = luma(cdc);
+    if (cs.depth == 0.0f) { di_out[i] = f4(cdc, cdv); return; }
+    float4 cgi = gi_in[i];
+    float3 cgc = xyz(cgi); float cgv = cgi.w; float cgl = luma(cgc);
+    float ls_di = lerpc(2.5f, 0.5f, sqrtf(cdv));
+    float ds_di = 0.33f / strength;
+    float ls_gi = lerpc(1.0f, 0.0f, sqrtf(cgv));
+    float ds_gi = 0.33f / strength;
+    float2 jf = (f2(bn.z, bn.w) - f2(0.5f, 0.5f)) * ((float)stride - 1.0f) * 0.5f;
+    int jx = to_i32_sat(jf.x), jy = to_i32_sat(jf.y);
+    float sdw = 1.0f; float3 sdc = cdc; float sdv = cdv;
+    float sgw = 1.0f; float3 sgc = cgc; float sgv = cgv;
+#pragma unroll
+    for (int oy = -1; oy <= 1; oy++) {
+#pragma unroll
+        for (int ox = -1; ox <= 1; ox++) {
+            if (ox == 0 && oy == 0) continue;
+            int sx = (int)p.x + jx + ox * (int)stride, sy = (int)p.y + jy + oy * (int)stride;
+            if (!cam_contains_i(cam.curr, sx, sy)) continue;
+            size_t si = pix(cam, (u32)sx, (u32)sy);
+            Surf ss = surf_decode(surf[si]);
+            if (ss.depth == 0.0f) continue;
+            float4 sdi = di_in[si];
+            float wd = svgf_weight(cdl, cs.depth, cs.normal, luma(xyz(sdi)), ss.depth, ss.normal, ls_di, ds_di);
+            if (wd > 0.0f) { sdw += wd; sdc = sdc + wd * xyz(sdi); sdv += sq(wd) * sdi.w; }
+            float4 sgi = gi_in[si];
+            float wg = svgf_weight(cgl, cs.depth, cs.normal, luma(xyz(sgi)), ss.depth, ss.normal, ls_gi, ds_gi);
+            if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
+        }
+    }
+    di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
+    gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
+}
+
+// R2 frame_composition::fs (frame_composition.rs:19-82), linear HDR out
+__global__ void __launch_bounds__(ST_BLOCK) k_composition(KPARAMS, int cur, u32 mode, const float4* __restrict__ di_diff, const float4* __restrict__ gi_diff) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    float3 color;
+    if (mode == 0u) {
+        GBuf g = gbuf_unpack(cam.prim_gbuffer_d0[cur][i], cam.prim_gbuffer_d1[cur][i]);
+        float3 dd = xyz(di_diff[i]), ds = xyz(cam.di_spec_samples[i]), gd = xyz(gi_diff[i]), gs = xyz(cam.gi_spec_samples[i]);
+        if (g.depth != 0.0f) color = g.emissive + (dd + gd) * xyz(g.base_color) + ds + gs;
+        else color = dd;
+    } else if (mode == 1u) color = xyz(di_diff[i]);
+    else if (mode == 2u) color = xyz(cam.di_spec_samples[i]);
+    else if (mode == 3u) color = xyz(gi_diff[i]);
+    else if (mode == 4u) color = xyz(cam.gi_spec_samples[i]);
+    else if (mode == 5u) color = xyz(cam.ref_colors[i]);
+    else if (mode == 6u) { float4 c = cam.ref_colors[i]; color = xyz(c) / c.w; }
+    else color = f3s(0.f);
+    cam.output[i] = f4(color, 1.0f);
+}
+
+// K1 ref_tracing::main (ref_tracing.rs:4-60)
+__global__ void __launch_bounds__(ST_BLOCK) k_ref_tracing(KPARAMS, u32 depth) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t idx = screen_idx(cam, p.x, p.y);
+    Ray ray;
+    if (depth == 0u) ray = cam_ray(cam.curr, p.x, p.y);
+    else {
+        float4 d0 = cam.ref_rays[3 * idx], d1 = cam.ref_rays[3 * idx + 1];
+        if (all_zero(d1)) return;
+        ray = ray_make(xyz(d0), xyz(d1));
+    }
+    TriHit h = trace_closest(ray, sc, stk);
+    float4 h0, h1; trihit_pack(h, &h0, &h1);
+    cam.ref_hits[2 * idx] = h0; cam.ref_hits[2 * idx + 1] = h1;
+}
+
+// K2 ref_shading::main (ref_shading.rs:4-177)
+__global__ void __launch_bounds__(ST_BLOCK) k_ref_shading(KPARAMS, u32 seed, u32 depth) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t idx = screen_idx(cam, p.x, p.y);
+    Rng rng = rng_make(seed, p.x, p.y);
+    float4* rays = cam.ref_rays;
+    if (depth == 255u) {
+        size_t i = pix(cam, p.x, p.y);
+        float4 prev = cam_is_eq(cam.curr, cam.prev) ? cam.ref_colors[i] : f4zero();
+        cam.ref_colors[i] = prev + f4(xyz(rays[3 * idx + 2]), 1.0f);
+        return;
+    }
+    Ray ray; float3 color, thr;
+    if (depth == 0u) { ray = cam_ray(cam.curr, p.x, p.y); color = f3s(0.f); thr = f3s(1.0f); }
+    else {
+        float4 d0 = rays[3 * idx], d1 = rays[3 * idx + 1], d2 = rays[3 * idx + 2];
+        if (all_zero(d1)) return;   // dead path: explicit no-op (the reference reaches the same state through 0 * x)
+        ray = ray_make(xyz(d0), xyz(d1)); color = xyz(d2); thr = f3(d0.w, d1.w, d2.w);
+    }
+    TriHit th = trihit_unpack(cam.ref_hits[2 * idx], cam.ref_hits[2 * idx + 1]);
+    if (!trihit_some(th)) {
+        color = color + thr * atmosphere_sample(sc, world_sun_dir(sc.world), ray.d);
+        rays[3 * idx] = f4zero(); rays[3 * idx + 1] = f4zero(); rays[3 * idx + 2] = f4(color, 0.0f);
+        return;
+    }
+    GpuMaterial m = sc.materials[th.material_id];
+    if (depth > 0u) m.roughness = rmax(m.roughness, 0.75f * 0.75f);
+    Hit hit;
+    hit.point = th.point + th.normal * 0.01f; hit.origin = ray.o; hit.dir = ray.d;
+    hit.g.base_color = mat_base_color(m, th.uv); hit.g.normal = th.normal; hit.g.metallic = m.metallic; hit.g.emissive = mat_emissive(m, th.uv);
+    hit.g.roughness = m.roughness; hit.g.reflectance = m.reflectance; hit.g.depth = 0.0f;
+    color = color + thr * hit.g.emissive;
+    if (sc.world.light_count > 0u) {
+        u32 lid = rng_u32(rng) % sc.world.light_count;
+        float lpdf = 1.0f / (float)sc.world.light_count;
+        GpuLight light = light_load(sc, lid);
+        bool occ = trace_any(light_ray_wnoise(light, rng, hit.point), sc, stk);
+        if (!occ) color = color + thr * lightrad_sum(light_radiance(light, hit)) / lpdf;
+    }
+    BrdfS rs = brdf_layered_sample(hit.g, rng, -hit.dir);
+    if (rs.pdf == 0.0f) { rays[3 * idx] = f4zero(); rays[3 * idx + 1] = f4zero(); return; }
+    thr = thr * dot(rs.dir, hit.g.normal);
+    thr = thr * (rs.radiance / rs.pdf);
+    rays[3 * idx] = f4(hit.point, thr.x);
+    rays[3 * idx + 1] = f4(rs.dir, thr.y);
+    rays[3 * idx + 2] = f4(color, thr.z);
+}
+
+// K3 bvh_heatmap::main (bvh_heatmap.rs:4-77)
+__global__ void __launch_bounds__(ST_BLOCK) k_bvh_heatmap(KPARAMS) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    u32 used = 0u;
+    trace_closest(cam_ray(cam.curr, p.x, p.y), sc, stk, &used);
+    float progress = (float)used / 8192.0f;
+    const float3 cols[4] = {f3(0.f, 0.f, 1.f), f3(0.f, 1.f, 0.f), f3(1.f, 0.f, 0.f), f3(0.f, 0.f, 0.f)};
+    float3 c = cols[3];
+    if (progress <= 0.0f) c = cols[0];
+    else {
+        float step = 1.0f / (4.0f - 1.0f);
+        bool done = false;
+        for (int k = 0; k < 3 && !done; k++) {
+            float mn = step * (float)k, mx = step * ((float)k + 1.0f);
+            if (progress >= mn && progress <= mx) { float rhs = (progress - mn) / step; float lhs = 1.0f - rhs; c = lhs * cols[k] + rhs * cols[k + 1]; done = true; }
+        }
+    }
+    cam.ref_colors[pix(cam, p.x, p.y)] = f4(c, 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Ray-stream kernels (the K1/K8/K16 shape without the screen): 8 floats per ray
+// (origin.xyz, len, dir.xyz, pad) in, packed hits / occlusion flags out.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_BLOCK) k_trace_stream_closest(const __grid_constant__ SceneDev sc, const float4* __restrict__ rays, long n, float4* __restrict__ out) {
+    ST_TRACE_STACK();
+    long i = (long)blockIdx.x * ST_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    float4 a = rays[2 * i], b = rays[2 * i + 1];
+    u32 used = 0u;
+    TriHit h = trace_closest(ray_make(xyz(a), xyz(b)), sc, stk, &used);
+    float4 h0, h1; trihit_pack(h, &h0, &h1);
+    out[3 * i] = h0; out[3 * i + 1] = h1; out[3 * i + 2] = f4(h.t, bitsf(h.triangle_id), bitsf(h.material_id), (float)used);
+}
+__global__ void __launch_bounds__(ST_BLOCK) k_trace_stream_any(const __grid_constant__ SceneDev sc, const float4* __restrict__ rays, long n, u32* __restrict__ out) {
+    ST_TRACE_STACK();
+    long i = (long)blockIdx.x * ST_BLOCK + threadIdx.x;
+    if (i >= n) return;
+    float4 a = rays[2 * i], b = rays[2 * i + 1];
+    out[i] = trace_any(ray_make(xyz(a), xyz(b), a.w), sc, stk) ? 1u : 0u;
+}
+// elementary-function test hook
+__global__ void k_math(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long n) {
+    long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float r = 0.f;
+    switch (op) {
+        case 0: r = sin_det(a[i]); break; case 1: r = cos_det(a[i]); break; case 2: r = acos_det(a[i]); break;
+        case 3: r = atan2_det(a[i], b[i]); break; case 4: r = exp_det(a[i]); break; case 5: r = pow_det(a[i], b[i]); break;
+    }
+    out[i] = r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Atmosphere LUT generation (strolle-shaders/src/atmosphere/*.rs; Hillaire 2020).  Runs once /
+// on sun change (90 k texels) — outside the per-frame hot path, kept on the GPU so that the
+// product needs no CPU fallback for it.  Rgba16Float storage == f32 rounded to binary16.
+// ---------------------------------------------------------------------------------------------
+ST_DEV float round_f16(float f) { return __half2float(__float2half_rn(f)); }
+ST_DEV void atm_scattering(float3 pos, float3* rayleigh, float* mie, float3* ext) {   // atmosphere/utils.rs:3-27
+    float alt_km = (len(pos) - ST_ATM_GROUND) * 1000.0f;
+    float rd = exp_det(-alt_km / 8.0f);
+    float md = exp_det(-alt_km / 1.2f);
+    float3 rs = f3(5.802f, 13.558f, 33.1f) * rd;
+    float ms = 3.996f * md;
+    float ma = 4.4f * md;
+    float3 oz = f3(0.650f, 1.881f, 0.085f) * rmax(1.0f - fabs_(alt_km - 25.0f) / 15.0f, 0.0f);
+    *rayleigh = rs; *mie = ms;
+    *ext = ((rs + f3s(ms)) + f3s(ma)) + oz;   // RAYLEIGH_ABSORPTION_BASE == 0.0 contributes nothing (quirk C-18)
+}
+ST_DEV float atm_mie_phase(float c) {
+    const float G = 0.8f; const float SCALE = 3.0f / (8.0f * kPi);
+    float num = (1.0f - G * G) * (1.0f + c * c);
+    float den = (2.0f + G * G) * pow_det(1.0f + G * G - 2.0f * G * c, 1.5f);
+    return SCALE * num / den;
+}
+ST_DEV float atm_rayleigh_phase(float c) { const float K = 3.0f / (16.0f * kPi); return K * (1.0f + c * c); }
+ST_DEV float3 exp3(float3 v) { return f3(exp_det(v.x), exp_det(v.y), exp_det(v.z)); }
+ST_DEV float3 atm_transmittance(float3 pos, float3 sun_dir) {   // generate_transmittance_lut.rs:29-59
+    if (ray_sphere(ray_make(pos, sun_dir), ST_ATM_GROUND) > 0.0f) return f3s(0.f);
+    float adist = ray_sphere(ray_make(pos, sun_dir), ST_ATM_TOP);
+    float t = 0.0f; float3 tr = f3s(1.0f);
+    for (float i = 0.0f; i < 40.0f; i += 1.0f) {
+        float nt = ((i + 0.3f) / 40.0f) * adist;
+        float dt = nt - t; t = nt;
+        float3 rs, ext; float ms; atm_scattering(pos + t * sun_dir, &rs, &ms, &ext);
+        tr = tr * exp3(-dt * ext);
+    }
+    return tr;
+}
+__global__ void k_atm_transmittance(float4* __restrict__ out) {   // 256x64
+    int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= 256 || y >= 64) return;
+    float2 uv = f2((float)x, (float)y) / f2(256.0f, 64.0f);
+    float sct = 2.0f * uv.x - 1.0f;
+    float sth = acos_det(rclamp(sct, -1.0f, 1.0f));
+    float height = lerpc(ST_ATM_GROUND, ST_ATM_TOP, uv.y);
+    float3 v = atm_transmittance(f3(0.0f, height, 0.0f), norm(f3(0.0f, sct, -sin_det(sth))));
+    out[y * 256 + x] = f4(round_f16(v.x), round_f16(v.y), round_f16(v.z), 1.0f);
+}
+__global__ void k_atm_sun_color(float4* __restrict__ out, GpuWorld world) {   // strolle/src/lights.rs:84-99
+    float3 sd = world_sun_dir(world);
+    float3 c = atm_transmittance(atm_view_pos(), sd);
+    c = c * 20.0f * 5.0f;
+    float3 pos = sd * 1000.0f;
+    out[0] = f4(pos, 25.0f); out[1] = f4(c, finf());
+}
+__global__ void k_atm_scattering(const float4* __restrict__ tl, float4* __restrict__ out) {   // 32x32, generate_scattering_lut.rs
+    int x = threadIdx.x, y = blockIdx.x;
+    float2 uv = f2((float)x, (float)y) / f2(32.0f, 32.0f);
+    float sct = 2.0f * uv.x - 1.0f;
+    float sth = acos_det(rclamp(sct, -1.0f, 1.0f));
+    float height = lerpc(ST_ATM_GROUND, ST_ATM_TOP, rmax(uv.y, 0.01f));
+    float3 pos = f3(0.0f, height, 0.0f);
+    float3 sun_dir = norm(f3(0.0f, sct, -sin_det(sth)));
+    float3 lum_total = f3s(0.f), fms = f3s(0.f);
+    const int S = 8;
+    float inv_samples = 1.0f / (float)(S * S);
+    for (int i = 0; i < S; i++) for (int j = 0; j < S; j++) {
+        float theta = kPi * ((float)i + 0.5f) / (float)S;
+        float phi = acos_det(rclamp(1.0f - 2.0f * ((float)j + 0.5f) / (float)S, -1.0f, 1.0f));
+        float sph, cph, sth2, cth2; sincos_det(phi, &sph, &cph); sincos_det(theta, &sth2, &cth2);
+        float3 rd = f3(sph * sth2, cph, sph * cth2);
+        float adist = ray_sphere(ray_make(pos, rd), ST_ATM_TOP);
+        float gdist = ray_sphere(ray_make(pos, rd), ST_ATM_GROUND);
+        float t_max = (gdist > 0.0f) ? gdist : adist;
+        float ct = dot(rd, sun_dir);
+        float mp = atm_mie_phase(ct), rp = atm_rayleigh_phase(-ct);
+        float3 lum = f3s(0.f), lf = f3s(0.f), tr = f3s(1.0f);
+        float t = 0.0f;
+        for (float s = 0.0f; s < 20.0f; s += 1.0f) {
+            float nt = ((s + 0.3f) / 20.0f) * t_max;
+            float dt = nt - t; t = nt;
+            float3 np = pos + t * rd;
+            float3 rs, ext; float ms; atm_scattering(np, &rs, &ms, &ext);
+            float3 st_ = exp3(-dt * ext);
+            float3 snp = rs + f3s(ms);
+            float3 sf = (snp - snp * st_) / ext;
+            lf = lf + tr * sf;
+            float3 sun_t = atm_lut(tl, 256, 64, np, sun_dir);
+            float3 ri = rs * rp;
+            float mi = ms * mp;
+            float3 ins = (ri + f3s(mi)) * sun_t;
+            float3 si = (ins - ins * st_) / ext;
+            lum = lum + si * tr;
+            tr = tr * st_;
+        }
+        if (gdist > 0.0f) {
+            float3 hp = pos + gdist * rd;
+            if (dot(pos, sun_dir) > 0.0f) {
+                hp = norm(hp) * ST_ATM_GROUND;
+                lum = lum + tr * f3s(0.25f) * atm_lut(tl, 256, 64, hp, sun_dir);
+            }
+        }
+        fms = fms + lf * inv_samples;
+        lum_total = lum_total + lum * inv_samples;
+    }
+    float3 o = lum_total / (f3s(1.0f) - fms);
+    out[y * 32 + x] = f4(round_f16(o.x), round_f16(o.y), round_f16(o.z), 1.0f);
+}
+__global__ void k_atm_sky(const float4* __restrict__ tl, const float4* __restrict__ sl, float sun_altitude, float4* __restrict__ out) {   // 256x256, generate_sky_lut.rs
+    int x = threadIdx.x, y = blockIdx.x;
+    float2 uv = f2((float)x, (float)y) / f2(256.0f, 256.0f);
+    float azimuth = (uv.x - 0.5f) * 2.0f * kPi;
+    float v;
+    if (uv.y < 0.5f) { float c = 1.0f - 2.0f * uv.y; v = -c * c; }
+    else { float c = uv.y * 2.0f - 1.0f; v = c * c; }
+    float3 vp = atm_view_pos();
+    float height = len(vp);
+    float horizon;
+    { float t = sq(height) - sq(ST_ATM_GROUND); t = sqrtf(t) / height; horizon = acos_det(rclamp(t, -1.0f, 1.0f)) - 0.5f * kPi; }
+    float altitude = v * 0.5f * kPi - horizon;
+    float sa, ca, sz, cz; sincos_det(altitude, &sa, &ca); sincos_det(azimuth, &sz, &cz);
+    float3 rd = f3(ca * sz, sa, -ca * cz);
+    float sal = fmodf(sun_altitude, 2.0f * kPi);
+    float ss, cs_; sincos_det(sal, &ss, &cs_);
+    float3 sun_dir = (sal < 0.5f * kPi) ? f3(0.0f, ss, -cs_) : f3(0.0f, ss, cs_);
+    float adist = ray_sphere(ray_make(vp, rd), ST_ATM_TOP);
+    float gdist = ray_sphere(ray_make(vp, rd), ST_ATM_GROUND);
+    float t_max = (gdist < 0.0f) ? adist : gdist;
+    float ct = dot(rd, sun_dir);
+    float mp = atm_mie_phase(ct), rp = atm_rayleigh_phase(-ct);
+    float3 lum = f3s(0.f), tr = f3s(1.0f);
+    float t = 0.0f;
+    for (float i = 0.0f; i < 32.0f; i += 1.0f) {
+        float nt = ((i + 0.3f) / 32.0f) * t_max;
+        float dt = nt - t; t = nt;
+        float3 np = vp + t * rd;
+        float3 rs, ext; float ms; atm_scattering(np, &rs, &ms, &ext);
+        float3 st_ = exp3(-dt * ext);
+        float3 sun_t = atm_lut(tl, 256, 64, np, sun_dir);
+        float3 psi = atm_lut(sl, 32, 32, np, sun_dir);
+        float3 ri = rs * (rp * sun_t + psi);
+        float3 mi = ms * (mp * sun_t + psi);
+        float3 ins = ri + mi;
+        float3 si = (ins - ins * st_) / ext;
+        lum = lum + si * tr;
+        tr = tr * st_;
+    }
+    out[y * 256 + x] = f4(round_f16(lum.x), round_f16(lum.y), round_f16(lum.z), 1.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-side launchers
+// ---------------------------------------------------------------------------------------------
+static dim3 grid_full(const CameraDev& cam) { return dim3((cam.w + TILE_W - 1) / TILE_W, (cam.y1 - cam.y0 + TILE_H - 1) / TILE_H); }
+static dim3 grid_half(const CameraDev& cam) { int hw = 8 * (((cam.w + 7) / 8) / 2); return dim3((hw + TILE_W - 1) / TILE_W, (cam.y1 - cam.y0 + TILE_H - 1) / TILE_H); }
+
+void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
+void launch_frame_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_frame_reprojection<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
+void launch_di_sampling(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_di_sampling<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
+void launch_di_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, cudaStream_t st) { k_di_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed); }
+void launch_di_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_di_spatial_pick<<<grid_half(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
+void launch_spatial_trace(const CameraDev& c, const SceneDev& s, const float4* d0, const float4* d1, float4* d2, cudaStream_t st) { k_spatial_trace<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, d0, d1, d2); }
+void launch_di_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st) { k_di_spatial_sample<<<grid_half(c), ST_BLOCK, 0, st>>>(c, s, seed, frame); }
+void launch_di_resolving(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_di_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
+void launch_gi_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_gi_reprojection<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
+void launch_gi_sampling_a(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_gi_sampling_a<<<grid_half(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
+void launch_gi_sampling_b(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_gi_sampling_b<<<grid_half(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
+void launch_gi_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_gi_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
+void launch_gi_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_gi_spatial_pick<<<grid_half(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
+void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st) { k_gi_spatial_sample<<<grid_half(c), ST_BLOCK, 0, st>>>(c, s, seed, frame); }
+void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out); }
+void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
+void launch_denoise_reproject(const CameraDev& c, const SceneDev& s, int cur, const float4* pc, const float4* pm, const float4* smp, float4* col, float4* mom, cudaStream_t st) { k_denoise_reproject<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, pc, pm, smp, col, mom); }
+void launch_denoise_variance(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_denoise_variance<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
+void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, cudaStream_t st) {
+    k_denoise_wavelet<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
+}
+void launch_composition(const CameraDev& c, const SceneDev& s, int cur, u32 mode, const float4* di_diff, const float4* gi_diff, cudaStream_t st) { k_composition<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, mode, di_diff, gi_diff); }
+void launch_ref_tracing(const CameraDev& c, const SceneDev& s, u32 depth, cudaStream_t st) { k_ref_tracing<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, depth); }
+void launch_ref_shading(const CameraDev& c, const SceneDev& s, u32 seed, u32 depth, cudaStream_t st) { k_ref_shading<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, seed, depth); }
+void launch_bvh_heatmap(const CameraDev& c, const SceneDev& s, cudaStream_t st) { k_bvh_heatmap<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s); }
+void launch_trace_stream_closest(const SceneDev& s, const float4* rays, long n, float4* out, cudaStream_t st) { k_trace_stream_closest<<<(unsigned)((n + ST_BLOCK - 1) / ST_BLOCK), ST_BLOCK, 0, st>>>(s, rays, n, out); }
+void launch_trace_stream_any(const SceneDev& s, const float4* rays, long n, u32* out, cudaStream_t st) { k_trace_stream_any<<<(unsigned)((n + ST_BLOCK - 1) / ST_BLOCK), ST_BLOCK, 0, st>>>(s, rays, n, out); }
+void launch_math(int op, const float* a, const float* b, float* out, long n, cudaStream_t st) { k_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, a, b, out, n); }
+void launch_atm_transmittance(float4* out, cudaStream_t st) { k_atm_transmittance<<<dim3(2, 64), 128, 0, st>>>(out); }
+void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st) { k_atm_scattering<<<32, 32, 0, st>>>(tl, out); }
+void launch_atm_sky(const float4* tl, const float4* sl, float sun_altitude, float4* out, cudaStream_t st) { k_atm_sky<<<256, 256, 0, st>>>(tl, sl, sun_altitude, out); }
+void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st) { k_atm_sun_color<<<1, 1, 0, st>>>(out2, world); }
+
+}  // namespace st

@@ -1,0 +1,40 @@
+// strolle_b200 — host-callable launchers for the kernels in kernels.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "st_types.h"
+
+namespace st {
+typedef uint32_t u32;
+
+void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
+void launch_frame_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
+void launch_di_sampling(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
+void launch_di_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, cudaStream_t st);
+void launch_di_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
+void launch_spatial_trace(const CameraDev& c, const SceneDev& s, const float4* d0, const float4* d1, float4* d2, cudaStream_t st);
+void launch_di_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st);
+void launch_di_resolving(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
+void launch_gi_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
+void launch_gi_sampling_a(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
+void launch_gi_sampling_b(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
+void launch_gi_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
+void launch_gi_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
+void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st);
+void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st);
+void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st);
+void launch_denoise_reproject(const CameraDev& c, const SceneDev& s, int cur, const float4* pc, const float4* pm, const float4* smp, float4* col, float4* mom, cudaStream_t st);
+void launch_denoise_variance(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
+void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, cudaStream_t st);
+void launch_composition(const CameraDev& c, const SceneDev& s, int cur, u32 mode, const float4* di_diff, const float4* gi_diff, cudaStream_t st);
+void launch_ref_tracing(const CameraDev& c, const SceneDev& s, u32 depth, cudaStream_t st);
+void launch_ref_shading(const CameraDev& c, const SceneDev& s, u32 seed, u32 depth, cudaStream_t st);
+void launch_bvh_heatmap(const CameraDev& c, const SceneDev& s, cudaStream_t st);
+void launch_trace_stream_closest(const SceneDev& s, const float4* rays, long n, float4* out, cudaStream_t st);
+void launch_trace_stream_any(const SceneDev& s, const float4* rays, long n, u32* out, cudaStream_t st);
+void launch_math(int op, const float* a, const float* b, float* out, long n, cudaStream_t st);
+void launch_atm_transmittance(float4* out, cudaStream_t st);
+void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st);
+void launch_atm_sky(const float4* tl, const float4* sl, float sun_altitude, float4* out, cudaStream_t st);
+void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st);
+
+}  // namespace st

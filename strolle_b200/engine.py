@@ -1,0 +1,281 @@
+"""ctypes mirror of strolle::Engine (strolle/src/lib.rs:104-395) over libstrolle_b200.so.
+
+Method names follow the reference's Engine API: insert_mesh / insert_material / insert_instance /
+insert_light / update_sun / create_camera / update_camera / tick / render_camera, plus the test
+hooks of include/strolle_b200.h (read_buffer, trace_closest, pass_times, ...).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+PASS_COUNT = 26
+FORMAT_RGBA32F, FORMAT_RGBA8_SRGB = 0, 1
+
+
+class StrolleError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return os.path.join(_HERE, "_lib", "libstrolle_b200.so")
+
+
+class _MeshTriangle(C.Structure):
+    _fields_ = [("positions", C.c_float * 9), ("normals", C.c_float * 9), ("uvs", C.c_float * 6), ("tangents", C.c_float * 12)]
+
+
+class _Material(C.Structure):
+    _fields_ = [("base_color", C.c_float * 4), ("emissive", C.c_float * 4), ("perceptual_roughness", C.c_float), ("metallic", C.c_float),
+                ("reflectance", C.c_float), ("ior", C.c_float), ("alpha_blend", C.c_int32)]
+
+
+class _Light(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("position", C.c_float * 3), ("radius", C.c_float), ("color", C.c_float * 3), ("range", C.c_float),
+                ("direction", C.c_float * 3), ("angle", C.c_float)]
+
+
+class _Camera(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("denoise", C.c_int32), ("ref_depth", C.c_int32), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("transform", C.c_float * 16), ("projection", C.c_float * 16)]
+
+
+_LIB = None
+
+
+def load_library():
+    """Loads the C-ABI library; raises if it has not been built (python -m strolle_b200.build)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise StrolleError(f"{path} is missing: build it with `python -m strolle_b200.build` (no CPU fallback exists)")
+    lib = C.CDLL(path)
+    P, u64, i32, u32, f32p = C.c_void_p, C.c_uint64, C.c_int32, C.c_uint32, C.POINTER(C.c_float)
+    sig = {
+        "st_engine_create": [C.c_int, C.POINTER(P)], "st_engine_destroy": [P],
+        "st_insert_mesh": [P, u64, C.POINTER(_MeshTriangle), C.c_size_t], "st_remove_mesh": [P, u64],
+        "st_insert_material": [P, u64, C.POINTER(_Material)], "st_has_material": [P, u64], "st_remove_material": [P, u64],
+        "st_insert_instance": [P, u64, u64, u64, f32p], "st_remove_instance": [P, u64],
+        "st_insert_light": [P, u64, C.POINTER(_Light)], "st_remove_light": [P, u64], "st_update_sun": [P, C.c_float, C.c_float],
+        "st_create_camera": [P, C.POINTER(_Camera), C.POINTER(i32)], "st_update_camera": [P, i32, C.POINTER(_Camera)], "st_delete_camera": [P, i32],
+        "st_tick": [P], "st_render_camera": [P, i32, P, C.c_int], "st_synchronize": [P],
+        "st_set_seed_base": [P, u32], "st_set_blue_noise": [P, C.c_void_p],
+        "st_read_buffer": [P, i32, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
+        "st_read_scene": [P, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
+        "st_bvh_depth": [P, C.POINTER(C.c_int)],
+        "st_trace_closest": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p], "st_trace_any": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p],
+        "st_device_math": [P, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
+        "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int],
+        "st_camera_set_strip": [P, i32, C.c_int, C.c_int],
+        "st_buffer_device_ptr": [P, i32, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
+        "st_frame_schedule": [P, i32, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)], "st_render_range": [P, i32, C.c_int, C.c_int],
+    }
+    for name, args in sig.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = None if name == "st_engine_destroy" else C.c_int
+    lib.st_last_error.restype = C.c_char_p
+    lib.st_pass_name.restype = C.c_char_p
+    lib.st_pass_name.argtypes = [C.c_int]
+    lib.st_frame.restype = C.c_uint32
+    lib.st_frame.argtypes = [P]
+    _LIB = lib
+    return lib
+
+
+def _pass_names():
+    lib = load_library()
+    return [lib.st_pass_name(i).decode() for i in range(PASS_COUNT)]
+
+
+class _LazyNames(list):
+    def _fill(self):
+        if not len(self):
+            self.extend(_pass_names())
+
+    def __getitem__(self, i):
+        self._fill()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._fill()
+        return list.__iter__(self)
+
+
+PASS_NAMES = _LazyNames()
+
+
+def _f(a, n=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+    if n is not None and a.size != n:
+        raise ValueError(f"expected {n} floats, got {a.size}")
+    return a
+
+
+class Engine:
+    """strolle::Engine on one B200 (CUDA device `device`)."""
+
+    def __init__(self, device=0, blue_noise=None, seed_base=0xC0FFEE):
+        self.lib = load_library()
+        h = C.c_void_p()
+        self._h = None
+        self._check(self.lib.st_engine_create(device, C.byref(h)))
+        self._h = h
+        if blue_noise is None:
+            from . import scenes
+            blue_noise = scenes.blue_noise()
+        bn = np.ascontiguousarray(blue_noise, dtype=np.uint8).reshape(-1)
+        self._check(self.lib.st_set_blue_noise(self._h, bn.ctypes.data))
+        self._check(self.lib.st_set_seed_base(self._h, seed_base))
+        self._cams = {}
+
+    def _check(self, rc):
+        if rc != 0:
+            raise StrolleError(f"strolle_b200 error {rc}: {self.lib.st_last_error().decode()}")
+
+    def close(self):
+        if self._h:
+            self.lib.st_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene ------------------------------------------------------------------------------
+    def insert_mesh(self, handle, triangles36):
+        t = _f(triangles36)
+        n = t.size // 36
+        self._check(self.lib.st_insert_mesh(self._h, handle, t.ctypes.data_as(C.POINTER(_MeshTriangle)), n))
+
+    def insert_material(self, handle, params12, alpha_blend=False):
+        p = _f(params12, 12)
+        m = _Material((C.c_float * 4)(*p[0:4]), (C.c_float * 4)(*p[4:8]), p[8], p[9], p[10], p[11], int(alpha_blend))
+        self._check(self.lib.st_insert_material(self._h, handle, C.byref(m)))
+
+    def insert_instance(self, handle, mesh, material, affine12):
+        a = _f(affine12, 12)
+        self._check(self.lib.st_insert_instance(self._h, handle, mesh, material, a.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def remove_instance(self, handle):
+        self._check(self.lib.st_remove_instance(self._h, handle))
+
+    def insert_light(self, handle, kind, params12):
+        p = _f(params12, 12)
+        l = _Light(kind, (C.c_float * 3)(*p[0:3]), p[3], (C.c_float * 3)(*p[4:7]), p[7], (C.c_float * 3)(*p[8:11]), p[11])
+        self._check(self.lib.st_insert_light(self._h, handle, C.byref(l)))
+
+    def remove_light(self, handle):
+        self._check(self.lib.st_remove_light(self._h, handle))
+
+    def update_sun(self, azimuth, altitude):
+        self._check(self.lib.st_update_sun(self._h, azimuth, altitude))
+
+    # ---- cameras ----------------------------------------------------------------------------
+    @staticmethod
+    def _cam(mode, denoise, ref_depth, w, h, transform16, projection16):
+        return _Camera(mode, int(denoise), ref_depth, w, h, (C.c_float * 16)(*_f(transform16, 16)), (C.c_float * 16)(*_f(projection16, 16)))
+
+    def create_camera(self, mode, denoise, ref_depth, w, h, transform16, projection16):
+        c = self._cam(mode, denoise, ref_depth, w, h, transform16, projection16)
+        out = C.c_int32()
+        self._check(self.lib.st_create_camera(self._h, C.byref(c), C.byref(out)))
+        self._cams[out.value] = (w, h)
+        return out.value
+
+    def update_camera(self, cam, mode, denoise, ref_depth, w, h, transform16, projection16):
+        c = self._cam(mode, denoise, ref_depth, w, h, transform16, projection16)
+        self._check(self.lib.st_update_camera(self._h, cam, C.byref(c)))
+        self._cams[cam] = (w, h)
+
+    def set_strip(self, cam, y0, y1):
+        self._check(self.lib.st_camera_set_strip(self._h, cam, y0, y1))
+
+    # ---- frame ------------------------------------------------------------------------------
+    def tick(self):
+        self._check(self.lib.st_tick(self._h))
+
+    def render_camera(self, cam, out=None, fmt=FORMAT_RGBA32F):
+        """Runs the frame's passes.  With `out` (host ndarray) the composed frame is copied back."""
+        ptr = out.ctypes.data if out is not None else None
+        self._check(self.lib.st_render_camera(self._h, cam, ptr, fmt))
+
+    def render_range(self, cam, first, last):
+        self._check(self.lib.st_render_range(self._h, cam, first, last))
+
+    def frame_schedule(self, cam):
+        ids = (C.c_int * 64)()
+        n = C.c_int()
+        self._check(self.lib.st_frame_schedule(self._h, cam, ids, 64, C.byref(n)))
+        return list(ids[: n.value])
+
+    def synchronize(self):
+        self._check(self.lib.st_synchronize(self._h))
+
+    def frame(self):
+        return self.lib.st_frame(self._h)
+
+    # ---- hooks ------------------------------------------------------------------------------
+    def read_buffer(self, cam, name):
+        n = C.c_size_t()
+        self._check(self.lib.st_read_buffer(self._h, cam, name.encode(), None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        self._check(self.lib.st_read_buffer(self._h, cam, name.encode(), out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def buffer_device_ptr(self, cam, name):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._check(self.lib.st_buffer_device_ptr(self._h, cam, name.encode(), C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def read_scene(self, name):
+        n = C.c_size_t()
+        self._check(self.lib.st_read_scene(self._h, name.encode(), None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        if n.value:
+            self._check(self.lib.st_read_scene(self._h, name.encode(), out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def bvh_depth(self):
+        d = C.c_int()
+        self._check(self.lib.st_bvh_depth(self._h, C.byref(d)))
+        return d.value
+
+    def trace_closest(self, rays8, return_ms=False):
+        r = _f(rays8)
+        n = r.size // 8
+        out = np.empty(n * 12, dtype=np.float32)
+        ms = C.c_float()
+        self._check(self.lib.st_trace_closest(self._h, r.ctypes.data, n, out.ctypes.data, C.byref(ms)))
+        out = out.reshape(n, 12)
+        return (out, ms.value) if return_ms else out
+
+    def trace_any(self, rays8, return_ms=False):
+        r = _f(rays8)
+        n = r.size // 8
+        out = np.empty(n, dtype=np.uint32)
+        ms = C.c_float()
+        self._check(self.lib.st_trace_any(self._h, r.ctypes.data, n, out.ctypes.data, C.byref(ms)))
+        return (out, ms.value) if return_ms else out
+
+    def device_math(self, op, a, b=None):
+        ops = {"sin": 0, "cos": 1, "acos": 2, "atan2": 3, "exp": 4, "pow": 5}
+        a = _f(a)
+        b = _f(b) if b is not None else np.zeros_like(a)
+        out = np.empty_like(a)
+        self._check(self.lib.st_device_math(self._h, ops[op], a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size))
+        return out
+
+    def enable_timing(self, enabled=True):
+        self._check(self.lib.st_enable_timing(self._h, int(enabled)))
+
+    def pass_times(self, reset=False):
+        ms = np.zeros(PASS_COUNT, dtype=np.float32)
+        launches = np.zeros(PASS_COUNT, dtype=np.uint32)
+        self._check(self.lib.st_pass_times(self._h, ms.ctypes.data, launches.ctypes.data, int(reset)))
+        return ms, launches

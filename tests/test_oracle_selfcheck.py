@@ -1,0 +1,138 @@
+"""Self-checks that strengthen the (unpinned) oracle: SURVEY.md §8c."""
+import numpy as np
+import pytest
+
+from strolle_b200 import scenes
+from tests.util import assert_bits_equal, random_rays, rel_l2
+
+
+@pytest.fixture(scope="module")
+def cornell_oracle(oracle, blue_noise):
+    e = oracle.OracleEngine(blue_noise=blue_noise)
+    cam = scenes.apply(e, scenes.cornell(96, 64))
+    e.tick()
+    return e, cam
+
+
+def test_bvh_invariants(cornell_oracle):
+    e, _ = cornell_oracle
+    bvh = e.read_scene("bvh").reshape(-1, 4)
+    bits = bvh.view(np.uint32)
+    tris = e.read_scene("triangles").reshape(-1, 9, 4)
+    assert tris.shape[0] == 32
+    seen = []
+    def visit(ptr, lo, hi, depth):
+        assert depth <= 24
+        if bits[ptr, 3] == 0:   # internal: [L.min,0][L.max,right_ptr][R.min,0][R.max,0], left child at ptr+4
+            lmin, lmax, rmin, rmax = bvh[ptr, :3], bvh[ptr + 1, :3], bvh[ptr + 2, :3], bvh[ptr + 3, :3]
+            visit(ptr + 4, lmin, lmax, depth + 1)
+            visit(int(bits[ptr + 1, 3]), rmin, rmax, depth + 1)
+        else:
+            while True:
+                flags, tid = int(bits[ptr, 0]), int(bits[ptr, 1])
+                seen.append(tid)
+                pos = tris[tid, [0, 3, 6], :3]
+                if lo is not None:
+                    assert (pos >= lo - 1e-6).all() and (pos <= hi + 1e-6).all()
+                assert int(bits[ptr, 3]) == 1
+                if not (flags & 1):
+                    break
+                ptr += 1
+    visit(0, None, None, 1)
+    assert sorted(seen) == list(range(32)), "every triangle is referenced exactly once"
+    assert e.bvh_depth() <= 24
+
+
+def test_bvh_quirk_multi_triangle_leaves(cornell_oracle):
+    # quirk C-7: primitives whose centroids share a bit-identical x never split -> leaves with > 1 entry
+    e, _ = cornell_oracle
+    bits = e.read_scene("bvh").reshape(-1, 4).view(np.uint32)
+    leaves = bits[bits[:, 3] == 1]
+    assert (leaves[:, 0] & 1).any()
+
+
+def test_traversal_matches_brute_force(cornell_oracle):
+    e, _ = cornell_oracle
+    rays = random_rays(20000, 1, (-1.0, 0.0, -1.0), (1.0, 2.0, 3.0))
+    hits = e.trace_closest(rays)
+    dist, tri = e.trace_brute(rays)
+    bvh_tri = hits[:, 9].copy().view(np.uint32)
+    assert_bits_equal(hits[:, 8], dist, "closest distance")
+    # triangle ids agree except for exact distance ties (different visiting order)
+    differ = bvh_tri != tri
+    assert differ.mean() < 1e-3
+    # any-hit == closest-hit within len
+    rays_len = rays.copy()
+    rays_len[:, 3] = np.float32(2.0)
+    occ = e.trace_any(rays_len)
+    assert ((dist < 2.0) == (occ == 1)).all()
+
+
+def test_deterministic_and_frame_progress(oracle, blue_noise):
+    outs = []
+    for _ in range(2):
+        e = oracle.OracleEngine(blue_noise=blue_noise)
+        cam = scenes.apply(e, scenes.cornell(64, 48))
+        for _f in range(3):
+            e.tick()
+            e.render_camera(cam)
+        outs.append(e.read_buffer(cam, "output"))
+    assert_bits_equal(outs[0], outs[1], "oracle is deterministic")
+    assert np.isfinite(outs[0]).all()
+
+
+def test_libm_variant_agrees_within_tolerance(oracle, blue_noise):
+    """Swapping the Cephes-style elementary functions for the host libm moves the image by far less
+    than the 1e-3 relative-L2 parity tolerance of BASELINE.json's north_star."""
+    imgs = []
+    for libm in (False, True):
+        e = oracle.OracleEngine(libm=libm, blue_noise=blue_noise)
+        cam = scenes.apply(e, scenes.cornell(96, 64))
+        e.tick()
+        e.render_camera(cam)
+        imgs.append(e.read_buffer(cam, "output").reshape(-1, 4)[:, :3])
+    assert rel_l2(imgs[0], imgs[1]) < 1e-3
+    for op, a, b in [("sin", np.linspace(-7, 7, 1001), None), ("cos", np.linspace(-7, 7, 1001), None), ("acos", np.linspace(-1, 1, 1001), None),
+                     ("exp", np.linspace(-20, 20, 1001), None), ("pow", np.linspace(0.001, 1.0, 1001), np.full(1001, 2.2)),
+                     ("atan2", np.sin(np.linspace(-3, 3, 1001)), np.cos(np.linspace(-3, 3, 1001)))]:
+        x = oracle.math(op, a, b)
+        y = oracle.math(op, a, b, libm=True)
+        np.testing.assert_allclose(x, y, rtol=2e-6, atol=2e-7)
+
+
+def test_reference_mode_energy_matches_restir(oracle, blue_noise):
+    """Statistical cross-check: the path-traced reference mode and the ReSTIR+SVGF
+    image agree in mean radiance on Cornell."""
+    e1 = oracle.OracleEngine(blue_noise=blue_noise)
+    c1 = scenes.apply(e1, scenes.cornell(96, 54))
+    for _ in range(12):
+        e1.tick(); e1.render_camera(c1)
+    e2 = oracle.OracleEngine(blue_noise=blue_noise)
+    c2 = scenes.apply(e2, scenes.cornell(96, 54, mode=scenes.MODE_REFERENCE, ref_depth=2))
+    for _ in range(48):
+        e2.tick(); e2.render_camera(c2)
+    a = e1.read_buffer(c1, "output").reshape(-1, 4)[:, :3].mean()
+    b = e2.read_buffer(c2, "output").reshape(-1, 4)[:, :3].mean()
+    assert abs(a - b) / b < 0.2
+
+
+def test_light_slot_protocol(oracle, blue_noise):
+    # strolle/src/lights.rs:101-162: removing a light kills its slot for one frame and remaps the tail
+    e = oracle.OracleEngine(blue_noise=blue_noise)
+    sc = scenes.cornell(32, 32)
+    cam = scenes.apply(e, sc)
+    e.insert_light(401, scenes.LIGHT_POINT, scenes.point_light((0.5, 1.0, 0.0), 0.1, (1, 1, 1), 10.0))
+    e.insert_light(402, scenes.LIGHT_POINT, scenes.point_light((-0.5, 1.0, 0.0), 0.1, (2, 2, 2), 10.0))
+    e.tick()
+    l0 = e.read_scene("lights").reshape(-1, 28)
+    assert e.read_scene("world").view(np.uint32)[0] == 4
+    assert (l0[1:4, 16:28] == 0).all(), "created lights upload with zero prev_d* on their first frame"
+    e.remove_light(401)
+    e.tick()
+    l1 = e.read_scene("lights").reshape(-1, 28)
+    slot = l1[:, 12].copy().view(np.uint32)
+    assert e.read_scene("world").view(np.uint32)[0] == 3
+    assert slot[2] == 0xCAFEBABE or slot[3] == 3, "killed / remapped slot markers are visible for one frame"
+    e.tick()
+    l2 = e.read_scene("lights").reshape(-1, 28)
+    assert (l2[:, 12].view(np.uint32) == 0).all()
