@@ -119,6 +119,9 @@ int st_tick(st_engine* e);
  * copied to it and the call returns when the copy is done; with NULL the call only enqueues
  * (use st_synchronize). */
 int st_render_camera(st_engine* e, st_camera_handle camera, void* host_out, int format);
+/* Converts the camera's composed frame to `format` and copies it to host memory (what
+ * st_render_camera does when host_out != NULL), without re-running the passes. */
+int st_copy_output(st_engine* e, st_camera_handle camera, void* host_out, int format);
 int st_synchronize(st_engine* e);
 
 /* ---- hooks that the reference does not have -------------------------------- */
@@ -150,6 +153,16 @@ int st_device_math(st_engine* e, int op, const float* a, const float* b, float* 
 int st_enable_timing(st_engine* e, int enabled);
 int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset);
 const char* st_pass_name(int pass);
+/* Runs the engine on a caller-owned CUDA stream (e.g. the host runtime's stream that NCCL halo
+ * exchanges are ordered against); NULL restores a private non-blocking stream. */
+int st_set_stream(st_engine* e, void* cuda_stream);
+/* Ray statistics: counts executed Ray::trace / Ray::intersect calls (the Mrays/s numerator). */
+int st_count_rays(st_engine* e, int enabled);
+int st_ray_count(st_engine* e, uint64_t* rays, int reset);
+/* Device-side stopwatch on the engine's stream (CUDA events): st_mark_begin records, st_mark_end
+ * records + waits and returns the elapsed milliseconds between the two. */
+int st_mark_begin(st_engine* e);
+int st_mark_end(st_engine* e, float* ms);
 /* Row-strip partition for multi-GPU runs: this engine computes rows [y0, y1) of the
  * camera's frame; full-frame buffers stay addressable for halo rows. */
 int st_camera_set_strip(st_engine* e, st_camera_handle camera, int y0, int y1);

@@ -193,6 +193,11 @@ void orc_allocator_script(const long* ops, int n, long* out) {
         else { size_t s, e; if (al.take((size_t)a, &s, &e)) { out[3 * i] = 1; out[3 * i + 1] = (long)s; out[3 * i + 2] = (long)e; } }
     }
 }
+unsigned long long orc_ray_count(int reset) {
+    unsigned long long t = 0;
+    for (int i = 0; i < 256; i++) { t += g_ray_counters[i].n; if (reset) g_ray_counters[i].n = 0; }
+    return t;
+}
 int orc_is_libm() {
 #ifdef ORC_LIBM
     return 1;

@@ -6,6 +6,9 @@
 // file:line (relative to /root/reference) it follows.
 #pragma once
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "orc_math.hpp"
 
 namespace orc {
@@ -159,11 +162,23 @@ static inline void material_regularize(Material& m) { m.roughness = fmax_(m.roug
 
 enum Tracing { ReturnClosest, ReturnFirst };
 
+// executed Ray::trace / Ray::intersect calls (the Mrays/s numerator); one padded slot per OpenMP thread
+struct RayCounter { unsigned long long n; char pad[56]; };
+static RayCounter g_ray_counters[256];
+static inline void count_ray() {
+#ifdef _OPENMP
+    g_ray_counters[omp_get_thread_num() & 255].n += 1;
+#else
+    g_ray_counters[0].n += 1;
+#endif
+}
+
 // Ray::traverse (strolle-gpu/src/ray.rs:114-266).  Returns `used_memory`.
 // `overflow` (not in the reference) is set when the 24-entry stack would
 // overflow — the reference silently corrupts a neighbour's stack there
 // (strolle-gpu/src/lib.rs:72-76); both oracle and product assert at upload.
 static inline size_t ray_traverse(const Ray& self, const Scene& sc, Tracing tracing, TriangleHit* hit, u32* visited_nodes = nullptr) {
+    count_ray();
     size_t used_memory = 0;
     u32 bvh_ptr = 0;
     u32 stack[BVH_STACK_SIZE];

@@ -68,6 +68,8 @@ def _load(libm=False):
     lib.orc_read_scene.restype = C.c_long
     lib.orc_u32_bytes_roundtrip.restype = C.c_uint32
     lib.orc_u32_bytes_roundtrip.argtypes = [C.c_uint32]
+    lib.orc_ray_count.restype = C.c_uint64
+    lib.orc_ray_count.argtypes = [C.c_int]
     lib.orc_frame.restype = C.c_uint32
     lib.orc_frame.argtypes = [C.c_void_p]
     return lib
@@ -185,6 +187,10 @@ class OracleEngine:
         t = np.empty(n, dtype=np.uint32)
         self.lib.orc_trace_brute(self.h, r, n, d, t)
         return d, t
+
+
+def ray_count(reset=False, libm=False):
+    return int(lib(libm).orc_ray_count(int(reset)))
 
 
 def math(op, a, b=None, libm=False):

@@ -254,6 +254,7 @@ struct DevMem {
         size_t want = std::max<size_t>(bytes, 256);
         CK(cudaMalloc(&p, want));
         CK(cudaMemset(p, 0, want));
+        CK(cudaDeviceSynchronize());   // the fill runs on the legacy stream; engine streams are non-blocking
         cap = want;
         return ST_OK;
     }
@@ -293,7 +294,7 @@ using namespace st;
 
 struct st_engine {
     int device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr; bool own_stream = true;
     // meshes / materials / instances / triangles -------------------------------------------------
     std::unordered_map<st_handle, std::vector<st_mesh_triangle>> meshes;
     std::vector<st_material> materials; std::vector<st_handle> material_handles; bool materials_dirty = false;
@@ -313,7 +314,8 @@ struct st_engine {
     GpuWorld world;
     uint32_t frame = 1, seed_base = 0xC0FFEEu;
     // device scene ------------------------------------------------------------------------------
-    DevMem d_triangles, d_bvh, d_materials, d_lights, d_noise, d_tlut, d_slut, d_skylut, d_scratch;
+    DevMem d_triangles, d_bvh, d_materials, d_lights, d_noise, d_tlut, d_slut, d_skylut, d_scratch, d_raycount;
+    bool count_rays = false;
     bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
     std::vector<CameraSlot*> cameras;
     // timing ---------------------------------------------------------------------------------------
@@ -321,6 +323,7 @@ struct st_engine {
     float pass_ms[P_COUNT] = {}; uint32_t pass_launches[P_COUNT] = {};
     struct Timed { int pass; cudaEvent_t a, b; };
     std::vector<Timed> pending; std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t mark_a = nullptr, mark_b = nullptr;
 
     SceneDev scene() const {
         SceneDev s;
@@ -328,6 +331,7 @@ struct st_engine {
         s.lights = (const GpuLight*)d_lights.p; s.blue_noise = (const uchar4*)d_noise.p;
         s.transmittance_lut = (const float4*)d_tlut.p; s.scattering_lut = (const float4*)d_slut.p; s.sky_lut = (const float4*)d_skylut.p;
         s.world = world;
+        s.ray_counter = count_rays ? (unsigned long long*)d_raycount.p : nullptr;
         return s;
     }
     uint32_t* light_slot(st_handle h) { for (auto& p : light_slots) if (p.first == h) return &p.second; return nullptr; }
@@ -618,11 +622,11 @@ void st_engine_destroy(st_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); delete c; }
-    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch};
+    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
-    cudaStreamDestroy(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
 
@@ -832,13 +836,26 @@ int st_render_range(st_engine* e, st_camera_handle h, int first, int last) {
     CK(cudaGetLastError());
     return ST_OK;
 }
+int st_copy_output(st_engine* e, st_camera_handle h, void* host_out, int format);
 int st_render_camera(st_engine* e, st_camera_handle h, void* host_out, int format) {
     int rc = st_render_range(e, h, 0, -1); if (rc) return rc;
-    if (host_out) {
-        CameraSlot* cs = get_camera(e, h);
+    if (host_out) return st_copy_output(e, h, host_out, format);
+    return ST_OK;
+}
+int st_copy_output(st_engine* e, st_camera_handle h, void* host_out, int format) {
+    CameraSlot* cs0 = e ? get_camera(e, h) : nullptr;
+    if (!cs0 || !host_out) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    CK(cudaSetDevice(e->device));
+    {
+        CameraSlot* cs = cs0;
         size_t n = (size_t)cs->desc.width * cs->desc.height;
         if (format == ST_FORMAT_RGBA32F) CK(cudaMemcpyAsync(host_out, cs->dev.output, n * 16, cudaMemcpyDeviceToHost, e->stream));
-        else return fail(ST_ERR_INVALID, "unsupported output format");
+        else if (format == ST_FORMAT_RGBA8_SRGB) {
+            int rc2 = cs->rgba8.ensure(n * 4); if (rc2) return rc2;
+            SceneDev sc = e->scene(); uchar4* dst8 = (uchar4*)cs->rgba8.p; CameraDev cd = cs->dev;
+            e->run_timed(P_COMPOSITION, [=](cudaStream_t s) { launch_output_rgba8(cd, sc, dst8, s); });
+            CK(cudaMemcpyAsync(host_out, cs->rgba8.p, n * 4, cudaMemcpyDeviceToHost, e->stream));
+        } else return fail(ST_ERR_INVALID, "unsupported output format");
         CK(cudaStreamSynchronize(e->stream));
     }
     return ST_OK;
@@ -927,6 +944,48 @@ int st_device_math(st_engine* e, int op, const float* a, const float* b, float* 
     return ST_OK;
 }
 
+int st_set_stream(st_engine* e, void* cuda_stream) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    CK(cudaStreamSynchronize(e->stream));
+    if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
+    if (cuda_stream) e->stream = (cudaStream_t)cuda_stream;
+    else { CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
+    return ST_OK;
+}
+int st_count_rays(st_engine* e, int enabled) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    int rc = e->d_raycount.ensure(8); if (rc) return rc;
+    e->count_rays = enabled != 0;
+    return ST_OK;
+}
+int st_ray_count(st_engine* e, uint64_t* rays, int reset) {
+    if (!e || !rays) return fail(ST_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    *rays = 0;
+    if (!e->d_raycount.p) return ST_OK;
+    CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(rays, e->d_raycount.p, 8, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(e->d_raycount.p, 0, 8));
+    CK(cudaDeviceSynchronize());
+    return ST_OK;
+}
+int st_mark_begin(st_engine* e) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    if (!e->mark_a) { CK(cudaEventCreate(&e->mark_a)); CK(cudaEventCreate(&e->mark_b)); }
+    CK(cudaEventRecord(e->mark_a, e->stream));
+    return ST_OK;
+}
+int st_mark_end(st_engine* e, float* ms) {
+    if (!e || !ms || !e->mark_a) return fail(ST_ERR_INVALID, "st_mark_begin first");
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventRecord(e->mark_b, e->stream));
+    CK(cudaEventSynchronize(e->mark_b));
+    CK(cudaEventElapsedTime(ms, e->mark_a, e->mark_b));
+    return ST_OK;
+}
 int st_enable_timing(st_engine* e, int enabled) { if (!e) return fail(ST_ERR_INVALID, "null engine"); e->timing = enabled != 0; return ST_OK; }
 int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");

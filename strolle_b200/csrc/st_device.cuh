@@ -111,7 +111,15 @@ ST_DEV u32 stk_get(const TraceStack& s, u32 level) { return s.base[level * ST_BL
 
 // Ray::traverse, closest hit (ray.rs:114-266, Tracing::ReturnClosest).  Same visiting order as the
 // reference (near child first, far child pushed iff far_d < best), hence the same winner on ties.
+// one red.global per warp per traced ray batch, only when the host asked for ray statistics
+ST_DEV void count_ray(const SceneDev& sc) {
+    if (sc.ray_counter) {
+        unsigned m = __activemask();
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(m) - 1)) atomicAdd(sc.ray_counter, (unsigned long long)__popc(m));
+    }
+}
 ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack& stk, u32* used_memory = nullptr) {
+    count_ray(sc);
     TriHit hit = trihit_none();
     float hu = 0.f, hv = 0.f, hid = 0.f;
     u32 ptr = 0u, sp = 0u, used = 0u;
@@ -150,6 +158,7 @@ ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack
 // Ray::intersect, any hit (ray.rs:84-112, Tracing::ReturnFirst): true iff some triangle has 0 < t < len.
 // The answer does not depend on visiting order; the reference's order is kept anyway.
 ST_DEV bool trace_any(const Ray& ray, const SceneDev& sc, const TraceStack& stk) {
+    count_ray(sc);
     const float best = ray.len;
     u32 ptr = 0u, sp = 0u;
     for (;;) {

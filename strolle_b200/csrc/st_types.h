@@ -36,6 +36,7 @@ struct SceneDev {
     const float4* scattering_lut;      // 32x32
     const float4* sky_lut;             // 256x256
     GpuWorld world;
+    unsigned long long* ray_counter;   // optional: counts executed Ray::trace / Ray::intersect calls (Mrays/s)
 };
 
 // Per-camera device buffers: the logical buffers of

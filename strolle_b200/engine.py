@@ -61,13 +61,16 @@ def load_library():
         "st_insert_instance": [P, u64, u64, u64, f32p], "st_remove_instance": [P, u64],
         "st_insert_light": [P, u64, C.POINTER(_Light)], "st_remove_light": [P, u64], "st_update_sun": [P, C.c_float, C.c_float],
         "st_create_camera": [P, C.POINTER(_Camera), C.POINTER(i32)], "st_update_camera": [P, i32, C.POINTER(_Camera)], "st_delete_camera": [P, i32],
-        "st_tick": [P], "st_render_camera": [P, i32, P, C.c_int], "st_synchronize": [P],
+        "st_tick": [P], "st_render_camera": [P, i32, P, C.c_int], "st_copy_output": [P, i32, P, C.c_int], "st_synchronize": [P],
         "st_set_seed_base": [P, u32], "st_set_blue_noise": [P, C.c_void_p],
         "st_read_buffer": [P, i32, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
         "st_read_scene": [P, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)],
         "st_bvh_depth": [P, C.POINTER(C.c_int)],
         "st_trace_closest": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p], "st_trace_any": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p],
         "st_device_math": [P, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
+        "st_set_stream": [P, C.c_void_p],
+        "st_count_rays": [P, C.c_int], "st_ray_count": [P, C.POINTER(C.c_uint64), C.c_int],
+        "st_mark_begin": [P], "st_mark_end": [P, f32p],
         "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int],
         "st_camera_set_strip": [P, i32, C.c_int, C.c_int],
         "st_buffer_device_ptr": [P, i32, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
@@ -205,6 +208,9 @@ class Engine:
         ptr = out.ctypes.data if out is not None else None
         self._check(self.lib.st_render_camera(self._h, cam, ptr, fmt))
 
+    def copy_output(self, cam, out, fmt=FORMAT_RGBA32F):
+        self._check(self.lib.st_copy_output(self._h, cam, out.ctypes.data, fmt))
+
     def render_range(self, cam, first, last):
         self._check(self.lib.st_render_range(self._h, cam, first, last))
 
@@ -270,6 +276,25 @@ class Engine:
         out = np.empty_like(a)
         self._check(self.lib.st_device_math(self._h, ops[op], a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size))
         return out
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self.lib.st_set_stream(self._h, cuda_stream_ptr))
+
+    def count_rays(self, enabled=True):
+        self._check(self.lib.st_count_rays(self._h, int(enabled)))
+
+    def ray_count(self, reset=False):
+        n = C.c_uint64()
+        self._check(self.lib.st_ray_count(self._h, C.byref(n), int(reset)))
+        return n.value
+
+    def mark_begin(self):
+        self._check(self.lib.st_mark_begin(self._h))
+
+    def mark_end(self):
+        ms = C.c_float()
+        self._check(self.lib.st_mark_end(self._h, C.byref(ms)))
+        return ms.value
 
     def enable_timing(self, enabled=True):
         self._check(self.lib.st_enable_timing(self._h, int(enabled)))

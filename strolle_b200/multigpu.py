@@ -1,0 +1,205 @@
+"""Row-strip partitioning of a frame across GPUs.
+
+One process per GPU.  Every rank holds full-frame per-camera buffers, computes rows [y0, y1) of each
+pass and, before every *gathering* pass, receives the halo rows that pass reads from the ranks that own
+them (NCCL send/recv over NVLink through torch.distributed).  RNG streams and buffer indices are keyed on
+absolute pixel coordinates, so a strip-partitioned run reproduces the single-GPU frame bit for bit.
+
+`plan_frame` (pure Python, no GPU) turns a frame's pass schedule into exchange points; `StripRunner`
+executes it.  The transport is pluggable so the plan can be exercised with gloo on CPU tensors and with
+several engines inside one process on a single GPU (tests).
+"""
+from dataclasses import dataclass
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+# pass ids (strolle_b200/csrc/st_types.h PassId)
+P_PRIM_GBUFFER, P_DI_SAMPLING, P_DI_TEMPORAL, P_DI_SPATIAL_PICK, P_DI_SPATIAL_TRACE, P_DI_SPATIAL_SAMPLE = 0, 1, 2, 3, 4, 5
+P_DI_RESOLVING, P_GI_REPROJECTION, P_GI_SAMPLING_A, P_GI_SAMPLING_B, P_GI_TEMPORAL, P_GI_SPATIAL_PICK = 6, 7, 8, 9, 10, 11
+P_GI_SPATIAL_TRACE, P_GI_SPATIAL_SAMPLE, P_GI_PREVIEW, P_GI_RESOLVING, P_FRAME_REPROJECTION = 12, 13, 14, 15, 16
+P_DENOISE_REPROJECT, P_DENOISE_VARIANCE, P_DENOISE_WAVELET, P_COMPOSITION = 17, 18, 19, 20
+
+SPATIAL_REACH = 128      # ReSTIR spatial taps: radius <= 128 px (di_spatial_resampling.rs:55-56)
+PREVIEW2_REACH = 64      # second preview pass (gi_preview_resampling.rs:64-70)
+VARIANCE_REACH = 3       # estimate_variance window (frame_denoising.rs:128-190)
+WAVELET_REACH = [1, 2, 4, 9, 19]   # stride s plus jitter trunc((s-1)/4) (frame_denoising.rs:269-286)
+
+# float4s per pixel of every exchangeable buffer
+VEC4_PER_PIXEL = {"di_reservoirs_0": 2, "di_reservoirs_1": 2, "di_reservoirs_2": 2,
+                  "gi_reservoirs_0": 4, "gi_reservoirs_1": 4, "gi_reservoirs_2": 4, "gi_reservoirs_3": 4}
+
+
+def strip_bounds(height: int, world: int) -> List[Tuple[int, int]]:
+    """Rows [y0, y1) of every rank: contiguous, near-equal, multiples of 8 where possible."""
+    edges = [(height * r // world) for r in range(world + 1)]
+    return [(edges[r], edges[r + 1]) for r in range(world)]
+
+
+@dataclass
+class Exchange:
+    before_step: int                       # index into the frame schedule; len(schedule) = after the last pass
+    buffers: List[Tuple[str, int]]         # (buffer name, reach in rows)
+
+
+def plan_frame(schedule: Sequence[int], frame: int, temporal_reach: int = 16) -> List[Exchange]:
+    """Exchange points of one frame.  `schedule` = pass ids in launch order (st_frame_schedule)."""
+    cur = "b" if frame % 2 == 1 else "a"
+    prv = "a" if cur == "b" else "b"
+    plan: List[Exchange] = []
+    have_gbuffer = False
+    nth_preview = 0
+    nth_wavelet = 0
+    # ping-pong of the wavelet passes (strolle/src/camera_controller/passes/frame_denoising.rs:78-108)
+    wavelet_inputs = ["stash", "prev_colors", "stash", "curr_colors", "stash"]
+    gi_source = None
+    if P_GI_PREVIEW in schedule:
+        gi_source = 2 if P_GI_SPATIAL_SAMPLE in schedule else 1
+    for i, p in enumerate(schedule):
+        bufs: List[Tuple[str, int]] = []
+        if i == 0 and temporal_reach > 0:
+            # last frame's outputs that this frame gathers at reprojected positions (K4, K6, K11, K14, K20)
+            bufs += [(f"prim_surface_map_{prv}", temporal_reach), (f"prim_gbuffer_d0_{prv}", temporal_reach), (f"prim_gbuffer_d1_{prv}", temporal_reach),
+                     ("di_reservoirs_0", temporal_reach), ("gi_reservoirs_0", temporal_reach), ("di_diff_prev_colors", temporal_reach),
+                     ("gi_diff_prev_colors", temporal_reach), (f"di_diff_moments_{prv}", temporal_reach), (f"gi_diff_moments_{prv}", temporal_reach)]
+        if p in (P_DI_SPATIAL_PICK, P_GI_SPATIAL_PICK):
+            if not have_gbuffer:
+                bufs += [(f"prim_gbuffer_d0_{cur}", SPATIAL_REACH), (f"prim_gbuffer_d1_{cur}", SPATIAL_REACH)]
+                have_gbuffer = True
+            bufs.append(("di_reservoirs_1" if p == P_DI_SPATIAL_PICK else "gi_reservoirs_1", SPATIAL_REACH))
+        elif p == P_GI_PREVIEW:
+            if nth_preview == 0:
+                bufs += [(f"prim_surface_map_{cur}", SPATIAL_REACH), (f"gi_reservoirs_{gi_source}", SPATIAL_REACH)]
+            else:
+                bufs.append(("gi_reservoirs_3", PREVIEW2_REACH))
+            nth_preview += 1
+        elif p == P_DENOISE_VARIANCE:
+            bufs += [("di_diff_curr_colors", VARIANCE_REACH), ("gi_diff_curr_colors", VARIANCE_REACH)]
+            if P_GI_PREVIEW not in schedule:
+                bufs.append((f"prim_surface_map_{cur}", WAVELET_REACH[-1]))
+        elif p == P_DENOISE_WAVELET:
+            src = wavelet_inputs[nth_wavelet]
+            bufs += [(f"di_diff_{src}", WAVELET_REACH[nth_wavelet]), (f"gi_diff_{src}", WAVELET_REACH[nth_wavelet])]
+            nth_wavelet += 1
+        if bufs:
+            plan.append(Exchange(i, bufs))
+    return plan
+
+
+def halo_transfers(bounds: Sequence[Tuple[int, int]], height: int, reach: int) -> List[Tuple[int, int, int, int]]:
+    """(src_rank, dst_rank, row0, row1) for every block of rows rank `dst` needs (its strip grown by `reach`)
+    and rank `src` owns.  Deterministic order shared by all ranks."""
+    out = []
+    for dst, (d0, d1) in enumerate(bounds):
+        need0, need1 = max(0, d0 - reach), min(height, d1 + reach)
+        for src, (s0, s1) in enumerate(bounds):
+            if src == dst:
+                continue
+            a, b = max(need0, s0), min(need1, s1)
+            if a < b:
+                out.append((src, dst, a, b))
+    return out
+
+
+class _DevArray:
+    """Exposes an engine-owned device allocation through __cuda_array_interface__ (zero-copy torch view)."""
+
+    def __init__(self, ptr, nfloats):
+        self.__cuda_array_interface__ = {"shape": (nfloats,), "typestr": "<f4", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class TorchDistTransport:
+    """NCCL (or gloo) point-to-point over torch.distributed; ordered against torch's current stream."""
+
+    def __init__(self, rank):
+        import torch.distributed as dist
+        self.dist = dist
+        self.rank = rank
+
+    def run(self, ops):
+        """ops: list of (src, dst, tensor_view) where tensor_view is this rank's view of the rows."""
+        dist = self.dist
+        reqs = []
+        for src, dst, view in ops:
+            if src == self.rank:
+                reqs.append(dist.P2POp(dist.isend, view, dst))
+            elif dst == self.rank:
+                reqs.append(dist.P2POp(dist.irecv, view, src))
+        if reqs:
+            for w in dist.batch_isend_irecv(reqs):
+                w.wait()
+
+
+class StripRunner:
+    """Renders one camera on one rank of a strip-partitioned (or single-GPU) run."""
+
+    def __init__(self, engine, cam, width, height, rank=0, world=1, transport=None, temporal_reach=16):
+        self.engine, self.cam, self.w, self.h, self.rank, self.world = engine, cam, width, height, rank, world
+        self.bounds = strip_bounds(height, world)
+        self.y0, self.y1 = self.bounds[rank]
+        self.temporal_reach = temporal_reach
+        self.transport = transport
+        self._views: Dict[str, object] = {}
+        self.halo_bytes_last_frame = 0
+        if world > 1:
+            import torch
+            engine.set_strip(cam, self.y0, self.y1)
+            engine.set_stream(torch.cuda.current_stream().cuda_stream)
+            if transport is None:
+                self.transport = TorchDistTransport(rank)
+
+    def _view(self, name):
+        """(H, floats_per_row) torch view of an engine buffer."""
+        import torch
+        if name not in self._views:
+            ptr, nbytes = self.engine.buffer_device_ptr(self.cam, name)
+            t = torch.as_tensor(_DevArray(ptr, nbytes // 4), device="cuda")
+            self._views[name] = t.view(self.h, -1)
+        return self._views[name]
+
+    def _exchange(self, ex: Exchange):
+        ops = []
+        nbytes = 0
+        for name, reach in ex.buffers:
+            v = self._view(name)
+            for src, dst, a, b in halo_transfers(self.bounds, self.h, reach):
+                if src == self.rank or dst == self.rank:
+                    ops.append((src, dst, v[a:b]))
+                    if dst == self.rank:
+                        nbytes += v[a:b].numel() * 4
+        self.halo_bytes_last_frame += nbytes
+        self.transport.run(ops)
+
+    def render(self, out=None, fmt=0):
+        eng, cam = self.engine, self.cam
+        if self.world == 1:
+            eng.render_camera(cam, out, fmt)
+            return
+        schedule = eng.frame_schedule(cam)
+        frame = eng.frame() - 1   # tick() already advanced the engine's counter; the camera renders frame-1
+        plan = plan_frame(schedule, frame, self.temporal_reach)
+        self.halo_bytes_last_frame = 0
+        first = 0
+        for ex in plan:
+            if ex.before_step > first:
+                eng.render_range(cam, first, ex.before_step - 1)
+                first = ex.before_step
+            self._exchange(ex)
+        eng.render_range(cam, first, len(schedule) - 1)
+        if out is not None:
+            self.gather_output(out, fmt)
+
+    def gather_output(self, out, fmt):
+        """Assembles the full composed frame on every rank (all strips), then copies it to `out` on rank 0."""
+        v = self._view("output")
+        ops = []
+        for src, (s0, s1) in enumerate(self.bounds):
+            if src != 0 and (self.rank == 0 or self.rank == src):
+                ops.append((src, 0, v[s0:s1]))
+        self.transport.run(ops)
+        if self.rank == 0:
+            self.engine.set_strip(self.cam, 0, self.h)
+            n = len(self.engine.frame_schedule(self.cam))
+            # re-run only the output conversion + copy on the assembled frame
+            self.engine.copy_output(self.cam, out, fmt)
+            self.engine.set_strip(self.cam, self.y0, self.y1)

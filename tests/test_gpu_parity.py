@@ -67,7 +67,7 @@ def test_trace_streams_bit_exact(gpu, oracle, blue_noise, scene_name):
     assert (hg[:, 9].view(np.uint32) == ho[:, 9].view(np.uint32)).all(), "hit triangle ids are bit-exact"
     assert (hg[:, 10].view(np.uint32) == ho[:, 10].view(np.uint32)).all(), "hit material ids are bit-exact"
     assert_bits_equal(hg, ho, "closest-hit records (point, oct normal, uv, distance, used_memory)")
-    assert (ho[:, 8] < 3e38).mean() > 0.5
+    assert (ho[:, 8] < 3e38).mean() > 0.3
     rays_any = random_rays(200000, 4, lo, hi, max_len=4.0)
     og, oo = eg.trace_any(rays_any), eo.trace_any(rays_any)
     assert (og == oo).all() and 0.05 < og.mean() < 0.95
@@ -174,3 +174,70 @@ def test_libm_oracle_within_tolerance(gpu, oracle, blue_noise):
     tid_g = eg.read_buffer(cg, "prim_triangle_ids").view(np.uint32)
     tid_o = eo.read_buffer(co, "prim_triangle_ids").view(np.uint32)
     assert (tid_g == tid_o).all(), "primary-hit triangle indices are bit-exact regardless of the libm flavour"
+
+
+class _LocalTransport:
+    """Several strip engines inside one process on one GPU: the same exchange plan, executed as row copies
+    between the engines' buffers (stands in for NCCL so that strip correctness is testable on a 1-GPU box)."""
+
+    def __init__(self):
+        self.runners = []
+
+    def run_all(self, per_rank_ops):
+        import torch
+        torch.cuda.synchronize()
+        for ops in per_rank_ops:
+            for src, dst, name, a, b in ops:
+                self.runners[dst]._view(name)[a:b].copy_(self.runners[src]._view(name)[a:b])
+        torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("world,size", [(2, (160, 96)), (4, (128, 160))])
+def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size):
+    """Strip-partitioned rendering (SURVEY §8e, config C4's shape) is bit-identical to the single-GPU frame:
+    `world` engines each compute one row strip and exchange halo rows according to multigpu.plan_frame."""
+    import torch
+    from strolle_b200 import multigpu as mg
+    w, h = size
+    scene = scenes.cornell(w, h)
+    ref = gpu.Engine(blue_noise=blue_noise)
+    cref = scenes.apply(ref, scene)
+    engines, cams, runners = [], [], []
+    lt = _LocalTransport()
+    for r in range(world):
+        e = gpu.Engine(blue_noise=blue_noise)
+        c = scenes.apply(e, scene)
+        rn = mg.StripRunner(e, c, w, h, rank=0, world=1)   # built as single, then configured as a strip by hand
+        rn.rank, rn.world = r, world
+        rn.bounds = mg.strip_bounds(h, world)
+        rn.y0, rn.y1 = rn.bounds[r]
+        e.set_strip(c, rn.y0, rn.y1)
+        e.set_stream(torch.cuda.current_stream().cuda_stream)
+        engines.append(e); cams.append(c); runners.append(rn)
+    lt.runners = runners
+    for f in range(7):
+        ref.tick(); ref.render_camera(cref)
+        for e in engines:
+            e.tick()
+        schedule = engines[0].frame_schedule(cams[0])
+        plan = mg.plan_frame(schedule, engines[0].frame() - 1, temporal_reach=16)
+        first = 0
+        for ex in plan:
+            if ex.before_step > first:
+                for e, c in zip(engines, cams):
+                    e.render_range(c, first, ex.before_step - 1)
+                first = ex.before_step
+            per_rank = []
+            for name, reach in ex.buffers:
+                per_rank.append([(s, d, name, a, b) for s, d, a, b in mg.halo_transfers(runners[0].bounds, h, reach)])
+            lt.run_all(per_rank)
+        for e, c in zip(engines, cams):
+            e.render_range(c, first, len(schedule) - 1)
+        full = ref.read_buffer(cref, "output").reshape(h, w, 4)
+        for name in ["output", "di_reservoirs_0", "gi_reservoirs_0", "di_diff_curr_colors", "gi_diff_curr_colors", "di_diff_prev_colors"]:
+            want = ref.read_buffer(cref, name).reshape(h, -1)
+            for rn, e, c in zip(runners, engines, cams):
+                got = e.read_buffer(c, name).reshape(h, -1)
+                ok, msg = bits_equal(got[rn.y0:rn.y1], want[rn.y0:rn.y1])
+                assert ok, f"strip {rn.rank}/{world} frame {f + 1} {name}: {msg}"
+        assert np.isfinite(full).all()

@@ -1,0 +1,100 @@
+"""Host-side logic of the strip partition, on CPU: exchange plan, halo geometry, and the
+torch.distributed transport with the gloo backend at world_size 2."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+from strolle_b200 import multigpu as mg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_strip_bounds_cover_frame():
+    for h, n in [(1080, 1), (1080, 2), (2160, 8), (4320, 8), (67, 3)]:
+        b = mg.strip_bounds(h, n)
+        assert b[0][0] == 0 and b[-1][1] == h
+        assert all(b[i][1] == b[i + 1][0] for i in range(n - 1))
+        assert all(y1 > y0 for y0, y1 in b)
+
+
+def test_halo_transfers_cover_reach():
+    bounds = mg.strip_bounds(1080, 8)   # 135-row strips: a 128-row halo stays inside the adjacent strips
+    tr = mg.halo_transfers(bounds, 1080, 128)
+    for dst, (d0, d1) in enumerate(bounds):
+        need = set(range(max(0, d0 - 128), min(1080, d1 + 128))) - set(range(d0, d1))
+        got = set()
+        for s, d, a, b in tr:
+            if d == dst:
+                assert bounds[s][0] <= a < b <= bounds[s][1]
+                got |= set(range(a, b))
+        assert got == need
+    # strips shorter than the reach pull from more than one neighbour
+    tr = mg.halo_transfers(mg.strip_bounds(400, 8), 400, 128)
+    assert len({s for s, d, a, b in tr if d == 3}) >= 4
+
+
+def test_plan_frame_matches_schedule():
+    P = mg
+    image_odd = [P.P_PRIM_GBUFFER, P.P_FRAME_REPROJECTION, P.P_DI_SAMPLING, P.P_DI_TEMPORAL, P.P_DI_SPATIAL_PICK, P.P_DI_SPATIAL_TRACE,
+                 P.P_DI_SPATIAL_SAMPLE, P.P_DI_RESOLVING, P.P_GI_REPROJECTION, P.P_GI_TEMPORAL, P.P_GI_SPATIAL_PICK, P.P_GI_SPATIAL_TRACE,
+                 P.P_GI_SPATIAL_SAMPLE, P.P_GI_PREVIEW, P.P_GI_PREVIEW, P.P_GI_RESOLVING, P.P_DENOISE_REPROJECT, P.P_DENOISE_REPROJECT,
+                 P.P_DENOISE_VARIANCE] + [P.P_DENOISE_WAVELET] * 5 + [P.P_COMPOSITION]
+    plan = mg.plan_frame(image_odd, frame=1)
+    by_step = {e.before_step: dict(e.buffers) for e in plan}
+    assert by_step[0]["di_reservoirs_0"] == 16 and "prim_surface_map_a" in by_step[0]
+    pick = by_step[image_odd.index(P.P_DI_SPATIAL_PICK)]
+    assert pick == {"prim_gbuffer_d0_b": 128, "prim_gbuffer_d1_b": 128, "di_reservoirs_1": 128}
+    assert by_step[image_odd.index(P.P_GI_SPATIAL_PICK)] == {"gi_reservoirs_1": 128}
+    prev0 = image_odd.index(P.P_GI_PREVIEW)
+    assert by_step[prev0] == {"prim_surface_map_b": 128, "gi_reservoirs_2": 128}
+    assert by_step[prev0 + 1] == {"gi_reservoirs_3": 64}
+    w0 = image_odd.index(P.P_DENOISE_WAVELET)
+    assert [list(by_step[w0 + i].values())[0] for i in range(5)] == [1, 2, 4, 9, 19]
+    assert list(by_step[w0].keys()) == ["di_diff_stash", "gi_diff_stash"] and list(by_step[w0 + 1].keys()) == ["di_diff_prev_colors", "gi_diff_prev_colors"]
+    # even (sampling) frame: preview reads gi[1]
+    even = [p for p in image_odd if p not in (P.P_GI_SPATIAL_PICK, P.P_GI_SPATIAL_TRACE, P.P_GI_SPATIAL_SAMPLE)]
+    plan = mg.plan_frame(even, frame=2)
+    by_step = {e.before_step: dict(e.buffers) for e in plan}
+    assert by_step[even.index(P.P_GI_PREVIEW)] == {"prim_surface_map_a": 128, "gi_reservoirs_1": 128}
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+from strolle_b200 import multigpu as mg
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+H, W = 64, 10
+bounds = mg.strip_bounds(H, world)
+full = torch.arange(H * W, dtype=torch.float32).view(H, W)
+mine = torch.full((H, W), -1.0)
+y0, y1 = bounds[rank]
+mine[y0:y1] = full[y0:y1]            # each rank only holds its own rows
+tr = mg.TorchDistTransport(rank)
+for reach in (3, 20):
+    ops = [(s, d, mine[a:b]) for s, d, a, b in mg.halo_transfers(bounds, H, reach) if s == rank or d == rank]
+    tr.run(ops)
+    lo, hi = max(0, y0 - reach), min(H, y1 + reach)
+    assert torch.equal(mine[lo:hi], full[lo:hi]), (rank, reach)
+    outside = torch.cat([mine[:lo], mine[hi:]])
+    assert (outside == -1).all() or reach == 20
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+def test_gloo_halo_exchange_world2(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
