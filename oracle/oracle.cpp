@@ -198,6 +198,18 @@ unsigned long long orc_ray_count(int reset) {
     for (int i = 0; i < 256; i++) { t += g_ray_counters[i].n; if (reset) g_ray_counters[i].n = 0; }
     return t;
 }
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#endif
+}
+int orc_get_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
 int orc_is_libm() {
 #ifdef ORC_LIBM
     return 1;

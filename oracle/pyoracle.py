@@ -70,6 +70,8 @@ def _load(libm=False):
     lib.orc_u32_bytes_roundtrip.argtypes = [C.c_uint32]
     lib.orc_ray_count.restype = C.c_uint64
     lib.orc_ray_count.argtypes = [C.c_int]
+    lib.orc_set_threads.argtypes = [C.c_int]
+    lib.orc_get_threads.restype = C.c_int
     lib.orc_frame.restype = C.c_uint32
     lib.orc_frame.argtypes = [C.c_void_p]
     return lib
@@ -187,6 +189,25 @@ class OracleEngine:
         t = np.empty(n, dtype=np.uint32)
         self.lib.orc_trace_brute(self.h, r, n, d, t)
         return d, t
+
+
+def usable_cpus():
+    """CPUs this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def set_threads(n=None, libm=False):
+    """Sets the oracle's OpenMP thread count (default: usable_cpus()); returns the count in effect."""
+    l = lib(libm)
+    l.orc_set_threads(int(n if n else usable_cpus()))
+    return int(l.orc_get_threads())
 
 
 def ray_count(reset=False, libm=False):
