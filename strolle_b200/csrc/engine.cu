@@ -491,7 +491,7 @@ static int allocate_camera(st_engine* e, CameraSlot* cs) {
     reg("gi_diff_moments_a", &d.gi_diff_moments[0], n); reg("gi_diff_moments_b", &d.gi_diff_moments[1], n); reg("gi_diff_stash", &d.gi_diff_stash, n);
     reg("gi_spec_samples", &d.gi_spec_samples, n);
     reg("ref_hits", &d.ref_hits, 2 * n); reg("ref_rays", &d.ref_rays, 3 * n); reg("ref_colors", &d.ref_colors, n);
-    reg("prim_triangle_ids", &d.prim_triangle_ids, n); reg("output", &d.output, n);
+    reg("prim_triangle_ids", &d.prim_triangle_ids, n); reg("surface_nd", &d.surface_nd, n); reg("output", &d.output, n);
     size_t total = 0;
     for (auto& s : cs->sizes) total += (s.second * 16 + 255) / 256 * 256;
     cs->arena.release();

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_prim_gbuffer(KPARAMS, int cur) {
     if (!p.in) return;
     Ray ray = cam_ray(cam.curr, p.x, p.y);
     TriHit th = trace_closest(ray, sc, stk);
-    float4 g0 = f4zero(), g1 = f4zero(), surf = f4zero(), vel = f4zero(), tid = f4(bitsf(0xffffffffu), 0.f, 0.f, 0.f);
+    float4 g0 = f4zero(), g1 = f4zero(), surf = f4zero(), vel = f4zero(), tid = f4(bitsf(0xffffffffu), 0.f, 0.f, 0.f), nd = f4zero();
     if (trihit_some(th)) {
         const GpuMaterial m = sc.materials[th.material_id];
         GBuf g;
@@ -61,13 +61,14 @@ __global__ void __launch_bounds__(ST_BLOCK) k_prim_gbuffer(KPARAMS, int cur) {
         gbuf_pack(g, &g0, &g1);
         float2 n = oct_encode(th.normal);
         surf = f4(n.x, n.y, g.depth, m.roughness);
+        nd = f4(oct_decode(n), g.depth);   // what every consumer of the surface map decodes, computed once
         float2 v = cam_world_to_screen(cam.curr, th.point) - cam_world_to_screen(cam.prev, th.point);
         if (len2(v) >= 0.001f) vel = f4(v.x, v.y, 0.f, 0.f);
         tid.x = bitsf(th.triangle_id);
     }
     size_t i = pix(cam, p.x, p.y);
     cam.prim_gbuffer_d0[cur][i] = g0; cam.prim_gbuffer_d1[cur][i] = g1; cam.prim_surface_map[cur][i] = surf;
-    cam.velocity_map[i] = vel; cam.prim_triangle_ids[i] = tid;
+    cam.velocity_map[i] = vel; cam.prim_triangle_ids[i] = tid; cam.surface_nd[i] = nd;
 }
 
 // K4 frame_reprojection::main (frame_reprojection.rs:7-95)
@@ -622,14 +623,18 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject(KPARAMS, int cur
     moments[i] = f4(moment, 0.0f);
 }
 
-// frame_denoising::sample_weight (frame_denoising.rs:363-392)
-ST_DEV float svgf_weight(float center_luma, float c_depth, float3 c_normal, float sample_luma, float s_depth, float3 s_normal, float luma_sigma, float depth_sigma) {
-    float lw = fabs_(sqrtf(center_luma) - sqrtf(sample_luma)) * luma_sigma;
+// frame_denoising::sample_weight (frame_denoising.rs:363-392), split into the part that is common to
+// the DI and GI signals (depth ramp, normal^64) and the per-signal luminance term:
+//   weight = exp(-|sqrt(lc) - sqrt(ls)| * luma_sigma) * depth_weight * normal_weight
+// A zero depth or normal factor makes the product 0 (or NaN), never > 0, so the caller may skip the tap.
+ST_DEV float svgf_depth_weight(float c_depth, float s_depth, float depth_sigma) {
     float leeway = c_depth * depth_sigma;
     float diff = fabs_(s_depth - c_depth);
-    float dw = (diff >= leeway) ? 0.0f : 1.0f - diff / leeway;
-    float nw = pow_det(rmax(dot(s_normal, c_normal), 0.0f), 64.0f);
-    return exp_det(-lw) * dw * nw;
+    return (diff >= leeway) ? 0.0f : 1.0f - diff / leeway;
+}
+ST_DEV float svgf_normal_weight(float3 c_normal, float3 s_normal) { return pow_det(rmax(dot(s_normal, c_normal), 0.0f), 64.0f); }
+ST_DEV float svgf_luma_weight(float sqrt_center_luma, float sample_luma, float luma_sigma) {
+    return exp_det(-(fabs_(sqrt_center_luma - sqrtf(sample_luma)) * luma_sigma));
 }
 
 // K21 frame_denoising::estimate_variance (frame_denoising.rs:81-217)
@@ -637,29 +642,32 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur)
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t i = pix(cam, p.x, p.y);
-    const float4* surf = cam.prim_surface_map[cur];
-    const float4* di_colors = cam.di_diff_curr_colors; const float4* gi_colors = cam.gi_diff_curr_colors;
-    Surf cs = surf_decode(surf[i]);
+    const float4* __restrict__ snd = cam.surface_nd;
+    const float4* __restrict__ di_colors = cam.di_diff_curr_colors; const float4* __restrict__ gi_colors = cam.gi_diff_curr_colors;
+    float4 cnd = snd[i];
     float4 cdi = di_colors[i], cgi = gi_colors[i];
-    if (cs.depth == 0.0f) { cam.di_diff_stash[i] = cdi; cam.gi_diff_stash[i] = cgi; return; }
+    if (cnd.w == 0.0f) { cam.di_diff_stash[i] = cdi; cam.gi_diff_stash[i] = cgi; return; }
     float4 mdi = cam.di_diff_moments[cur][i], mgi = cam.gi_diff_moments[cur][i];
-    float cdl = luma(xyz(cdi)), cgl = luma(xyz(cgi));
     float di_var, gi_var;
     if (mdi.x >= 4.0f) { di_var = mdi.z - sq(mdi.y); gi_var = mgi.z - sq(mgi.y); }
     else {
+        float3 cn = xyz(cnd);
+        float scdl = sqrtf(luma(xyz(cdi))), scgl = sqrtf(luma(xyz(cgi)));
         float3 sdi = f3s(0.f), sgi = f3s(0.f);
         int ox = -2, oy = -2;
         for (;;) {   // quirk C-3: row -2 spans x in [-2,2], rows -1..2 span x in [-3,2]
             int sx = (int)p.x + ox, sy = (int)p.y + oy;
             if (cam_contains_i(cam.curr, sx, sy)) {
                 size_t si = pix(cam, (u32)sx, (u32)sy);
-                Surf ss = surf_decode(surf[si]);
-                if (ss.depth != 0.0f) {
+                float4 nds = snd[si];
+                if (nds.w != 0.0f) {
+                    float common = svgf_depth_weight(cnd.w, nds.w, 0.2f);
+                    float nw = svgf_normal_weight(cn, xyz(nds));
                     float sl = luma(xyz(di_colors[si]));
-                    float w = svgf_weight(cdl, cs.depth, cs.normal, sl, ss.depth, ss.normal, 1.0f, 0.2f);
+                    float w = svgf_luma_weight(scdl, sl, 1.0f) * common * nw;
                     sdi = sdi + f3(sl, sl * sl, 1.0f) * f3s(w);
                     float gl = luma(xyz(gi_colors[si]));
-                    float wg = svgf_weight(cgl, cs.depth, cs.normal, gl, ss.depth, ss.normal, 1.0f, 0.2f);
+                    float wg = svgf_luma_weight(scgl, gl, 1.0f) * common * nw;
                     sgi = sgi + f3(gl, gl * gl, 1.0f) * f3s(wg);
                 }
             }
@@ -674,25 +682,28 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur)
     cam.gi_diff_stash[i] = f4(xyz(cgi), gi_var);
 }
 
-// K22 frame_denoising::wavelet (frame_denoising.rs:220-361): 3x3 à-trous, DI and GI together
+// K22 frame_denoising::wavelet (frame_denoising.rs:220-361): 3x3 à-trous, DI and GI together.
+// Per tap: one (normal, depth) float4 + the two signal float4s; the depth ramp and normal^64 factors are
+// evaluated once and shared by both signals, taps whose shared factor is 0 are skipped (weight cannot be > 0).
 __global__ void __launch_bounds__(ST_BLOCK) k_denoise_wavelet(KPARAMS, int cur, u32 frame, u32 stride, float strength,
                                                               const float4* __restrict__ di_in, float4* __restrict__ di_out,
                                                               const float4* __restrict__ gi_in, float4* __restrict__ gi_out) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t i = pix(cam, p.x, p.y);
-    const float4* surf = cam.prim_surface_map[cur];
-    float4 bn = blue_noise(sc, p.x, p.y, frame);
-    Surf cs = surf_decode(surf[i]);
+    const float4* __restrict__ snd = cam.surface_nd;
+    float4 cnd = snd[i];
     float4 cdi = di_in[i];
-    float3 cdc = xyz(cdi); float cdv = cdi.w; float cdl = luma(cdc);
-    if (cs.depth == 0.0f) { di_out[i] = f4(cdc, cdv); return; }
+    float3 cdc = xyz(cdi); float cdv = cdi.w;
+    if (cnd.w == 0.0f) { di_out[i] = f4(cdc, cdv); return; }
+    float4 bn = blue_noise(sc, p.x, p.y, frame);
     float4 cgi = gi_in[i];
-    float3 cgc = xyz(cgi); float cgv = cgi.w; float cgl = luma(cgc);
+    float3 cgc = xyz(cgi); float cgv = cgi.w;
+    float3 cn = xyz(cnd);
+    float scdl = sqrtf(luma(cdc)), scgl = sqrtf(luma(cgc));
     float ls_di = lerpc(2.5f, 0.5f, sqrtf(cdv));
-    float ds_di = 0.33f / strength;
     float ls_gi = lerpc(1.0f, 0.0f, sqrtf(cgv));
-    float ds_gi = 0.33f / strength;
+    float depth_sigma = 0.33f / strength;   // same for DI and GI (frame_denoising.rs:264,267)
     float2 jf = (f2(bn.z, bn.w) - f2(0.5f, 0.5f)) * ((float)stride - 1.0f) * 0.5f;
     int jx = to_i32_sat(jf.x), jy = to_i32_sat(jf.y);
     float sdw = 1.0f; float3 sdc = cdc; float sdv = cdv;
@@ -705,13 +716,16 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_wavelet(KPARAMS, int cur, 
             int sx = (int)p.x + jx + ox * (int)stride, sy = (int)p.y + jy + oy * (int)stride;
             if (!cam_contains_i(cam.curr, sx, sy)) continue;
             size_t si = pix(cam, (u32)sx, (u32)sy);
-            Surf ss = surf_decode(surf[si]);
-            if (ss.depth == 0.0f) continue;
+            float4 nds = snd[si];
+            if (nds.w == 0.0f) continue;
+            float dw = svgf_depth_weight(cnd.w, nds.w, depth_sigma);
+            float nw = svgf_normal_weight(cn, xyz(nds));
+            if (dw == 0.0f || nw == 0.0f) continue;
             float4 sdi = di_in[si];
-            float wd = svgf_weight(cdl, cs.depth, cs.normal, luma(xyz(sdi)), ss.depth, ss.normal, ls_di, ds_di);
+            float wd = svgf_luma_weight(scdl, luma(xyz(sdi)), ls_di) * dw * nw;
             if (wd > 0.0f) { sdw += wd; sdc = sdc + wd * xyz(sdi); sdv += sq(wd) * sdi.w; }
             float4 sgi = gi_in[si];
-            float wg = svgf_weight(cgl, cs.depth, cs.normal, luma(xyz(sgi)), ss.depth, ss.normal, ls_gi, ds_gi);
+            float wg = svgf_luma_weight(scgl, luma(xyz(sgi)), ls_gi) * dw * nw;
             if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
         }
     }

@@ -134,6 +134,11 @@ ST_DEV float pow_det(float x, float y) {
     if (x == finf()) return (y > 0.0f) ? finf() : 0.0f;
     if (y == 1.0f) return x;
     if (y == 2.0f) return x * x;
+    if (y == 3.0f) return (x * x) * x;
+    if (y == 5.0f) { float x2 = x * x; return (x2 * x2) * x; }
+    if (y == 8.0f) { float x2 = x * x; float x4 = x2 * x2; return x4 * x4; }
+    if (y == 64.0f) { float x2 = x * x; float x4 = x2 * x2; float x8 = x4 * x4; float x16 = x8 * x8; float x32 = x16 * x16; return x32 * x32; }
+    if (y == 1.5f) return x * sqrtf(x);
     return exp_det(y * log_det(x));
 }
 

@@ -55,6 +55,7 @@ struct CameraDev {
     float4* gi_diff_samples; float4* gi_diff_prev_colors; float4* gi_diff_curr_colors; float4* gi_diff_moments[2]; float4* gi_diff_stash; float4* gi_spec_samples;
     float4* ref_hits; float4* ref_rays; float4* ref_colors;
     float4* prim_triangle_ids;
+    float4* surface_nd;          // derived: (decoded surface normal.xyz, depth) of the current frame, written with the G-buffer
     float4* output;
 };
 

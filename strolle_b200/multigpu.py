@@ -74,9 +74,7 @@ def plan_frame(schedule: Sequence[int], frame: int, temporal_reach: int = 16) ->
                 bufs.append(("gi_reservoirs_3", PREVIEW2_REACH))
             nth_preview += 1
         elif p == P_DENOISE_VARIANCE:
-            bufs += [("di_diff_curr_colors", VARIANCE_REACH), ("gi_diff_curr_colors", VARIANCE_REACH)]
-            if P_GI_PREVIEW not in schedule:
-                bufs.append((f"prim_surface_map_{cur}", WAVELET_REACH[-1]))
+            bufs += [("di_diff_curr_colors", VARIANCE_REACH), ("gi_diff_curr_colors", VARIANCE_REACH), ("surface_nd", WAVELET_REACH[-1])]
         elif p == P_DENOISE_WAVELET:
             src = wavelet_inputs[nth_wavelet]
             bufs += [(f"di_diff_{src}", WAVELET_REACH[nth_wavelet]), (f"gi_diff_{src}", WAVELET_REACH[nth_wavelet])]
