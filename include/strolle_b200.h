@@ -153,6 +153,12 @@ int st_device_math(st_engine* e, int op, const float* a, const float* b, float* 
 int st_enable_timing(st_engine* e, int enabled);
 int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset);
 const char* st_pass_name(int pass);
+/* Engine options.  ST_OPT_SVGF_FAST_MATH (default 1): the SVGF edge-stopping weights (K21/K22) use the
+ * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
+ * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
+ * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
+enum { ST_OPT_SVGF_FAST_MATH = 1 };
+int st_set_option(st_engine* e, int option, int value);
 /* Runs the engine on a caller-owned CUDA stream (e.g. the host runtime's stream that NCCL halo
  * exchanges are ordered against); NULL restores a private non-blocking stream. */
 int st_set_stream(st_engine* e, void* cuda_stream);

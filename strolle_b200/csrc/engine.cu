@@ -316,6 +316,7 @@ struct st_engine {
     // device scene ------------------------------------------------------------------------------
     DevMem d_triangles, d_bvh, d_materials, d_lights, d_noise, d_tlut, d_slut, d_skylut, d_scratch, d_raycount;
     bool count_rays = false;
+    bool svgf_fast = true;   // ST_OPT_SVGF_FAST_MATH
     bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
     std::vector<CameraSlot*> cameras;
     // timing ---------------------------------------------------------------------------------------
@@ -574,14 +575,15 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
     if (d.denoise) {   // FrameDenoisingPass::run (passes/frame_denoising.rs:143-190)
         add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.di_diff_prev_colors, cam.di_diff_moments[cur ^ 1], cam.di_diff_samples, cam.di_diff_curr_colors, cam.di_diff_moments[cur], s); });
         add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.gi_diff_prev_colors, cam.gi_diff_moments[cur ^ 1], cam.gi_diff_samples, cam.gi_diff_curr_colors, cam.gi_diff_moments[cur], s); });
-        add(P_DENOISE_VARIANCE, [=](cudaStream_t s) { launch_denoise_variance(cam, sc, cur, s); });
+        const bool fast = e->svgf_fast;
+        add(P_DENOISE_VARIANCE, [=](cudaStream_t s) { launch_denoise_variance(cam, sc, cur, fast, s); });
         float4* di_io[5][2] = {{cam.di_diff_stash, cam.di_diff_prev_colors}, {cam.di_diff_prev_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors},
                                {cam.di_diff_curr_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors}};
         float4* gi_io[5][2] = {{cam.gi_diff_stash, cam.gi_diff_prev_colors}, {cam.gi_diff_prev_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors},
                                {cam.gi_diff_curr_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors}};
         for (uint32_t nth = 0; nth < 5; nth++) {
             float4 *a = di_io[nth][0], *b = di_io[nth][1], *c = gi_io[nth][0], *g = gi_io[nth][1];
-            add(P_DENOISE_WAVELET, [=](cudaStream_t s) { launch_denoise_wavelet(cam, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, s); });
+            add(P_DENOISE_WAVELET, [=](cudaStream_t s) { launch_denoise_wavelet(cam, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s); });
         }
     }
     uint32_t mode = (uint32_t)d.mode;
@@ -944,6 +946,11 @@ int st_device_math(st_engine* e, int op, const float* a, const float* b, float* 
     return ST_OK;
 }
 
+int st_set_option(st_engine* e, int option, int value) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    if (option == ST_OPT_SVGF_FAST_MATH) { e->svgf_fast = value != 0; return ST_OK; }
+    return fail(ST_ERR_INVALID, "unknown option");
+}
 int st_set_stream(st_engine* e, void* cuda_stream) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     CK(cudaSetDevice(e->device));

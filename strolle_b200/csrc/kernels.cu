@@ -627,17 +627,35 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject(KPARAMS, int cur
 // the DI and GI signals (depth ramp, normal^64) and the per-signal luminance term:
 //   weight = exp(-|sqrt(lc) - sqrt(ls)| * luma_sigma) * depth_weight * normal_weight
 // A zero depth or normal factor makes the product 0 (or NaN), never > 0, so the caller may skip the tap.
-ST_DEV float svgf_depth_weight(float c_depth, float s_depth, float depth_sigma) {
+//
+// Two arithmetic flavours (template parameter FAST):
+//   FAST = false  strict IEEE f32 with the polynomial exp: bit-identical to the CPU oracle.
+//   FAST = true   the SFU approximations a GPU shader compiler emits for GLSL exp/sqrt/div
+//                 (ex2.approx, sqrt.approx, rcp.approx; <= 2 ulp each) and fused multiply-adds.  Only the
+//                 edge-stopping weights / normalisation of the denoiser use it; reservoirs, hits and every
+//                 other buffer stay bit-exact, the denoised colours stay inside north_star's 1e-3 tolerance.
+ST_DEV float sfu_ex2(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+ST_DEV float sfu_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+ST_DEV float sfu_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+template <bool FAST> ST_DEV float sv_sqrt(float x) { return FAST ? sfu_sqrt(x) : sqrtf(x); }
+template <bool FAST> ST_DEV float sv_luma(float3 c) { return FAST ? __fmaf_rn(c.z, 0.0722f, __fmaf_rn(c.y, 0.7152f, c.x * 0.2126f)) : luma(c); }
+template <bool FAST> ST_DEV float svgf_depth_weight(float c_depth, float s_depth, float depth_sigma) {
     float leeway = c_depth * depth_sigma;
     float diff = fabs_(s_depth - c_depth);
-    return (diff >= leeway) ? 0.0f : 1.0f - diff / leeway;
+    if (diff >= leeway) return 0.0f;
+    return FAST ? __fmaf_rn(-diff, sfu_rcp(leeway), 1.0f) : 1.0f - diff / leeway;
 }
-ST_DEV float svgf_normal_weight(float3 c_normal, float3 s_normal) { return pow_det(rmax(dot(s_normal, c_normal), 0.0f), 64.0f); }
-ST_DEV float svgf_luma_weight(float sqrt_center_luma, float sample_luma, float luma_sigma) {
-    return exp_det(-(fabs_(sqrt_center_luma - sqrtf(sample_luma)) * luma_sigma));
+template <bool FAST> ST_DEV float svgf_normal_weight(float3 c_normal, float3 s_normal) {
+    float d = FAST ? __fmaf_rn(s_normal.z, c_normal.z, __fmaf_rn(s_normal.y, c_normal.y, s_normal.x * c_normal.x)) : dot(s_normal, c_normal);
+    return pow_det(rmax(d, 0.0f), 64.0f);   // six squarings
+}
+template <bool FAST> ST_DEV float svgf_luma_weight(float sqrt_center_luma, float sample_luma, float luma_sigma) {
+    float lw = fabs_(sqrt_center_luma - sv_sqrt<FAST>(sample_luma)) * luma_sigma;
+    return FAST ? sfu_ex2(lw * -1.44269504088896341f) : exp_det(-lw);
 }
 
 // K21 frame_denoising::estimate_variance (frame_denoising.rs:81-217)
+template <bool FAST>
 __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur) {
     Px p = pixel_full(cam);
     if (!p.in) return;
@@ -652,7 +670,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur)
     if (mdi.x >= 4.0f) { di_var = mdi.z - sq(mdi.y); gi_var = mgi.z - sq(mgi.y); }
     else {
         float3 cn = xyz(cnd);
-        float scdl = sqrtf(luma(xyz(cdi))), scgl = sqrtf(luma(xyz(cgi)));
+        float scdl = sv_sqrt<FAST>(sv_luma<FAST>(xyz(cdi))), scgl = sv_sqrt<FAST>(sv_luma<FAST>(xyz(cgi)));
         float3 sdi = f3s(0.f), sgi = f3s(0.f);
         int ox = -2, oy = -2;
         for (;;) {   // quirk C-3: row -2 spans x in [-2,2], rows -1..2 span x in [-3,2]
@@ -661,13 +679,13 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur)
                 size_t si = pix(cam, (u32)sx, (u32)sy);
                 float4 nds = snd[si];
                 if (nds.w != 0.0f) {
-                    float common = svgf_depth_weight(cnd.w, nds.w, 0.2f);
-                    float nw = svgf_normal_weight(cn, xyz(nds));
-                    float sl = luma(xyz(di_colors[si]));
-                    float w = svgf_luma_weight(scdl, sl, 1.0f) * common * nw;
+                    float common = svgf_depth_weight<FAST>(cnd.w, nds.w, 0.2f);
+                    float nw = svgf_normal_weight<FAST>(cn, xyz(nds));
+                    float sl = sv_luma<FAST>(xyz(di_colors[si]));
+                    float w = svgf_luma_weight<FAST>(scdl, sl, 1.0f) * common * nw;
                     sdi = sdi + f3(sl, sl * sl, 1.0f) * f3s(w);
-                    float gl = luma(xyz(gi_colors[si]));
-                    float wg = svgf_luma_weight(scgl, gl, 1.0f) * common * nw;
+                    float gl = sv_luma<FAST>(xyz(gi_colors[si]));
+                    float wg = svgf_luma_weight<FAST>(scgl, gl, 1.0f) * common * nw;
                     sgi = sgi + f3(gl, gl * gl, 1.0f) * f3s(wg);
                 }
             }
@@ -685,6 +703,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur)
 // K22 frame_denoising::wavelet (frame_denoising.rs:220-361): 3x3 à-trous, DI and GI together.
 // Per tap: one (normal, depth) float4 + the two signal float4s; the depth ramp and normal^64 factors are
 // evaluated once and shared by both signals, taps whose shared factor is 0 are skipped (weight cannot be > 0).
+template <bool FAST>
 __global__ void __launch_bounds__(ST_BLOCK) k_denoise_wavelet(KPARAMS, int cur, u32 frame, u32 stride, float strength,
                                                               const float4* __restrict__ di_in, float4* __restrict__ di_out,
                                                               const float4* __restrict__ gi_in, float4* __restrict__ gi_out) {
@@ -700,9 +719,9 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_wavelet(KPARAMS, int cur, 
     float4 cgi = gi_in[i];
     float3 cgc = xyz(cgi); float cgv = cgi.w;
     float3 cn = xyz(cnd);
-    float scdl = sqrtf(luma(cdc)), scgl = sqrtf(luma(cgc));
-    float ls_di = lerpc(2.5f, 0.5f, sqrtf(cdv));
-    float ls_gi = lerpc(1.0f, 0.0f, sqrtf(cgv));
+    float scdl = sv_sqrt<FAST>(sv_luma<FAST>(cdc)), scgl = sv_sqrt<FAST>(sv_luma<FAST>(cgc));
+    float ls_di = lerpc(2.5f, 0.5f, sv_sqrt<FAST>(cdv));
+    float ls_gi = lerpc(1.0f, 0.0f, sv_sqrt<FAST>(cgv));
     float depth_sigma = 0.33f / strength;   // same for DI and GI (frame_denoising.rs:264,267)
     float2 jf = (f2(bn.z, bn.w) - f2(0.5f, 0.5f)) * ((float)stride - 1.0f) * 0.5f;
     int jx = to_i32_sat(jf.x), jy = to_i32_sat(jf.y);
@@ -718,19 +737,33 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_wavelet(KPARAMS, int cur, 
             size_t si = pix(cam, (u32)sx, (u32)sy);
             float4 nds = snd[si];
             if (nds.w == 0.0f) continue;
-            float dw = svgf_depth_weight(cnd.w, nds.w, depth_sigma);
-            float nw = svgf_normal_weight(cn, xyz(nds));
+            float dw = svgf_depth_weight<FAST>(cnd.w, nds.w, depth_sigma);
+            float nw = svgf_normal_weight<FAST>(cn, xyz(nds));
             if (dw == 0.0f || nw == 0.0f) continue;
+            float dnw = dw * nw;
             float4 sdi = di_in[si];
-            float wd = svgf_luma_weight(scdl, luma(xyz(sdi)), ls_di) * dw * nw;
-            if (wd > 0.0f) { sdw += wd; sdc = sdc + wd * xyz(sdi); sdv += sq(wd) * sdi.w; }
             float4 sgi = gi_in[si];
-            float wg = svgf_luma_weight(scgl, luma(xyz(sgi)), ls_gi) * dw * nw;
-            if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
+            if (FAST) {
+                float wd = svgf_luma_weight<true>(scdl, sv_luma<true>(xyz(sdi)), ls_di) * dnw;
+                if (wd > 0.0f) { sdw += wd; sdc = f3(__fmaf_rn(wd, sdi.x, sdc.x), __fmaf_rn(wd, sdi.y, sdc.y), __fmaf_rn(wd, sdi.z, sdc.z)); sdv = __fmaf_rn(wd * wd, sdi.w, sdv); }
+                float wg = svgf_luma_weight<true>(scgl, sv_luma<true>(xyz(sgi)), ls_gi) * dnw;
+                if (wg > 0.0f) { sgw += wg; sgc = f3(__fmaf_rn(wg, sgi.x, sgc.x), __fmaf_rn(wg, sgi.y, sgc.y), __fmaf_rn(wg, sgi.z, sgc.z)); sgv = __fmaf_rn(wg * wg, sgi.w, sgv); }
+            } else {
+                float wd = svgf_luma_weight<false>(scdl, luma(xyz(sdi)), ls_di) * dw * nw;
+                if (wd > 0.0f) { sdw += wd; sdc = sdc + wd * xyz(sdi); sdv += sq(wd) * sdi.w; }
+                float wg = svgf_luma_weight<false>(scgl, luma(xyz(sgi)), ls_gi) * dw * nw;
+                if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
+            }
         }
     }
-    di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
-    gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
+    if (FAST) {
+        float rd = sfu_rcp(sdw), rg = sfu_rcp(sgw);
+        di_out[i] = f4(sdc * rd, sdv * (rd * rd));
+        gi_out[i] = f4(sgc * rg, sgv * (rg * rg));
+    } else {
+        di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
+        gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
+    }
 }
 
 // R2 frame_composition::fs (frame_composition.rs:19-82), linear HDR out
@@ -1069,9 +1102,12 @@ void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u
 void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out); }
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
 void launch_denoise_reproject(const CameraDev& c, const SceneDev& s, int cur, const float4* pc, const float4* pm, const float4* smp, float4* col, float4* mom, cudaStream_t st) { k_denoise_reproject<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, pc, pm, smp, col, mom); }
-void launch_denoise_variance(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_denoise_variance<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
-void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, cudaStream_t st) {
-    k_denoise_wavelet<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
+void launch_denoise_variance(const CameraDev& c, const SceneDev& s, int cur, bool fast, cudaStream_t st) {
+    if (fast) k_denoise_variance<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); else k_denoise_variance<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur);
+}
+void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, bool fast, cudaStream_t st) {
+    if (fast) k_denoise_wavelet<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
+    else k_denoise_wavelet<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
 }
 void launch_composition(const CameraDev& c, const SceneDev& s, int cur, u32 mode, const float4* di_diff, const float4* gi_diff, cudaStream_t st) { k_composition<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, mode, di_diff, gi_diff); }
 void launch_output_rgba8(const CameraDev& c, const SceneDev& s, uchar4* out, cudaStream_t st) { k_output_rgba8<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, out); }

@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PASS_COUNT = 26
 FORMAT_RGBA32F, FORMAT_RGBA8_SRGB = 0, 1
+OPT_SVGF_FAST_MATH = 1
 
 
 class StrolleError(RuntimeError):
@@ -68,7 +69,7 @@ def load_library():
         "st_bvh_depth": [P, C.POINTER(C.c_int)],
         "st_trace_closest": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p], "st_trace_any": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p],
         "st_device_math": [P, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
-        "st_set_stream": [P, C.c_void_p],
+        "st_set_stream": [P, C.c_void_p], "st_set_option": [P, C.c_int, C.c_int],
         "st_count_rays": [P, C.c_int], "st_ray_count": [P, C.POINTER(C.c_uint64), C.c_int],
         "st_mark_begin": [P], "st_mark_end": [P, f32p],
         "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int],
@@ -121,7 +122,8 @@ def _f(a, n=None):
 class Engine:
     """strolle::Engine on one B200 (CUDA device `device`)."""
 
-    def __init__(self, device=0, blue_noise=None, seed_base=0xC0FFEE):
+    def __init__(self, device=0, blue_noise=None, seed_base=0xC0FFEE, exact=False):
+        """`exact=True` switches the SVGF weights to strict IEEE arithmetic (bit-identical to the CPU oracle)."""
         self.lib = load_library()
         h = C.c_void_p()
         self._h = None
@@ -133,6 +135,8 @@ class Engine:
         bn = np.ascontiguousarray(blue_noise, dtype=np.uint8).reshape(-1)
         self._check(self.lib.st_set_blue_noise(self._h, bn.ctypes.data))
         self._check(self.lib.st_set_seed_base(self._h, seed_base))
+        if exact:
+            self.set_option(OPT_SVGF_FAST_MATH, 0)
         self._cams = {}
 
     def _check(self, rc):
@@ -276,6 +280,9 @@ class Engine:
         out = np.empty_like(a)
         self._check(self.lib.st_device_math(self._h, ops[op], a.ctypes.data, b.ctypes.data, out.ctypes.data, a.size))
         return out
+
+    def set_option(self, option, value):
+        self._check(self.lib.st_set_option(self._h, option, int(value)))
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self.lib.st_set_stream(self._h, cuda_stream_ptr))

@@ -20,8 +20,8 @@ def gpu():
     return strolle_b200
 
 
-def make_pair(gpu, oracle, blue_noise, scene, libm=False):
-    eg = gpu.Engine(blue_noise=blue_noise)
+def make_pair(gpu, oracle, blue_noise, scene, libm=False, exact=True):
+    eg = gpu.Engine(blue_noise=blue_noise, exact=exact)
     eo = oracle.OracleEngine(libm=libm, blue_noise=blue_noise)
     cg = scenes.apply(eg, scene)
     co = scenes.apply(eo, scene)
@@ -200,7 +200,7 @@ def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size):
     from strolle_b200 import multigpu as mg
     w, h = size
     scene = scenes.cornell(w, h)
-    ref = gpu.Engine(blue_noise=blue_noise)
+    ref = gpu.Engine(blue_noise=blue_noise)   # default (fast SVGF weights): strips must match it bit for bit too
     cref = scenes.apply(ref, scene)
     engines, cams, runners = [], [], []
     lt = _LocalTransport()
@@ -241,3 +241,24 @@ def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size):
                 ok, msg = bits_equal(got[rn.y0:rn.y1], want[rn.y0:rn.y1])
                 assert ok, f"strip {rn.rank}/{world} frame {f + 1} {name}: {msg}"
         assert np.isfinite(full).all()
+
+
+SVGF_BUFFERS = {"di_diff_prev_colors", "di_diff_curr_colors", "di_diff_stash", "gi_diff_prev_colors", "gi_diff_curr_colors", "gi_diff_stash", "output"}
+
+
+def test_default_fast_svgf_mode_within_tolerance(gpu, oracle, blue_noise):
+    """The product default evaluates the SVGF edge-stopping weights with SFU approximations (ST_OPT_SVGF_FAST_MATH).
+    Everything that is not a denoiser colour buffer stays bit-exact; the denoised colours and the composed image stay
+    inside north_star's tolerance: 1e-3 relative per-channel L2, after 13 frames of temporal feedback."""
+    eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scenes.cornell(192, 108), exact=False)
+    for f in range(13):
+        eg.tick(); eo.tick(); eg.render_camera(cg); eo.render_camera(co)
+        for name in CAMERA_BUFFERS:
+            a, b = eg.read_buffer(cg, name), eo.read_buffer(co, name)
+            if name in SVGF_BUFFERS:
+                a3, b3 = a.reshape(-1, 4)[:, :3], b.reshape(-1, 4)[:, :3]
+                for ch in range(3):
+                    assert rel_l2(a3[:, ch], b3[:, ch]) <= 1e-3, f"frame {f + 1} {name} channel {ch}: {rel_l2(a3[:, ch], b3[:, ch])}"
+            else:
+                ok, msg = bits_equal(a, b)
+                assert ok, f"fast-SVGF mode must leave {name} bit-exact (frame {f + 1}): {msg}"
