@@ -124,14 +124,15 @@ def _torus(major=0.5, minor=0.25, nu=24, nv=12):
     return tris
 
 
-def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cells=14):
+def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cells=13):
     """Config C3 stand-in: a *synthetic* dungeon (BASELINE.json: "synthetic Cornell and dungeon scenes").
 
-    The reference's demo level (bevy-strolle/assets/demo.zip, 8,393 triangles + 3 emissive
-    tori, 6 point lights, sun az 3.0 / alt 0.35, bevy-strolle/examples/demo.rs:150-237) needs
-    the texture atlas (a "next" row); this generator builds an untextured level of
-    the same scale procedurally: a grid of rooms/corridors from boxes (floor, ceiling, walls,
-    pillars, crates), 3 emissive tori, 6 point lights, same sun, camera inside a corridor.
+    The reference's demo level (bevy-strolle/assets/demo.zip, 8,393 triangles + 3 emissive tori, 6 point
+    lights, sun az 3.0 / alt 0.35, bevy-strolle/examples/demo.rs:150-237) needs the texture atlas (SURVEY
+    §8f-3, a "next" row); this generator builds an untextured level of the same scale procedurally: a grid of
+    4 m cells with floor/ceiling slabs, random partition walls, pillars and crates (boxes), an open corridor in
+    front of the camera, 3 emissive tori, 6 point lights, the same sun, the same camera pose
+    (eye (-5.75, 0.5, -16.8) looking down -Z).  Some ceiling slabs are missing so that the sky is visible.
     """
     rng = np.random.RandomState(seed)
     meshes, materials, instances, lights = {}, {}, [], []
@@ -140,23 +141,39 @@ def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cell
         materials[100 + i] = (material(col, perceptual_roughness=1.0, reflectance=0.0), False)
     materials[150] = (material((0.9, 0.6, 0.3, 1), emissive=(9.0, 6.0, 3.0, 1.0), perceptual_roughness=1.0, reflectance=0.0), False)
     nid = [0]
+
     def add(tris, mat, xf=IDENTITY_AFFINE):
-        h = nid[0]; nid[0] += 1
+        h = nid[0]
+        nid[0] += 1
         meshes[1000 + h] = np.stack(tris)
         instances.append((5000 + h, 1000 + h, mat, np.asarray(xf, np.float32)))
-    S = 4.0  # cell size
-    wall_h = 3.0
-    ox, oz = -cells * S / 2 - 5.75 + cells * S / 2, -17.0 - 3 * S
-    # floor + ceiling slabs per cell, walls on random cell borders, pillars and crates
-    for cx in range(cells):
-        for cz in range(cells):
-            x0, z0 = ox + (cx - cells / 2) * S, oz + (cz - cells / 2) * S + cells * S / 2
-            add(_box((x0, -0.2, z0), (x0 + S, 0.0, z0 + S)), 100 + (cx + cz) % 2)
-            add(_box((x0, wall_h, z0), (x0 + S, wall_h + 0.2, z0 + S)), 101)
-            if rng.rand() < 0.45:
-                add(_box((x0, 0.0, z0), (x0 + S, wall_h, z0 + 0.3)), 102 + rng.randint(0, 3))
-            if rng.rand() < 0.45:
+
+    S, wall_h = 4.0, 3.0
+    eye = np.array([-5.75, 0.5, -16.8])
+    half = cells // 2
+    # cell (i, j) spans x in [cx(i), cx(i)+S), z in [cz(j), cz(j)+S); the camera sits in the middle of cell (half, half)
+    cx = lambda i: eye[0] - S / 2 + (i - half) * S
+    cz = lambda j: eye[2] - S / 2 + (j - half) * S
+    corridor = {(half, j) for j in range(max(half - 5, 0), half + 1)}
+    for i in range(cells):
+        for j in range(cells):
+            x0, z0 = cx(i), cz(j)
+            add(_box((x0, -0.2, z0), (x0 + S, 0.0, z0 + S)), 100 + (i + j) % 2)
+            if rng.rand() < 0.85:
+                add(_box((x0, wall_h, z0), (x0 + S, wall_h + 0.2, z0 + S)), 101)
+            # partition walls on the -z and -x borders, never across the corridor
+            if (i, j) not in corridor or (i, j - 1) not in corridor:
+                if rng.rand() < 0.4 and not ((i, j) in corridor and (i, j - 1) in corridor):
+                    add(_box((x0, 0.0, z0), (x0 + S, wall_h, z0 + 0.3)), 102 + rng.randint(0, 3))
+            if (i, j) not in corridor and (i - 1, j) not in corridor and rng.rand() < 0.4:
                 add(_box((x0, 0.0, z0), (x0 + 0.3, wall_h, z0 + S)), 102 + rng.randint(0, 3))
+            if (i, j) in corridor:
+                for side in (-1, 1):   # crates along the corridor sides
+                    if rng.rand() < 0.6:
+                        px, pz = x0 + S / 2 + side * 1.5, z0 + rng.rand() * (S - 1) + 0.5
+                        hgt = 0.3 + rng.rand() * 0.9
+                        add(_box((px - 0.25, 0.0, pz - 0.25), (px + 0.25, hgt, pz + 0.25)), 102 + rng.randint(0, 3))
+                continue
             for _ in range(rng.randint(0, 4)):
                 px, pz = x0 + rng.rand() * (S - 1) + 0.5, z0 + rng.rand() * (S - 1) + 0.5
                 hgt = 0.3 + rng.rand() * 1.2
@@ -164,15 +181,19 @@ def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cell
             if rng.rand() < 0.3:
                 px, pz = x0 + S / 2, z0 + S / 2
                 add(_box((px - 0.2, 0.0, pz - 0.2), (px + 0.2, wall_h, pz + 0.2)), 103)
+    lo, hi = cx(0), cx(cells)
+    zlo, zhi = cz(0), cz(cells)
+    add(_box((lo - 0.3, 0.0, zlo), (lo, wall_h, zhi)), 104); add(_box((hi, 0.0, zlo), (hi + 0.3, wall_h, zhi)), 104)
+    add(_box((lo, 0.0, zlo - 0.3), (hi, wall_h, zlo)), 104); add(_box((lo, 0.0, zhi), (hi, wall_h, zhi + 0.3)), 104)
     torus = _torus()
-    for k, (tx, tz) in enumerate([(-5.75, -20.0), (-1.5, -22.0), (-9.5, -24.0)]):
-        xf = np.array([0.5, 0, 0, 0, 0.5, 0, 0, 0, 0.5, tx, 1.0, tz], np.float32)
+    for k, (dx, dz) in enumerate([(0.0, -6.0), (4.0, -9.0), (-4.0, -12.0)]):
+        xf = np.array([0.5, 0, 0, 0, 0.5, 0, 0, 0, 0.5, eye[0] + dx, 1.2, eye[2] + dz], np.float32)
         add(torus, 150, xf)
-    inten = 5000.0 / (4.0 * math.pi)
-    for k, (lx, lz) in enumerate([(-5.75, -19.0), (-1.0, -23.0), (-10.0, -23.0), (-5.75, -28.0), (2.0, -18.0), (-13.0, -18.0)]):
-        lights.append((9000 + k, LIGHT_POINT, point_light((lx, 2.2, lz), 0.15, (inten,) * 3, 35.0)))
+    inten = 120.0 / (4.0 * math.pi)
+    for k, (dx, dz) in enumerate([(0.0, -3.0), (4.5, -7.0), (-4.5, -7.0), (0.0, -13.0), (8.0, -2.0), (-8.0, -2.0)]):
+        lights.append((9000 + k, LIGHT_POINT, point_light((eye[0] + dx, 2.4, eye[2] + dz), 0.15, (inten,) * 3, 35.0)))
     cam = dict(mode=mode, denoise=denoise, ref_depth=1, w=width, h=height,
-               transform=look_at_transform((-5.75, 0.5, -16.8), (-5.75, 0.5, -17.0)),
+               transform=look_at_transform(tuple(eye), (eye[0], eye[1], eye[2] - 0.2)),
                projection=perspective_infinite_reverse_rh(math.pi / 4.0, width / height, 0.1))
     return dict(name="dungeon_synthetic", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(3.0, 0.35), camera=cam)
 
