@@ -139,6 +139,9 @@ int st_read_buffer(st_engine* e, st_camera_handle camera, const char* name, floa
 int st_read_scene(st_engine* e, const char* name, float* dst, size_t cap_floats, size_t* count);
 int st_bvh_depth(st_engine* e, int* depth);
 uint32_t st_frame(st_engine* e);
+/* Sets the id of the frame the next st_tick prepares (ids start at 1, strolle/src/lib.rs:152).  Used by the
+ * sample-parallel reference mode: rank g renders accumulations g+1, g+1+N, .... */
+int st_set_frame(st_engine* e, uint32_t frame);
 /* Ray-stream entry points (the ref_tracing / *_spatial_resampling::trace shape): `rays` = n x 8
  * host floats (origin.xyz, len, dir.xyz, pad).  closest: out = n x 12 floats (packed hit d0, d1
  * as in strolle-gpu/src/hit.rs:112-120, then distance, triangle id bits, material id bits,
@@ -159,9 +162,10 @@ const char* st_pass_name(int pass);
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
 enum { ST_OPT_SVGF_FAST_MATH = 1 };
 int st_set_option(st_engine* e, int option, int value);
-/* Runs the engine on a caller-owned CUDA stream (e.g. the host runtime's stream that NCCL halo
- * exchanges are ordered against); NULL restores a private non-blocking stream. */
-int st_set_stream(st_engine* e, void* cuda_stream);
+/* external != 0: run the engine on the caller-owned CUDA stream `cuda_stream` (NULL = the legacy default
+ * stream), e.g. the host runtime's stream that NCCL halo exchanges are ordered against; external == 0:
+ * back to a private non-blocking stream. */
+int st_set_stream(st_engine* e, void* cuda_stream, int external);
 /* Ray statistics: counts executed Ray::trace / Ray::intersect calls (the Mrays/s numerator). */
 int st_count_rays(st_engine* e, int enabled);
 int st_ray_count(st_engine* e, uint64_t* rays, int reset);

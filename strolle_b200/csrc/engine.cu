@@ -724,6 +724,7 @@ int st_set_blue_noise(st_engine* e, const uint8_t* rgba) {
     return ST_OK;
 }
 uint32_t st_frame(st_engine* e) { return e ? e->frame : 0; }
+int st_set_frame(st_engine* e, uint32_t frame) { if (!e || frame == 0) return fail(ST_ERR_INVALID, "frame ids start at 1"); e->frame = frame; return ST_OK; }
 
 int st_create_camera(st_engine* e, const st_camera* c, st_camera_handle* out) {   // CameraController::new (camera_controller.rs:24-43)
     if (!e || !c || !out) return fail(ST_ERR_INVALID, "null argument");
@@ -951,12 +952,12 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_SVGF_FAST_MATH) { e->svgf_fast = value != 0; return ST_OK; }
     return fail(ST_ERR_INVALID, "unknown option");
 }
-int st_set_stream(st_engine* e, void* cuda_stream) {
+int st_set_stream(st_engine* e, void* cuda_stream, int external) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     if (e->own_stream) { cudaStreamDestroy(e->stream); e->own_stream = false; }
-    if (cuda_stream) e->stream = (cudaStream_t)cuda_stream;
+    if (external) e->stream = (cudaStream_t)cuda_stream;   // NULL is the legacy default stream
     else { CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)); e->own_stream = true; }
     return ST_OK;
 }

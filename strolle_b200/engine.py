@@ -69,7 +69,7 @@ def load_library():
         "st_bvh_depth": [P, C.POINTER(C.c_int)],
         "st_trace_closest": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p], "st_trace_any": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p],
         "st_device_math": [P, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
-        "st_set_stream": [P, C.c_void_p], "st_set_option": [P, C.c_int, C.c_int],
+        "st_set_stream": [P, C.c_void_p, C.c_int], "st_set_option": [P, C.c_int, C.c_int],
         "st_count_rays": [P, C.c_int], "st_ray_count": [P, C.POINTER(C.c_uint64), C.c_int],
         "st_mark_begin": [P], "st_mark_end": [P, f32p],
         "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int],
@@ -86,6 +86,8 @@ def load_library():
     lib.st_pass_name.argtypes = [C.c_int]
     lib.st_frame.restype = C.c_uint32
     lib.st_frame.argtypes = [P]
+    lib.st_set_frame.argtypes = [P, u32]
+    lib.st_set_frame.restype = C.c_int
     _LIB = lib
     return lib
 
@@ -230,6 +232,9 @@ class Engine:
     def frame(self):
         return self.lib.st_frame(self._h)
 
+    def set_frame(self, frame):
+        self._check(self.lib.st_set_frame(self._h, frame))
+
     # ---- hooks ------------------------------------------------------------------------------
     def read_buffer(self, cam, name):
         n = C.c_size_t()
@@ -284,8 +289,9 @@ class Engine:
     def set_option(self, option, value):
         self._check(self.lib.st_set_option(self._h, option, int(value)))
 
-    def set_stream(self, cuda_stream_ptr):
-        self._check(self.lib.st_set_stream(self._h, cuda_stream_ptr))
+    def set_stream(self, cuda_stream_ptr, external=True):
+        """Runs the engine on a caller-owned stream (handle 0/None = the legacy default stream)."""
+        self._check(self.lib.st_set_stream(self._h, cuda_stream_ptr or None, int(external)))
 
     def count_rays(self, enabled=True):
         self._check(self.lib.st_count_rays(self._h, int(enabled)))

@@ -201,3 +201,41 @@ class StripRunner:
             # re-run only the output conversion + copy on the assembled frame
             self.engine.copy_output(self.cam, out, fmt)
             self.engine.set_strip(self.cam, self.y0, self.y1)
+
+
+class ReferenceAccumulator:
+    """Sample-parallel path-traced reference mode (BASELINE config C5).
+
+    `CameraMode::Reference` accumulates one path-traced sample per frame into `ref_colors`
+    (strolle-shaders/src/ref_shading.rs:53-66).  Seeds depend on the frame id only, so rank g renders
+    accumulations g+1, g+1+N, ... on its own full frame; the partial sums are then added with one NCCL
+    reduce (f32 sum of 16 B/pixel) and rank 0 composes `rgb / w`.  The result equals the single-GPU sum up to
+    f32 addition order.
+    """
+
+    def __init__(self, engine, cam, rank=0, world=1):
+        self.engine, self.cam, self.rank, self.world = engine, cam, rank, world
+        if world > 1:
+            import torch
+            engine.set_stream(torch.cuda.current_stream().cuda_stream)
+
+    def accumulate(self, total):
+        eng, cam = self.engine, self.cam
+        for k in range(self.rank, total, self.world):
+            eng.set_frame(k + 1)
+            eng.tick()
+            n = len(eng.frame_schedule(cam))
+            eng.render_range(cam, 0, n - 2)      # every pass but the final composition
+
+    def reduce_and_compose(self):
+        """Sums ref_colors onto rank 0 and composes there; returns nothing (read "output" on rank 0)."""
+        eng, cam = self.engine, self.cam
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            ptr, nbytes = eng.buffer_device_ptr(cam, "ref_colors")
+            t = torch.as_tensor(_DevArray(ptr, nbytes // 4), device="cuda")
+            dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        if self.rank == 0:
+            n = len(eng.frame_schedule(cam))
+            eng.render_range(cam, n - 1, n - 1)

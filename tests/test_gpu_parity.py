@@ -262,3 +262,31 @@ def test_default_fast_svgf_mode_within_tolerance(gpu, oracle, blue_noise):
             else:
                 ok, msg = bits_equal(a, b)
                 assert ok, f"fast-SVGF mode must leave {name} bit-exact (frame {f + 1}): {msg}"
+
+
+def test_sample_parallel_reference_mode(gpu, blue_noise):
+    """Config C5's shape: Reference{depth:1} accumulations split across ranks (here 4 engines on one GPU, the
+    NCCL reduce replaced by a tensor sum) equal the single-engine accumulation up to f32 addition order."""
+    import torch
+    from strolle_b200 import multigpu as mg
+    w, h, total, world = 128, 72, 16, 4
+    scene = scenes.cornell(w, h, mode=scenes.MODE_REFERENCE, ref_depth=1)
+    ref = gpu.Engine(blue_noise=blue_noise)
+    cref = scenes.apply(ref, scene)
+    for _ in range(total):
+        ref.tick(); ref.render_camera(cref)
+    want = ref.read_buffer(cref, "ref_colors").reshape(-1, 4)
+    assert (want[:, 3] == total).all()
+    parts = []
+    for r in range(world):
+        e = gpu.Engine(blue_noise=blue_noise)
+        c = scenes.apply(e, scene)
+        acc = mg.ReferenceAccumulator(e, c, rank=r, world=1)
+        acc.rank, acc.world = r, world
+        acc.accumulate(total)
+        parts.append(e.read_buffer(c, "ref_colors").reshape(-1, 4))
+        assert (parts[-1][:, 3] == total // world).all()
+    got = np.sum(parts, axis=0, dtype=np.float32)
+    assert (got[:, 3] == total).all()
+    for ch in range(3):
+        assert rel_l2(got[:, ch], want[:, ch]) <= 1e-6
