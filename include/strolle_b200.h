@@ -160,7 +160,10 @@ const char* st_pass_name(int pass);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2 };
+/* ST_OPT_ASYNC_OUTPUT (default 0): st_render_camera / st_copy_output only enqueue the device->host copy of
+ * the composed frame and return; the caller keeps `host_out` (pinned) untouched until st_synchronize, and
+ * alternates between two host buffers to pipeline frame N's copy with frame N+1's passes. */
 int st_set_option(st_engine* e, int option, int value);
 /* external != 0: run the engine on the caller-owned CUDA stream `cuda_stream` (NULL = the legacy default
  * stream), e.g. the host runtime's stream that NCCL halo exchanges are ordered against; external == 0:

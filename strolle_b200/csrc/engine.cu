@@ -283,7 +283,7 @@ struct CameraSlot {
     std::vector<std::pair<std::string, float4**>> named;   // buffer name -> pointer slot in `dev`
     std::vector<std::pair<std::string, size_t>> sizes;      // float4 count per named buffer
     DevMem arena;
-    DevMem rgba8;
+    DevMem rgba8; int rgba8_slot = 0;
 };
 
 struct Step { int pass; std::function<void(cudaStream_t)> run; };
@@ -314,9 +314,10 @@ struct st_engine {
     GpuWorld world;
     uint32_t frame = 1, seed_base = 0xC0FFEEu;
     // device scene ------------------------------------------------------------------------------
-    DevMem d_triangles, d_bvh, d_materials, d_lights, d_noise, d_tlut, d_slut, d_skylut, d_scratch, d_raycount;
+    DevMem d_triangles, d_bvh, d_materials, d_matpacked, d_unpacklut, d_lights, d_noise, d_tlut, d_slut, d_skylut, d_scratch, d_raycount;
     bool count_rays = false;
     bool svgf_fast = true;   // ST_OPT_SVGF_FAST_MATH
+    bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
     std::vector<CameraSlot*> cameras;
     // timing ---------------------------------------------------------------------------------------
@@ -332,6 +333,7 @@ struct st_engine {
         s.lights = (const GpuLight*)d_lights.p; s.blue_noise = (const uchar4*)d_noise.p;
         s.transmittance_lut = (const float4*)d_tlut.p; s.scattering_lut = (const float4*)d_slut.p; s.sky_lut = (const float4*)d_skylut.p;
         s.world = world;
+        s.material_packed = (const uint32_t*)d_matpacked.p; s.unpack_lut = (const float*)d_unpacklut.p;
         s.ray_counter = count_rays ? (unsigned long long*)d_raycount.p : nullptr;
         return s;
     }
@@ -616,6 +618,8 @@ int st_engine_create(int device, st_engine** out) {
     e->h_lights.push_back(make_sun(make_float4(0, 0, 0, 25.0f), make_float4(0, 0, 0, std::numeric_limits<float>::infinity())));   // Lights::new (lights.rs:33-50)
     e->light_slots.push_back({st_engine::kSun, 0u});
     int rc = e->d_noise.ensure(256 * 256 * 4); if (rc) { delete e; return rc; }
+    rc = e->d_unpacklut.ensure(512 * 4); if (rc) { delete e; return rc; }
+    launch_unpack_lut((float*)e->d_unpacklut.p, e->stream);
     *out = e;
     return ST_OK;
 }
@@ -624,7 +628,7 @@ void st_engine_destroy(st_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); delete c; }
-    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount};
+    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
@@ -781,6 +785,8 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
             e->h_materials[i] = g;
         }
         if ((rc = upload(e, e->d_materials, e->h_materials.data(), e->h_materials.size() * sizeof(GpuMaterial)))) return rc;
+        if ((rc = e->d_matpacked.ensure(e->h_materials.size() * 4))) return rc;
+        launch_material_derive((const GpuMaterial*)e->d_materials.p, (uint32_t)e->h_materials.size(), (uint32_t*)e->d_matpacked.p, e->stream);
     }
     if (refresh_instances(e)) {   // Bvh::refresh (bvh.rs:48-70)
         e->bvh.build(e->prims);
@@ -854,12 +860,13 @@ int st_copy_output(st_engine* e, st_camera_handle h, void* host_out, int format)
         size_t n = (size_t)cs->desc.width * cs->desc.height;
         if (format == ST_FORMAT_RGBA32F) CK(cudaMemcpyAsync(host_out, cs->dev.output, n * 16, cudaMemcpyDeviceToHost, e->stream));
         else if (format == ST_FORMAT_RGBA8_SRGB) {
-            int rc2 = cs->rgba8.ensure(n * 4); if (rc2) return rc2;
-            SceneDev sc = e->scene(); uchar4* dst8 = (uchar4*)cs->rgba8.p; CameraDev cd = cs->dev;
+            int rc2 = cs->rgba8.ensure(2 * n * 4); if (rc2) return rc2;
+            cs->rgba8_slot ^= 1;
+            SceneDev sc = e->scene(); uchar4* dst8 = (uchar4*)cs->rgba8.p + (cs->rgba8_slot ? n : 0); CameraDev cd = cs->dev;
             e->run_timed(P_COMPOSITION, [=](cudaStream_t s) { launch_output_rgba8(cd, sc, dst8, s); });
-            CK(cudaMemcpyAsync(host_out, cs->rgba8.p, n * 4, cudaMemcpyDeviceToHost, e->stream));
+            CK(cudaMemcpyAsync(host_out, dst8, n * 4, cudaMemcpyDeviceToHost, e->stream));
         } else return fail(ST_ERR_INVALID, "unsupported output format");
-        CK(cudaStreamSynchronize(e->stream));
+        if (!e->async_output) CK(cudaStreamSynchronize(e->stream));
     }
     return ST_OK;
 }
@@ -950,6 +957,7 @@ int st_device_math(st_engine* e, int op, const float* a, const float* b, float* 
 int st_set_option(st_engine* e, int option, int value) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     if (option == ST_OPT_SVGF_FAST_MATH) { e->svgf_fast = value != 0; return ST_OK; }
+    if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     return fail(ST_ERR_INVALID, "unknown option");
 }
 int st_set_stream(st_engine* e, void* cuda_stream, int external) {

@@ -37,6 +37,10 @@ ST_DEV void tex_store(float4* __restrict__ t, const CameraDev& cam, u32 x, u32 y
 ST_DEV Hit load_hit(const GpuCamera& c, const float4* __restrict__ d0, const float4* __restrict__ d1, const CameraDev& cam, u32 x, u32 y) {
     return hit_make(cam_ray(c, x, y), gbuf_unpack(tex_or_zero(d0, cam, x, y), tex_or_zero(d1, cam, x, y)));
 }
+// variant whose base colour comes from the byte table (kernels that consume hit.g.base_color)
+ST_DEV Hit load_hit_lut(const SceneDev& sc, const GpuCamera& c, const float4* __restrict__ d0, const float4* __restrict__ d1, const CameraDev& cam, u32 x, u32 y) {
+    return hit_make(cam_ray(c, x, y), gbuf_unpack(sc, tex_or_zero(d0, cam, x, y), tex_or_zero(d1, cam, x, y)));
+}
 #define ST_TRACE_STACK()                                          \
     __shared__ u32 s_stack[ST_BVH_STACK * ST_BLOCK];              \
     TraceStack stk; stk.base = s_stack + threadIdx.x;
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_prim_gbuffer(KPARAMS, int cur) {
         GBuf g;
         g.base_color = mat_base_color(m, th.uv); g.normal = th.normal; g.metallic = m.metallic; g.emissive = mat_emissive(m, th.uv);
         g.roughness = m.roughness; g.reflectance = m.reflectance; g.depth = dist(ray.o, th.point);
-        gbuf_pack(g, &g0, &g1);
+        gbuf_pack_pre(g, __ldg(sc.material_packed + th.material_id), &g0, &g1);
         float2 n = oct_encode(th.normal);
         surf = f4(n.x, n.y, g.depth, m.roughness);
         nd = f4(oct_decode(n), g.depth);   // what every consumer of the surface map decodes, computed once
@@ -189,13 +193,14 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_pick(KPARAMS, int cur, 
         float2 fp = f2((float)lp.x, (float)lp.y) + off;
         uint2 rpos = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
         if (rpos.x == lp.x && rpos.y == lp.y) continue;
-        rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
-        if (!hit_some(rhs_hit)) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
-        if (fabs_(rhs_hit.g.depth - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
-        if (dot(rhs_hit.g.normal, lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        // the rejection tests only need the neighbour's depth and normal: one (normal, depth) float4
+        float4 nd = tex_or_zero(cam.surface_nd, cam, rpos.x, rpos.y);
+        if (nd.w == 0.0f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (fabs_(nd.w - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (dot(xyz(nd), lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
         rhs_idx = screen_idx(cam, rpos.x, rpos.y);
         rhs = di_load(cam.di_reservoirs[1], rhs_idx);
-        if (rhs.m != 0.0f) break;
+        if (rhs.m != 0.0f) { rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y); break; }
     }
     if (rhs.m == 0.0f) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
     float lhs_rhs_pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), rhs_hit);
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_a(KPARAMS, int cur, u3
         gg.base_color = mat_base_color(m, gh.uv); gg.normal = gh.normal; gg.metallic = m.metallic; gg.emissive = mat_emissive(m, gh.uv);
         gg.roughness = m.roughness; gg.reflectance = m.reflectance; gg.depth = dist(gi_r.o, gh.point);
     }
-    float4 d1, d2; gbuf_pack(gg, &d1, &d2);
+    float4 d1, d2; gbuf_pack_pre(gg, trihit_some(gh) ? __ldg(sc.material_packed + gh.material_id) : 0u, &d1, &d2);
     size_t gi = pix(cam, g.x, g.y);
     cam.gi_d0[gi] = f4(gi_r.d, gi_pdf_); cam.gi_d1[gi] = d1; cam.gi_d2[gi] = d2;
 }
@@ -355,13 +360,13 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_b(KPARAMS, int cur, u3
     Rng rng; Hit gh; float gi_pdf_;
     if (tracing) {
         rng = rng_make(seed, sp.x, sp.y);
-        gh = hit_make(ray_make(prim.point, xyz(d0)), gbuf_unpack(d1, d2));
+        gh = hit_make(ray_make(prim.point, xyz(d0)), gbuf_unpack(sc, d1, d2));
         gi_pdf_ = d0.w;
     } else {
         GiRes res = gi_load(cam.gi_reservoirs[2], idx);
         if (res.m == 0.0f) return;
         rng.s = res.rng;
-        gh = hit_make(ray_make(res.v1, xyz(d0)), gbuf_unpack(d1, d2));
+        gh = hit_make(ray_make(res.v1, xyz(d0)), gbuf_unpack(sc, d1, d2));
         gi_pdf_ = 1.0f;
     }
     u32 rng_state = rng.s;
@@ -480,16 +485,17 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_pick(KPARAMS, int cur, 
         float2 fp = f2((float)lp.x, (float)lp.y) + off;
         uint2 rpos = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
         if (rpos.x == lp.x && rpos.y == lp.y) continue;
-        rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
-        if (!hit_some(rhs_hit)) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
-        if (fabs_(rhs_hit.g.depth - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
-        if (dot(rhs_hit.g.normal, lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        float4 nd = tex_or_zero(cam.surface_nd, cam, rpos.x, rpos.y);
+        if (nd.w == 0.0f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (fabs_(nd.w - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (dot(xyz(nd), lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
         rhs_idx = screen_idx(cam, rpos.x, rpos.y);
         rhs = gi_load(reservoirs, rhs_idx);
         if (rhs.m == 0.0f) continue;
         rhs_jac = gi_jacobian(rhs, lhs_hit.point);
         if (rhs_jac < 1.0f / 10.0f || rhs_jac > 10.0f) { rhs.m = 0.0f; continue; }
         rhs_jac = rclamp(rhs_jac, 1.0f / 3.0f, 3.0f);
+        rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
         break;
     }
     if (rhs.m == 0.0f || !hit_some(rhs_hit)) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
@@ -554,17 +560,17 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_preview(KPARAMS, int cur, u32 s
     if (gi_merge(main_, rng, center, center.pdf)) main_pdf = center.pdf;
     u32 max_samples = to_u32_sat(lerpc(8.0f, 0.0f, main_.m / 8.0f));
     float max_radius = (nth == 0u) ? 128.0f : 64.0f;
-    const float4* surf = cam.prim_surface_map[cur];
+    const float4* __restrict__ surf = cam.surface_nd;
     for (u32 k = 0u; k < max_samples; k++) {
         float2 off = rng_disk(rng) * max_radius;
         float2 fp = f2((float)p.x, (float)p.y) + off;
         uint2 sp = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
         if (sp.x == p.x && sp.y == p.y) return;   // quirk C-6: the kernel exits without writing
         if (!cam_contains_u(cam.curr, sp.x, sp.y)) continue;
-        Surf ss = surf_decode(surf[pix(cam, sp.x, sp.y)]);
-        if (ss.depth == 0.0f) continue;
-        if (fabs_(ss.depth - chit.g.depth) > 0.25f * chit.g.depth) continue;
-        if (dot(ss.normal, chit.g.normal) < 0.5f) continue;
+        float4 nd = surf[pix(cam, sp.x, sp.y)];
+        if (nd.w == 0.0f) continue;
+        if (fabs_(nd.w - chit.g.depth) > 0.25f * chit.g.depth) continue;
+        if (dot(xyz(nd), chit.g.normal) < 0.5f) continue;
         GiRes s = gi_load(in, screen_idx(cam, sp.x, sp.y));
         if (s.m == 0.0f) continue;
         float s_pdf = gi_pdf(s, chit);
@@ -703,8 +709,11 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur)
 // K22 frame_denoising::wavelet (frame_denoising.rs:220-361): 3x3 à-trous, DI and GI together.
 // Per tap: one (normal, depth) float4 + the two signal float4s; the depth ramp and normal^64 factors are
 // evaluated once and shared by both signals, taps whose shared factor is 0 are skipped (weight cannot be > 0).
+#ifndef ST_WAVELET_MIN_BLOCKS
+#define ST_WAVELET_MIN_BLOCKS 10
+#endif
 template <bool FAST>
-__global__ void __launch_bounds__(ST_BLOCK) k_denoise_wavelet(KPARAMS, int cur, u32 frame, u32 stride, float strength,
+__global__ void __launch_bounds__(ST_BLOCK, ST_WAVELET_MIN_BLOCKS) k_denoise_wavelet(KPARAMS, int cur, u32 frame, u32 stride, float strength,
                                                               const float4* __restrict__ di_in, float4* __restrict__ di_out,
                                                               const float4* __restrict__ gi_in, float4* __restrict__ gi_out) {
     Px p = pixel_full(cam);
@@ -773,7 +782,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_composition(KPARAMS, int cur, u32 
     size_t i = pix(cam, p.x, p.y);
     float3 color;
     if (mode == 0u) {
-        GBuf g = gbuf_unpack(cam.prim_gbuffer_d0[cur][i], cam.prim_gbuffer_d1[cur][i]);
+        GBuf g = gbuf_unpack(sc, cam.prim_gbuffer_d0[cur][i], cam.prim_gbuffer_d1[cur][i]);
         float3 dd = xyz(di_diff[i]), ds = xyz(cam.di_spec_samples[i]), gd = xyz(gi_diff[i]), gs = xyz(cam.gi_spec_samples[i]);
         if (g.depth != 0.0f) color = g.emissive + (dd + gd) * xyz(g.base_color) + ds + gs;
         else color = dd;
@@ -880,7 +889,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_bvh_heatmap(KPARAMS) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     u32 used = 0u;
-    trace_closest(cam_ray(cam.curr, p.x, p.y), sc, stk, &used);
+    trace_closest<true>(cam_ray(cam.curr, p.x, p.y), sc, stk, &used);
     float progress = (float)used / 8192.0f;
     const float3 cols[4] = {f3(0.f, 0.f, 1.f), f3(0.f, 1.f, 0.f), f3(1.f, 0.f, 0.f), f3(0.f, 0.f, 0.f)};
     float3 c = cols[3];
@@ -906,7 +915,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_trace_stream_closest(const __grid_
     if (i >= n) return;
     float4 a = rays[2 * i], b = rays[2 * i + 1];
     u32 used = 0u;
-    TriHit h = trace_closest(ray_make(xyz(a), xyz(b)), sc, stk, &used);
+    TriHit h = trace_closest<true>(ray_make(xyz(a), xyz(b)), sc, stk, &used);
     float4 h0, h1; trihit_pack(h, &h0, &h1);
     out[3 * i] = h0; out[3 * i + 1] = h1; out[3 * i + 2] = f4(h.t, bitsf(h.triangle_id), bitsf(h.material_id), (float)used);
 }
@@ -927,6 +936,17 @@ __global__ void k_math(int op, const float* __restrict__ a, const float* __restr
         case 3: r = atan2_det(a[i], b[i]); break; case 4: r = exp_det(a[i]); break; case 5: r = pow_det(a[i], b[i]); break;
     }
     out[i] = r;
+}
+
+// derived tables: packed gamma colour per material, byte -> linear table for GBufferEntry::unpack
+__global__ void k_material_derive(const GpuMaterial* __restrict__ mats, u32 n, u32* __restrict__ packed) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) packed[i] = gbuf_pack_color(mats[i].base_color);
+}
+__global__ void k_unpack_lut(float* __restrict__ lut) {
+    u32 i = threadIdx.x;   // 256 threads
+    lut[i] = pow_det((float)i / 255.0f, 2.2f);
+    lut[256u + i] = pow_det((float)i / 63.0f, 2.2f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1117,6 +1137,8 @@ void launch_bvh_heatmap(const CameraDev& c, const SceneDev& s, cudaStream_t st) 
 void launch_trace_stream_closest(const SceneDev& s, const float4* rays, long n, float4* out, cudaStream_t st) { k_trace_stream_closest<<<(unsigned)((n + ST_BLOCK - 1) / ST_BLOCK), ST_BLOCK, 0, st>>>(s, rays, n, out); }
 void launch_trace_stream_any(const SceneDev& s, const float4* rays, long n, u32* out, cudaStream_t st) { k_trace_stream_any<<<(unsigned)((n + ST_BLOCK - 1) / ST_BLOCK), ST_BLOCK, 0, st>>>(s, rays, n, out); }
 void launch_math(int op, const float* a, const float* b, float* out, long n, cudaStream_t st) { k_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, a, b, out, n); }
+void launch_material_derive(const GpuMaterial* mats, u32 n, u32* packed, cudaStream_t st) { if (n) k_material_derive<<<(n + 127) / 128, 128, 0, st>>>(mats, n, packed); }
+void launch_unpack_lut(float* lut, cudaStream_t st) { k_unpack_lut<<<1, 256, 0, st>>>(lut); }
 void launch_atm_transmittance(float4* out, cudaStream_t st) { k_atm_transmittance<<<dim3(2, 64), 128, 0, st>>>(out); }
 void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st) { k_atm_scattering<<<32, 32, 0, st>>>(tl, out); }
 void launch_atm_sky(const float4* tl, const float4* sl, float sun_altitude, float4* out, cudaStream_t st) { k_atm_sky<<<256, 256, 0, st>>>(tl, sl, sun_altitude, out); }

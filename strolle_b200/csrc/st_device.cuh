@@ -118,16 +118,17 @@ ST_DEV void count_ray(const SceneDev& sc) {
         if ((threadIdx.x & 31u) == (unsigned)(__ffs(m) - 1)) atomicAdd(sc.ray_counter, (unsigned long long)__popc(m));
     }
 }
+template <bool COUNT_MEMORY = false>
 ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack& stk, u32* used_memory = nullptr) {
     count_ray(sc);
     TriHit hit = trihit_none();
     float hu = 0.f, hv = 0.f, hid = 0.f;
     u32 ptr = 0u, sp = 0u, used = 0u;
     for (;;) {
-        used += 16u;
+        if (COUNT_MEMORY) used += 16u;
         float4 d0 = ldg4(sc.bvh + ptr);
         if (fbits(d0.w) == 0u) {
-            used += 48u;
+            if (COUNT_MEMORY) used += 48u;
             float4 d1 = ldg4(sc.bvh + ptr + 1), d2 = ldg4(sc.bvh + ptr + 2), d3 = ldg4(sc.bvh + ptr + 3);
             u32 near_ptr = ptr + 4u, far_ptr = fbits(d1.w);
             float near_d = box_entry(ray, xyz(d0), xyz(d1));
@@ -136,7 +137,7 @@ ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack
             if (far_d < hit.t) { stk_push(stk, sp, far_ptr); sp += 1u; }
             if (near_d < hit.t) { ptr = near_ptr; continue; }
         } else {
-            used += 144u;
+            if (COUNT_MEMORY) used += 144u;
             u32 flags = fbits(d0.x), tid = fbits(d0.y), mid = fbits(d0.z);
             float t, u, v, inv_det;
             if (tri_test(sc.triangles + 9u * (size_t)tid, ray, hit.t, &t, &u, &v, &inv_det)) {
@@ -152,7 +153,7 @@ ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack
         tri_shade(sc.triangles + 9u * (size_t)hit.triangle_id, hu, hv, hid, &hit.normal, &hit.uv);
         hit.point = ray_at(ray, hit.t);
     }
-    if (used_memory) *used_memory = used;
+    if (COUNT_MEMORY && used_memory) *used_memory = used;
     return hit;
 }
 // Ray::intersect, any hit (ray.rs:84-112, Tracing::ReturnFirst): true iff some triangle has 0 < t < len.
@@ -185,6 +186,22 @@ ST_DEV bool trace_any(const Ray& ray, const SceneDev& sc, const TraceStack& stk)
 // ---- G-buffer entry (strolle-gpu/src/gbuffer.rs:19-112) ------------------------
 struct GBuf { float4 base_color; float3 normal; float metallic; float3 emissive; float roughness, reflectance, depth; };
 ST_DEV GBuf gbuf_zero() { GBuf g; g.base_color = f4zero(); g.normal = f3s(0.f); g.metallic = 0.f; g.emissive = f3s(0.f); g.roughness = 0.f; g.reflectance = 0.f; g.depth = 0.f; return g; }
+// Exact same values as the arithmetic form: the four base-colour channels are bytes, so
+// pow(b / 255, 2.2) (and pow(a / 63, 2.2)) come from a 2 x 256-entry table built on the device with pow_det.
+ST_DEV GBuf gbuf_unpack(const SceneDev& sc, float4 d0, float4 d1) {
+    GBuf g;
+    g.depth = d0.x;
+    g.normal = oct_decode(f2(d0.y, d0.z));
+    u32 b = fbits(d0.w);
+    g.metallic = (float)(b & 0xffu) / 255.0f;
+    g.roughness = sq((float)((b >> 8) & 0xffu) / 255.0f);
+    g.reflectance = (float)((b >> 16) & 0xffu) / 255.0f;
+    g.emissive = xyz(d1);
+    u32 c = fbits(d1.w);
+    g.base_color = f4(__ldg(sc.unpack_lut + (c & 0xffu)), __ldg(sc.unpack_lut + ((c >> 8) & 0xffu)), __ldg(sc.unpack_lut + ((c >> 16) & 0xffu)),
+                      __ldg(sc.unpack_lut + 256u + ((c >> 24) & 0xffu)));
+    return g;
+}
 ST_DEV GBuf gbuf_unpack(float4 d0, float4 d1) {
     GBuf g;
     g.depth = d0.x;
@@ -211,6 +228,23 @@ ST_DEV void gbuf_pack(const GBuf& g, float4* d0, float4* d1) {
     u32 cz = to_u32_sat(rclamp(pow_det(g.base_color.z, ig), 0.0f, 1.0f) * 255.0f);
     u32 cw = to_u32_sat(rclamp(pow_det(g.base_color.w, ig), 0.0f, 1.0f) * 63.0f);
     *d1 = f4(g.emissive.x, g.emissive.y, g.emissive.z, bitsf(pack_bytes(cx, cy, cz, cw)));
+}
+ST_DEV u32 gbuf_pack_color(float4 base_color) {
+    const float ig = 1.0f / 2.2f;
+    u32 cx = to_u32_sat(rclamp(pow_det(base_color.x, ig), 0.0f, 1.0f) * 255.0f);
+    u32 cy = to_u32_sat(rclamp(pow_det(base_color.y, ig), 0.0f, 1.0f) * 255.0f);
+    u32 cz = to_u32_sat(rclamp(pow_det(base_color.z, ig), 0.0f, 1.0f) * 255.0f);
+    u32 cw = to_u32_sat(rclamp(pow_det(base_color.w, ig), 0.0f, 1.0f) * 63.0f);
+    return pack_bytes(cx, cy, cz, cw);
+}
+// gbuf_pack with the colour bytes already packed (per-material table for untextured materials)
+ST_DEV void gbuf_pack_pre(const GBuf& g, u32 color_bits, float4* d0, float4* d1) {
+    float2 n = oct_encode(g.normal);
+    u32 m = to_u32_sat(rclamp(g.metallic, 0.0f, 1.0f) * 255.0f);
+    u32 r = to_u32_sat(rclamp(sqrtf(g.roughness), 0.0f, 1.0f) * 255.0f);
+    u32 f = to_u32_sat(rclamp(g.reflectance, 0.0f, 1.0f) * 255.0f);
+    *d0 = f4(g.depth, n.x, n.y, bitsf(pack_bytes(m, r, f, 1u)));
+    *d1 = f4(g.emissive.x, g.emissive.y, g.emissive.z, bitsf(color_bits));
 }
 ST_DEV float gbuf_clamped_roughness(const GBuf& g) { return rclamp(g.roughness, 0.089f * 0.089f, 1.0f); }
 

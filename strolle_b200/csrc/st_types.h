@@ -36,6 +36,8 @@ struct SceneDev {
     const float4* scattering_lut;      // 32x32
     const float4* sky_lut;             // 256x256
     GpuWorld world;
+    const uint32_t* material_packed;   // derived per material: byte-packed gamma-2.2 base colour (GBufferEntry::pack d1.w)
+    const float* unpack_lut;           // derived: [0..255] pow(b/255, 2.2), [256..511] pow(b/63, 2.2) (GBufferEntry::unpack)
     unsigned long long* ray_counter;   // optional: counts executed Ray::trace / Ray::intersect calls (Mrays/s)
 };
 

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 PASS_COUNT = 26
 FORMAT_RGBA32F, FORMAT_RGBA8_SRGB = 0, 1
 OPT_SVGF_FAST_MATH = 1
+OPT_ASYNC_OUTPUT = 2
 
 
 class StrolleError(RuntimeError):

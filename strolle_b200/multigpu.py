@@ -64,17 +64,22 @@ def plan_frame(schedule: Sequence[int], frame: int, temporal_reach: int = 16) ->
                      ("gi_diff_prev_colors", temporal_reach), (f"di_diff_moments_{prv}", temporal_reach), (f"gi_diff_moments_{prv}", temporal_reach)]
         if p in (P_DI_SPATIAL_PICK, P_GI_SPATIAL_PICK):
             if not have_gbuffer:
-                bufs += [(f"prim_gbuffer_d0_{cur}", SPATIAL_REACH), (f"prim_gbuffer_d1_{cur}", SPATIAL_REACH)]
+                bufs += [(f"prim_gbuffer_d0_{cur}", SPATIAL_REACH), (f"prim_gbuffer_d1_{cur}", SPATIAL_REACH), ("surface_nd", SPATIAL_REACH)]
                 have_gbuffer = True
             bufs.append(("di_reservoirs_1" if p == P_DI_SPATIAL_PICK else "gi_reservoirs_1", SPATIAL_REACH))
         elif p == P_GI_PREVIEW:
             if nth_preview == 0:
                 bufs += [(f"prim_surface_map_{cur}", SPATIAL_REACH), (f"gi_reservoirs_{gi_source}", SPATIAL_REACH)]
+                if not have_gbuffer:
+                    bufs.append(("surface_nd", SPATIAL_REACH))
+                    have_gbuffer = True
             else:
                 bufs.append(("gi_reservoirs_3", PREVIEW2_REACH))
             nth_preview += 1
         elif p == P_DENOISE_VARIANCE:
-            bufs += [("di_diff_curr_colors", VARIANCE_REACH), ("gi_diff_curr_colors", VARIANCE_REACH), ("surface_nd", WAVELET_REACH[-1])]
+            bufs += [("di_diff_curr_colors", VARIANCE_REACH), ("gi_diff_curr_colors", VARIANCE_REACH)]
+            if not have_gbuffer:
+                bufs.append(("surface_nd", WAVELET_REACH[-1]))
         elif p == P_DENOISE_WAVELET:
             src = wavelet_inputs[nth_wavelet]
             bufs += [(f"di_diff_{src}", WAVELET_REACH[nth_wavelet]), (f"gi_diff_{src}", WAVELET_REACH[nth_wavelet])]

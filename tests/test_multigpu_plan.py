@@ -46,7 +46,7 @@ def test_plan_frame_matches_schedule():
     by_step = {e.before_step: dict(e.buffers) for e in plan}
     assert by_step[0]["di_reservoirs_0"] == 16 and "prim_surface_map_a" in by_step[0]
     pick = by_step[image_odd.index(P.P_DI_SPATIAL_PICK)]
-    assert pick == {"prim_gbuffer_d0_b": 128, "prim_gbuffer_d1_b": 128, "di_reservoirs_1": 128}
+    assert pick == {"prim_gbuffer_d0_b": 128, "prim_gbuffer_d1_b": 128, "surface_nd": 128, "di_reservoirs_1": 128}
     assert by_step[image_odd.index(P.P_GI_SPATIAL_PICK)] == {"gi_reservoirs_1": 128}
     prev0 = image_odd.index(P.P_GI_PREVIEW)
     assert by_step[prev0] == {"prim_surface_map_b": 128, "gi_reservoirs_2": 128}
