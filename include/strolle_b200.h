@@ -94,6 +94,15 @@ int st_remove_mesh(st_engine* e, st_handle mesh);
 int st_insert_material(st_engine* e, st_handle material, const st_material* m);
 int st_has_material(st_engine* e, st_handle material);
 int st_remove_material(st_engine* e, st_handle material);
+/* Engine::insert_image / remove_image (lib.rs:198-214), ImageData::Raw only: tightly packed RGBA8 pixels in
+ * the atlas format Rgba8UnormSrgb (strolle/src/images.rs:38-43).  ST_ERR_LIMIT when the 8192^2 atlas is full
+ * (the reference warns and drops the image, images.rs:71-79). */
+int st_insert_image(st_engine* e, st_handle image, const uint8_t* rgba8, uint32_t width, uint32_t height);
+int st_remove_image(st_engine* e, st_handle image);
+/* The Option<ImageHandle> fields of strolle::Material (strolle/src/material.rs:13-22); bit i of `mask` = texture i set
+ * (0 base_color, 1 emissive, 2 metallic_roughness, 3 normal_map — the last is carried but unused, as in the reference). */
+typedef struct st_material_textures { st_handle base_color, emissive, metallic_roughness, normal_map; uint32_t mask; } st_material_textures;
+int st_set_material_textures(st_engine* e, st_handle material, const st_material_textures* textures);
 /* Engine::insert_instance / remove_instance (lib.rs:217-229); affine = glam::Affine3A as
  * matrix3 columns x,y,z then translation (12 floats) */
 int st_insert_instance(st_engine* e, st_handle instance, st_handle mesh, st_handle material, const float affine[12]);

@@ -40,6 +40,15 @@ void orc_insert_material(void* e, uint64_t handle, const float* p, int alpha_ble
     m.perceptual_roughness = p[8]; m.metallic = p[9]; m.reflectance = p[10]; m.ior = p[11]; m.alpha_blend = alpha_blend != 0;
     ((Engine*)e)->insert_material(handle, m);
 }
+int orc_insert_image(void* e, uint64_t handle, const uint8_t* rgba, int w, int h) { return ((Engine*)e)->insert_image(handle, rgba, (u32)w, (u32)h) ? 0 : -1; }
+// tex[i] for i in base_color, emissive, metallic_roughness, normal_map; mask bit i = texture present
+void orc_set_material_textures(void* e, uint64_t handle, const uint64_t* tex, uint32_t mask) {
+    Engine* en = (Engine*)e;
+    for (auto& p : en->material_index) if (p.first == handle) {
+        for (int i = 0; i < 4; i++) { en->materials[p.second].tex[i] = tex[i]; en->materials[p.second].has_tex[i] = (mask >> i) & 1u; }
+        en->dirty_materials = true;
+    }
+}
 // affine12: matrix3 columns x,y,z then translation
 void orc_insert_instance(void* e, uint64_t handle, uint64_t mesh, uint64_t material, const float* a) {
     Affine xf; xf.x = v3(a[0], a[1], a[2]); xf.y = v3(a[3], a[4], a[5]); xf.z = v3(a[6], a[7], a[8]); xf.t = v3(a[9], a[10], a[11]);

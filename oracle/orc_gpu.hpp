@@ -38,7 +38,10 @@ struct Scene {
     World world;
     const uint8_t* blue_noise;  // 256x256 RGBA8 (strolle/assets/blue-noise.png)
     Lut transmittance_lut, sky_lut;
+    const uint8_t* atlas;       // ATLAS_SIZE^2 RGBA8 (Rgba8UnormSrgb), or null when no image was inserted
+    const float* srgb_lut;      // 256-entry sRGB -> linear table (hardware decode of the atlas format)
 };
+static const u32 ATLAS_SIZE = 8192;   // strolle/src/images.rs:29-30
 
 static const u32 BVH_STACK_SIZE = 24;  // strolle-gpu/src/lib.rs:76
 
@@ -152,12 +155,31 @@ static inline bool triangle_hit(const V4* t, const Ray& ray, TriangleHit* hit) {
     return true;
 }
 
-// Material::sample_atlas (strolle-gpu/src/material.rs:76-104).  The texture
-// atlas is a "next" row: materials with a texture rect are not
-// supported by this oracle yet and are treated as untextured.
-static inline V4 material_sample_atlas(V2 /*uv*/, V4 multiplier, V4 /*texture*/) { return multiplier; }
-static inline V4 material_base_color(const Material& m, V2 uv) { return material_sample_atlas(uv, m.base_color, m.base_color_texture); }
-static inline V3 material_emissive(const Material& m, V2 uv) { return xyz(material_sample_atlas(uv, m.emissive, m.emissive_texture)); }
+// Material::sample_atlas (strolle-gpu/src/material.rs:76-104).  The atlas sampler is wgpu's default
+// (nearest filter, clamp-to-edge, strolle/src/images.rs:38-43); the texture format Rgba8UnormSrgb decodes
+// r,g,b through the sRGB transfer function (table) and alpha linearly.
+static inline float wrap_uv(float t) { return (t > 0.0f) ? fmod_(t, 1.0f) : 1.0f - fmod_(-t, 1.0f); }
+static inline V4 atlas_fetch(const Scene& sc, V2 uv) {
+    if (!sc.atlas) return v4z();
+    i32 x = f2i_sat(floor_(uv.x * (float)ATLAS_SIZE)), y = f2i_sat(floor_(uv.y * (float)ATLAS_SIZE));
+    if (x < 0) x = 0; if (x > (i32)ATLAS_SIZE - 1) x = (i32)ATLAS_SIZE - 1;
+    if (y < 0) y = 0; if (y > (i32)ATLAS_SIZE - 1) y = (i32)ATLAS_SIZE - 1;
+    const uint8_t* p = sc.atlas + 4 * ((size_t)y * ATLAS_SIZE + (size_t)x);
+    return v4(sc.srgb_lut[p[0]], sc.srgb_lut[p[1]], sc.srgb_lut[p[2]], (float)p[3] / 255.0f);
+}
+static inline V4 material_sample_atlas(const Scene& sc, V2 hit_uv, V4 multiplier, V4 texture) {
+    if (is_zero(texture)) return multiplier;
+    hit_uv.x = wrap_uv(hit_uv.x); hit_uv.y = wrap_uv(hit_uv.y);
+    V2 uv = v2(texture.x, texture.y) + hit_uv * v2(texture.z, texture.w);
+    return multiplier * atlas_fetch(sc, uv);
+}
+static inline V4 material_base_color(const Scene& sc, const Material& m, V2 uv) { return material_sample_atlas(sc, uv, m.base_color, m.base_color_texture); }
+static inline V3 material_emissive(const Scene& sc, const Material& m, V2 uv) { return xyz(material_sample_atlas(sc, uv, m.emissive, m.emissive_texture)); }
+// Material::metallic_roughness (material.rs:44-58): (metallic, roughness) = (1, roughness, metallic, 1) * texel -> .zy()
+static inline V2 material_metallic_roughness(const Scene& sc, const Material& m, V2 uv) {
+    V4 t = material_sample_atlas(sc, uv, v4(1.0f, m.roughness, m.metallic, 1.0f), m.metallic_roughness_texture);
+    return v2(t.z, t.y);
+}
 static inline void material_regularize(Material& m) { m.roughness = fmax_(m.roughness, 0.75f * 0.75f); }  // material.rs:25-27
 
 enum Tracing { ReturnClosest, ReturnFirst };
@@ -209,7 +231,7 @@ static inline size_t ray_traverse(const Ray& self, const Scene& sc, Tracing trac
             bool found = triangle_hit(sc.triangles + 9 * (size_t)triangle_id, self, hit);
             if (found && has_alpha) {
                 used_memory += 112; used_memory += 16;
-                V4 base = material_base_color(sc.materials[material_id], hit->uv);
+                V4 base = material_base_color(sc, sc.materials[material_id], hit->uv);
                 if (base.w < 1.0f) { found = false; hit->uv = prev_uv; hit->normal = prev_normal; hit->distance = prev_distance; }
             }
             if (found) {

@@ -421,7 +421,9 @@ static inline u32 dispatch_seed(u32 base, u32 frame, u32 k) {
 // replaced by insertion-ordered containers (the reference iterates a std
 // HashMap, SURVEY §0 — order there is unspecified).
 // ---------------------------------------------------------------------------
-struct HostMaterial { V4 base_color, emissive; float perceptual_roughness, metallic, reflectance, ior; bool alpha_blend; };
+struct HostMaterial { V4 base_color, emissive; float perceptual_roughness, metallic, reflectance, ior; bool alpha_blend;
+                      uint64_t tex[4]; bool has_tex[4];   // base_color, emissive, metallic_roughness, normal_map (strolle/src/material.rs:13-22)
+                      HostMaterial() { for (int i = 0; i < 4; i++) { tex[i] = 0; has_tex[i] = false; } } };
 struct HostLight { int type; V3 position; float radius; V3 color; float range; V3 direction; float angle; };
 enum CamMode { MODE_IMAGE = 0, MODE_DI_DIFFUSE, MODE_DI_SPECULAR, MODE_GI_DIFFUSE, MODE_GI_SPECULAR, MODE_BVH_HEATMAP, MODE_REFERENCE };
 struct HostCamera { int mode; bool denoise; u32 ref_depth; u32 w, h; M4 transform, projection; };
@@ -446,6 +448,12 @@ struct Engine {
     std::vector<uint8_t> blue_noise;
     AtmosphereLuts luts;
     u32 seed_base = 0xC0FFEEu;
+    // images (strolle/src/images.rs): a shelf allocator stands in for the guillotiere crate (pinned 0.6 in
+    // Cargo.lock, not vendored) — rect placement is an implementation detail, only the rect handed to the
+    // material (Images::lookup, images.rs:114-123) matters to the shaders
+    struct ImageRect { uint64_t handle; u32 x, y, w, h; };
+    std::vector<ImageRect> images; u32 shelf_x = 0, shelf_y = 0, shelf_h = 0; bool dirty_images = false;
+    std::vector<uint8_t> atlas; std::vector<float> srgb_lut;
     // cameras
     struct Cam { HostCamera cam; CamState st; u32 frame; bool alive; };
     std::vector<Cam*> cameras;
@@ -507,6 +515,31 @@ struct Engine {
     }
     void update_sun(float az, float alt) { sun_azimuth = az; sun_altitude = alt; dirty_sun = true; }
 
+    bool insert_image(uint64_t h, const uint8_t* rgba, u32 w, u32 hgt) {   // images.rs:54-104 (ImageData::Raw)
+        if (atlas.empty()) {
+            atlas.assign((size_t)ATLAS_SIZE * ATLAS_SIZE * 4, 0);
+            srgb_lut.resize(256);
+            for (int i = 0; i < 256; i++) { float c = (float)i / 255.0f; srgb_lut[i] = (c <= 0.04045f) ? c / 12.92f : pow_((c + 0.055f) / 1.055f, 2.4f); }
+        }
+        ImageRect* r = nullptr;
+        for (ImageRect& k : images) if (k.handle == h) r = &k;
+        if (!r || r->w != w || r->h != hgt) {
+            if (shelf_x + w > ATLAS_SIZE) { shelf_x = 0; shelf_y += shelf_h; shelf_h = 0; }
+            if (w > ATLAS_SIZE || shelf_y + hgt > ATLAS_SIZE) return false;   // "no more space in the atlas"
+            ImageRect nr = {h, shelf_x, shelf_y, w, hgt};
+            shelf_x += w; if (hgt > shelf_h) shelf_h = hgt;
+            if (r) *r = nr; else { images.push_back(nr); r = &images.back(); }
+        }
+        for (u32 y = 0; y < hgt; y++) std::memcpy(&atlas[4 * ((size_t)(r->y + y) * ATLAS_SIZE + r->x)], rgba + 4 * (size_t)y * w, 4 * (size_t)w);
+        dirty_images = true;
+        return true;
+    }
+    V4 image_lookup(bool has, uint64_t h) const {   // images.rs:114-127
+        if (!has) return v4z();
+        for (const ImageRect& k : images) if (k.handle == h)
+            return v4((float)k.x / (float)ATLAS_SIZE, (float)k.y / (float)ATLAS_SIZE, (float)k.w / (float)ATLAS_SIZE, (float)k.h / (float)ATLAS_SIZE);
+        return v4z();
+    }
     void insert_mesh(uint64_t h, const std::vector<MeshTriangle>& tris) { meshes[h] = tris; }
     void insert_material(uint64_t h, const HostMaterial& m) {  // materials.rs:36-55
         for (auto& p : material_index) if (p.first == h) { materials[p.second] = m; dirty_materials = true; return; }
@@ -582,12 +615,13 @@ struct Engine {
     // Engine::tick (lib.rs:301-395)
     void tick() {
         bool any_material_modified = dirty_materials; dirty_materials = false;
-        if (any_material_modified) {  // materials.rs:79-85, material.rs:29-50
+        bool any_image_modified = dirty_images; dirty_images = false;
+        if (any_material_modified || any_image_modified) {  // materials.rs:79-85, material.rs:29-50
             gpu_materials.clear();
             for (const HostMaterial& m : materials) {
-                Material g; g.base_color = m.base_color; g.base_color_texture = v4z(); g.emissive = m.emissive; g.emissive_texture = v4z();
+                Material g; g.base_color = m.base_color; g.base_color_texture = image_lookup(m.has_tex[0], m.tex[0]); g.emissive = m.emissive; g.emissive_texture = image_lookup(m.has_tex[1], m.tex[1]);
                 g.roughness = pow_(m.perceptual_roughness, 2.0f); g.metallic = m.metallic; g.reflectance = m.reflectance; g.ior = m.ior;
-                g.metallic_roughness_texture = v4z(); g.normal_map_texture = v4z();
+                g.metallic_roughness_texture = image_lookup(m.has_tex[2], m.tex[2]); g.normal_map_texture = image_lookup(m.has_tex[3], m.tex[3]);
                 gpu_materials.push_back(g);
             }
         }
@@ -628,6 +662,7 @@ struct Engine {
         sc.world = world; sc.blue_noise = blue_noise.data();
         sc.transmittance_lut.w = 256; sc.transmittance_lut.h = 64; sc.transmittance_lut.texels = luts.transmittance.data();
         sc.sky_lut.w = 256; sc.sky_lut.h = 256; sc.sky_lut.texels = luts.sky.data();
+        sc.atlas = atlas.empty() ? nullptr : atlas.data(); sc.srgb_lut = srgb_lut.data();
         return sc;
     }
     void run_atmosphere() {  // passes/atmosphere.rs:67-111

@@ -104,11 +104,12 @@ static void pass_prim_gbuffer(CamState& cs, const Scene& sc, bool alternate) {
         if (trihit_is_some(th)) {
             const Material& m = sc.materials[th.material_id];
             GBufferEntry g;
-            g.base_color = material_base_color(m, th.uv);
+            V2 mr = material_metallic_roughness(sc, m, th.uv);
+            g.base_color = material_base_color(sc, m, th.uv);
             g.normal = th.normal;
-            g.metallic = m.metallic;      // metallic_roughness().x (untextured)
-            g.emissive = material_emissive(m, th.uv);
-            g.roughness = m.roughness;    // metallic_roughness().y (untextured)
+            g.metallic = mr.x;
+            g.emissive = material_emissive(sc, m, th.uv);
+            g.roughness = mr.y;
             g.reflectance = m.reflectance;
             g.depth = distance(ray.origin, th.point);
             gbuffer_pack(g, &g0, &g1);
@@ -424,8 +425,8 @@ static void pass_gi_sampling_a(CamState& cs, const Scene& sc, bool alternate, u3
         if (trihit_is_some(gh)) {
             Material m = sc.materials[gh.material_id];
             material_regularize(m);
-            gg.base_color = material_base_color(m, gh.uv);
-            gg.normal = gh.normal; gg.metallic = m.metallic; gg.emissive = material_emissive(m, gh.uv);
+            gg.base_color = material_base_color(sc, m, gh.uv);
+            gg.normal = gh.normal; gg.metallic = m.metallic; gg.emissive = material_emissive(sc, m, gh.uv);
             gg.roughness = m.roughness; gg.reflectance = m.reflectance;
             gg.depth = distance(gi_ray.origin, gh.point);
         }
@@ -961,8 +962,8 @@ static void pass_ref_shading(CamState& cs, const Scene& sc, u32 seed, u32 depth)
         if (depth > 0) material_regularize(material);
         Hit hit;
         hit.point = th.point + th.normal * 0.01f; hit.origin = ray.origin; hit.dir = ray.dir;
-        hit.gbuffer.base_color = material_base_color(material, th.uv); hit.gbuffer.normal = th.normal; hit.gbuffer.metallic = material.metallic;
-        hit.gbuffer.emissive = material_emissive(material, th.uv); hit.gbuffer.roughness = material.roughness;
+        hit.gbuffer.base_color = material_base_color(sc, material, th.uv); hit.gbuffer.normal = th.normal; hit.gbuffer.metallic = material.metallic;
+        hit.gbuffer.emissive = material_emissive(sc, material, th.uv); hit.gbuffer.roughness = material.roughness;
         hit.gbuffer.reflectance = material.reflectance; hit.gbuffer.depth = 0.0f;
         color += throughput * hit.gbuffer.emissive;
         if (sc.world.light_count > 0) {

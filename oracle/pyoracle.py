@@ -39,6 +39,8 @@ def _load(libm=False):
         "orc_set_seed_base": [C.c_void_p, C.c_uint32],
         "orc_insert_mesh": [C.c_void_p, C.c_uint64, _f32p, C.c_int],
         "orc_insert_material": [C.c_void_p, C.c_uint64, _f32p, C.c_int],
+        "orc_insert_image": [C.c_void_p, C.c_uint64, _u8p, C.c_int, C.c_int],
+        "orc_set_material_textures": [C.c_void_p, C.c_uint64, np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS"), C.c_uint32],
         "orc_insert_instance": [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, _f32p],
         "orc_remove_instance": [C.c_void_p, C.c_uint64],
         "orc_insert_light": [C.c_void_p, C.c_uint64, C.c_int, _f32p],
@@ -118,6 +120,17 @@ class OracleEngine:
 
     def insert_material(self, handle, params12, alpha_blend=False):
         self.lib.orc_insert_material(self.h, handle, _f(params12), int(alpha_blend))
+
+    def insert_image(self, handle, rgba8):
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        h, w = a.shape[0], a.shape[1]
+        if self.lib.orc_insert_image(self.h, handle, a.reshape(-1), w, h) != 0:
+            raise RuntimeError("atlas full")
+
+    def set_material_textures(self, handle, base_color=None, emissive=None, metallic_roughness=None, normal_map=None):
+        t = [base_color, emissive, metallic_roughness, normal_map]
+        mask = sum((1 << i) for i, v in enumerate(t) if v is not None)
+        self.lib.orc_set_material_textures(self.h, handle, np.array([v or 0 for v in t], dtype=np.uint64), mask)
 
     def insert_instance(self, handle, mesh, material, affine12):
         self.lib.orc_insert_instance(self.h, handle, mesh, material, _f(affine12))

@@ -298,6 +298,13 @@ struct st_engine {
     // meshes / materials / instances / triangles -------------------------------------------------
     std::unordered_map<st_handle, std::vector<st_mesh_triangle>> meshes;
     std::vector<st_material> materials; std::vector<st_handle> material_handles; bool materials_dirty = false;
+    struct MatTex { st_handle tex[4]; uint32_t mask; };
+    std::vector<MatTex> material_textures;
+    // images (strolle/src/images.rs): shelf allocator in place of the guillotiere crate; only the rect handed to the
+    // materials (Images::lookup) is visible to the kernels
+    struct ImageRect { st_handle handle; uint32_t x, y, w, h; };
+    std::vector<ImageRect> images; uint32_t shelf_x = 0, shelf_y = 0, shelf_h = 0; bool images_dirty = false;
+    DevMem d_atlas, d_srgb;
     struct Inst { st_handle handle, mesh, material; Affine3 xf, xf_inv, prev_xf; bool dirty; };
     std::vector<Inst> instances; bool instances_dirty = false;
     struct Range { st_handle handle; size_t b, e; };
@@ -333,6 +340,7 @@ struct st_engine {
         s.lights = (const GpuLight*)d_lights.p; s.blue_noise = (const uchar4*)d_noise.p;
         s.transmittance_lut = (const float4*)d_tlut.p; s.scattering_lut = (const float4*)d_slut.p; s.sky_lut = (const float4*)d_skylut.p;
         s.world = world;
+        s.atlas = (const uchar4*)d_atlas.p; s.srgb_lut = (const float*)d_srgb.p;
         s.material_packed = (const uint32_t*)d_matpacked.p; s.unpack_lut = (const float*)d_unpacklut.p;
         s.ray_counter = count_rays ? (unsigned long long*)d_raycount.p : nullptr;
         return s;
@@ -628,7 +636,7 @@ void st_engine_destroy(st_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); delete c; }
-    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut};
+    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
@@ -647,7 +655,7 @@ int st_insert_material(st_engine* e, st_handle h, const st_material* m) {   // M
     if (!e || !m) return fail(ST_ERR_INVALID, "null argument");
     auto it = std::find(e->material_handles.begin(), e->material_handles.end(), h);
     if (it != e->material_handles.end()) e->materials[it - e->material_handles.begin()] = *m;
-    else { e->material_handles.push_back(h); e->materials.push_back(*m); }
+    else { e->material_handles.push_back(h); e->materials.push_back(*m); st_engine::MatTex mt; std::memset(&mt, 0, sizeof mt); e->material_textures.push_back(mt); }
     e->materials_dirty = true;
     return ST_OK;
 }
@@ -662,6 +670,44 @@ int st_remove_material(st_engine* e, st_handle h) {
     return ST_OK;
 }
 
+int st_insert_image(st_engine* e, st_handle h, const uint8_t* rgba8, uint32_t w, uint32_t hgt) {   // Images::insert (images.rs:54-104), ImageData::Raw
+    if (!e || !rgba8 || w == 0 || hgt == 0) return fail(ST_ERR_INVALID, "null argument");
+    CK(cudaSetDevice(e->device));
+    int rc;
+    if (!e->d_atlas.p) {
+        if ((rc = e->d_atlas.ensure((size_t)kAtlasSize * kAtlasSize * 4))) return rc;
+        if ((rc = e->d_srgb.ensure(256 * 4))) return rc;
+        launch_srgb_lut((float*)e->d_srgb.p, e->stream);
+    }
+    st_engine::ImageRect* r = nullptr;
+    for (auto& k : e->images) if (k.handle == h) r = &k;
+    if (!r || r->w != w || r->h != hgt) {
+        if (e->shelf_x + w > kAtlasSize) { e->shelf_x = 0; e->shelf_y += e->shelf_h; e->shelf_h = 0; }
+        if (w > kAtlasSize || e->shelf_y + hgt > kAtlasSize) return fail(ST_ERR_LIMIT, "no more space in the atlas");   // images.rs:71-79 (warn!)
+        st_engine::ImageRect nr = {h, e->shelf_x, e->shelf_y, w, hgt};
+        e->shelf_x += w; if (hgt > e->shelf_h) e->shelf_h = hgt;
+        if (r) *r = nr; else { e->images.push_back(nr); r = &e->images.back(); }
+    }
+    CK(cudaMemcpy2DAsync((char*)e->d_atlas.p + 4 * ((size_t)r->y * kAtlasSize + r->x), (size_t)kAtlasSize * 4, rgba8, (size_t)w * 4, (size_t)w * 4, hgt, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));   // the caller's pixels may be freed after return
+    e->images_dirty = true;
+    return ST_OK;
+}
+int st_remove_image(st_engine* e, st_handle h) {   // Images::remove (images.rs:106-112): the rect is released, materials keep their stale rect until re-serialised
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    e->images.erase(std::remove_if(e->images.begin(), e->images.end(), [&](const st_engine::ImageRect& r) { return r.handle == h; }), e->images.end());
+    e->images_dirty = true;
+    return ST_OK;
+}
+int st_set_material_textures(st_engine* e, st_handle material, const st_material_textures* t) {
+    if (!e || !t) return fail(ST_ERR_INVALID, "null argument");
+    auto it = std::find(e->material_handles.begin(), e->material_handles.end(), material);
+    if (it == e->material_handles.end()) return fail(ST_ERR_NOT_FOUND, "unknown material");
+    st_engine::MatTex& mt = e->material_textures[it - e->material_handles.begin()];
+    mt.tex[0] = t->base_color; mt.tex[1] = t->emissive; mt.tex[2] = t->metallic_roughness; mt.tex[3] = t->normal_map; mt.mask = t->mask;
+    e->materials_dirty = true;
+    return ST_OK;
+}
 int st_insert_instance(st_engine* e, st_handle h, st_handle mesh, st_handle material, const float a[12]) {   // Instances::insert (instances.rs:29-50)
     if (!e || !a) return fail(ST_ERR_INVALID, "null argument");
     Affine3 xf; xf.x = h3(a[0], a[1], a[2]); xf.y = h3(a[3], a[4], a[5]); xf.z = h3(a[6], a[7], a[8]); xf.t = h3(a[9], a[10], a[11]);
@@ -773,8 +819,14 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     CK(cudaSetDevice(e->device));
     int rc;
-    if (e->materials_dirty) {   // Materials::refresh + Material::serialize (materials.rs:79-85, material.rs:29-50)
-        e->materials_dirty = false;
+    if (e->materials_dirty || e->images_dirty) {   // Materials::refresh + Material::serialize (materials.rs:79-85, material.rs:29-50)
+        e->materials_dirty = false; e->images_dirty = false;
+        auto rect = [&](const st_engine::MatTex& mt, int k) {   // Images::lookup (images.rs:114-127)
+            if (!((mt.mask >> k) & 1u)) return make_float4(0, 0, 0, 0);
+            for (const auto& r : e->images) if (r.handle == mt.tex[k])
+                return make_float4((float)r.x / (float)kAtlasSize, (float)r.y / (float)kAtlasSize, (float)r.w / (float)kAtlasSize, (float)r.h / (float)kAtlasSize);
+            return make_float4(0, 0, 0, 0);
+        };
         e->h_materials.resize(e->materials.size());
         for (size_t i = 0; i < e->materials.size(); i++) {
             const st_material& m = e->materials[i];
@@ -782,6 +834,8 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
             g.base_color = make_float4(m.base_color[0], m.base_color[1], m.base_color[2], m.base_color[3]);
             g.emissive = make_float4(m.emissive[0], m.emissive[1], m.emissive[2], m.emissive[3]);
             g.roughness = m.perceptual_roughness * m.perceptual_roughness; g.metallic = m.metallic; g.reflectance = m.reflectance; g.ior = m.ior;
+            const st_engine::MatTex& mt = e->material_textures[i];
+            g.base_color_texture = rect(mt, 0); g.emissive_texture = rect(mt, 1); g.metallic_roughness_texture = rect(mt, 2); g.normal_map_texture = rect(mt, 3);
             e->h_materials[i] = g;
         }
         if ((rc = upload(e, e->d_materials, e->h_materials.data(), e->h_materials.size() * sizeof(GpuMaterial)))) return rc;

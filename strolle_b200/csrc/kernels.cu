@@ -60,9 +60,11 @@ __global__ void __launch_bounds__(ST_BLOCK) k_prim_gbuffer(KPARAMS, int cur) {
     if (trihit_some(th)) {
         const GpuMaterial m = sc.materials[th.material_id];
         GBuf g;
-        g.base_color = mat_base_color(m, th.uv); g.normal = th.normal; g.metallic = m.metallic; g.emissive = mat_emissive(m, th.uv);
-        g.roughness = m.roughness; g.reflectance = m.reflectance; g.depth = dist(ray.o, th.point);
-        gbuf_pack_pre(g, __ldg(sc.material_packed + th.material_id), &g0, &g1);
+        float2 mr = mat_metallic_roughness(sc, m, th.uv);
+        g.base_color = mat_base_color(sc, m, th.uv); g.normal = th.normal; g.metallic = mr.x; g.emissive = mat_emissive(sc, m, th.uv);
+        g.roughness = mr.y; g.reflectance = m.reflectance; g.depth = dist(ray.o, th.point);
+        // untextured base colour: its gamma-encoded bytes come from the per-material table
+        gbuf_pack_pre(g, all_zero(m.base_color_texture) ? __ldg(sc.material_packed + th.material_id) : gbuf_pack_color(g.base_color), &g0, &g1);
         float2 n = oct_encode(th.normal);
         surf = f4(n.x, n.y, g.depth, m.roughness);
         nd = f4(oct_decode(n), g.depth);   // what every consumer of the surface map decodes, computed once
@@ -333,13 +335,15 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_a(KPARAMS, int cur, u3
     }
     TriHit gh = trace_closest(gi_r, sc, stk);
     GBuf gg = gbuf_zero();
+    u32 gi_color_bits = 0u;
     if (trihit_some(gh)) {
         GpuMaterial m = sc.materials[gh.material_id];
         m.roughness = rmax(m.roughness, 0.75f * 0.75f);   // Material::regularize (material.rs:25-27)
-        gg.base_color = mat_base_color(m, gh.uv); gg.normal = gh.normal; gg.metallic = m.metallic; gg.emissive = mat_emissive(m, gh.uv);
+        gg.base_color = mat_base_color(sc, m, gh.uv); gg.normal = gh.normal; gg.metallic = m.metallic; gg.emissive = mat_emissive(sc, m, gh.uv);
+        gi_color_bits = all_zero(m.base_color_texture) ? __ldg(sc.material_packed + gh.material_id) : gbuf_pack_color(gg.base_color);
         gg.roughness = m.roughness; gg.reflectance = m.reflectance; gg.depth = dist(gi_r.o, gh.point);
     }
-    float4 d1, d2; gbuf_pack_pre(gg, trihit_some(gh) ? __ldg(sc.material_packed + gh.material_id) : 0u, &d1, &d2);
+    float4 d1, d2; gbuf_pack_pre(gg, gi_color_bits, &d1, &d2);
     size_t gi = pix(cam, g.x, g.y);
     cam.gi_d0[gi] = f4(gi_r.d, gi_pdf_); cam.gi_d1[gi] = d1; cam.gi_d2[gi] = d2;
 }
@@ -864,7 +868,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_ref_shading(KPARAMS, u32 seed, u32
     if (depth > 0u) m.roughness = rmax(m.roughness, 0.75f * 0.75f);
     Hit hit;
     hit.point = th.point + th.normal * 0.01f; hit.origin = ray.o; hit.dir = ray.d;
-    hit.g.base_color = mat_base_color(m, th.uv); hit.g.normal = th.normal; hit.g.metallic = m.metallic; hit.g.emissive = mat_emissive(m, th.uv);
+    hit.g.base_color = mat_base_color(sc, m, th.uv); hit.g.normal = th.normal; hit.g.metallic = m.metallic; hit.g.emissive = mat_emissive(sc, m, th.uv);
     hit.g.roughness = m.roughness; hit.g.reflectance = m.reflectance; hit.g.depth = 0.0f;
     color = color + thr * hit.g.emissive;
     if (sc.world.light_count > 0u) {
@@ -942,6 +946,11 @@ __global__ void k_math(int op, const float* __restrict__ a, const float* __restr
 __global__ void k_material_derive(const GpuMaterial* __restrict__ mats, u32 n, u32* __restrict__ packed) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) packed[i] = gbuf_pack_color(mats[i].base_color);
+}
+__global__ void k_srgb_lut(float* __restrict__ lut) {   // sRGB electro-optical transfer function per byte
+    u32 i = threadIdx.x;
+    float c = (float)i / 255.0f;
+    lut[i] = (c <= 0.04045f) ? c / 12.92f : pow_det((c + 0.055f) / 1.055f, 2.4f);
 }
 __global__ void k_unpack_lut(float* __restrict__ lut) {
     u32 i = threadIdx.x;   // 256 threads
@@ -1138,6 +1147,7 @@ void launch_trace_stream_closest(const SceneDev& s, const float4* rays, long n, 
 void launch_trace_stream_any(const SceneDev& s, const float4* rays, long n, u32* out, cudaStream_t st) { k_trace_stream_any<<<(unsigned)((n + ST_BLOCK - 1) / ST_BLOCK), ST_BLOCK, 0, st>>>(s, rays, n, out); }
 void launch_math(int op, const float* a, const float* b, float* out, long n, cudaStream_t st) { k_math<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(op, a, b, out, n); }
 void launch_material_derive(const GpuMaterial* mats, u32 n, u32* packed, cudaStream_t st) { if (n) k_material_derive<<<(n + 127) / 128, 128, 0, st>>>(mats, n, packed); }
+void launch_srgb_lut(float* lut, cudaStream_t st) { k_srgb_lut<<<1, 256, 0, st>>>(lut); }
 void launch_unpack_lut(float* lut, cudaStream_t st) { k_unpack_lut<<<1, 256, 0, st>>>(lut); }
 void launch_atm_transmittance(float4* out, cudaStream_t st) { k_atm_transmittance<<<dim3(2, 64), 128, 0, st>>>(out); }
 void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st) { k_atm_scattering<<<32, 32, 0, st>>>(tl, out); }

@@ -34,6 +34,7 @@ void launch_trace_stream_closest(const SceneDev& s, const float4* rays, long n, 
 void launch_trace_stream_any(const SceneDev& s, const float4* rays, long n, u32* out, cudaStream_t st);
 void launch_math(int op, const float* a, const float* b, float* out, long n, cudaStream_t st);
 void launch_material_derive(const GpuMaterial* mats, u32 n, u32* packed, cudaStream_t st);
+void launch_srgb_lut(float* lut, cudaStream_t st);
 void launch_unpack_lut(float* lut, cudaStream_t st);
 void launch_atm_transmittance(float4* out, cudaStream_t st);
 void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st);

@@ -98,9 +98,33 @@ ST_DEV void tri_shade(const float4* __restrict__ tri, float u, float v, float in
     *uv = uv0 + (uv1 - uv0) * u + (uv2 - uv0) * v;
 }
 
-// Material::sample_atlas (material.rs:76-104): texture atlas not bound yet
-ST_DEV float4 mat_base_color(const GpuMaterial& m, float2) { return m.base_color; }
-ST_DEV float3 mat_emissive(const GpuMaterial& m, float2) { return xyz(m.emissive); }
+// Material::sample_atlas (strolle-gpu/src/material.rs:76-104): repeat-wrap the hit uv, map it into the
+// image's atlas rect, nearest-texel fetch (wgpu default sampler, clamp-to-edge), sRGB decode of r,g,b.
+ST_DEV float wrap_uv(float t) { return (t > 0.0f) ? fmodf(t, 1.0f) : 1.0f - fmodf(-t, 1.0f); }
+ST_DEV float4 atlas_fetch(const SceneDev& sc, float2 uv) {
+    if (!sc.atlas) return f4zero();
+    int x = to_i32_sat(floorf(uv.x * (float)kAtlasSize)), y = to_i32_sat(floorf(uv.y * (float)kAtlasSize));
+    x = max(0, min(x, (int)kAtlasSize - 1)); y = max(0, min(y, (int)kAtlasSize - 1));
+    uchar4 t = __ldg(sc.atlas + (size_t)y * kAtlasSize + (size_t)x);
+    return f4(__ldg(sc.srgb_lut + t.x), __ldg(sc.srgb_lut + t.y), __ldg(sc.srgb_lut + t.z), (float)t.w / 255.0f);
+}
+ST_DEV float4 sample_atlas(const SceneDev& sc, float2 hit_uv, float4 multiplier, float4 texture) {
+    if (all_zero(texture)) return multiplier;
+    float2 uv = f2(texture.x, texture.y) + f2(wrap_uv(hit_uv.x), wrap_uv(hit_uv.y)) * f2(texture.z, texture.w);
+    return multiplier * atlas_fetch(sc, uv);
+}
+ST_DEV float4 mat_base_color(const SceneDev& sc, const GpuMaterial& m, float2 uv) { return sample_atlas(sc, uv, m.base_color, m.base_color_texture); }
+ST_DEV float3 mat_emissive(const SceneDev& sc, const GpuMaterial& m, float2 uv) { return xyz(sample_atlas(sc, uv, m.emissive, m.emissive_texture)); }
+ST_DEV float2 mat_metallic_roughness(const SceneDev& sc, const GpuMaterial& m, float2 uv) {   // material.rs:44-58
+    float4 t = sample_atlas(sc, uv, f4(1.0f, m.roughness, m.metallic, 1.0f), m.metallic_roughness_texture);
+    return f2(t.z, t.y);
+}
+// alpha of base_color at `uv` for the alpha test of Blend materials (ray.rs:212-229): reads only what it needs
+ST_DEV float mat_alpha(const SceneDev& sc, u32 material_id, float2 uv) {
+    const float4* m = reinterpret_cast<const float4*>(sc.materials + material_id);
+    float4 base = ldg4(m), tex = ldg4(m + 1);
+    return sample_atlas(sc, uv, base, tex).w;
+}
 
 // Per-thread traversal stack: a column of a CTA-shared array, stack[level * ST_BLOCK + tid]
 // (bank = tid % 32 -> conflict-free), mirroring the reference's workgroup-shared stack
@@ -141,8 +165,14 @@ ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack
             u32 flags = fbits(d0.x), tid = fbits(d0.y), mid = fbits(d0.z);
             float t, u, v, inv_det;
             if (tri_test(sc.triangles + 9u * (size_t)tid, ray, hit.t, &t, &u, &v, &inv_det)) {
-                // alpha-blended materials (flag bit 1) need the atlas: all materials are opaque until §8f-3
-                hit.t = t; hu = u; hv = v; hid = inv_det; hit.triangle_id = tid; hit.material_id = mid;
+                bool accept = true;
+                if (flags & 2u) {   // AlphaMode::Blend: the hit only counts where the base colour is opaque (ray.rs:212-229)
+                    if (COUNT_MEMORY) used += 128u;   // size_of::<Material>() + one atlas texel (ray.rs:213-214)
+                    float3 n_; float2 uv_;
+                    tri_shade(sc.triangles + 9u * (size_t)tid, u, v, inv_det, &n_, &uv_);
+                    accept = !(mat_alpha(sc, mid, uv_) < 1.0f);
+                }
+                if (accept) { hit.t = t; hu = u; hv = v; hid = inv_det; hit.triangle_id = tid; hit.material_id = mid; }
             }
             if (flags & 1u) { ptr += 1u; continue; }
         }
@@ -174,7 +204,12 @@ ST_DEV bool trace_any(const Ray& ray, const SceneDev& sc, const TraceStack& stk)
             if (near_d < best) { ptr = near_ptr; continue; }
         } else {
             float t, u, v, inv_det;
-            if (tri_test(sc.triangles + 9u * (size_t)fbits(d0.y), ray, best, &t, &u, &v, &inv_det)) return true;
+            if (tri_test(sc.triangles + 9u * (size_t)fbits(d0.y), ray, best, &t, &u, &v, &inv_det)) {
+                if (!(fbits(d0.x) & 2u)) return true;
+                float3 n_; float2 uv_;
+                tri_shade(sc.triangles + 9u * (size_t)fbits(d0.y), u, v, inv_det, &n_, &uv_);
+                if (!(mat_alpha(sc, fbits(d0.z), uv_) < 1.0f)) return true;
+            }
             if (fbits(d0.x) & 1u) { ptr += 1u; continue; }
         }
         if (sp > 0u) { sp -= 1u; ptr = stk_get(stk, sp); }

@@ -25,6 +25,8 @@ static_assert(sizeof(GpuMaterial) == 112, "material layout");
 static_assert(sizeof(GpuLight) == 112, "light layout");
 static_assert(sizeof(GpuCamera) == 160, "camera layout");
 
+static const uint32_t kAtlasSize = 8192;   // strolle/src/images.rs:29-30
+
 // Scene-wide device pointers (replicated on every GPU).
 struct SceneDev {
     const float4* triangles;   // 9 float4 per triangle (strolle-gpu/src/triangle.rs:8-21)
@@ -36,6 +38,8 @@ struct SceneDev {
     const float4* scattering_lut;      // 32x32
     const float4* sky_lut;             // 256x256
     GpuWorld world;
+    const uchar4* atlas;               // kAtlasSize^2 RGBA8 (Rgba8UnormSrgb), null until an image is inserted (strolle/src/images.rs:29-43)
+    const float* srgb_lut;             // 256-entry sRGB -> linear table
     const uint32_t* material_packed;   // derived per material: byte-packed gamma-2.2 base colour (GBufferEntry::pack d1.w)
     const float* unpack_lut;           // derived: [0..255] pow(b/255, 2.2), [256..511] pow(b/63, 2.2) (GBufferEntry::unpack)
     unsigned long long* ray_counter;   // optional: counts executed Ray::trace / Ray::intersect calls (Mrays/s)

@@ -33,6 +33,10 @@ class _Material(C.Structure):
                 ("reflectance", C.c_float), ("ior", C.c_float), ("alpha_blend", C.c_int32)]
 
 
+class _MaterialTextures(C.Structure):
+    _fields_ = [("base_color", C.c_uint64), ("emissive", C.c_uint64), ("metallic_roughness", C.c_uint64), ("normal_map", C.c_uint64), ("mask", C.c_uint32)]
+
+
 class _Light(C.Structure):
     _fields_ = [("kind", C.c_int32), ("position", C.c_float * 3), ("radius", C.c_float), ("color", C.c_float * 3), ("range", C.c_float),
                 ("direction", C.c_float * 3), ("angle", C.c_float)]
@@ -60,6 +64,7 @@ def load_library():
         "st_engine_create": [C.c_int, C.POINTER(P)], "st_engine_destroy": [P],
         "st_insert_mesh": [P, u64, C.POINTER(_MeshTriangle), C.c_size_t], "st_remove_mesh": [P, u64],
         "st_insert_material": [P, u64, C.POINTER(_Material)], "st_has_material": [P, u64], "st_remove_material": [P, u64],
+        "st_insert_image": [P, u64, C.c_void_p, u32, u32], "st_remove_image": [P, u64], "st_set_material_textures": [P, u64, C.POINTER(_MaterialTextures)],
         "st_insert_instance": [P, u64, u64, u64, f32p], "st_remove_instance": [P, u64],
         "st_insert_light": [P, u64, C.POINTER(_Light)], "st_remove_light": [P, u64], "st_update_sun": [P, C.c_float, C.c_float],
         "st_create_camera": [P, C.POINTER(_Camera), C.POINTER(i32)], "st_update_camera": [P, i32, C.POINTER(_Camera)], "st_delete_camera": [P, i32],
@@ -167,6 +172,16 @@ class Engine:
         p = _f(params12, 12)
         m = _Material((C.c_float * 4)(*p[0:4]), (C.c_float * 4)(*p[4:8]), p[8], p[9], p[10], p[11], int(alpha_blend))
         self._check(self.lib.st_insert_material(self._h, handle, C.byref(m)))
+
+    def insert_image(self, handle, rgba8):
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        self._check(self.lib.st_insert_image(self._h, handle, a.ctypes.data, a.shape[1], a.shape[0]))
+
+    def set_material_textures(self, handle, base_color=None, emissive=None, metallic_roughness=None, normal_map=None):
+        t = [base_color, emissive, metallic_roughness, normal_map]
+        mask = sum((1 << i) for i, v in enumerate(t) if v is not None)
+        mt = _MaterialTextures(*[v or 0 for v in t], mask)
+        self._check(self.lib.st_set_material_textures(self._h, handle, C.byref(mt)))
 
     def insert_instance(self, handle, mesh, material, affine12):
         a = _f(affine12, 12)

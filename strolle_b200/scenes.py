@@ -198,12 +198,69 @@ def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cell
     return dict(name="dungeon_synthetic", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(3.0, 0.35), camera=cam)
 
 
+def _quad(p0, p1, p2, p3, normal, uv_lo=(0.0, 0.0), uv_hi=(1.0, 1.0)):
+    """Two triangles wound so that the geometric normal agrees with `normal` (Triangle::hit flips the shading normal by
+    the sign of the determinant, strolle-gpu/src/triangle.rs:95-101, i.e. it trusts the winding)."""
+    (u0, v0), (u1, v1) = uv_lo, uv_hi
+    c = [np.asarray(p, np.float64) for p in (p0, p1, p2, p3)]
+    uv = [[u0, v0], [u1, v0], [u1, v1], [u0, v1]]
+    if np.dot(np.cross(c[1] - c[0], c[2] - c[0]), np.asarray(normal, np.float64)) < 0:
+        c = [c[0], c[3], c[2], c[1]]
+        uv = [uv[0], uv[3], uv[2], uv[1]]
+    return [tri36([c[0], c[1], c[2]], [normal] * 3, [uv[0], uv[1], uv[2]]), tri36([c[0], c[2], c[3]], [normal] * 3, [uv[0], uv[2], uv[3]])]
+
+
+def textured_room(width=320, height=180, mode=MODE_IMAGE, denoise=True):
+    """Exercises the texture atlas: sRGB base-colour textures with repeat-wrapped (also negative) uvs,
+    an emissive texture, a metallic-roughness texture, and an alpha-cutout AlphaMode::Blend fence whose holes must let
+    primary, shadow and bounce rays through (strolle-gpu/src/ray.rs:212-229, material.rs:76-104)."""
+    rng = np.random.RandomState(3)
+    def checker(n, cell, a, b):
+        img = np.zeros((n, n, 4), np.uint8)
+        yy, xx = np.mgrid[0:n, 0:n]
+        m = ((xx // cell) + (yy // cell)) % 2 == 0
+        img[m] = a; img[~m] = b
+        return img
+    images = {
+        700: checker(64, 8, (200, 180, 150, 255), (90, 60, 40, 255)),                      # floor base colour
+        701: checker(32, 4, (255, 255, 255, 255), (0, 0, 0, 0)),                             # fence: alpha cutout
+        702: (rng.randint(0, 256, size=(16, 48, 4))).astype(np.uint8),                       # emissive noise (non-square)
+        703: checker(16, 2, (255, 64, 255, 255), (255, 255, 32, 255)),                       # metallic-roughness (g = roughness, b = metallic)
+    }
+    images[702][..., 3] = 255
+    materials = {
+        100: (material((1.0, 1.0, 1.0, 1.0)), False), 101: (material((0.7, 0.7, 0.75, 1.0)), False),
+        102: (material((1.0, 1.0, 1.0, 1.0)), True),                                           # fence, AlphaMode::Blend
+        103: (material((0.2, 0.2, 0.2, 1.0), emissive=(3.0, 2.0, 1.0, 1.0)), False),
+        104: (material((0.9, 0.8, 0.6, 1.0), perceptual_roughness=0.8, metallic=1.0), False),
+    }
+    material_textures = {100: dict(base_color=700), 102: dict(base_color=701), 103: dict(emissive=702), 104: dict(metallic_roughness=703, base_color=700)}
+    meshes = {
+        200: np.stack(_quad((-3, 0, -3), (3, 0, -3), (3, 0, 3), (-3, 0, 3), (0, 1, 0), (-1.5, -1.5), (2.5, 2.5))),     # floor, uvs span [-1.5, 2.5]
+        201: np.stack(_quad((-3, 0, -3), (-3, 3, -3), (3, 3, -3), (3, 0, -3), (0, 0, 1))),                              # back wall
+        202: np.stack(_quad((-1.5, 0, 0.5), (1.5, 0, 0.5), (1.5, 2.0, 0.5), (-1.5, 2.0, 0.5), (0, 0, 1), (0, 0), (3, 2))),  # fence
+        203: np.stack(_quad((-3, 0.5, -2.9), (-3, 2.5, -2.9), (-1, 2.5, -2.9), (-1, 0.5, -2.9), (0, 0, 1))),            # emissive panel
+        204: np.stack(_box((0.8, 0.0, -1.6), (1.8, 1.0, -0.6))),                                                         # metal box
+    }
+    instances = [(300, 200, 100, IDENTITY_AFFINE), (301, 201, 101, IDENTITY_AFFINE), (302, 202, 102, IDENTITY_AFFINE),
+                 (303, 203, 103, IDENTITY_AFFINE), (304, 204, 104, IDENTITY_AFFINE)]
+    lights = [(400, LIGHT_POINT, point_light((0.0, 2.5, 2.0), 0.1, (6.0, 6.0, 6.0), 20.0)), (401, LIGHT_POINT, point_light((-1.0, 1.5, -1.5), 0.1, (2.0, 2.0, 3.0), 20.0))]
+    cam = dict(mode=mode, denoise=denoise, ref_depth=1, w=width, h=height, transform=look_at_transform((0.3, 1.2, 4.0), (0.0, 0.9, 0.0)),
+               projection=perspective_infinite_reverse_rh(math.pi / 4.0, width / height, 0.1))
+    return dict(name="textured_room", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(1.0, 0.6), camera=cam,
+                images=images, material_textures=material_textures)
+
+
 def apply(engine, scene):
     """Feed a scene through the Engine API in a fixed order; returns the camera handle."""
+    for h, rgba in scene.get("images", {}).items():
+        engine.insert_image(h, rgba)
     for h, tris in scene["meshes"].items():
         engine.insert_mesh(h, tris)
     for h, (params, alpha) in scene["materials"].items():
         engine.insert_material(h, params, alpha)
+    for h, tex in scene.get("material_textures", {}).items():
+        engine.set_material_textures(h, **tex)
     for h, mesh, mat, xf in scene["instances"]:
         engine.insert_instance(h, mesh, mat, xf)
     for h, kind, params in scene["lights"]:

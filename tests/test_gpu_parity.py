@@ -290,3 +290,25 @@ def test_sample_parallel_reference_mode(gpu, blue_noise):
     assert (got[:, 3] == total).all()
     for ch in range(3):
         assert rel_l2(got[:, ch], want[:, ch]) <= 1e-6
+
+
+def test_texture_atlas_and_alpha_cutout(gpu, oracle, blue_noise):
+    """sRGB atlas textures (repeat-wrapped, negative uvs), emissive / metallic-roughness textures and an
+    AlphaMode::Blend cutout that primary, shadow and bounce rays must pass through — bit-exact over 7 frames, plus a
+    ray stream through the fence."""
+    scene = scenes.textured_room(192, 108)
+    eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
+    eg.tick(); eo.tick()
+    assert_bits_equal(eg.read_scene("materials"), eo.read_scene("materials"), "materials with atlas rects")
+    bvh = eo.read_scene("bvh").reshape(-1, 4).view(np.uint32)
+    assert ((bvh[:, 3] == 1) & ((bvh[:, 0] & 2) == 2)).any(), "the fence's leaf entries carry the alpha-blend flag"
+    rays = random_rays(100000, 9, (-2.0, 0.1, 1.0), (2.0, 2.0, 4.0))
+    rays[:, 4:7] = np.array([0.0, 0.0, -1.0], np.float32) + 0.2 * rays[:, 4:7]
+    rays[:, 4:7] /= np.linalg.norm(rays[:, 4:7], axis=1, keepdims=True)
+    hg, ho = eg.trace_closest(rays), eo.trace_closest(rays)
+    assert_bits_equal(hg, ho, "closest hits through the alpha cutout")
+    fence = (ho[:, 10].view(np.uint32) == 2) & (ho[:, 8] < 3e38)
+    behind = (ho[:, 10].view(np.uint32) != 2) & (ho[:, 8] < 3e38) & (ho[:, 2] < 0.4)
+    assert fence.mean() > 0.1 and behind.mean() > 0.1, "some rays stop at opaque fence texels, others pass through the holes"
+    eg2, cg2, eo2, co2 = make_pair(gpu, oracle, blue_noise, scene)
+    run_and_compare(eg2, cg2, eo2, co2, 7, what="textured room")

@@ -136,3 +136,24 @@ def test_light_slot_protocol(oracle, blue_noise):
     e.tick()
     l2 = e.read_scene("lights").reshape(-1, 28)
     assert (l2[:, 12].view(np.uint32) == 0).all()
+
+
+def test_textured_scene_oracle(oracle, blue_noise):
+    """The atlas path of the oracle: textures change the image, the alpha cutout lets light through."""
+    sc = scenes.textured_room(96, 54)
+    e = oracle.OracleEngine(blue_noise=blue_noise)
+    cam = scenes.apply(e, sc)
+    for _ in range(3):
+        e.tick(); e.render_camera(cam)
+    img = e.read_buffer(cam, "output").reshape(54, 96, 4)[..., :3]
+    assert np.isfinite(img).all() and img.mean() > 0.01
+    mats = e.read_scene("materials").reshape(-1, 28)
+    assert mats[0, 4:8].tolist() == [0.0, 0.0, 64 / 8192, 64 / 8192]   # first image sits at the atlas origin
+    assert mats[2, 4] == 64 / 8192                                       # second image packed to its right on the shelf
+    plain = dict(sc); plain["material_textures"] = {}
+    e2 = oracle.OracleEngine(blue_noise=blue_noise)
+    c2 = scenes.apply(e2, plain)
+    for _ in range(3):
+        e2.tick(); e2.render_camera(c2)
+    img2 = e2.read_buffer(c2, "output").reshape(54, 96, 4)[..., :3]
+    assert rel_l2(img, img2) > 0.05
