@@ -38,6 +38,8 @@ struct Scene {
     World world;
     const uint8_t* blue_noise;  // 256x256 RGBA8 (strolle/assets/blue-noise.png)
     Lut transmittance_lut, sky_lut;
+    const u32* tri_instance;    // per triangle: index into instance_xforms (6 vec4 each), prim_raster.rs push constants
+    const V4* instance_xforms;  // per instance: curr_xform_inv d0..d2, prev_xform d0..d2 (PrimRasterPassParams::encode_affine, passes.rs:54-77)
     const uint8_t* atlas;       // ATLAS_SIZE^2 RGBA8 (Rgba8UnormSrgb), or null when no image was inserted
     const float* srgb_lut;      // 256-entry sRGB -> linear table (hardware decode of the atlas format)
 };

@@ -439,6 +439,7 @@ struct Engine {
     struct IdxInst { uint64_t handle; size_t s, e; };
     std::vector<IdxInst> tri_index; Allocator tri_alloc; std::vector<V4> gpu_triangles; std::vector<BvhPrimitive> bvh_all;
     BvhBuilder bvh; std::vector<V4> gpu_bvh; int bvh_depth = 0;
+    std::vector<u32> tri_instance; std::vector<V4> instance_xforms;
     // lights (strolle/src/lights.rs); handle UINT64_MAX is the sun
     std::vector<Light> lights; std::vector<std::pair<uint64_t, u32>> light_index;
     std::vector<uint64_t> l_created, l_updated; std::vector<std::pair<uint64_t, u32>> l_remapped; std::vector<u32> l_killed; u32 next_light_id = 1;
@@ -631,6 +632,19 @@ struct Engine {
             gpu_bvh.clear(); bvh_depth = 0;
             bvh.serialize(gpu_bvh, alpha, 0, 1, &bvh_depth);
         }
+        // per-instance motion for the velocity map (passes/prim_raster.rs:198-223): curr_xform_inv + prev_transform
+        tri_instance.assign(gpu_triangles.size() / 9, 0u);
+        instance_xforms.assign(6 * std::max<size_t>(instances.size(), 1), v4z());
+        for (size_t k = 0; k < instances.size(); k++) {
+            const Inst& in = instances[k];
+            const Affine* a[2] = {&in.xf_inv, &in.prev_xf};
+            for (int j = 0; j < 2; j++) {
+                instance_xforms[6 * k + 3 * j + 0] = v4(a[j]->x, a[j]->t.x);
+                instance_xforms[6 * k + 3 * j + 1] = v4(a[j]->y, a[j]->t.y);
+                instance_xforms[6 * k + 3 * j + 2] = v4(a[j]->z, a[j]->t.z);
+            }
+            for (const IdxInst& r : tri_index) if (r.handle == in.handle) for (size_t t = r.s; t < r.e; t++) tri_instance[t] = (u32)k;
+        }
         world.light_count = next_light_id; world.sun_azimuth = sun_azimuth; world.sun_altitude = sun_altitude;
         if (dirty_sun) {  // lights.rs:84-99
             dirty_sun = false;
@@ -663,6 +677,7 @@ struct Engine {
         sc.transmittance_lut.w = 256; sc.transmittance_lut.h = 64; sc.transmittance_lut.texels = luts.transmittance.data();
         sc.sky_lut.w = 256; sc.sky_lut.h = 256; sc.sky_lut.texels = luts.sky.data();
         sc.atlas = atlas.empty() ? nullptr : atlas.data(); sc.srgb_lut = srgb_lut.data();
+        sc.tri_instance = tri_instance.data(); sc.instance_xforms = instance_xforms.data();
         return sc;
     }
     void run_atmosphere() {  // passes/atmosphere.rs:67-111

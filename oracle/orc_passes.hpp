@@ -115,8 +115,12 @@ static void pass_prim_gbuffer(CamState& cs, const Scene& sc, bool alternate) {
             gbuffer_pack(g, &g0, &g1);
             V2 n = normal_encode(th.normal);
             surf = v4(n.x, n.y, g.depth, m.roughness);
+            // prim_raster::vs (prim_raster.rs:25-34): prev_point = prev_xform * (curr_xform_inv * point), per instance
+            const V4* xf = sc.instance_xforms + 6 * (size_t)sc.tri_instance[th.triangle_id];
+            V3 local = ((v3(xf[0].x, xf[0].y, xf[0].z) * th.point.x + v3(xf[1].x, xf[1].y, xf[1].z) * th.point.y) + v3(xf[2].x, xf[2].y, xf[2].z) * th.point.z) + v3(xf[0].w, xf[1].w, xf[2].w);
+            V3 prev_point = ((v3(xf[3].x, xf[3].y, xf[3].z) * local.x + v3(xf[4].x, xf[4].y, xf[4].z) * local.y) + v3(xf[5].x, xf[5].y, xf[5].z) * local.z) + v3(xf[3].w, xf[4].w, xf[5].w);
             V2 velocity = camera_clip_to_screen(cam, camera_world_to_clip(cam, th.point)) -
-                          camera_clip_to_screen(cs.prev_camera, camera_world_to_clip(cs.prev_camera, th.point));
+                          camera_clip_to_screen(cs.prev_camera, camera_world_to_clip(cs.prev_camera, prev_point));
             if (length_squared(velocity) >= 0.001f) vel = v4(velocity.x, velocity.y, 0, 0);
             tid.x = u2f(th.triangle_id);
         }

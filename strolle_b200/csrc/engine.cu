@@ -304,7 +304,8 @@ struct st_engine {
     // materials (Images::lookup) is visible to the kernels
     struct ImageRect { st_handle handle; uint32_t x, y, w, h; };
     std::vector<ImageRect> images; uint32_t shelf_x = 0, shelf_y = 0, shelf_h = 0; bool images_dirty = false;
-    DevMem d_atlas, d_srgb;
+    DevMem d_atlas, d_srgb, d_tri_instance, d_instance_xforms;
+    bool motion_dirty = true;
     struct Inst { st_handle handle, mesh, material; Affine3 xf, xf_inv, prev_xf; bool dirty; };
     std::vector<Inst> instances; bool instances_dirty = false;
     struct Range { st_handle handle; size_t b, e; };
@@ -340,6 +341,7 @@ struct st_engine {
         s.lights = (const GpuLight*)d_lights.p; s.blue_noise = (const uchar4*)d_noise.p;
         s.transmittance_lut = (const float4*)d_tlut.p; s.scattering_lut = (const float4*)d_slut.p; s.sky_lut = (const float4*)d_skylut.p;
         s.world = world;
+        s.tri_instance = (const uint32_t*)d_tri_instance.p; s.instance_xforms = (const float4*)d_instance_xforms.p;
         s.atlas = (const uchar4*)d_atlas.p; s.srgb_lut = (const float*)d_srgb.p;
         s.material_packed = (const uint32_t*)d_matpacked.p; s.unpack_lut = (const float*)d_unpacklut.p;
         s.ray_counter = count_rays ? (unsigned long long*)d_raycount.p : nullptr;
@@ -636,7 +638,7 @@ void st_engine_destroy(st_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); delete c; }
-    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb};
+    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb, &e->d_tri_instance, &e->d_instance_xforms};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
@@ -711,9 +713,9 @@ int st_set_material_textures(st_engine* e, st_handle material, const st_material
 int st_insert_instance(st_engine* e, st_handle h, st_handle mesh, st_handle material, const float a[12]) {   // Instances::insert (instances.rs:29-50)
     if (!e || !a) return fail(ST_ERR_INVALID, "null argument");
     Affine3 xf; xf.x = h3(a[0], a[1], a[2]); xf.y = h3(a[3], a[4], a[5]); xf.z = h3(a[6], a[7], a[8]); xf.t = h3(a[9], a[10], a[11]);
-    for (auto& in : e->instances) if (in.handle == h) { in.prev_xf = in.xf; in.mesh = mesh; in.material = material; in.xf = xf; in.xf_inv = aff_inverse(xf); in.dirty = true; e->instances_dirty = true; return ST_OK; }
+    for (auto& in : e->instances) if (in.handle == h) { in.prev_xf = in.xf; in.mesh = mesh; in.material = material; in.xf = xf; in.xf_inv = aff_inverse(xf); in.dirty = true; e->instances_dirty = true; e->motion_dirty = true; return ST_OK; }
     st_engine::Inst in; in.handle = h; in.mesh = mesh; in.material = material; in.xf = xf; in.xf_inv = aff_inverse(xf); in.prev_xf = xf; in.dirty = true;
-    e->instances.push_back(in); e->instances_dirty = true;
+    e->instances.push_back(in); e->instances_dirty = true; e->motion_dirty = true;
     return ST_OK;
 }
 int st_remove_instance(st_engine* e, st_handle h) {   // Engine::remove_instance (lib.rs:226-229)
@@ -721,6 +723,7 @@ int st_remove_instance(st_engine* e, st_handle h) {   // Engine::remove_instance
     size_t before = e->instances.size();
     e->instances.erase(std::remove_if(e->instances.begin(), e->instances.end(), [&](const st_engine::Inst& i) { return i.handle == h; }), e->instances.end());
     if (e->instances.size() != before) e->instances_dirty = true;
+    e->motion_dirty = true;
     release_range(e, h);
     return ST_OK;
 }
@@ -849,6 +852,24 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
         e->bvh.flatten(alpha, &e->bvh_out);
         if (e->bvh_out.depth - 1 > 24) return fail(ST_ERR_LIMIT, "BVH deeper than the 24-entry traversal stack (strolle-gpu/src/lib.rs:72-76)");
         if ((rc = upload(e, e->d_bvh, e->bvh_out.buf.data(), e->bvh_out.buf.size() * 16))) return rc;
+    }
+    if (e->motion_dirty) {   // per-instance curr_xform_inv / prev_transform for the velocity map (passes/prim_raster.rs:198-223)
+        e->motion_dirty = false;
+        std::vector<uint32_t> tri_inst(e->h_triangles.size() / 9, 0u);
+        std::vector<float4> xf(6 * std::max<size_t>(e->instances.size(), 1), make_float4(0, 0, 0, 0));
+        for (size_t k = 0; k < e->instances.size(); k++) {
+            const st_engine::Inst& in = e->instances[k];
+            const Affine3* a[2] = {&in.xf_inv, &in.prev_xf};
+            for (int j = 0; j < 2; j++) {
+                xf[6 * k + 3 * j + 0] = make_float4(a[j]->x.x, a[j]->x.y, a[j]->x.z, a[j]->t.x);
+                xf[6 * k + 3 * j + 1] = make_float4(a[j]->y.x, a[j]->y.y, a[j]->y.z, a[j]->t.y);
+                xf[6 * k + 3 * j + 2] = make_float4(a[j]->z.x, a[j]->z.y, a[j]->z.z, a[j]->t.z);
+            }
+            for (const auto& r : e->tri_ranges) if (r.handle == in.handle) for (size_t t = r.b; t < r.e; t++) tri_inst[t] = (uint32_t)k;
+        }
+        if ((rc = upload(e, e->d_tri_instance, tri_inst.data(), tri_inst.size() * 4))) return rc;
+        if ((rc = upload(e, e->d_instance_xforms, xf.data(), xf.size() * 16))) return rc;
+        CK(cudaStreamSynchronize(e->stream));   // host staging vectors go out of scope
     }
     if (e->triangles_dirty) { e->triangles_dirty = false; if ((rc = upload(e, e->d_triangles, e->h_triangles.data(), e->h_triangles.size() * 16))) return rc; }
     e->world.light_count = e->next_light; e->world.sun_azimuth = e->sun_azimuth; e->world.sun_altitude = e->sun_altitude;

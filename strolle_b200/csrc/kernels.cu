@@ -68,7 +68,12 @@ __global__ void __launch_bounds__(ST_BLOCK) k_prim_gbuffer(KPARAMS, int cur) {
         float2 n = oct_encode(th.normal);
         surf = f4(n.x, n.y, g.depth, m.roughness);
         nd = f4(oct_decode(n), g.depth);   // what every consumer of the surface map decodes, computed once
-        float2 v = cam_world_to_screen(cam.curr, th.point) - cam_world_to_screen(cam.prev, th.point);
+        // prim_raster::vs (prim_raster.rs:25-34): where this surface point was last frame, per instance
+        const float4* xf = sc.instance_xforms + 6u * (size_t)__ldg(sc.tri_instance + th.triangle_id);
+        float4 c0 = ldg4(xf), c1 = ldg4(xf + 1), c2 = ldg4(xf + 2), q0 = ldg4(xf + 3), q1 = ldg4(xf + 4), q2 = ldg4(xf + 5);
+        float3 local = ((xyz(c0) * th.point.x + xyz(c1) * th.point.y) + xyz(c2) * th.point.z) + f3(c0.w, c1.w, c2.w);
+        float3 prev_point = ((xyz(q0) * local.x + xyz(q1) * local.y) + xyz(q2) * local.z) + f3(q0.w, q1.w, q2.w);
+        float2 v = cam_world_to_screen(cam.curr, th.point) - cam_world_to_screen(cam.prev, prev_point);
         if (len2(v) >= 0.001f) vel = f4(v.x, v.y, 0.f, 0.f);
         tid.x = bitsf(th.triangle_id);
     }

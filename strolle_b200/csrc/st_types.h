@@ -38,6 +38,8 @@ struct SceneDev {
     const float4* scattering_lut;      // 32x32
     const float4* sky_lut;             // 256x256
     GpuWorld world;
+    const uint32_t* tri_instance;      // per triangle: instance slot
+    const float4* instance_xforms;     // per instance 6 float4: curr_xform_inv d0..d2, prev_xform d0..d2 (strolle-gpu/src/passes.rs:54-77)
     const uchar4* atlas;               // kAtlasSize^2 RGBA8 (Rgba8UnormSrgb), null until an image is inserted (strolle/src/images.rs:29-43)
     const float* srgb_lut;             // 256-entry sRGB -> linear table
     const uint32_t* material_packed;   // derived per material: byte-packed gamma-2.2 base colour (GBufferEntry::pack d1.w)

@@ -312,3 +312,29 @@ def test_texture_atlas_and_alpha_cutout(gpu, oracle, blue_noise):
     assert fence.mean() > 0.1 and behind.mean() > 0.1, "some rays stop at opaque fence texels, others pass through the holes"
     eg2, cg2, eo2, co2 = make_pair(gpu, oracle, blue_noise, scene)
     run_and_compare(eg2, cg2, eo2, co2, 7, what="textured room")
+
+
+def test_moving_instance_rebuilds_bvh_and_velocity(gpu, oracle, blue_noise):
+    """Dynamic scene: re-inserting an instance with a new transform re-bakes its triangles, rebuilds the BVH
+    (strolle/src/instances.rs:69-139, bvh.rs:48-70) and feeds prev_transform into the velocity map
+    (passes/prim_raster.rs:198-223); removing an instance frees its triangle slots."""
+    scene = scenes.cornell(128, 72)
+    eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
+    h, mesh, mat, xf = scene["instances"][6]   # the short box
+    for f in range(7):
+        if 1 <= f <= 4:
+            moved = np.array(xf, np.float32).copy(); moved[9] += 0.05 * f; moved[10] += 0.02 * f
+            for e in (eg, eo):
+                e.insert_instance(h, mesh, mat, moved)
+        if f == 5:
+            for e in (eg, eo):
+                e.remove_instance(scene["instances"][7][0])   # drop the tall box
+        eg.tick(); eo.tick()
+        for name in ["triangles", "bvh"]:
+            assert_bits_equal(eg.read_scene(name), eo.read_scene(name), f"frame {f + 1} scene:{name}")
+        eg.render_camera(cg); eo.render_camera(co)
+        for name in CAMERA_BUFFERS:
+            ok, msg = bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name))
+            assert ok, f"moving instance frame {f + 1} {name}: {msg}"
+    vel = eo.read_buffer(co, "velocity_map").reshape(-1, 4)
+    assert (vel[:, :2] != 0).any(), "the moved box still reports a velocity (stale prev_transform, as in the reference)"
