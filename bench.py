@@ -320,7 +320,7 @@ def main():
 
     # ---- CPU baseline (bounded sample) -----------------------------------------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         cfps, cdt, crays = run_cpu(args, args.cpu_sample_frames)
         cpu = {"value": crays / cdt / 1e6, "unit": "Mrays/s", "fps": cfps, "cores": CPU_THREADS, "kind": "port",
                "sample": f"{args.cpu_sample_frames} full-resolution frames of the same workload (frames 1..{args.cpu_sample_frames}), {cdt:.1f} s, oracle/ with OpenMP over rows"}

@@ -181,6 +181,18 @@ int st_set_stream(st_engine* e, void* cuda_stream, int external);
 /* Ray statistics: counts executed Ray::trace / Ray::intersect calls (the Mrays/s numerator). */
 int st_count_rays(st_engine* e, int enabled);
 int st_ray_count(st_engine* e, uint64_t* rays, int reset);
+/* Native strip-parallel frame: one engine per GPU/process, NCCL communicator owned by the engine.
+ * rank 0 obtains an id (st_nccl_unique_id), the host runtime broadcasts the 128 bytes, every rank calls
+ * st_nccl_init; st_render_strips then runs the frame's passes on this rank's row strip with an NCCL halo
+ * exchange (grouped ncclSend/ncclRecv on the engine's stream) before each gathering pass, and, when `gather`
+ * is non-zero (same value on every rank), assembles the composed frame on rank 0 in `format` (copied to `host_out`
+ * there if non-NULL).  st_plan_frame exposes the exchange plan
+ * ("step:buffer:reach;..." text) for tests. */
+int st_nccl_unique_id(uint8_t* out128);
+int st_nccl_init(st_engine* e, const uint8_t* id128, int rank, int world);
+int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap);
+int st_render_strips(st_engine* e, st_camera_handle camera, void* host_out, int format, int temporal_reach, int gather);
+int st_halo_bytes(st_engine* e, uint64_t* bytes);
 /* Device-side stopwatch on the engine's stream (CUDA events): st_mark_begin records, st_mark_end
  * records + waits and returns the elapsed milliseconds between the two. */
 int st_mark_begin(st_engine* e);

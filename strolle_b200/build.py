@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         if verbose:
             print(out)
     if force or procs or _stale(LIB, objs):
-        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread"])
+        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
     return LIB
 
 

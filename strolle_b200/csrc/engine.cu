@@ -16,8 +16,42 @@
 #include <unordered_map>
 #include <vector>
 
+#include <nccl.h>
+
 #include "../../include/strolle_b200.h"
 #include "kernels.h"
+
+// NCCL is bound at run time (dlopen), never at link time: the host process normally already holds the NCCL that
+// its torch build ships, and a second copy with the same soname must not shadow it.
+#include <dlfcn.h>
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool load(std::string* err) {
+        if (lib) return true;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
+        if (!h) { *err = std::string("cannot load libnccl.so.2: ") + dlerror(); return false; }
+        auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) *err = std::string("libnccl.so.2 lacks ") + n; return p; };
+        GetUniqueId = (decltype(GetUniqueId))sym("ncclGetUniqueId"); CommInitRank = (decltype(CommInitRank))sym("ncclCommInitRank");
+        CommDestroy = (decltype(CommDestroy))sym("ncclCommDestroy"); GroupStart = (decltype(GroupStart))sym("ncclGroupStart");
+        GroupEnd = (decltype(GroupEnd))sym("ncclGroupEnd"); Send = (decltype(Send))sym("ncclSend"); Recv = (decltype(Recv))sym("ncclRecv");
+        GetErrorString = (decltype(GetErrorString))sym("ncclGetErrorString");
+        if (!GetUniqueId || !CommInitRank || !CommDestroy || !GroupStart || !GroupEnd || !Send || !Recv || !GetErrorString) return false;
+        lib = h; return true;
+    }
+};
+NcclApi g_nccl;
+}
+
 
 namespace st {
 
@@ -334,6 +368,9 @@ struct st_engine {
     struct Timed { int pass; cudaEvent_t a, b; };
     std::vector<Timed> pending; std::vector<cudaEvent_t> event_pool;
     cudaEvent_t mark_a = nullptr, mark_b = nullptr;
+    // row-strip partition: NCCL communicator over the ranks that share the frame
+    ncclComm_t comm = nullptr; int rank = 0, n_ranks = 1;
+    uint64_t halo_bytes_last_frame = 0;
 
     SceneDev scene() const {
         SceneDev s;
@@ -602,6 +639,88 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
     add(P_COMPOSITION, [=](cudaStream_t s) { launch_composition(cam, sc, cur, mode, di_final, gi_final, s); });
 }
 
+
+// ---- strip partition: exchange plan (which rows of which buffers a gathering pass needs from other ranks) ----
+struct HaloItem { std::string name; int reach; };
+struct HaloExchange { int before_step; std::vector<HaloItem> items; };
+static const int kSpatialReach = 128;    // ReSTIR spatial taps, di_spatial_resampling.rs:55-56
+static const int kPreview2Reach = 64;    // gi_preview_resampling.rs:64-70
+static const int kVarianceReach = 3;     // frame_denoising.rs:128-190
+static const int kWaveletReach[5] = {1, 2, 4, 9, 19};   // stride + trunc((stride-1)/4) jitter (frame_denoising.rs:269-286)
+
+static void plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, std::vector<HaloExchange>* plan) {
+    const char* cur = (frame % 2u == 1u) ? "b" : "a";
+    const char* prv = (frame % 2u == 1u) ? "a" : "b";
+    bool have_gbuffer = false; int nth_preview = 0, nth_wavelet = 0;
+    const char* wavelet_inputs[5] = {"stash", "prev_colors", "stash", "curr_colors", "stash"};
+    bool has_preview = false, has_gi_spatial = false;
+    for (int i = 0; i < n; i++) { if (schedule[i] == P_GI_PREVIEW) has_preview = true; if (schedule[i] == P_GI_SPATIAL_SAMPLE) has_gi_spatial = true; }
+    std::string gi_source = has_gi_spatial ? "gi_reservoirs_2" : "gi_reservoirs_1";
+    for (int i = 0; i < n; i++) {
+        int p = schedule[i];
+        HaloExchange ex; ex.before_step = i;
+        auto add = [&](const std::string& name, int reach) { ex.items.push_back({name, reach}); };
+        if (i == 0 && temporal_reach > 0) {   // last frame's outputs gathered at reprojected positions (K4, K6, K11, K14, K20)
+            add(std::string("prim_surface_map_") + prv, temporal_reach); add(std::string("prim_gbuffer_d0_") + prv, temporal_reach); add(std::string("prim_gbuffer_d1_") + prv, temporal_reach);
+            add("di_reservoirs_0", temporal_reach); add("gi_reservoirs_0", temporal_reach); add("di_diff_prev_colors", temporal_reach); add("gi_diff_prev_colors", temporal_reach);
+            add(std::string("di_diff_moments_") + prv, temporal_reach); add(std::string("gi_diff_moments_") + prv, temporal_reach);
+        }
+        if (p == P_DI_SPATIAL_PICK || p == P_GI_SPATIAL_PICK) {
+            if (!have_gbuffer) { add(std::string("prim_gbuffer_d0_") + cur, kSpatialReach); add(std::string("prim_gbuffer_d1_") + cur, kSpatialReach); add("surface_nd", kSpatialReach); have_gbuffer = true; }
+            add(p == P_DI_SPATIAL_PICK ? "di_reservoirs_1" : "gi_reservoirs_1", kSpatialReach);
+        } else if (p == P_GI_PREVIEW) {
+            if (nth_preview == 0) {
+                add(std::string("prim_surface_map_") + cur, kSpatialReach); add(gi_source, kSpatialReach);
+                if (!have_gbuffer) { add("surface_nd", kSpatialReach); have_gbuffer = true; }
+            } else add("gi_reservoirs_3", kPreview2Reach);
+            nth_preview++;
+        } else if (p == P_DENOISE_VARIANCE) {
+            add("di_diff_curr_colors", kVarianceReach); add("gi_diff_curr_colors", kVarianceReach);
+            if (!have_gbuffer) add("surface_nd", kWaveletReach[4]);
+        } else if (p == P_DENOISE_WAVELET && nth_wavelet < 5) {
+            add(std::string("di_diff_") + wavelet_inputs[nth_wavelet], kWaveletReach[nth_wavelet]); add(std::string("gi_diff_") + wavelet_inputs[nth_wavelet], kWaveletReach[nth_wavelet]);
+            nth_wavelet++;
+        }
+        (void)has_preview;
+        if (!ex.items.empty()) plan->push_back(ex);
+    }
+}
+static void strip_bounds(int height, int world, std::vector<std::pair<int, int>>* b) {
+    b->clear();
+    for (int r = 0; r < world; r++) b->push_back({(int)((long long)height * r / world), (int)((long long)height * (r + 1) / world)});
+}
+static float4* camera_buffer(CameraSlot* cs, const std::string& name, size_t* vec4_per_pixel) {
+    size_t n = (size_t)cs->desc.width * cs->desc.height;
+    for (size_t i = 0; i < cs->named.size(); i++) if (cs->named[i].first == name) { *vec4_per_pixel = cs->sizes[i].second / n; return *cs->named[i].second; }
+    return nullptr;
+}
+// one NCCL group per exchange point: every rank sends the rows it owns that another rank's grown strip needs
+static int halo_exchange(st_engine* e, CameraSlot* cs, const HaloExchange& ex) {
+    std::vector<std::pair<int, int>> bounds; strip_bounds((int)cs->desc.height, e->n_ranks, &bounds);
+    const int H = (int)cs->desc.height; const size_t W = cs->desc.width;
+    ncclResult_t nr = g_nccl.GroupStart();
+    if (nr != ncclSuccess) return fail(ST_ERR_CUDA, std::string("ncclGroupStart: ") + g_nccl.GetErrorString(nr));
+    for (const HaloItem& it : ex.items) {
+        size_t k = 0; float4* base = camera_buffer(cs, it.name, &k);
+        if (!base) { g_nccl.GroupEnd(); return fail(ST_ERR_NOT_FOUND, "halo plan names unknown buffer " + it.name); }
+        for (int dst = 0; dst < e->n_ranks; dst++) {
+            int need0 = std::max(0, bounds[dst].first - it.reach), need1 = std::min(H, bounds[dst].second + it.reach);
+            for (int src = 0; src < e->n_ranks; src++) {
+                if (src == dst || (src != e->rank && dst != e->rank)) continue;
+                int a = std::max(need0, bounds[src].first), b = std::min(need1, bounds[src].second);
+                if (a >= b) continue;
+                float4* ptr = base + (size_t)a * W * k; size_t count = (size_t)(b - a) * W * k * 4;
+                if (src == e->rank) nr = g_nccl.Send(ptr, count, ncclFloat, dst, e->comm, e->stream);
+                else { nr = g_nccl.Recv(ptr, count, ncclFloat, src, e->comm, e->stream); e->halo_bytes_last_frame += count * 4; }
+                if (nr != ncclSuccess) { g_nccl.GroupEnd(); return fail(ST_ERR_CUDA, std::string("nccl p2p: ") + g_nccl.GetErrorString(nr)); }
+            }
+        }
+    }
+    nr = g_nccl.GroupEnd();
+    if (nr != ncclSuccess) return fail(ST_ERR_CUDA, std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(nr));
+    return ST_OK;
+}
+
 static CameraSlot* get_camera(st_engine* e, st_camera_handle h) { return (h >= 0 && (size_t)h < e->cameras.size() && e->cameras[h]->alive) ? e->cameras[h] : nullptr; }
 
 }  // namespace st
@@ -611,6 +730,7 @@ static CameraSlot* get_camera(st_engine* e, st_camera_handle h) { return (h >= 0
 // =================================================================================================
 extern "C" {
 
+int st_copy_output(st_engine* e, st_camera_handle h, void* host_out, int format);
 const char* st_last_error(void) { return g_err.c_str(); }
 const char* st_pass_name(int pass) { return (pass >= 0 && pass < P_COUNT) ? kPassNames[pass] : ""; }
 
@@ -624,7 +744,7 @@ int st_engine_create(int device, st_engine** out) {
     st_engine* e = new st_engine();
     e->device = device;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    std::memset(&e->world, 0, sizeof e->world);
+    std::memset(&e->n_ranks, 0, sizeof e->n_ranks);
     e->h_lights.push_back(make_sun(make_float4(0, 0, 0, 25.0f), make_float4(0, 0, 0, std::numeric_limits<float>::infinity())));   // Lights::new (lights.rs:33-50)
     e->light_slots.push_back({st_engine::kSun, 0u});
     int rc = e->d_noise.ensure(256 * 256 * 4); if (rc) { delete e; return rc; }
@@ -642,6 +762,7 @@ void st_engine_destroy(st_engine* e) {
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
+    if (e->comm) g_nccl.CommDestroy(e->comm);
     if (e->own_stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -920,7 +1041,6 @@ int st_render_range(st_engine* e, st_camera_handle h, int first, int last) {
     CK(cudaGetLastError());
     return ST_OK;
 }
-int st_copy_output(st_engine* e, st_camera_handle h, void* host_out, int format);
 int st_render_camera(st_engine* e, st_camera_handle h, void* host_out, int format) {
     int rc = st_render_range(e, h, 0, -1); if (rc) return rc;
     if (host_out) return st_copy_output(e, h, host_out, format);
@@ -973,7 +1093,7 @@ int st_read_scene(st_engine* e, const char* name, float* dst, size_t cap, size_t
     CK(cudaSetDevice(e->device));
     std::string s(name);
     const void* dev = nullptr; size_t n = 0;
-    if (s == "world") { *count = 4; if (dst) std::memcpy(dst, &e->world, 4 * std::min<size_t>(cap, 4)); return ST_OK; }
+    if (s == "world") { *count = 4; if (dst) std::memcpy(dst, &e->n_ranks, 4 * std::min<size_t>(cap, 4)); return ST_OK; }
     if (s == "triangles") { dev = e->d_triangles.p; n = e->h_triangles.size() * 4; }
     else if (s == "bvh") { dev = e->d_bvh.p; n = e->bvh_out.buf.size() * 4; }
     else if (s == "materials") { dev = e->d_materials.p; n = e->h_materials.size() * 28; }
@@ -1062,6 +1182,84 @@ int st_ray_count(st_engine* e, uint64_t* rays, int reset) {
     CK(cudaDeviceSynchronize());
     return ST_OK;
 }
+int st_nccl_unique_id(uint8_t* out128) {
+    if (!out128) return fail(ST_ERR_INVALID, "null argument");
+    { std::string err; if (!g_nccl.load(&err)) return fail(ST_ERR_CUDA, err); }
+    ncclUniqueId id; ncclResult_t r = g_nccl.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(ST_ERR_CUDA, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    std::memcpy(out128, &id, 128);
+    return ST_OK;
+}
+int st_nccl_init(st_engine* e, const uint8_t* id128, int rank, int world) {
+    if (!e || !id128 || world < 1 || rank < 0 || rank >= world) return fail(ST_ERR_INVALID, "bad argument");
+    { std::string err; if (!g_nccl.load(&err)) return fail(ST_ERR_CUDA, err); }
+    CK(cudaSetDevice(e->device));
+    ncclUniqueId id; std::memcpy(&id, id128, 128);
+    if (e->comm) { g_nccl.CommDestroy(e->comm); e->comm = nullptr; }
+    ncclResult_t r = g_nccl.CommInitRank(&e->comm, world, id, rank);
+    if (r != ncclSuccess) return fail(ST_ERR_CUDA, std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(r));
+    e->rank = rank; e->n_ranks = world;
+    return ST_OK;
+}
+int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap) {
+    if (!schedule || !out || cap == 0) return fail(ST_ERR_INVALID, "null argument");
+    std::vector<HaloExchange> plan; plan_frame(schedule, n, frame, temporal_reach, &plan);
+    std::string text;
+    for (const HaloExchange& ex : plan) for (const HaloItem& it : ex.items) text += std::to_string(ex.before_step) + ":" + it.name + ":" + std::to_string(it.reach) + ";";
+    if (text.size() + 1 > cap) return fail(ST_ERR_LIMIT, "plan text buffer too small");
+    std::memcpy(out, text.c_str(), text.size() + 1);
+    return ST_OK;
+}
+int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int format, int temporal_reach, int gather) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    if (e->n_ranks > 1 && !e->comm) return fail(ST_ERR_INVALID, "st_nccl_init first");
+    if (cs->frame == 0) return fail(ST_ERR_INVALID, "st_tick must precede rendering");
+    CK(cudaSetDevice(e->device));
+    int rc = ensure_luts(e); if (rc) return rc;
+    std::vector<std::pair<int, int>> bounds; strip_bounds((int)cs->desc.height, e->n_ranks, &bounds);
+    cs->dev.y0 = bounds[e->rank].first; cs->dev.y1 = bounds[e->rank].second;
+    std::vector<Step> steps; build_schedule(e, cs, &steps);
+    std::vector<int> ids; for (const Step& s : steps) ids.push_back(s.pass);
+    std::vector<HaloExchange> plan;
+    if (e->n_ranks > 1) plan_frame(ids.data(), (int)ids.size(), cs->frame, temporal_reach, &plan);
+    e->halo_bytes_last_frame = 0;
+    size_t next = 0;
+    for (int i = 0; i < (int)steps.size(); i++) {
+        if (next < plan.size() && plan[next].before_step == i) { if ((rc = halo_exchange(e, cs, plan[next]))) return rc; next++; }
+        e->run_timed(steps[i].pass, steps[i].run);
+    }
+    CK(cudaGetLastError());
+    if (!gather) return ST_OK;
+    // assemble the composed frame on rank 0 (strips travel in the requested output format)
+    const size_t W = cs->desc.width, n = W * cs->desc.height;
+    char* base; size_t px_bytes; ncclDataType_t dt; size_t per_px;
+    if (format == ST_FORMAT_RGBA32F) { base = (char*)cs->dev.output; px_bytes = 16; dt = ncclFloat; per_px = 4; }
+    else if (format == ST_FORMAT_RGBA8_SRGB) {
+        if ((rc = cs->rgba8.ensure(2 * n * 4))) return rc;
+        cs->rgba8_slot ^= 1;
+        SceneDev sc = e->scene(); uchar4* dst8 = (uchar4*)cs->rgba8.p + (cs->rgba8_slot ? n : 0); CameraDev cd = cs->dev;
+        e->run_timed(P_COMPOSITION, [=](cudaStream_t s) { launch_output_rgba8(cd, sc, dst8, s); });
+        base = (char*)dst8; px_bytes = 4; dt = ncclUint8; per_px = 4;
+    } else return fail(ST_ERR_INVALID, "unsupported output format");
+    if (e->n_ranks > 1) {
+        g_nccl.GroupStart();
+        for (int src = 1; src < e->n_ranks; src++) {
+            char* ptr = base + (size_t)bounds[src].first * W * px_bytes; size_t count = (size_t)(bounds[src].second - bounds[src].first) * W * per_px;
+            if (e->rank == src) g_nccl.Send(ptr, count, dt, 0, e->comm, e->stream);
+            else if (e->rank == 0) g_nccl.Recv(ptr, count, dt, src, e->comm, e->stream);
+        }
+        ncclResult_t r = g_nccl.GroupEnd();
+        if (r != ncclSuccess) return fail(ST_ERR_CUDA, std::string("output gather: ") + g_nccl.GetErrorString(r));
+    }
+    if (host_out && e->rank == 0) {
+        CK(cudaMemcpyAsync(host_out, base, n * px_bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (!e->async_output) CK(cudaStreamSynchronize(e->stream));
+    }
+    return ST_OK;
+}
+int st_halo_bytes(st_engine* e, uint64_t* bytes) { if (!e || !bytes) return fail(ST_ERR_INVALID, "null argument"); *bytes = e->halo_bytes_last_frame; return ST_OK; }
 int st_mark_begin(st_engine* e) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     CK(cudaSetDevice(e->device));

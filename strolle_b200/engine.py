@@ -77,6 +77,9 @@ def load_library():
         "st_device_math": [P, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
         "st_set_stream": [P, C.c_void_p, C.c_int], "st_set_option": [P, C.c_int, C.c_int],
         "st_count_rays": [P, C.c_int], "st_ray_count": [P, C.POINTER(C.c_uint64), C.c_int],
+        "st_nccl_unique_id": [C.c_void_p], "st_nccl_init": [P, C.c_void_p, C.c_int, C.c_int],
+        "st_plan_frame": [C.POINTER(C.c_int), C.c_int, u32, C.c_int, C.c_char_p, C.c_size_t],
+        "st_render_strips": [P, i32, P, C.c_int, C.c_int, C.c_int], "st_halo_bytes": [P, C.POINTER(C.c_uint64)],
         "st_mark_begin": [P], "st_mark_end": [P, f32p],
         "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int],
         "st_camera_set_strip": [P, i32, C.c_int, C.c_int],
@@ -317,6 +320,19 @@ class Engine:
         self._check(self.lib.st_ray_count(self._h, C.byref(n), int(reset)))
         return n.value
 
+    def nccl_init(self, id128, rank, world):
+        buf = (C.c_uint8 * 128)(*bytes(id128))
+        self._check(self.lib.st_nccl_init(self._h, buf, rank, world))
+
+    def render_strips(self, cam, out=None, fmt=FORMAT_RGBA32F, temporal_reach=16, gather=False):
+        ptr = out.ctypes.data if out is not None else None
+        self._check(self.lib.st_render_strips(self._h, cam, ptr, fmt, temporal_reach, 1 if (gather or out is not None) else 0))
+
+    def halo_bytes(self):
+        n = C.c_uint64()
+        self._check(self.lib.st_halo_bytes(self._h, C.byref(n)))
+        return n.value
+
     def mark_begin(self):
         self._check(self.lib.st_mark_begin(self._h))
 
@@ -333,3 +349,24 @@ class Engine:
         launches = np.zeros(PASS_COUNT, dtype=np.uint32)
         self._check(self.lib.st_pass_times(self._h, ms.ctypes.data, launches.ctypes.data, int(reset)))
         return ms, launches
+
+
+def nccl_unique_id():
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.st_nccl_unique_id(buf)
+    if rc != 0:
+        raise StrolleError(lib.st_last_error().decode())
+    return bytes(buf)
+
+
+def plan_frame_native(schedule, frame, temporal_reach=16):
+    """The engine's C++ exchange plan as [(before_step, name, reach), ...] (for tests against multigpu.plan_frame)."""
+    lib = load_library()
+    arr = (C.c_int * len(schedule))(*schedule)
+    out = C.create_string_buffer(8192)
+    rc = lib.st_plan_frame(arr, len(schedule), frame, temporal_reach, out, 8192)
+    if rc != 0:
+        raise StrolleError(lib.st_last_error().decode())
+    items = [x for x in out.value.decode().split(";") if x]
+    return [(int(a), b, int(c)) for a, b, c in (i.split(":") for i in items)]

@@ -136,7 +136,10 @@ class TorchDistTransport:
 class StripRunner:
     """Renders one camera on one rank of a strip-partitioned (or single-GPU) run."""
 
-    def __init__(self, engine, cam, width, height, rank=0, world=1, transport=None, temporal_reach=16):
+    def __init__(self, engine, cam, width, height, rank=0, world=1, transport=None, temporal_reach=16, native=None):
+        """`native` (default when no transport is injected): the whole frame, halo exchanges included, is enqueued
+        by one st_render_strips call over the engine's own NCCL communicator; otherwise the exchanges go through
+        `transport` (torch.distributed P2P, or an in-process emulation in tests) between st_render_range calls."""
         self.engine, self.cam, self.w, self.h, self.rank, self.world = engine, cam, width, height, rank, world
         self.bounds = strip_bounds(height, world)
         self.y0, self.y1 = self.bounds[rank]
@@ -144,11 +147,19 @@ class StripRunner:
         self.transport = transport
         self._views: Dict[str, object] = {}
         self.halo_bytes_last_frame = 0
+        self.native = False
         if world > 1:
             import torch
             engine.set_strip(cam, self.y0, self.y1)
             engine.set_stream(torch.cuda.current_stream().cuda_stream)
-            if transport is None:
+            self.native = (transport is None) if native is None else native
+            if self.native:
+                import torch.distributed as dist
+                from .engine import nccl_unique_id
+                box = [nccl_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(box, src=0)
+                engine.nccl_init(box[0], rank, world)
+            elif transport is None:
                 self.transport = TorchDistTransport(rank)
 
     def _view(self, name):
@@ -177,6 +188,10 @@ class StripRunner:
         eng, cam = self.engine, self.cam
         if self.world == 1:
             eng.render_camera(cam, out, fmt)
+            return
+        if self.native:
+            eng.render_strips(cam, out, fmt, self.temporal_reach, gather=out is not None)
+            self.halo_bytes_last_frame = eng.halo_bytes()
             return
         schedule = eng.frame_schedule(cam)
         frame = eng.frame() - 1   # tick() already advanced the engine's counter; the camera renders frame-1

@@ -98,3 +98,20 @@ def test_gloo_halo_exchange_world2(tmp_path):
     outs = [p.communicate(timeout=120)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_native_plan_matches_python_plan():
+    """The engine's C++ exchange plan (st_plan_frame, used by st_render_strips) is the same list as plan_frame."""
+    from strolle_b200.engine import plan_frame_native
+    full = ([mg.P_PRIM_GBUFFER, mg.P_FRAME_REPROJECTION, mg.P_DI_SAMPLING, mg.P_DI_TEMPORAL, mg.P_DI_SPATIAL_PICK, mg.P_DI_SPATIAL_TRACE,
+             mg.P_DI_SPATIAL_SAMPLE, mg.P_DI_RESOLVING, mg.P_GI_REPROJECTION, mg.P_GI_SAMPLING_A, mg.P_GI_SAMPLING_B, mg.P_GI_TEMPORAL,
+             mg.P_GI_SPATIAL_PICK, mg.P_GI_SPATIAL_TRACE, mg.P_GI_SPATIAL_SAMPLE, mg.P_GI_PREVIEW, mg.P_GI_PREVIEW, mg.P_GI_RESOLVING,
+             mg.P_DENOISE_REPROJECT, mg.P_DENOISE_REPROJECT, mg.P_DENOISE_VARIANCE] + [mg.P_DENOISE_WAVELET] * 5 + [mg.P_COMPOSITION])
+    gi_spatial = (mg.P_GI_SPATIAL_PICK, mg.P_GI_SPATIAL_TRACE, mg.P_GI_SPATIAL_SAMPLE)
+    schedules = [full, [p for p in full if p not in gi_spatial], [p for p in full if p not in gi_spatial + (mg.P_GI_PREVIEW,)], [mg.P_PRIM_GBUFFER, mg.P_COMPOSITION]]
+    for sched in schedules:
+        for frame in (1, 2, 6, 7):
+            for reach in (0, 16):
+                native = plan_frame_native(sched, frame, reach)
+                python = [(ex.before_step, name, r) for ex in mg.plan_frame(sched, frame, reach) for name, r in ex.buffers]
+                assert native == python

@@ -23,26 +23,46 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 W, H, FRAMES = 640, 360 * world, 9
 
 scene = scenes.cornell(W, H)
-eng = strolle_b200.Engine(device=local)
-cam = scenes.apply(eng, scene)
-runner = StripRunner(eng, cam, W, H, rank, world)
-full = None
-if rank == 0:
-    full = strolle_b200.Engine(device=local)
-    cfull = scenes.apply(full, scene)
-ok = True
-out = np.zeros((H, W, 4), dtype=np.float32)
-for f in range(FRAMES):
-    eng.tick(); runner.render(out=out, fmt=strolle_b200.engine.FORMAT_RGBA32F)
+
+
+def check_strips(native):
+    eng = strolle_b200.Engine(device=local)
+    cam = scenes.apply(eng, scene)
+    runner = StripRunner(eng, cam, W, H, rank, world, native=native)
+    full = None
     if rank == 0:
-        full.tick(); full.render_camera(cfull)
-        want = full.read_buffer(cfull, "output").reshape(H, W, 4)
-        same = (out.view(np.uint32) == want.view(np.uint32)) | (np.isnan(out) & np.isnan(want))
-        if not same.all():
-            ok = False
-            print(f"FAIL strips frame {f + 1}: {int((~same).sum())} words differ", flush=True)
-if rank == 0:
-    print(f"{'OK' if ok else 'FAIL'} strips: {world} ranks x {W}x{H // world} rows, {FRAMES} frames, gathered frame bit-identical to single GPU; halo bytes/frame rank0 = {runner.halo_bytes_last_frame}", flush=True)
+        full = strolle_b200.Engine(device=local)
+        cfull = scenes.apply(full, scene)
+    ok = True
+    out = np.zeros((H, W, 4), dtype=np.float32)
+    out8 = np.zeros((H, W, 4), dtype=np.uint8)
+    want8 = np.zeros((H, W, 4), dtype=np.uint8)
+    for f in range(FRAMES):
+        last = f == FRAMES - 1
+        eng.tick()
+        if last:
+            runner.render(out=out8, fmt=strolle_b200.engine.FORMAT_RGBA8_SRGB)
+        else:
+            runner.render(out=out, fmt=strolle_b200.engine.FORMAT_RGBA32F)
+        if rank == 0:
+            full.tick(); full.render_camera(cfull, want8 if last else None, strolle_b200.engine.FORMAT_RGBA8_SRGB)
+            if last:
+                same = out8 == want8
+            else:
+                want = full.read_buffer(cfull, "output").reshape(H, W, 4)
+                same = (out.view(np.uint32) == want.view(np.uint32)) | (np.isnan(out) & np.isnan(want))
+            if not same.all():
+                ok = False
+                print(f"FAIL strips frame {f + 1}: {int((~same).sum())} words differ", flush=True)
+    if rank == 0:
+        how = "engine-owned NCCL (st_render_strips)" if native else "torch.distributed P2P between st_render_range calls"
+        print(f"{'OK' if ok else 'FAIL'} strips via {how}: {world} ranks x {W}x{H // world} rows, {FRAMES} frames (last gathered as RGBA8), "
+              f"gathered frame bit-identical to single GPU; halo bytes/frame rank0 = {runner.halo_bytes_last_frame}", flush=True)
+    dist.barrier()
+
+
+check_strips(True)
+check_strips(False)
 
 # ---- sample-parallel reference mode ------------------------------------------------------------------
 W2, H2, TOTAL = 320, 180, 8 * world
