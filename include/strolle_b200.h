@@ -161,7 +161,7 @@ int st_trace_any(st_engine* e, const float* rays, size_t n, uint32_t* out, float
 int st_device_math(st_engine* e, int op, const float* a, const float* b, float* out, size_t n);
 /* Per-pass device time (ms, CUDA events) accumulated since the last reset; `ms`/`launches`
  * have ST_PASS_COUNT entries indexed by st_pass_name(). */
-#define ST_PASS_COUNT 26
+#define ST_PASS_COUNT 27
 int st_enable_timing(st_engine* e, int enabled);
 int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset);
 const char* st_pass_name(int pass);
@@ -169,7 +169,8 @@ const char* st_pass_name(int pass);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3 };
+/* ST_OPT_HALO_NCCL (default 0): 1 keeps NCCL send/recv for the halo rows even when peer memory is linked. */
 /* ST_OPT_ASYNC_OUTPUT (default 0): st_render_camera / st_copy_output only enqueue the device->host copy of
  * the composed frame and return; the caller keeps `host_out` (pinned) untouched until st_synchronize, and
  * alternates between two host buffers to pipeline frame N's copy with frame N+1's passes. */
@@ -193,6 +194,15 @@ int st_nccl_init(st_engine* e, const uint8_t* id128, int rank, int world);
 int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap);
 int st_render_strips(st_engine* e, st_camera_handle camera, void* host_out, int format, int temporal_reach, int gather);
 int st_halo_bytes(st_engine* e, uint64_t* bytes);
+/* Peer-memory halo transport (default once linked): every rank exports CUDA IPC handles of the camera's buffers
+ * (st_peer_export, ST_PEER_HANDLE_BYTES bytes), the host runtime all-gathers them, st_peer_import maps the other
+ * ranks' buffers.  From then on st_render_strips replaces each NCCL exchange with ONE kernel that stores this
+ * rank's boundary rows straight into the neighbours' buffers over NVLink, raises a sequence flag in every peer and
+ * waits for theirs (a device-side barrier; no host involvement).  st_peer_errors counts barrier time-outs. */
+#define ST_PEER_HANDLE_BYTES 192
+int st_peer_export(st_engine* e, st_camera_handle camera, uint8_t* out192);
+int st_peer_import(st_engine* e, st_camera_handle camera, const uint8_t* all_handles, int rank, int world);
+int st_peer_errors(st_engine* e, st_camera_handle camera, uint32_t* count);
 /* Device-side stopwatch on the engine's stream (CUDA events): st_mark_begin records, st_mark_end
  * records + waits and returns the elapsed milliseconds between the two. */
 int st_mark_begin(st_engine* e);

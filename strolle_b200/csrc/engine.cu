@@ -300,7 +300,7 @@ static const char* kPassNames[P_COUNT] = {
     "di_resolving", "gi_reprojection", "gi_sampling_a", "gi_sampling_b", "gi_temporal_resampling", "gi_spatial_resampling_pick",
     "gi_spatial_resampling_trace", "gi_spatial_resampling_sample", "gi_preview_resampling", "gi_resolving", "frame_reprojection",
     "frame_denoising_reproject", "frame_denoising_estimate_variance", "frame_denoising_wavelet", "frame_composition", "ref_tracing",
-    "ref_shading", "bvh_heatmap", "atmosphere", "trace_stream"};
+    "ref_shading", "bvh_heatmap", "atmosphere", "trace_stream", "halo_exchange"};
 
 static uint32_t dispatch_seed(uint32_t base, uint32_t frame, uint32_t k) {
     uint32_t s = base ^ (frame * 64u + k);
@@ -318,6 +318,8 @@ struct CameraSlot {
     std::vector<std::pair<std::string, size_t>> sizes;      // float4 count per named buffer
     DevMem arena;
     DevMem rgba8; int rgba8_slot = 0;
+    // peer-memory link of the strip partition: other ranks' arena / flag / rgba8 allocations mapped through CUDA IPC
+    struct PeerLink { bool ready = false; std::vector<char*> arena, rgba8; std::vector<uint32_t*> flags; DevMem sync; uint32_t seq = 0; } peer;
 };
 
 struct Step { int pass; std::function<void(cudaStream_t)> run; };
@@ -360,6 +362,7 @@ struct st_engine {
     bool count_rays = false;
     bool svgf_fast = true;   // ST_OPT_SVGF_FAST_MATH
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
+    bool halo_nccl = false;      // ST_OPT_HALO_NCCL
     bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
     std::vector<CameraSlot*> cameras;
     // timing ---------------------------------------------------------------------------------------
@@ -718,6 +721,45 @@ static int halo_exchange(st_engine* e, CameraSlot* cs, const HaloExchange& ex) {
     }
     nr = g_nccl.GroupEnd();
     if (nr != ncclSuccess) return fail(ST_ERR_CUDA, std::string("ncclGroupEnd: ") + g_nccl.GetErrorString(nr));
+    return ST_OK;
+}
+
+// the same exchange over mapped peer memory: one kernel stores my rows into every neighbour and runs the barrier
+static void peer_fill(st_engine* e, CameraSlot* cs, PeerExchange* x) {
+    uint32_t* sync = (uint32_t*)cs->peer.sync.p;   // [0..16) flags, [16] completion counter, [17] time-outs
+    x->nseg = 0; x->n_ranks = e->n_ranks; x->rank = e->rank; x->my_flags = sync; x->counter = sync + 16; x->errors = sync + 17; x->signal = 0; x->seq = 0;
+    for (int r = 0; r < ST_PEER_MAX_RANKS; r++) x->peer_flags[r] = (r < e->n_ranks && r != e->rank) ? cs->peer.flags[r] + e->rank : nullptr;
+}
+static void peer_flush(st_engine* e, CameraSlot* cs, PeerExchange* x, bool last) {
+    if (last) { x->signal = 1; x->seq = ++cs->peer.seq; }
+    PeerExchange copy = *x;
+    e->run_timed(P_HALO_EXCHANGE, [copy](cudaStream_t s) { launch_peer_exchange(copy, s); });
+    x->nseg = 0;
+}
+static int halo_exchange_peer(st_engine* e, CameraSlot* cs, const HaloExchange* ex) {   // ex == nullptr: barrier only
+    PeerExchange x; peer_fill(e, cs, &x);
+    if (ex) {
+        std::vector<std::pair<int, int>> bounds; strip_bounds((int)cs->desc.height, e->n_ranks, &bounds);
+        const int H = (int)cs->desc.height; const size_t W = cs->desc.width;
+        const int s0 = bounds[e->rank].first, s1 = bounds[e->rank].second;
+        for (const HaloItem& it : ex->items) {
+            size_t k = 0; float4* base = camera_buffer(cs, it.name, &k);
+            if (!base) return fail(ST_ERR_NOT_FOUND, "halo plan names unknown buffer " + it.name);
+            size_t arena_off = (size_t)((char*)base - (char*)cs->arena.p);
+            for (int dst = 0; dst < e->n_ranks; dst++) {
+                if (dst == e->rank) continue;
+                int a = std::max(std::max(0, bounds[dst].first - it.reach), s0), b = std::min(std::min(H, bounds[dst].second + it.reach), s1);
+                if (a >= b) continue;
+                if (x.nseg == ST_PEER_MAX_SEGMENTS) peer_flush(e, cs, &x, false);
+                size_t first = (size_t)a * W * k, count = (size_t)(b - a) * W * k;
+                x.seg[x.nseg++] = {(const uint4*)(base + first), (uint4*)(cs->peer.arena[dst] + arena_off) + first, count};
+                // incoming rows mirror what I send (same reach both ways): count them as this rank's received bytes
+                int ra = std::max(std::max(0, s0 - it.reach), bounds[dst].first), rb = std::min(std::min(H, s1 + it.reach), bounds[dst].second);
+                if (ra < rb) e->halo_bytes_last_frame += (uint64_t)(rb - ra) * W * k * 16;
+            }
+        }
+    }
+    peer_flush(e, cs, &x, true);
     return ST_OK;
 }
 
@@ -1153,6 +1195,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     if (option == ST_OPT_SVGF_FAST_MATH) { e->svgf_fast = value != 0; return ST_OK; }
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
+    if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     return fail(ST_ERR_INVALID, "unknown option");
 }
 int st_set_stream(st_engine* e, void* cuda_stream, int external) {
@@ -1202,6 +1245,46 @@ int st_nccl_init(st_engine* e, const uint8_t* id128, int rank, int world) {
     e->rank = rank; e->n_ranks = world;
     return ST_OK;
 }
+int st_peer_export(st_engine* e, st_camera_handle h, uint8_t* out192) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !out192) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    CK(cudaSetDevice(e->device));
+    size_t n = (size_t)cs->desc.width * cs->desc.height;
+    int rc = cs->rgba8.ensure(2 * n * 4); if (rc) return rc;
+    if ((rc = cs->peer.sync.ensure(256))) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
+    cudaIpcMemHandle_t hs[3];
+    CK(cudaIpcGetMemHandle(&hs[0], cs->arena.p)); CK(cudaIpcGetMemHandle(&hs[1], cs->peer.sync.p)); CK(cudaIpcGetMemHandle(&hs[2], cs->rgba8.p));
+    std::memcpy(out192, hs, ST_PEER_HANDLE_BYTES);
+    return ST_OK;
+}
+int st_peer_import(st_engine* e, st_camera_handle h, const uint8_t* all, int rank, int world) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !all) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    if (world < 1 || world > ST_PEER_MAX_RANKS || rank < 0 || rank >= world) return fail(ST_ERR_LIMIT, "peer transport supports up to 16 ranks");
+    if (!cs->peer.sync.p || !cs->rgba8.p) return fail(ST_ERR_INVALID, "st_peer_export first");
+    CK(cudaSetDevice(e->device));
+    cs->peer.arena.assign(world, nullptr); cs->peer.rgba8.assign(world, nullptr); cs->peer.flags.assign(world, nullptr);
+    for (int r = 0; r < world; r++) {
+        if (r == rank) { cs->peer.arena[r] = (char*)cs->arena.p; cs->peer.flags[r] = (uint32_t*)cs->peer.sync.p; cs->peer.rgba8[r] = (char*)cs->rgba8.p; continue; }
+        cudaIpcMemHandle_t hs[3]; std::memcpy(hs, all + (size_t)r * ST_PEER_HANDLE_BYTES, ST_PEER_HANDLE_BYTES);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, hs[0], cudaIpcMemLazyEnablePeerAccess)); cs->peer.arena[r] = (char*)p;
+        CK(cudaIpcOpenMemHandle(&p, hs[1], cudaIpcMemLazyEnablePeerAccess)); cs->peer.flags[r] = (uint32_t*)p;
+        CK(cudaIpcOpenMemHandle(&p, hs[2], cudaIpcMemLazyEnablePeerAccess)); cs->peer.rgba8[r] = (char*)p;
+    }
+    e->rank = rank; e->n_ranks = world; cs->peer.seq = 0; cs->peer.ready = true;
+    return ST_OK;
+}
+int st_peer_errors(st_engine* e, st_camera_handle h, uint32_t* count) {
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !count) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    *count = 0;
+    if (!cs->peer.sync.p) return ST_OK;
+    CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemcpy(count, (uint32_t*)cs->peer.sync.p + 17, 4, cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
 int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap) {
     if (!schedule || !out || cap == 0) return fail(ST_ERR_INVALID, "null argument");
     std::vector<HaloExchange> plan; plan_frame(schedule, n, frame, temporal_reach, &plan);
@@ -1214,7 +1297,8 @@ int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach
 int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int format, int temporal_reach, int gather) {
     CameraSlot* cs = e ? get_camera(e, h) : nullptr;
     if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
-    if (e->n_ranks > 1 && !e->comm) return fail(ST_ERR_INVALID, "st_nccl_init first");
+    const bool peer = e->n_ranks > 1 && cs->peer.ready && !e->halo_nccl;
+    if (e->n_ranks > 1 && !peer && !e->comm) return fail(ST_ERR_INVALID, "st_nccl_init or st_peer_import first");
     if (cs->frame == 0) return fail(ST_ERR_INVALID, "st_tick must precede rendering");
     CK(cudaSetDevice(e->device));
     int rc = ensure_luts(e); if (rc) return rc;
@@ -1226,8 +1310,9 @@ int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int forma
     if (e->n_ranks > 1) plan_frame(ids.data(), (int)ids.size(), cs->frame, temporal_reach, &plan);
     e->halo_bytes_last_frame = 0;
     size_t next = 0;
+    if (peer && (rc = halo_exchange_peer(e, cs, nullptr))) return rc;   // frame barrier: nobody still reads last frame's rows
     for (int i = 0; i < (int)steps.size(); i++) {
-        if (next < plan.size() && plan[next].before_step == i) { if ((rc = halo_exchange(e, cs, plan[next]))) return rc; next++; }
+        if (next < plan.size() && plan[next].before_step == i) { if ((rc = peer ? halo_exchange_peer(e, cs, &plan[next]) : halo_exchange(e, cs, plan[next]))) return rc; next++; }
         e->run_timed(steps[i].pass, steps[i].run);
     }
     CK(cudaGetLastError());
@@ -1243,7 +1328,16 @@ int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int forma
         e->run_timed(P_COMPOSITION, [=](cudaStream_t s) { launch_output_rgba8(cd, sc, dst8, s); });
         base = (char*)dst8; px_bytes = 4; dt = ncclUint8; per_px = 4;
     } else return fail(ST_ERR_INVALID, "unsupported output format");
-    if (e->n_ranks > 1) {
+    if (peer) {
+        PeerExchange x; peer_fill(e, cs, &x);
+        if (e->rank != 0) {
+            size_t first = (size_t)bounds[e->rank].first * W * px_bytes, bytes = (size_t)(bounds[e->rank].second - bounds[e->rank].first) * W * px_bytes;
+            if (first % 16 || bytes % 16) return fail(ST_ERR_INVALID, "RGBA8 strip gather needs strips that start and end on 16-byte boundaries");
+            char* remote = format == ST_FORMAT_RGBA32F ? cs->peer.arena[0] + (size_t)(base - (char*)cs->arena.p) : cs->peer.rgba8[0] + (size_t)(base - (char*)cs->rgba8.p);
+            x.seg[x.nseg++] = {(const uint4*)(base + first), (uint4*)(remote + first), bytes / 16};
+        }
+        peer_flush(e, cs, &x, true);
+    } else if (e->n_ranks > 1) {
         g_nccl.GroupStart();
         for (int src = 1; src < e->n_ranks; src++) {
             char* ptr = base + (size_t)bounds[src].first * W * px_bytes; size_t count = (size_t)(bounds[src].second - bounds[src].first) * W * per_px;

@@ -7,6 +7,7 @@
 // that a warp reads two 256-byte row segments of every float4 texture (coalesced 16-byte
 // loads); BVH nodes / triangles go through the read-only path (ld.global.nc.v4.f32) and the
 // traversal stack lives in shared memory, one conflict-free column per thread.
+#include <algorithm>
 #include <cuda_fp16.h>
 #include "st_device.cuh"
 #include "kernels.h"
@@ -1154,6 +1155,43 @@ void launch_math(int op, const float* a, const float* b, float* out, long n, cud
 void launch_material_derive(const GpuMaterial* mats, u32 n, u32* packed, cudaStream_t st) { if (n) k_material_derive<<<(n + 127) / 128, 128, 0, st>>>(mats, n, packed); }
 void launch_srgb_lut(float* lut, cudaStream_t st) { k_srgb_lut<<<1, 256, 0, st>>>(lut); }
 void launch_unpack_lut(float* lut, cudaStream_t st) { k_unpack_lut<<<1, 256, 0, st>>>(lut); }
+// ---- strips: push boundary rows into the neighbours' buffers, then barrier --------------------------------------
+// One launch per exchange point.  blockIdx.y = segment (a run of rows of one buffer for one peer), blockIdx.x strides
+// it with 16-byte stores that land in the peer's HBM through NVLink.  The last block to finish (completion counter)
+// publishes `seq` in every peer's flag array after a system-scope fence and then spins until every peer has published
+// the same `seq` here, so the next kernel on this stream sees all incoming rows.  Every exchange is a barrier over all
+// ranks, which also orders a buffer's next overwrite after its last remote read.
+__global__ void __launch_bounds__(256) k_peer_exchange(const __grid_constant__ PeerExchange x) {
+    if (x.nseg > 0) {
+        const PeerSegment& sg = x.seg[blockIdx.y];
+        const uint4* __restrict__ src = sg.src; uint4* __restrict__ dst = sg.dst;
+        for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < sg.n; i += (unsigned long long)gridDim.x * blockDim.x) dst[i] = src[i];
+    }
+    if (!x.signal) return;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    unsigned total = gridDim.x * gridDim.y;
+    if (atomicAdd(x.counter, 1u) != total - 1u) return;
+    *x.counter = 0u;
+    __threadfence_system();
+    for (int r = 0; r < x.n_ranks; r++) if (r != x.rank) *(volatile u32*)x.peer_flags[r] = x.seq;
+    long long t0 = clock64();
+    for (int r = 0; r < x.n_ranks; r++) {
+        if (r == x.rank) continue;
+        const volatile u32* f = x.my_flags + r;
+        while ((int)(*f - x.seq) < 0) {
+            if (clock64() - t0 > 20000000000ll) { atomicAdd(x.errors, 1u); break; }   // ~10 s: a peer died; do not hang the GPU
+            __nanosleep(100);
+        }
+    }
+    __threadfence_system();
+}
+void launch_peer_exchange(const PeerExchange& x, cudaStream_t st) {
+    unsigned ny = x.nseg > 0 ? (unsigned)x.nseg : 1u;
+    unsigned nx = x.nseg > 0 ? std::max(4u, std::min(64u, 1184u / ny)) : 1u;
+    k_peer_exchange<<<dim3(nx, ny), 256, 0, st>>>(x);
+}
 void launch_atm_transmittance(float4* out, cudaStream_t st) { k_atm_transmittance<<<dim3(2, 64), 128, 0, st>>>(out); }
 void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st) { k_atm_scattering<<<32, 32, 0, st>>>(tl, out); }
 void launch_atm_sky(const float4* tl, const float4* sl, float sun_altitude, float4* out, cudaStream_t st) { k_atm_sky<<<256, 256, 0, st>>>(tl, sl, sun_altitude, out); }

@@ -39,6 +39,19 @@ void launch_unpack_lut(float* lut, cudaStream_t st);
 void launch_atm_transmittance(float4* out, cudaStream_t st);
 void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st);
 void launch_atm_sky(const float4* tl, const float4* sl, float sun_altitude, float4* out, cudaStream_t st);
+
+// Halo rows over NVLink peer memory + device-side barrier (multi-GPU strips)
+#define ST_PEER_MAX_SEGMENTS 40
+#define ST_PEER_MAX_RANKS 16
+struct PeerSegment { const uint4* src; uint4* dst; unsigned long long n; };
+struct PeerExchange {
+    PeerSegment seg[ST_PEER_MAX_SEGMENTS]; int nseg;
+    u32* peer_flags[ST_PEER_MAX_RANKS];   // slot [my rank] of every peer's flag array (mapped peer memory); null for self
+    const u32* my_flags;                  // my flag array, slot [r] raised by rank r
+    u32* counter; u32* errors;            // block completion counter (self-resetting), barrier time-out count
+    int n_ranks, rank; u32 seq; int signal;
+};
+void launch_peer_exchange(const PeerExchange& x, cudaStream_t st);
 void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st);
 
 }  // namespace st

@@ -73,7 +73,7 @@ enum PassId {
     P_DI_RESOLVING = 6, P_GI_REPROJECTION = 7, P_GI_SAMPLING_A = 8, P_GI_SAMPLING_B = 9, P_GI_TEMPORAL = 10, P_GI_SPATIAL_PICK = 11,
     P_GI_SPATIAL_TRACE = 12, P_GI_SPATIAL_SAMPLE = 13, P_GI_PREVIEW = 14, P_GI_RESOLVING = 15, P_FRAME_REPROJECTION = 16,
     P_DENOISE_REPROJECT = 17, P_DENOISE_VARIANCE = 18, P_DENOISE_WAVELET = 19, P_COMPOSITION = 20, P_REF_TRACING = 21,
-    P_REF_SHADING = 22, P_BVH_HEATMAP = 23, P_ATMOSPHERE = 24, P_TRACE_STREAM = 25, P_COUNT = 26,
+    P_REF_SHADING = 22, P_BVH_HEATMAP = 23, P_ATMOSPHERE = 24, P_TRACE_STREAM = 25, P_HALO_EXCHANGE = 26, P_COUNT = 27,
     P_REF_SHADING_SEED = 32
 };
 

@@ -10,10 +10,11 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PASS_COUNT = 26
+PASS_COUNT = 27
 FORMAT_RGBA32F, FORMAT_RGBA8_SRGB = 0, 1
 OPT_SVGF_FAST_MATH = 1
 OPT_ASYNC_OUTPUT = 2
+OPT_HALO_NCCL = 3
 
 
 class StrolleError(RuntimeError):
@@ -80,6 +81,8 @@ def load_library():
         "st_nccl_unique_id": [C.c_void_p], "st_nccl_init": [P, C.c_void_p, C.c_int, C.c_int],
         "st_plan_frame": [C.POINTER(C.c_int), C.c_int, u32, C.c_int, C.c_char_p, C.c_size_t],
         "st_render_strips": [P, i32, P, C.c_int, C.c_int, C.c_int], "st_halo_bytes": [P, C.POINTER(C.c_uint64)],
+        "st_peer_export": [P, i32, C.c_void_p], "st_peer_import": [P, i32, C.c_void_p, C.c_int, C.c_int],
+        "st_peer_errors": [P, i32, C.POINTER(u32)],
         "st_mark_begin": [P], "st_mark_end": [P, f32p],
         "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int],
         "st_camera_set_strip": [P, i32, C.c_int, C.c_int],
@@ -323,6 +326,21 @@ class Engine:
     def nccl_init(self, id128, rank, world):
         buf = (C.c_uint8 * 128)(*bytes(id128))
         self._check(self.lib.st_nccl_init(self._h, buf, rank, world))
+
+    def peer_export(self, cam):
+        buf = (C.c_uint8 * 192)()
+        self._check(self.lib.st_peer_export(self._h, cam, buf))
+        return bytes(buf)
+
+    def peer_import(self, cam, handles, rank, world):
+        blob = b"".join(handles)
+        buf = (C.c_uint8 * len(blob))(*blob)
+        self._check(self.lib.st_peer_import(self._h, cam, buf, rank, world))
+
+    def peer_errors(self, cam):
+        n = u32()
+        self._check(self.lib.st_peer_errors(self._h, cam, C.byref(n)))
+        return n.value
 
     def render_strips(self, cam, out=None, fmt=FORMAT_RGBA32F, temporal_reach=16, gather=False):
         ptr = out.ctypes.data if out is not None else None

@@ -136,7 +136,7 @@ class TorchDistTransport:
 class StripRunner:
     """Renders one camera on one rank of a strip-partitioned (or single-GPU) run."""
 
-    def __init__(self, engine, cam, width, height, rank=0, world=1, transport=None, temporal_reach=16, native=None):
+    def __init__(self, engine, cam, width, height, rank=0, world=1, transport=None, temporal_reach=16, native=None, peer=True):
         """`native` (default when no transport is injected): the whole frame, halo exchanges included, is enqueued
         by one st_render_strips call over the engine's own NCCL communicator; otherwise the exchanges go through
         `transport` (torch.distributed P2P, or an in-process emulation in tests) between st_render_range calls."""
@@ -148,6 +148,7 @@ class StripRunner:
         self._views: Dict[str, object] = {}
         self.halo_bytes_last_frame = 0
         self.native = False
+        self.peer = False
         if world > 1:
             import torch
             engine.set_strip(cam, self.y0, self.y1)
@@ -159,6 +160,12 @@ class StripRunner:
                 box = [nccl_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(box, src=0)
                 engine.nccl_init(box[0], rank, world)
+                self.peer = bool(peer)
+                if self.peer:   # map every rank's camera buffers (CUDA IPC): halo rows then travel as peer stores, not NCCL
+                    handles = [None] * world
+                    dist.all_gather_object(handles, engine.peer_export(cam))
+                    engine.peer_import(cam, handles, rank, world)
+                    dist.barrier()
             elif transport is None:
                 self.transport = TorchDistTransport(rank)
 

@@ -25,10 +25,10 @@ W, H, FRAMES = 640, 360 * world, 9
 scene = scenes.cornell(W, H)
 
 
-def check_strips(native):
+def check_strips(native, peer=False):
     eng = strolle_b200.Engine(device=local)
     cam = scenes.apply(eng, scene)
-    runner = StripRunner(eng, cam, W, H, rank, world, native=native)
+    runner = StripRunner(eng, cam, W, H, rank, world, native=native, peer=peer)
     full = None
     if rank == 0:
         full = strolle_b200.Engine(device=local)
@@ -55,12 +55,16 @@ def check_strips(native):
                 ok = False
                 print(f"FAIL strips frame {f + 1}: {int((~same).sum())} words differ", flush=True)
     if rank == 0:
-        how = "engine-owned NCCL (st_render_strips)" if native else "torch.distributed P2P between st_render_range calls"
+        how = ("peer-memory stores + device barrier (st_render_strips)" if peer else "engine-owned NCCL (st_render_strips)") if native else "torch.distributed P2P between st_render_range calls"
+        if peer and eng.peer_errors(cam):
+            ok = False
+            print(f"FAIL peer barrier time-outs: {eng.peer_errors(cam)}", flush=True)
         print(f"{'OK' if ok else 'FAIL'} strips via {how}: {world} ranks x {W}x{H // world} rows, {FRAMES} frames (last gathered as RGBA8), "
               f"gathered frame bit-identical to single GPU; halo bytes/frame rank0 = {runner.halo_bytes_last_frame}", flush=True)
     dist.barrier()
 
 
+check_strips(True, peer=True)
 check_strips(True)
 check_strips(False)
 
