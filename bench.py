@@ -94,14 +94,20 @@ class ClockSampler:
 
 
 def frame_size(args):
-    """Weak scaling: every GPU owns a 1920x1080-pixel row strip.  N=1 1920x1080 (configs[1]),
-    N=2 1920x2160, N=4 3840x2160 (configs[3]'s 4K frame), N=8 3840x4320; other N stack 1080p strips."""
+    """Weak scaling: every GPU owns a row strip of ~1920x1080 pixels of ONE 16:9 frame, so the picture
+    (and with it the rays per pixel) is the same at every N: N=1 1920x1080 (configs[1]), N=2 2720x1528,
+    N=4 3840x2160 (configs[3]'s 4K frame), N=8 5440x3056.  Other N: the 16:9 frame with N x the pixels, width
+    rounded to 16 and height to 8*N."""
     n = max(args.gpus, 1)
     if n == 1:
         return args.width, args.height
-    if (args.width, args.height) == (1920, 1080) and n % 4 == 0:
-        return 3840, 1080 * n // 2
-    return args.width, args.height * n
+    table = {2: (2720, 1528), 4: (3840, 2160), 8: (5440, 3056)}
+    if (args.width, args.height) == (1920, 1080) and n in table:
+        return table[n]
+    scale = n ** 0.5
+    w = int(round(args.width * scale / 16.0)) * 16
+    h = int(round(args.height * scale / (8.0 * n))) * 8 * n
+    return w, h
 
 
 def make_scene(args):
@@ -328,7 +334,7 @@ def main():
     line = {
         "metric": METRIC, "value": mrays, "unit": "Mrays/s", "fps": fps, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "partition": f"{world} row strip(s) of {W}x{rows} px, NCCL halo exchange before gathering passes", "l2": "per-frame working set (~1.8 GB of per-camera buffers at 1080p) exceeds the 126 MB L2; no explicit flush",
+        "config": {"workload": workload_name(args), "partition": f"{world} row strip(s) of {W}x{rows} px; halo rows before gathering passes travel as peer-memory stores over NVLink + device-side barrier (engine-owned NCCL as fallback)", "l2": "per-frame working set (~1.8 GB of per-camera buffers at 1080p) exceeds the 126 MB L2; no explicit flush",
                    "seed_base": "0xC0FFEE", "timing": "value: CUDA events around K frames on the engine stream, max over ranks; per-pass events + ray counter in a second K-frame region"},
         "exact_svgf_ms_per_step": exact_ms, "svgf_math": "fast (SFU approximations for the edge-stopping weights; everything else strict IEEE) — exact_svgf_ms_per_step is the fully bit-exact configuration",
         "rays_per_frame": rays_per_frame, "wall_ms_per_step": wall_ms / args.steps, "halo_bytes_per_frame_rank0": runner.halo_bytes_last_frame,

@@ -338,7 +338,7 @@ class Engine:
         self._check(self.lib.st_peer_import(self._h, cam, buf, rank, world))
 
     def peer_errors(self, cam):
-        n = u32()
+        n = C.c_uint32()
         self._check(self.lib.st_peer_errors(self._h, cam, C.byref(n)))
         return n.value
 

@@ -33,7 +33,7 @@ def test_every_declared_symbol_is_exported(lib):
 
 def test_pass_names(lib):
     names = list(strolle_b200.PASS_NAMES)
-    assert names[0] == "prim_gbuffer" and "frame_denoising_wavelet" in names and len(names) == 26
+    assert names[0] == "prim_gbuffer" and "frame_denoising_wavelet" in names and len(names) == 27
 
 
 def test_no_cpu_fallback(lib):
