@@ -786,7 +786,7 @@ int st_engine_create(int device, st_engine** out) {
     st_engine* e = new st_engine();
     e->device = device;
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-    std::memset(&e->n_ranks, 0, sizeof e->n_ranks);
+    std::memset(&e->world, 0, sizeof e->world);
     e->h_lights.push_back(make_sun(make_float4(0, 0, 0, 25.0f), make_float4(0, 0, 0, std::numeric_limits<float>::infinity())));   // Lights::new (lights.rs:33-50)
     e->light_slots.push_back({st_engine::kSun, 0u});
     int rc = e->d_noise.ensure(256 * 256 * 4); if (rc) { delete e; return rc; }
@@ -1135,7 +1135,7 @@ int st_read_scene(st_engine* e, const char* name, float* dst, size_t cap, size_t
     CK(cudaSetDevice(e->device));
     std::string s(name);
     const void* dev = nullptr; size_t n = 0;
-    if (s == "world") { *count = 4; if (dst) std::memcpy(dst, &e->n_ranks, 4 * std::min<size_t>(cap, 4)); return ST_OK; }
+    if (s == "world") { *count = 4; if (dst) std::memcpy(dst, &e->world, 4 * std::min<size_t>(cap, 4)); return ST_OK; }
     if (s == "triangles") { dev = e->d_triangles.p; n = e->h_triangles.size() * 4; }
     else if (s == "bvh") { dev = e->d_bvh.p; n = e->bvh_out.buf.size() * 4; }
     else if (s == "materials") { dev = e->d_materials.p; n = e->h_materials.size() * 28; }

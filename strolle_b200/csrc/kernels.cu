@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_sampling(KPARAMS, int cur, u32 
     Px p = pixel_full(cam);
     if (!p.in) return;
     Rng rng = rng_make(seed, p.x, p.y);
-    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     if (!hit_some(hit)) return;
     EphRes res = ephemeral_build(rng, sc, hit);
     DiRes out = di_zero();
@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_temporal(KPARAMS, int cur, u32 
     size_t npx = (size_t)cam.w * cam.h;
     size_t lhs_idx = screen_idx(cam, p.x, p.y);
     Rng rng = rng_make(seed, p.x, p.y);
-    Hit lhs_hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    Hit lhs_hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     if (!hit_some(lhs_hit)) return;
     DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
     if (lhs.m != 0.0f) lhs.pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), lhs_hit);
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_temporal(KPARAMS, int cur, u32 
             u32 slot = fbits(rl.d3.x);
             if (slot == 0xcafebabeu) { rhs.w = 0.0f; killed = true; }
             else if (slot > 0u) rhs.light_id = slot - 1u;
-            rhs_hit = load_hit(cam.prev, cam.prim_gbuffer_d0[cur ^ 1], cam.prim_gbuffer_d1[cur ^ 1], cam, rpos.x, rpos.y);
+            rhs_hit = load_hit_lut(sc, cam.prev, cam.prim_gbuffer_d0[cur ^ 1], cam.prim_gbuffer_d1[cur ^ 1], cam, rpos.x, rpos.y);
         }
     }
     MisIn mi;
@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_pick(KPARAMS, int cur, 
     float4* buf_d0 = cam.di_diff_samples; float4* buf_d1 = cam.di_diff_curr_colors;
     const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
     u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
-    Hit lhs_hit = load_hit(cam.curr, gd0, gd1, cam, lp.x, lp.y);
+    Hit lhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, lp.x, lp.y);
     if (!hit_some(lhs_hit)) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
     DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
     DiRes rhs = di_zero();
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_pick(KPARAMS, int cur, 
         if (dot(xyz(nd), lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
         rhs_idx = screen_idx(cam, rpos.x, rpos.y);
         rhs = di_load(cam.di_reservoirs[1], rhs_idx);
-        if (rhs.m != 0.0f) { rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y); break; }
+        if (rhs.m != 0.0f) { rhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, rpos.x, rpos.y); break; }
     }
     if (rhs.m == 0.0f) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
     float lhs_rhs_pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), rhs_hit);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_resolving(KPARAMS, int cur) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t idx = screen_idx(cam, p.x, p.y);
-    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     DiRes res = di_load(cam.di_reservoirs[2], idx);
     float confidence;
     LightRad rad;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) 
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t npx = (size_t)cam.w * cam.h;
-    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     if (!hit_some(hit)) return;
     Reproj rp = reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)]);
     GiRes res = gi_zero();
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_a(KPARAMS, int cur, u3
     Ray gi_r; float gi_pdf_;
     if (tracing) {
         Rng rng = rng_make(seed, sp.x, sp.y);
-        Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
+        Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
         if (!hit_some(hit)) return;
         BrdfS s = brdf_layered_sample(hit.g, rng, -hit.dir);
         gi_r = ray_make(hit.point, s.dir);
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_b(KPARAMS, int cur, u3
     uint2 sp = tracing ? checker(g.x, g.y, frame / 2u) : checker(g.x, g.y, frame);
     if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
     size_t idx = screen_idx(cam, sp.x, sp.y);
-    Hit prim = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
+    Hit prim = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
     if (!hit_some(prim)) return;
     size_t gi = pix(cam, g.x, g.y);
     float4 d0 = cam.gi_d0[gi], d1 = cam.gi_d1[gi], d2 = cam.gi_d2[gi];
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_temporal(KPARAMS, int cur, u32 
     bool tracing = gi_tracing_frame(frame);
     size_t lhs_idx = screen_idx(cam, p.x, p.y);
     Rng rng = rng_make(seed, p.x, p.y);
-    Hit lhs_hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    Hit lhs_hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     float4* curr = cam.gi_reservoirs[1];
     if (!hit_some(lhs_hit)) { gi_store(gi_zero(), curr, lhs_idx); return; }
     bool got = tracing ? (frame % 2u == 0u && checker_at(p.x, p.y, frame / 2u)) : checker_at(p.x, p.y, frame);
@@ -443,7 +443,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_temporal(KPARAMS, int cur, u32 
         }
         if (rhs.m != 0.0f) {
             uint2 rpos = reproj_round(rp);
-            rhs_hit = load_hit(cam.prev, cam.prim_gbuffer_d0[cur ^ 1], cam.prim_gbuffer_d1[cur ^ 1], cam, rpos.x, rpos.y);
+            rhs_hit = load_hit_lut(sc, cam.prev, cam.prim_gbuffer_d0[cur ^ 1], cam.prim_gbuffer_d1[cur ^ 1], cam, rpos.x, rpos.y);
         }
     }
     GiRes main_ = gi_zero();
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_pick(KPARAMS, int cur, 
     const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
     const float4* reservoirs = cam.gi_reservoirs[1];
     u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
-    Hit lhs_hit = load_hit(cam.curr, gd0, gd1, cam, lp.x, lp.y);
+    Hit lhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, lp.x, lp.y);
     GiRes lhs = gi_load(reservoirs, lhs_idx);
     if (!hit_some(lhs_hit) || lhs.m == 0.0f) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
     GiRes rhs = gi_zero();
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_pick(KPARAMS, int cur, 
         rhs_jac = gi_jacobian(rhs, lhs_hit.point);
         if (rhs_jac < 1.0f / 10.0f || rhs_jac > 10.0f) { rhs.m = 0.0f; continue; }
         rhs_jac = rclamp(rhs_jac, 1.0f / 3.0f, 3.0f);
-        rhs_hit = load_hit(cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
+        rhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
         break;
     }
     if (rhs.m == 0.0f || !hit_some(rhs_hit)) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
@@ -562,7 +562,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_preview(KPARAMS, int cur, u32 s
     if (!p.in) return;
     size_t cidx = screen_idx(cam, p.x, p.y);
     Rng rng = rng_make(seed, p.x, p.y);
-    Hit chit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    Hit chit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     if (!hit_some(chit)) { gi_store(gi_zero(), out, cidx); return; }
     GiRes main_ = gi_zero();
     float main_pdf = 0.0f;
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_resolving(KPARAMS, int cur, con
     if (!p.in) return;
     size_t idx = screen_idx(cam, p.x, p.y);
     float4* out = cam.gi_reservoirs[0];
-    Hit hit = load_hit(cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     GiRes res = gi_load(out, idx);
     float confidence; float3 radiance;
     if (hit_some(hit)) { confidence = res.confidence; radiance = res.w * gi_cosine(res, hit) * res.radiance; }

@@ -61,7 +61,7 @@ for func, secs in per_kernel.items():
             if not r[ii].isdigit():
                 continue
             n = int(r[ii])
-            if r[2].strip():      # SASS row (has an address)
+            if r[2].strip().startswith("0x"):      # SASS row (has an address)
                 t = r[3].split()
                 op = (t[1] if t and t[0].startswith("@") else (t[0] if t else "?")).split(".")[0]
                 ops[op] += n
