@@ -169,12 +169,25 @@ const char* st_pass_name(int pass);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6 };
+/* ST_OPT_WAVELET_TILED: bit i set = à-trous iteration i (stride 2^i, K22 frame_denoising::wavelet,
+ * strolle-shaders/src/frame_denoising.rs:220-361) runs the tile-staged kernel (pixel neighbourhood brought into
+ * shared memory by TMA tensor copies) instead of the per-tap gather kernel; both produce identical bits.
+ * ST_OPT_WAVELET_TILE_CFG: 4 bits per iteration, output-tile shape (0: 32x8, 1: 32x16, 2: 64x4, 3: 64x8 pixels). */
+#define ST_WAVELET_TILED_DEFAULT 0
+#define ST_WAVELET_CFG_DEFAULT 0
+/* ST_OPT_FUSE_REPROJECT: 1 = K20 frame_denoising::reproject (frame_denoising.rs:4-78) handles the DI and the GI
+ * signal in one launch (the reference dispatches it twice, passes/frame_denoising.rs:143-160); identical results. */
+#define ST_FUSE_REPROJECT_DEFAULT 0
 /* ST_OPT_HALO_NCCL (default 0): 1 keeps NCCL send/recv for the halo rows even when peer memory is linked. */
 /* ST_OPT_ASYNC_OUTPUT (default 0): st_render_camera / st_copy_output only enqueue the device->host copy of
  * the composed frame and return; the caller keeps `host_out` (pinned) untouched until st_synchronize, and
  * alternates between two host buffers to pipeline frame N's copy with frame N+1's passes. */
 int st_set_option(st_engine* e, int option, int value);
+/* Engine statistics (development / test aid): tile-staged wavelet launches since creation, and how many of its
+ * CTAs gave up waiting for their tensor copies (must stay 0). */
+enum { ST_STAT_WAVELET_TILED_LAUNCHES = 1, ST_STAT_WAVELET_TILED_ERRORS = 2 };
+int st_get_stat(st_engine* e, int stat, uint64_t* value);
 /* external != 0: run the engine on the caller-owned CUDA stream `cuda_stream` (NULL = the legacy default
  * stream), e.g. the host runtime's stream that NCCL halo exchanges are ordered against; external == 0:
  * back to a private non-blocking stream. */

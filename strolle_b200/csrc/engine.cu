@@ -363,6 +363,10 @@ struct st_engine {
     bool svgf_fast = true;   // ST_OPT_SVGF_FAST_MATH
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
+    int wavelet_tiled = ST_WAVELET_TILED_DEFAULT;   // ST_OPT_WAVELET_TILED: bit i = à-trous iteration i (stride 2^i) runs the tile-staged (TMA) kernel
+    int wavelet_cfg = ST_WAVELET_CFG_DEFAULT;       // ST_OPT_WAVELET_TILE_CFG: 4 bits per iteration, tile shape index (kernels.cu wavelet_tiled_cfg)
+    DevMem d_tile_errors; uint64_t wavelet_tiled_launches = 0;
+    bool fuse_reproject = ST_FUSE_REPROJECT_DEFAULT != 0;   // ST_OPT_FUSE_REPROJECT
     bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
     std::vector<CameraSlot*> cameras;
     // timing ---------------------------------------------------------------------------------------
@@ -625,8 +629,12 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
         }
     }
     if (d.denoise) {   // FrameDenoisingPass::run (passes/frame_denoising.rs:143-190)
-        add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.di_diff_prev_colors, cam.di_diff_moments[cur ^ 1], cam.di_diff_samples, cam.di_diff_curr_colors, cam.di_diff_moments[cur], s); });
-        add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.gi_diff_prev_colors, cam.gi_diff_moments[cur ^ 1], cam.gi_diff_samples, cam.gi_diff_curr_colors, cam.gi_diff_moments[cur], s); });
+        if (e->fuse_reproject) {   // ST_OPT_FUSE_REPROJECT: both signals in one launch (same arithmetic, shared surface/reprojection reads)
+            add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject_pair(cam, sc, cur, s); });
+        } else {
+            add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.di_diff_prev_colors, cam.di_diff_moments[cur ^ 1], cam.di_diff_samples, cam.di_diff_curr_colors, cam.di_diff_moments[cur], s); });
+            add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.gi_diff_prev_colors, cam.gi_diff_moments[cur ^ 1], cam.gi_diff_samples, cam.gi_diff_curr_colors, cam.gi_diff_moments[cur], s); });
+        }
         const bool fast = e->svgf_fast;
         add(P_DENOISE_VARIANCE, [=](cudaStream_t s) { launch_denoise_variance(cam, sc, cur, fast, s); });
         float4* di_io[5][2] = {{cam.di_diff_stash, cam.di_diff_prev_colors}, {cam.di_diff_prev_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors},
@@ -635,7 +643,12 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
                                {cam.gi_diff_curr_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors}};
         for (uint32_t nth = 0; nth < 5; nth++) {
             float4 *a = di_io[nth][0], *b = di_io[nth][1], *c = gi_io[nth][0], *g = gi_io[nth][1];
-            add(P_DENOISE_WAVELET, [=](cudaStream_t s) { launch_denoise_wavelet(cam, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s); });
+            const bool tiled = ((e->wavelet_tiled >> nth) & 1) != 0; const int cfg = (e->wavelet_cfg >> (4 * nth)) & 15;
+            uint32_t* terr = (uint32_t*)e->d_tile_errors.p;
+            add(P_DENOISE_WAVELET, [=](cudaStream_t s) {
+                if (tiled && launch_denoise_wavelet_tiled(cam, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, cfg, terr, s)) { e->wavelet_tiled_launches++; return; }
+                launch_denoise_wavelet(cam, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s);
+            });
         }
     }
     uint32_t mode = (uint32_t)d.mode;
@@ -791,6 +804,7 @@ int st_engine_create(int device, st_engine** out) {
     e->light_slots.push_back({st_engine::kSun, 0u});
     int rc = e->d_noise.ensure(256 * 256 * 4); if (rc) { delete e; return rc; }
     rc = e->d_unpacklut.ensure(512 * 4); if (rc) { delete e; return rc; }
+    rc = e->d_tile_errors.ensure(4); if (rc) { delete e; return rc; }
     launch_unpack_lut((float*)e->d_unpacklut.p, e->stream);
     *out = e;
     return ST_OK;
@@ -800,7 +814,7 @@ void st_engine_destroy(st_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); delete c; }
-    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb, &e->d_tri_instance, &e->d_instance_xforms};
+    DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb, &e->d_tri_instance, &e->d_instance_xforms, &e->d_tile_errors};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
@@ -1196,7 +1210,21 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_SVGF_FAST_MATH) { e->svgf_fast = value != 0; return ST_OK; }
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
+    if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
+    if (option == ST_OPT_FUSE_REPROJECT) { e->fuse_reproject = value != 0; return ST_OK; }
+    if (option == ST_OPT_WAVELET_TILE_CFG) { e->wavelet_cfg = value & 0xfffff; return ST_OK; }
     return fail(ST_ERR_INVALID, "unknown option");
+}
+int st_get_stat(st_engine* e, int stat, uint64_t* value) {
+    if (!e || !value) return fail(ST_ERR_INVALID, "null argument");
+    if (stat == ST_STAT_WAVELET_TILED_LAUNCHES) { *value = e->wavelet_tiled_launches; return ST_OK; }
+    if (stat == ST_STAT_WAVELET_TILED_ERRORS) {
+        CK(cudaSetDevice(e->device));
+        CK(cudaStreamSynchronize(e->stream));
+        uint32_t v = 0; CK(cudaMemcpy(&v, e->d_tile_errors.p, 4, cudaMemcpyDeviceToHost));
+        *value = v; return ST_OK;
+    }
+    return fail(ST_ERR_INVALID, "unknown statistic");
 }
 int st_set_stream(st_engine* e, void* cuda_stream, int external) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");

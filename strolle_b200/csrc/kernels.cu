@@ -9,6 +9,10 @@
 // traversal stack lives in shared memory, one conflict-free column per thread.
 #include <algorithm>
 #include <cuda_fp16.h>
+#include <cuda.h>   // CUtensorMap (type only; the encoder is reached through cudaGetDriverEntryPoint)
+#include <map>
+#include <mutex>
+#include <tuple>
 #include "st_device.cuh"
 #include "kernels.h"
 
@@ -639,6 +643,35 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject(KPARAMS, int cur
     moments[i] = f4(moment, 0.0f);
 }
 
+// K20 for the DI and the GI signal in one launch: the surface depth and the reprojection entry are read once
+// (192 instead of 2 x 112 B/px); per signal exactly the arithmetic of k_denoise_reproject.
+struct ReprojectSignal { const float4* prev_colors; const float4* prev_moments; const float4* samples; float4* colors; float4* moments; };
+ST_DEV void denoise_reproject_signal(const CameraDev& cam, size_t i, float4 sample, const Reproj& rp, bool has_rp, const ReprojectSignal& g) {
+    float sl = luma(xyz(sample));
+    float3 color, moment;
+    if (has_rp && sample.w > 0.0f) {
+        float4 pc = history_fetch(rp, g.prev_colors, cam.w, cam.h);
+        float4 pm = history_fetch(rp, g.prev_moments, cam.w, cam.h);
+        float hist = rmin(pm.x + 1.0f, 16.0f);
+        float alpha = 1.0f / hist;
+        color = lerpc(xyz(pc), xyz(sample), alpha);
+        moment = f3(hist, lerpc(pm.y, sl, alpha), lerpc(pm.z, sl * sl, alpha));
+    } else { color = xyz(sample); moment = f3(1.0f, sl, sl * sl); }
+    g.colors[i] = f4(color, 0.0f);
+    g.moments[i] = f4(moment, 0.0f);
+}
+__global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject_pair(KPARAMS, int cur, const __grid_constant__ ReprojectSignal di, const __grid_constant__ ReprojectSignal gi) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    float4 sd = di.samples[i], sg = gi.samples[i];
+    if (cam.prim_surface_map[cur][i].z == 0.0f) { di.colors[i] = sd; gi.colors[i] = sg; return; }
+    Reproj rp = reproj_decode(cam.reprojection_map[i]);
+    bool has_rp = reproj_some(rp);
+    denoise_reproject_signal(cam, i, sd, rp, has_rp, di);
+    denoise_reproject_signal(cam, i, sg, rp, has_rp, gi);
+}
+
 // frame_denoising::sample_weight (frame_denoising.rs:363-392), split into the part that is common to
 // the DI and GI signals (depth ramp, normal^64) and the per-signal luminance term:
 //   weight = exp(-|sqrt(lc) - sqrt(ls)| * luma_sigma) * depth_weight * normal_weight
@@ -762,6 +795,127 @@ __global__ void __launch_bounds__(ST_BLOCK, ST_WAVELET_MIN_BLOCKS) k_denoise_wav
             float dnw = dw * nw;
             float4 sdi = di_in[si];
             float4 sgi = gi_in[si];
+            if (FAST) {
+                float wd = svgf_luma_weight<true>(scdl, sv_luma<true>(xyz(sdi)), ls_di) * dnw;
+                if (wd > 0.0f) { sdw += wd; sdc = f3(__fmaf_rn(wd, sdi.x, sdc.x), __fmaf_rn(wd, sdi.y, sdc.y), __fmaf_rn(wd, sdi.z, sdc.z)); sdv = __fmaf_rn(wd * wd, sdi.w, sdv); }
+                float wg = svgf_luma_weight<true>(scgl, sv_luma<true>(xyz(sgi)), ls_gi) * dnw;
+                if (wg > 0.0f) { sgw += wg; sgc = f3(__fmaf_rn(wg, sgi.x, sgc.x), __fmaf_rn(wg, sgi.y, sgc.y), __fmaf_rn(wg, sgi.z, sgc.z)); sgv = __fmaf_rn(wg * wg, sgi.w, sgv); }
+            } else {
+                float wd = svgf_luma_weight<false>(scdl, luma(xyz(sdi)), ls_di) * dw * nw;
+                if (wd > 0.0f) { sdw += wd; sdc = sdc + wd * xyz(sdi); sdv += sq(wd) * sdi.w; }
+                float wg = svgf_luma_weight<false>(scgl, luma(xyz(sgi)), ls_gi) * dw * nw;
+                if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
+            }
+        }
+    }
+    if (FAST) {
+        float rd = sfu_rcp(sdw), rg = sfu_rcp(sgw);
+        di_out[i] = f4(sdc * rd, sdv * (rd * rd));
+        gi_out[i] = f4(sgc * rg, sgv * (rg * rg));
+    } else {
+        di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
+        gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K22, tile-staged variant: the (TW+2·HL) x (TH+2·HL) pixel neighbourhood of a TW x TH output tile is
+// brought into shared memory by three TMA tensor copies (surface_nd, DI colours, GI colours; one elected
+// thread, one mbarrier), out-of-frame texels arrive as zeros (= the reference's `contains` test, because a
+// zero depth skips the tap), and the 3x3 à-trous taps become LDS.128 at compile-time offsets.  HL = S + J,
+// J = the largest |jitter| the blue-noise term can produce for stride S (0 for S <= 4, 1 for 8, 3 for 16).
+// Same taps, same order, same arithmetic as k_denoise_wavelet: the two kernels are bit-identical in both
+// arithmetic flavours (tests/test_gpu_parity.py::test_tiled_wavelet_matches_gather).
+// ---------------------------------------------------------------------------------------------
+ST_DEV u32 smem_addr(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+ST_DEV void mbar_init(u32 bar, u32 count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+ST_DEV void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+ST_DEV void mbar_expect_tx(u32 bar, u32 bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory"); }
+ST_DEV bool mbar_try_wait(u32 bar, u32 parity) {
+    u32 ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+ST_DEV void tma_load_2d(u32 dst, const CUtensorMap* tm, int c0, int c1, u32 bar) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+
+template <int S, int J, int TW, int TH> struct WaveletTile {
+    static constexpr int HL = S + J, BW = TW + 2 * HL, BH = TH + 2 * HL;
+    static constexpr u32 BOX_BYTES = (u32)(BW * BH * 16);
+    static constexpr u32 PLANE = (BOX_BYTES + 127u) & ~127u;
+    static constexpr u32 SMEM = 3u * PLANE + 128u;   // + slack to align the first plane to 128 B
+};
+
+template <bool FAST, int S, int J, int TW, int TH>
+__global__ void __launch_bounds__(TW * TH) k_denoise_wavelet_tiled(KPARAMS, u32 frame, float strength,
+                                                                   const __grid_constant__ CUtensorMap tm_nd, const __grid_constant__ CUtensorMap tm_di,
+                                                                   const __grid_constant__ CUtensorMap tm_gi,
+                                                                   float4* __restrict__ di_out, float4* __restrict__ gi_out, u32* __restrict__ errors) {
+    typedef WaveletTile<S, J, TW, TH> T;
+    extern __shared__ unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int tx = (int)threadIdx.x % TW, ty = (int)threadIdx.x / TW;
+    const int x0 = (int)blockIdx.x * TW, y0 = cam.y0 + (int)blockIdx.y * TH;
+    const u32 bar = smem_addr(&s_bar);
+    const u32 raw = smem_addr(s_raw);
+    const u32 base = (raw + 127u) & ~127u;
+    if (threadIdx.x == 0) { mbar_init(bar, 1u); mbar_fence_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, 3u * T::BOX_BYTES);
+        tma_load_2d(base, &tm_nd, (x0 - T::HL) * 2, y0 - T::HL, bar);   // x in 8-byte elements (see wavelet_tensor_map)
+        tma_load_2d(base + T::PLANE, &tm_di, (x0 - T::HL) * 2, y0 - T::HL, bar);   // x in 8-byte elements (see wavelet_tensor_map)
+        tma_load_2d(base + 2u * T::PLANE, &tm_gi, (x0 - T::HL) * 2, y0 - T::HL, bar);   // x in 8-byte elements (see wavelet_tensor_map)
+    }
+    const u32 px = (u32)(x0 + tx), py = (u32)(y0 + ty);
+    const bool in = px < (u32)cam.w && py < (u32)cam.y1;
+    int jo = 0;
+    if (J > 0 && in) {   // the jitter only needs the blue-noise texel: fetched while the tile is in flight
+        float4 bn = blue_noise(sc, px, py, frame);
+        float2 jf = (f2(bn.z, bn.w) - f2(0.5f, 0.5f)) * ((float)S - 1.0f) * 0.5f;
+        jo = to_i32_sat(jf.y) * T::BW + to_i32_sat(jf.x);
+    }
+    {   // every thread waits (the CTA's shared memory must stay allocated until the copies have landed)
+        bool done = false;
+        for (u32 spin = 0; spin < (1u << 20) && !done; spin++) done = mbar_try_wait(bar, 0u);
+        if (!done) { if (threadIdx.x == 0) atomicAdd(errors, 1u); return; }
+    }
+    if (!in) return;
+    const float4* __restrict__ t_nd = reinterpret_cast<const float4*>(s_raw + (base - raw));
+    const float4* __restrict__ t_di = reinterpret_cast<const float4*>(s_raw + (base - raw) + T::PLANE);
+    const float4* __restrict__ t_gi = reinterpret_cast<const float4*>(s_raw + (base - raw) + 2u * T::PLANE);
+    const int c = (ty + T::HL) * T::BW + (tx + T::HL);
+    const size_t i = pix(cam, px, py);
+    float4 cnd = t_nd[c];
+    float4 cdi = t_di[c];
+    float3 cdc = xyz(cdi); float cdv = cdi.w;
+    if (cnd.w == 0.0f) { di_out[i] = f4(cdc, cdv); return; }
+    float4 cgi = t_gi[c];
+    float3 cgc = xyz(cgi); float cgv = cgi.w;
+    float3 cn = xyz(cnd);
+    float scdl = sv_sqrt<FAST>(sv_luma<FAST>(cdc)), scgl = sv_sqrt<FAST>(sv_luma<FAST>(cgc));
+    float ls_di = lerpc(2.5f, 0.5f, sv_sqrt<FAST>(cdv));
+    float ls_gi = lerpc(1.0f, 0.0f, sv_sqrt<FAST>(cgv));
+    float depth_sigma = 0.33f / strength;
+    float sdw = 1.0f; float3 sdc = cdc; float sdv = cdv;
+    float sgw = 1.0f; float3 sgc = cgc; float sgv = cgv;
+    const int cj = c + jo;
+#pragma unroll
+    for (int oy = -1; oy <= 1; oy++) {
+#pragma unroll
+        for (int ox = -1; ox <= 1; ox++) {
+            if (ox == 0 && oy == 0) continue;
+            const int k = cj + oy * S * T::BW + ox * S;
+            float4 nds = t_nd[k];
+            if (nds.w == 0.0f) continue;   // sky, or outside the frame (zero-filled by the tensor copy)
+            float dw = svgf_depth_weight<FAST>(cnd.w, nds.w, depth_sigma);
+            float nw = svgf_normal_weight<FAST>(cn, xyz(nds));
+            if (dw == 0.0f || nw == 0.0f) continue;
+            float dnw = dw * nw;
+            float4 sdi = t_di[k];
+            float4 sgi = t_gi[k];
             if (FAST) {
                 float wd = svgf_luma_weight<true>(scdl, sv_luma<true>(xyz(sdi)), ls_di) * dnw;
                 if (wd > 0.0f) { sdw += wd; sdc = f3(__fmaf_rn(wd, sdi.x, sdc.x), __fmaf_rn(wd, sdi.y, sdc.y), __fmaf_rn(wd, sdi.z, sdc.z)); sdv = __fmaf_rn(wd * wd, sdi.w, sdv); }
@@ -1137,12 +1291,95 @@ void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u
 void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out); }
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
 void launch_denoise_reproject(const CameraDev& c, const SceneDev& s, int cur, const float4* pc, const float4* pm, const float4* smp, float4* col, float4* mom, cudaStream_t st) { k_denoise_reproject<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, pc, pm, smp, col, mom); }
+void launch_denoise_reproject_pair(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) {
+    ReprojectSignal di{c.di_diff_prev_colors, c.di_diff_moments[cur ^ 1], c.di_diff_samples, c.di_diff_curr_colors, c.di_diff_moments[cur]};
+    ReprojectSignal gi{c.gi_diff_prev_colors, c.gi_diff_moments[cur ^ 1], c.gi_diff_samples, c.gi_diff_curr_colors, c.gi_diff_moments[cur]};
+    k_denoise_reproject_pair<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, di, gi);
+}
 void launch_denoise_variance(const CameraDev& c, const SceneDev& s, int cur, bool fast, cudaStream_t st) {
     if (fast) k_denoise_variance<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); else k_denoise_variance<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur);
 }
 void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, bool fast, cudaStream_t st) {
     if (fast) k_denoise_wavelet<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
     else k_denoise_wavelet<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
+}
+// ---- tile-staged K22: tensor maps + launcher --------------------------------------------------
+// A float4 image plane as a 2-D tensor of 8-byte elements (2W x H; the widest element type a tensor map
+// takes, so that a (TW+2·HL)-pixel box row stays under the 256-element box limit), row pitch W·16 B, no
+// swizzle / interleave, zero fill outside the frame.  Maps are cached per (plane, frame size, box).
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TensorMapEncodeFn tensor_map_encoder() {
+    static TensorMapEncodeFn fn = [] {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        return (TensorMapEncodeFn)p;
+    }();
+    return fn;
+}
+static bool wavelet_tensor_map(const float4* plane, int w, int h, int bw, int bh, CUtensorMap* out) {
+    typedef std::tuple<const void*, int, int, int, int> Key;
+    static std::map<Key, CUtensorMap> cache; static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    Key key(plane, w, h, bw, bh);
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
+    TensorMapEncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)w * 2u, (cuuint64_t)h};
+    cuuint64_t strides[1] = {(cuuint64_t)w * 16u};
+    cuuint32_t box[2] = {(cuuint32_t)bw * 2u, (cuuint32_t)bh};
+    cuuint32_t estr[2] = {1u, 1u};
+    CUtensorMap tm;
+    if (enc(&tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 2, const_cast<float4*>(plane), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = tm; *out = tm;
+    return true;
+}
+template <bool FAST, int S, int J, int TW, int TH>
+static bool wavelet_tiled_go(const CameraDev& c, const SceneDev& s, u32 frame, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out,
+                             u32* errors, cudaStream_t st) {
+    typedef WaveletTile<S, J, TW, TH> T;
+    if (T::BW * 2 > 256 || T::BH > 256) return false;
+    CUtensorMap tn, td, tg;
+    if (!wavelet_tensor_map(c.surface_nd, c.w, c.h, T::BW, T::BH, &tn) || !wavelet_tensor_map(di_in, c.w, c.h, T::BW, T::BH, &td) ||
+        !wavelet_tensor_map(gi_in, c.w, c.h, T::BW, T::BH, &tg)) return false;
+    auto kern = k_denoise_wavelet_tiled<FAST, S, J, TW, TH>;
+    static bool attr_set[64] = {};   // per instantiation and device
+    int dev = 0; cudaGetDevice(&dev); dev &= 63;
+    if (!attr_set[dev]) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM) != cudaSuccess) { cudaGetLastError(); return false; } attr_set[dev] = true; }
+    dim3 grid((c.w + TW - 1) / TW, (c.y1 - c.y0 + TH - 1) / TH);
+    kern<<<grid, TW * TH, T::SMEM, st>>>(c, s, frame, strength, tn, td, tg, di_out, gi_out, errors);
+    return true;
+}
+template <bool FAST, int S, int J>
+static bool wavelet_tiled_cfg(int cfg, const CameraDev& c, const SceneDev& s, u32 frame, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out,
+                              u32* errors, cudaStream_t st) {
+    switch (cfg) {
+    case 0: return wavelet_tiled_go<FAST, S, J, 32, 8>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
+    case 1: return wavelet_tiled_go<FAST, S, J, 32, 16>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
+    case 2: return wavelet_tiled_go<FAST, S, J, 64, 4>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
+    case 3: return wavelet_tiled_go<FAST, S, J, 64, 8>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
+    default: return false;
+    }
+}
+// Returns false when the tile-staged kernel cannot be used for this launch (the caller then runs the gather kernel):
+// the camera's screen is not the buffer size, no tensor-map encoder, or an unknown configuration.
+bool launch_denoise_wavelet_tiled(const CameraDev& c, const SceneDev& s, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in,
+                                  float4* gi_out, bool fast, int cfg, u32* errors, cudaStream_t st) {
+    if (c.curr.screen.x != (float)c.w || c.curr.screen.y != (float)c.h) return false;   // zero fill == Camera::contains only then
+#define ST_WT(S_, J_) (fast ? wavelet_tiled_cfg<true, S_, J_>(cfg, c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st) \
+                            : wavelet_tiled_cfg<false, S_, J_>(cfg, c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st))
+    switch (stride) {
+    case 1: return ST_WT(1, 0);
+    case 2: return ST_WT(2, 0);
+    case 4: return ST_WT(4, 0);
+    case 8: return ST_WT(8, 1);
+    case 16: return ST_WT(16, 3);
+    default: return false;
+    }
+#undef ST_WT
 }
 void launch_composition(const CameraDev& c, const SceneDev& s, int cur, u32 mode, const float4* di_diff, const float4* gi_diff, cudaStream_t st) { k_composition<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, mode, di_diff, gi_diff); }
 void launch_output_rgba8(const CameraDev& c, const SceneDev& s, uchar4* out, cudaStream_t st) { k_output_rgba8<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, out); }

@@ -15,6 +15,11 @@ FORMAT_RGBA32F, FORMAT_RGBA8_SRGB = 0, 1
 OPT_SVGF_FAST_MATH = 1
 OPT_ASYNC_OUTPUT = 2
 OPT_HALO_NCCL = 3
+OPT_WAVELET_TILED = 4      # bit i = à-trous iteration i runs the tile-staged (TMA) kernel
+OPT_WAVELET_TILE_CFG = 5   # 4 bits per iteration: 0 32x8, 1 32x16, 2 64x4, 3 64x8 output tile
+OPT_FUSE_REPROJECT = 6     # K20 for DI and GI in one launch
+STAT_WAVELET_TILED_LAUNCHES = 1
+STAT_WAVELET_TILED_ERRORS = 2
 
 
 class StrolleError(RuntimeError):
@@ -76,7 +81,7 @@ def load_library():
         "st_bvh_depth": [P, C.POINTER(C.c_int)],
         "st_trace_closest": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p], "st_trace_any": [P, C.c_void_p, C.c_size_t, C.c_void_p, f32p],
         "st_device_math": [P, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t],
-        "st_set_stream": [P, C.c_void_p, C.c_int], "st_set_option": [P, C.c_int, C.c_int],
+        "st_set_stream": [P, C.c_void_p, C.c_int], "st_set_option": [P, C.c_int, C.c_int], "st_get_stat": [P, C.c_int, C.POINTER(C.c_uint64)],
         "st_count_rays": [P, C.c_int], "st_ray_count": [P, C.POINTER(C.c_uint64), C.c_int],
         "st_nccl_unique_id": [C.c_void_p], "st_nccl_init": [P, C.c_void_p, C.c_int, C.c_int],
         "st_plan_frame": [C.POINTER(C.c_int), C.c_int, u32, C.c_int, C.c_char_p, C.c_size_t],
@@ -310,6 +315,11 @@ class Engine:
 
     def set_option(self, option, value):
         self._check(self.lib.st_set_option(self._h, option, int(value)))
+
+    def get_stat(self, stat):
+        v = C.c_uint64(0)
+        self._check(self.lib.st_get_stat(self._h, int(stat), C.byref(v)))
+        return int(v.value)
 
     def set_stream(self, cuda_stream_ptr, external=True):
         """Runs the engine on a caller-owned stream (handle 0/None = the legacy default stream)."""

@@ -192,20 +192,23 @@ class _LocalTransport:
         torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("world,size", [(2, (160, 96)), (4, (128, 160))])
-def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size):
+@pytest.mark.parametrize("world,size,tiled", [(2, (160, 96), 0), (4, (128, 160), 0), (2, (160, 96), 31), (3, (200, 150), 31)])
+def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size, tiled):
     """Strip-partitioned rendering (SURVEY §8e, config C4's shape) is bit-identical to the single-GPU frame:
     `world` engines each compute one row strip and exchange halo rows according to multigpu.plan_frame."""
     import torch
     from strolle_b200 import multigpu as mg
     w, h = size
     scene = scenes.cornell(w, h)
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_FUSE_REPROJECT
     ref = gpu.Engine(blue_noise=blue_noise)   # default (fast SVGF weights): strips must match it bit for bit too
+    ref.set_option(OPT_WAVELET_TILED, 0); ref.set_option(OPT_FUSE_REPROJECT, 0)   # the full frame runs the plain kernels ...
     cref = scenes.apply(ref, scene)
     engines, cams, runners = [], [], []
     lt = _LocalTransport()
     for r in range(world):
         e = gpu.Engine(blue_noise=blue_noise)
+        e.set_option(OPT_WAVELET_TILED, tiled); e.set_option(OPT_FUSE_REPROJECT, 1 if tiled else 0)   # ... the strips also the tile-staged K22 / fused K20
         c = scenes.apply(e, scene)
         rn = mg.StripRunner(e, c, w, h, rank=0, world=1)   # built as single, then configured as a strip by hand
         rn.rank, rn.world = r, world
@@ -338,3 +341,59 @@ def test_moving_instance_rebuilds_bvh_and_velocity(gpu, oracle, blue_noise):
             assert ok, f"moving instance frame {f + 1} {name}: {msg}"
     vel = eo.read_buffer(co, "velocity_map").reshape(-1, 4)
     assert (vel[:, :2] != 0).any(), "the moved box still reports a velocity (stale prev_transform, as in the reference)"
+
+
+DENOISER_BUFFERS = ["di_diff_prev_colors", "di_diff_curr_colors", "di_diff_stash", "di_diff_moments_a", "di_diff_moments_b",
+                    "gi_diff_prev_colors", "gi_diff_curr_colors", "gi_diff_stash", "gi_diff_moments_a", "gi_diff_moments_b", "output"]
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+@pytest.mark.parametrize("exact", [True, False])
+def test_tiled_wavelet_matches_gather(gpu, blue_noise, cfg, exact):
+    """K22 staged through shared memory by TMA tensor copies (all five strides, every tile shape) produces the same
+    bits as the per-tap gather kernel, in the strict-IEEE and in the fast-SVGF flavour, on frame sizes that are
+    not multiples of the tile (zero-filled borders) and smaller than the largest stride's reach."""
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_WAVELET_TILE_CFG, STAT_WAVELET_TILED_LAUNCHES, STAT_WAVELET_TILED_ERRORS
+    for size in [(200, 120), (67, 45)]:
+        scene = scenes.cornell(*size)
+        ea, eb = gpu.Engine(blue_noise=blue_noise, exact=exact), gpu.Engine(blue_noise=blue_noise, exact=exact)
+        ea.set_option(OPT_WAVELET_TILED, 0)
+        eb.set_option(OPT_WAVELET_TILED, 31); eb.set_option(OPT_WAVELET_TILE_CFG, cfg * 0x11111)
+        ca, cb = scenes.apply(ea, scene), scenes.apply(eb, scene)
+        for f in range(4):
+            ea.tick(); eb.tick(); ea.render_camera(ca); eb.render_camera(cb)
+            for name in DENOISER_BUFFERS:
+                assert_bits_equal(eb.read_buffer(cb, name), ea.read_buffer(ca, name), f"{size} cfg {cfg} frame {f + 1} {name}")
+        assert ea.get_stat(STAT_WAVELET_TILED_LAUNCHES) == 0
+        assert eb.get_stat(STAT_WAVELET_TILED_LAUNCHES) == 20, "the tile-staged kernel must be the one that ran"
+        assert eb.get_stat(STAT_WAVELET_TILED_ERRORS) == 0
+
+
+def test_tiled_wavelet_against_oracle(gpu, oracle, blue_noise):
+    """The tile-staged K22 (mixed tile shapes) against the CPU oracle: bit-exact in strict mode."""
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_WAVELET_TILE_CFG
+    for scene in (scenes.cornell(160, 96), scenes.dungeon(131, 77, cells=6)):
+        eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
+        eg.set_option(OPT_WAVELET_TILED, 31); eg.set_option(OPT_WAVELET_TILE_CFG, 0x10310)
+        run_and_compare(eg, cg, eo, co, 3, buffers=DENOISER_BUFFERS, what="tiled wavelet")
+
+
+def test_fused_reproject_matches_two_launches(gpu, oracle, blue_noise):
+    """K20 for both signals in one launch == the reference's two dispatches, bit for bit (moving camera, so the
+    bilinear history path is exercised), and still equal to the oracle."""
+    from strolle_b200.engine import OPT_FUSE_REPROJECT
+    scene = scenes.cornell(144, 90)
+    eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
+    eg.set_option(OPT_FUSE_REPROJECT, 1)
+    e2 = gpu.Engine(blue_noise=blue_noise, exact=True); e2.set_option(OPT_FUSE_REPROJECT, 0)
+    c2 = scenes.apply(e2, scene)
+    c = scene["camera"]
+    for f in range(5):
+        t = scenes.look_at_transform((0.02 * f, 1.0 + 0.01 * f, 3.2 - 0.03 * f), (0.0, 1.0, 0.0))
+        for e, cam in ((eg, cg), (eo, co), (e2, c2)):
+            e.update_camera(cam, c["mode"], c["denoise"], c["ref_depth"], c["w"], c["h"], t, c["projection"])
+            e.tick(); e.render_camera(cam)
+        assert len(eg.frame_schedule(cg)) == len(e2.frame_schedule(c2)) - 1
+        for name in DENOISER_BUFFERS:
+            assert_bits_equal(eg.read_buffer(cg, name), e2.read_buffer(c2, name), f"fused vs split frame {f + 1} {name}")
+            assert_bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name), f"fused vs oracle frame {f + 1} {name}")
