@@ -305,6 +305,9 @@ def main():
                     "di_spatial_resampling_trace": 48, "gi_spatial_resampling_trace": 48, "gi_preview_resampling": 176, "di_temporal_resampling": 176,
                     "gi_temporal_resampling": 272, "di_resolving": 128, "gi_resolving": 256, "di_sampling": 64, "gi_reprojection": 176,
                     "frame_reprojection": 64, "frame_composition": 112}
+    frames_timed = max(1, int(round(launches[names.index("prim_gbuffer")])))
+    if launches[names.index("frame_denoising_reproject")] <= frames_timed:
+        bytes_per_px["frame_denoising_reproject"] = 192   # DI + GI in one launch (ST_OPT_FUSE_REPROJECT): surface + reprojection read once
     def roof(name):
         i = names.index(name)
         if not launches[i]:
@@ -322,7 +325,7 @@ def main():
             roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
-    extra_roof = [r for r in (roof(n) for n in ["prim_gbuffer", "di_spatial_resampling_trace", "gi_spatial_resampling_trace", "frame_denoising_estimate_variance"]) if r]
+    extra_roof = [r for r in (roof(n) for n in ["prim_gbuffer", "di_spatial_resampling_trace", "gi_spatial_resampling_trace", "frame_denoising_estimate_variance", "frame_denoising_reproject"]) if r]
 
     # ---- CPU baseline (bounded sample) -----------------------------------------------------------------
     cpu = None

@@ -169,16 +169,22 @@ const char* st_pass_name(int pass);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7 };
+/* ST_OPT_BVH_REUSE (default 1): a BVH refresh takes over the subtrees of the previous tree whose primitive-centre
+ * sequence is unchanged, as the reference does (strolle/src/bvh/builder.rs:245-275, hash = primitive.rs:27-37);
+ * 0 = every refresh builds from scratch.  Both give the same tree unless a primitive changed while its centre did
+ * not (e.g. only the instance's material): the reference keeps the old primitive in the reused leaf then (quirk C-20). */
 /* ST_OPT_WAVELET_TILED: bit i set = à-trous iteration i (stride 2^i, K22 frame_denoising::wavelet,
  * strolle-shaders/src/frame_denoising.rs:220-361) runs the tile-staged kernel (pixel neighbourhood brought into
  * shared memory by TMA tensor copies) instead of the per-tap gather kernel; both produce identical bits.
  * ST_OPT_WAVELET_TILE_CFG: 4 bits per iteration, output-tile shape (0: 32x8, 1: 32x16, 2: 64x4, 3: 64x8 pixels). */
-#define ST_WAVELET_TILED_DEFAULT 0
-#define ST_WAVELET_CFG_DEFAULT 0
+/* Defaults measured on a B200 at 1920x1080 (tools/wavelet_tune.py, profiles/r1i_wavelet_tune.txt): strides 1, 2, 4, 8
+ * tile-staged (64x4, 64x4, 32x8, 32x16 output tiles), stride 16 gathers (its jittered 3x3 footprint does not fit a tile). */
+#define ST_WAVELET_TILED_DEFAULT 15
+#define ST_WAVELET_CFG_DEFAULT 0x01022
 /* ST_OPT_FUSE_REPROJECT: 1 = K20 frame_denoising::reproject (frame_denoising.rs:4-78) handles the DI and the GI
  * signal in one launch (the reference dispatches it twice, passes/frame_denoising.rs:143-160); identical results. */
-#define ST_FUSE_REPROJECT_DEFAULT 0
+#define ST_FUSE_REPROJECT_DEFAULT 1
 /* ST_OPT_HALO_NCCL (default 0): 1 keeps NCCL send/recv for the halo rows even when peer memory is linked. */
 /* ST_OPT_ASYNC_OUTPUT (default 0): st_render_camera / st_copy_output only enqueue the device->host copy of
  * the composed frame and return; the caller keeps `host_out` (pinned) untouched until st_synchronize, and
@@ -186,8 +192,20 @@ enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3,
 int st_set_option(st_engine* e, int option, int value);
 /* Engine statistics (development / test aid): tile-staged wavelet launches since creation, and how many of its
  * CTAs gave up waiting for their tensor copies (must stay 0). */
-enum { ST_STAT_WAVELET_TILED_LAUNCHES = 1, ST_STAT_WAVELET_TILED_ERRORS = 2 };
+enum { ST_STAT_WAVELET_TILED_LAUNCHES = 1, ST_STAT_WAVELET_TILED_ERRORS = 2, ST_STAT_BVH_GRAFTED_SUBTREES = 3 };
 int st_get_stat(st_engine* e, int stat, uint64_t* value);
+/* The host-side BVH builder on its own (no device needed): binned-SAH build (strolle/src/bvh/builder.rs:17-319) + DFS
+ * serialisation (serializer.rs:20-110) over `n` primitives of 11 floats each (triangle id bits, material id bits,
+ * centre xyz, bounds min xyz, bounds max xyz; centre.x == FLT_MAX marks a dead primitive, primitive.rs:18-24).  The
+ * builder object keeps the previous tree; `reuse` != 0 grafts its unchanged subtrees (builder.rs:245-359).  `out`
+ * receives the float4 stream the GPU traverses (`*n_floats` floats); with out == NULL only the size is returned and
+ * st_bvh_builder_read copies the stream of that build afterwards. */
+typedef struct st_bvh_builder st_bvh_builder;
+int st_bvh_builder_create(st_bvh_builder** out);
+void st_bvh_builder_destroy(st_bvh_builder* b);
+int st_bvh_builder_build(st_bvh_builder* b, const float* prims11, size_t n, int reuse, float* out, size_t cap_floats, size_t* n_floats,
+                         uint32_t* grafted_subtrees, int* depth);
+int st_bvh_builder_read(st_bvh_builder* b, float* out, size_t cap_floats);
 /* external != 0: run the engine on the caller-owned CUDA stream `cuda_stream` (NULL = the legacy default
  * stream), e.g. the host runtime's stream that NCCL halo exchanges are ordered against; external == 0:
  * back to a private non-blocking stream. */

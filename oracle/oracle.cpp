@@ -202,6 +202,36 @@ void orc_allocator_script(const long* ops, int n, long* out) {
         else { size_t s, e; if (al.take((size_t)a, &s, &e)) { out[3 * i] = 1; out[3 * i + 1] = (long)s; out[3 * i + 2] = (long)e; } }
     }
 }
+// BVH builder on its own (strolle/src/bvh/builder.rs + serializer.rs): prims = n x 11 floats (triangle id bits, material id bits,
+// centre, bounds min, bounds max); the handle keeps the previous tree for subtree reuse (builder.rs:245-359).
+void* orc_bvh_builder_create() { return new BvhBuilder(); }
+void orc_bvh_builder_destroy(void* b) { delete (BvhBuilder*)b; }
+long orc_bvh_builder_build(void* bp, const float* prims11, long n, int reuse, float* out, long cap_floats, uint32_t* reused, int* depth) {
+    BvhBuilder* b = (BvhBuilder*)bp;
+    std::vector<BvhPrimitive> all((size_t)n);
+    u32 max_mat = 0;
+    for (long i = 0; i < n; i++) {
+        const float* f = prims11 + 11 * i;
+        BvhPrimitive& p = all[(size_t)i];
+        p.triangle_id = f2u(f[0]); p.material_id = f2u(f[1]); p.center = v3(f[2], f[3], f[4]);
+        p.bounds = BBox(); p.bounds.mn = v3(f[5], f[6], f[7]); p.bounds.mx = v3(f[8], f[9], f[10]);
+        max_mat = std::max(max_mat, p.material_id);
+    }
+    b->reuse = reuse != 0;
+    b->run(all);
+    for (const BvhPrimitive& p : b->prims) max_mat = std::max(max_mat, p.material_id);
+    std::vector<uint8_t> alpha((size_t)max_mat + 1, 0);
+    std::vector<V4> buf; int d = 0;
+    b->serialize(buf, alpha, 0, 1, &d);
+    if (reused) *reused = b->reused_subtrees;
+    if (depth) *depth = d;
+    long nf = (long)buf.size() * 4;
+    if (out && cap_floats >= nf) std::memcpy(out, buf.data(), (size_t)nf * 4);
+    return nf;
+}
+void orc_set_bvh_reuse(void* e, int reuse) { ((Engine*)e)->bvh.reuse = reuse != 0; }
+uint32_t orc_bvh_reused(void* e) { return ((Engine*)e)->bvh.reused_subtrees; }
+
 unsigned long long orc_ray_count(int reset) {
     unsigned long long t = 0;
     for (int i = 0; i < 256; i++) { t += g_ray_counters[i].n; if (reset) g_ray_counters[i].n = 0; }

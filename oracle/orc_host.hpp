@@ -63,13 +63,28 @@ struct Allocator {
 // BVH (strolle/src/bvh/*.rs)
 // ---------------------------------------------------------------------------
 struct BvhPrimitive { u32 triangle_id, material_id; V3 center; BBox bounds; bool alive() const { return center.x != F32_MAX; } };
-struct BvhNode { bool internal; BBox bounds; u32 start, end; u32 left_id, right_id; };
+struct BvhNode { bool internal; BBox bounds; u32 start, end; u32 left_id, right_id; uint64_t left_hash, right_hash; };
+
+// fxhash 0.2.1 (crates.io, Cargo.lock; not vendored) FxHasher on a 64-bit target, restated from its published
+// definition: hash = (hash.rotate_left(5) ^ word) * 0x517cc1b727220a95 per written word; write_u32 widens to u64.
+struct FxHasher64 {
+    uint64_t h = 0;
+    void write_u32(u32 w) { h = (((h << 5) | (h >> 59)) ^ (uint64_t)w) * 0x517cc1b727220a95ull; }
+    // impl Hash for BvhPrimitive (strolle/src/bvh/primitive.rs:27-37): ONLY the centre's bits are hashed
+    void write(const BvhPrimitive& p) { write_u32(f2u(p.center.x)); write_u32(f2u(p.center.y)); write_u32(f2u(p.center.z)); }
+};
 
 struct BvhBuilder {
     static const int BINS = 12;  // strolle/src/bvh/builder.rs:15
+    static const u32 NONE = 0xffffffffu;
     std::vector<BvhNode> nodes;
     std::vector<BvhPrimitive> prims;  // "current"
+    std::vector<BvhNode> prev_nodes;       // last refresh's tree: the "ghost" nodes of builder.rs:245-275
+    std::vector<BvhPrimitive> prev_prims;  // BvhPrimitives::previous (primitives.rs:63-65)
+    bool reuse = true;                     // false: every refresh builds from scratch (what a first build does)
+    u32 reused_subtrees = 0;
     struct Plane { int axis; float at, cost; };
+    struct Ref { u32 id, ghost; };         // BvhNodeRef (builder.rs:367-382); ghost = index into prev_nodes
 
     static float axis_of(V3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
 
@@ -122,38 +137,78 @@ struct BvhBuilder {
         *out = best;
         return have;
     }
-    // builder.rs:183-319 (first build: no ghost nodes)
-    void split(u32 node_id, const Plane& plane, u32* left, u32* right) {
-        BvhNode node = nodes[node_id];
+    // builder.rs:321-359 `copy` + `offset_primitives`: the previous subtree rooted at prev_nodes[prev_id] is taken over as it
+    // was (node bounds, split structure AND its primitives in their previous order, whatever their other fields are now).
+    u32 copy_subtree(u32 prev_id, i32 offset) {
+        BvhNode n = prev_nodes[prev_id];
+        n.start = (u32)((i32)n.start + offset); n.end = (u32)((i32)n.end + offset);
+        u32 id = (u32)nodes.size(); nodes.push_back(n);
+        if (n.internal) {
+            u32 l = copy_subtree(prev_nodes[prev_id].left_id, offset), r = copy_subtree(prev_nodes[prev_id].right_id, offset);
+            nodes[id].left_id = l; nodes[id].right_id = r;
+        }
+        return id;
+    }
+    u32 adopt(u32 prev_id, u32 new_start) {
+        const BvhNode& pn = prev_nodes[prev_id];
+        for (u32 i = pn.start; i < pn.end; i++) prims[new_start + (i - pn.start)] = prev_prims[i];   // primitives.rs:52-59
+        reused_subtrees += 1;
+        return copy_subtree(prev_id, (i32)new_start - (i32)pn.start);
+    }
+    // builder.rs:183-319
+    void split(const Ref& ref, const Plane& plane, Ref* left, Ref* right) {
+        BvhNode node = nodes[ref.id];
         BvhPrimitive* data = prims.data() + node.start;
         i32 l = 0, r = (i32)(node.end - node.start) - 1;
         BBox lb, rb;
+        FxHasher64 lh, rh;
         while (l <= r) {
             BvhPrimitive pr = data[l];
-            if (axis_of(pr.center, plane.axis) < plane.at) { l += 1; lb.add(pr.bounds); }
-            else { std::swap(data[l], data[r]); r -= 1; rb.add(pr.bounds); }
+            if (axis_of(pr.center, plane.axis) < plane.at) { l += 1; lb.add(pr.bounds); lh.write(pr); }
+            else { std::swap(data[l], data[r]); r -= 1; rb.add(pr.bounds); rh.write(pr); }
         }
         u32 pivot = node.start + (u32)l;
-        BvhNode ln; ln.internal = false; ln.bounds = lb; ln.start = node.start; ln.end = pivot; ln.left_id = ln.right_id = 0;
-        BvhNode rn; rn.internal = false; rn.bounds = rb; rn.start = pivot; rn.end = node.end; rn.left_id = rn.right_id = 0;
-        nodes.push_back(ln); *left = (u32)nodes.size() - 1;
-        nodes.push_back(rn); *right = (u32)nodes.size() - 1;
-        nodes[node_id].internal = true; nodes[node_id].left_id = *left; nodes[node_id].right_id = *right;
+        u32 left_id = NONE, right_id = NONE;
+        left->ghost = right->ghost = NONE;
+        bool left_continue = true, right_continue = true;
+        if (reuse && ref.ghost != NONE && prev_nodes[ref.ghost].internal) {
+            const BvhNode g = prev_nodes[ref.ghost];
+            if (g.left_hash == lh.h) { left_id = adopt(g.left_id, node.start); left_continue = false; } else left->ghost = g.left_id;
+            if (g.right_hash == rh.h) { right_id = adopt(g.right_id, pivot); right_continue = false; } else right->ghost = g.right_id;
+        }
+        if (left_id == NONE) {
+            BvhNode ln; ln.internal = false; ln.bounds = lb; ln.start = node.start; ln.end = pivot; ln.left_id = ln.right_id = 0; ln.left_hash = ln.right_hash = 0;
+            nodes.push_back(ln); left_id = (u32)nodes.size() - 1;
+        }
+        if (right_id == NONE) {
+            BvhNode rn; rn.internal = false; rn.bounds = rb; rn.start = pivot; rn.end = node.end; rn.left_id = rn.right_id = 0; rn.left_hash = rn.right_hash = 0;
+            nodes.push_back(rn); right_id = (u32)nodes.size() - 1;
+        }
+        nodes[ref.id].internal = true; nodes[ref.id].left_id = left_id; nodes[ref.id].right_id = right_id;
+        nodes[ref.id].left_hash = lh.h; nodes[ref.id].right_hash = rh.h;
+        left->id = left_continue ? left_id : NONE;
+        right->id = right_continue ? right_id : NONE;
     }
-    // builder.rs:17-67
+    // builder.rs:17-67 + Bvh::refresh (bvh.rs:48-70): begin_refresh, build, (serialize), end_refresh
     void run(const std::vector<BvhPrimitive>& all) {
+        prev_nodes.swap(nodes); prev_prims.swap(prims);   // what end_refresh left behind
         prims.clear();
         for (const BvhPrimitive& p : all) if (p.alive()) prims.push_back(p);   // primitives.rs:58-61
         nodes.clear();
-        BvhNode root; root.internal = false; root.bounds = BBox(); root.start = 0; root.end = (u32)prims.size(); root.left_id = root.right_id = 0;
+        reused_subtrees = 0;
+        BvhNode root; root.internal = false; root.bounds = BBox(); root.start = 0; root.end = (u32)prims.size(); root.left_id = root.right_id = 0; root.left_hash = root.right_hash = 0;
         nodes.push_back(root);
-        std::deque<u32> queue; queue.push_back(0);
+        std::deque<Ref> queue; queue.push_back(Ref{0, prev_nodes.empty() ? NONE : 0u});
         while (!queue.empty()) {
-            u32 id = queue.front(); queue.pop_front();
+            Ref ref = queue.front(); queue.pop_front();
             Plane plane;
-            if (find_splitting_plane(id, &plane)) {
-                float sah = (float)(nodes[id].end - nodes[id].start) * nodes[id].bounds.half_area();  // node.rs:36-46
-                if (plane.cost < sah) { u32 l, r; split(id, plane, &l, &r); queue.push_back(l); queue.push_back(r); }
+            if (find_splitting_plane(ref.id, &plane)) {
+                float sah = (float)(nodes[ref.id].end - nodes[ref.id].start) * nodes[ref.id].bounds.half_area();  // node.rs:36-46
+                if (plane.cost < sah) {
+                    Ref l, r; split(ref, plane, &l, &r);
+                    if (l.id != NONE) queue.push_back(l);
+                    if (r.id != NONE) queue.push_back(r);
+                }
             }
         }
     }

@@ -63,10 +63,17 @@ def _load(libm=False):
         "orc_di_reservoir_roundtrip": [_f32p, C.c_long, _f32p, _f32p],
         "orc_reprojection_roundtrip": [_f32p, C.c_uint32, _f32p, _u32p],
         "orc_allocator_script": [_i64p, C.c_int, _i64p],
+        "orc_bvh_builder_destroy": [C.c_void_p],
+        "orc_bvh_builder_build": [C.c_void_p, _f32p, C.c_long, C.c_int, C.c_void_p, C.c_long, C.POINTER(C.c_uint32), C.POINTER(C.c_int)],
+        "orc_set_bvh_reuse": [C.c_void_p, C.c_int],
     }
     for name, args in sig.items():
         getattr(lib, name).argtypes = args
     lib.orc_read_buffer.restype = C.c_long
+    lib.orc_bvh_builder_create.restype = C.c_void_p
+    lib.orc_bvh_builder_build.restype = C.c_long
+    lib.orc_bvh_reused.restype = C.c_uint32
+    lib.orc_bvh_reused.argtypes = [C.c_void_p]
     lib.orc_read_scene.restype = C.c_long
     lib.orc_u32_bytes_roundtrip.restype = C.c_uint32
     lib.orc_u32_bytes_roundtrip.argtypes = [C.c_uint32]
@@ -90,6 +97,32 @@ def lib(libm=False):
 
 def _f(a):
     return np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1))
+
+
+class OracleBvhBuilder:
+    """strolle/src/bvh/builder.rs + serializer.rs on their own; same interface as strolle_b200.engine.BvhBuilder."""
+
+    def __init__(self, libm=False):
+        self.lib = lib(libm)
+        self._h = C.c_void_p(self.lib.orc_bvh_builder_create())
+        self.grafted = 0
+        self.depth = 0
+
+    def build(self, prims, reuse=True):
+        prims = np.ascontiguousarray(prims, dtype=np.float32).reshape(-1, 11)
+        g = C.c_uint32(0); d = C.c_int(0)
+        cap = max(16, prims.shape[0] * 4 * 4 * 2 + 16)   # <= n leaf entries + (n - 1) internal nodes of 4 float4 each
+        out = np.zeros(cap, dtype=np.float32)
+        n = self.lib.orc_bvh_builder_build(self._h, prims.reshape(-1), prims.shape[0], int(reuse), out.ctypes.data, cap, C.byref(g), C.byref(d))
+        assert n <= cap
+        self.grafted, self.depth = int(g.value), int(d.value)
+        return out[:n].reshape(-1, 4).copy()
+
+    def __del__(self):
+        try:
+            self.lib.orc_bvh_builder_destroy(self._h)
+        except Exception:
+            pass
 
 
 class OracleEngine:
@@ -177,6 +210,12 @@ class OracleEngine:
         out = np.empty(n, dtype=np.float32)
         self.lib.orc_read_scene(self.h, name.encode(), out.ctypes.data_as(C.c_void_p), n)
         return out
+
+    def set_bvh_reuse(self, reuse):
+        self.lib.orc_set_bvh_reuse(self.h, int(reuse))
+
+    def bvh_reused(self):
+        return int(self.lib.orc_bvh_reused(self.h))
 
     def bvh_depth(self):
         return self.lib.orc_bvh_depth(self.h)

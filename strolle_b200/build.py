@@ -27,29 +27,33 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), tag=""):
+    """tag/defines: tuning builds (e.g. tag="minb8", defines=["ST_MINB_ALL=8"]) -> _lib/libstrolle_b200_<tag>.so."""
     os.makedirs(OUT_DIR, exist_ok=True)
     deps = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
     objs = []
     procs = []
+    suffix = ("_" + tag) if tag else ""
+    lib = LIB.replace(".so", suffix + ".so")
+    flags = FLAGS + ["-D" + d for d in defines]
     for src in SOURCES:
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        obj = os.path.join(OUT_DIR, src.replace(".cu", suffix + ".o"))
         objs.append(obj)
         if force or _stale(obj, deps + [os.path.join(CSRC, src)]):
-            cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+            cmd = [NVCC] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for src, p in procs:
         out, _ = p.communicate()
-        with open(os.path.join(OUT_DIR, src + ".ptxas.log"), "w") as f:
+        with open(os.path.join(OUT_DIR, src + suffix + ".ptxas.log"), "w") as f:
             f.write(out)
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError("nvcc failed for " + src)
         if verbose:
             print(out)
-    if force or procs or _stale(LIB, objs):
-        subprocess.check_call([NVCC, "-shared", "-o", LIB] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
-    return LIB
+    if force or procs or _stale(lib, objs):
+        subprocess.check_call([NVCC, "-shared", "-o", lib] + objs + ["-lcudart_static", "-ldl", "-lrt", "-lpthread", "-Xlinker", "--no-undefined"])
+    return lib
 
 
 if __name__ == "__main__":

@@ -176,24 +176,42 @@ struct BvhOut { std::vector<float4> buf; int depth = 0; };
 class BvhBuild {
 public:
     static const int kBins = 12;   // builder.rs:15
-    struct Node { Box box; uint32_t b, e; int32_t left, right; };
+    struct Node { Box box; uint32_t b, e; int32_t left, right; uint64_t lhash, rhash; };
     std::vector<Node> nodes;
     std::vector<Prim> prims;
+    // Last refresh's tree and primitive order (BvhPrimitives::previous, primitives.rs:63-65): the donor of subtrees whose
+    // primitive-centre sequence is unchanged (builder.rs:245-275).
+    std::vector<Node> old_nodes;
+    std::vector<Prim> old_prims;
+    uint32_t grafted = 0;   // subtrees taken over by the last build
 
-    void build(const std::vector<Prim>& all) {
+    // `reuse` = the reference's behaviour.  A grafted subtree is the old one verbatim, including every field of its
+    // primitives as they were when it was built: the hash covers the centres only (primitive.rs:27-37), so a primitive
+    // whose centre is unchanged keeps its old triangle id, material id and bounds in the tree (quirk C-20).
+    void build(const std::vector<Prim>& all, bool reuse = true) {
+        old_nodes.swap(nodes); old_prims.swap(prims);
         prims.clear();
         for (const Prim& p : all) if (p.center.x != FMAX) prims.push_back(p);   // alive only (primitives.rs:58-61)
-        nodes.clear();
-        nodes.push_back(Node{Box(), 0u, (uint32_t)prims.size(), -1, -1});   // root bounds stay unset: SAH cost = +inf (quirk C-8)
-        std::deque<int> work; work.push_back(0);
+        nodes.clear(); grafted = 0;
+        nodes.push_back(Node{Box(), 0u, (uint32_t)prims.size(), -1, -1, 0, 0});   // root bounds stay unset: SAH cost = +inf (quirk C-8)
+        struct Item { int id, donor; };   // donor: node of the old tree at the same position, -1 = none
+        std::deque<Item> work; work.push_back(Item{0, (reuse && !old_nodes.empty()) ? 0 : -1});
         while (!work.empty()) {
-            int id = work.front(); work.pop_front();
+            Item it = work.front(); work.pop_front();
             int axis; float at, cost;
-            if (!best_plane(id, &axis, &at, &cost)) continue;
-            float leaf_cost = (float)(nodes[id].e - nodes[id].b) * nodes[id].box.half_area();
+            if (!best_plane(it.id, &axis, &at, &cost)) continue;
+            float leaf_cost = (float)(nodes[it.id].e - nodes[it.id].b) * nodes[it.id].box.half_area();
             if (!(cost < leaf_cost)) continue;
-            partition(id, axis, at);
-            work.push_back(nodes[id].left); work.push_back(nodes[id].right);
+            partition(it.id, axis, at);
+            const int li = nodes[it.id].left, ri = nodes[it.id].right;
+            int ldonor = -1, rdonor = -1; bool lgraft = false, rgraft = false;
+            if (it.donor >= 0 && old_nodes[it.donor].left >= 0) {
+                const Node& d = old_nodes[it.donor];
+                ldonor = d.left; rdonor = d.right;
+                lgraft = d.lhash == nodes[it.id].lhash; rgraft = d.rhash == nodes[it.id].rhash;
+            }
+            if (lgraft) graft(li, ldonor); else work.push_back(Item{li, ldonor});
+            if (rgraft) graft(ri, rdonor); else work.push_back(Item{ri, rdonor});
         }
     }
     void flatten(const std::vector<uint8_t>& alpha_blend, BvhOut* out) const { out->buf.clear(); out->depth = 0; emit(0, 1, alpha_blend, out); }
@@ -238,20 +256,45 @@ private:
         *cost_out = best;
         return any;
     }
-    void partition(int id, int axis, float at) {   // builder.rs:183-319 (fresh build: no subtree reuse)
+    // fxhash 0.2.1 FxHasher (64-bit) over the centre bits of each primitive, in the order the partition meets them
+    // (builder.rs:201-228, primitive.rs:27-37); third-party crate, restated from its published definition.
+    static void fx(uint64_t* h, uint32_t w) { *h = (((*h << 5) | (*h >> 59)) ^ (uint64_t)w) * 0x517cc1b727220a95ull; }
+    static void fx_prim(uint64_t* h, const Prim& p) { fx(h, f2bits(p.center.x)); fx(h, f2bits(p.center.y)); fx(h, f2bits(p.center.z)); }
+    void partition(int id, int axis, float at) {   // builder.rs:183-319
         uint32_t b = nodes[id].b, e = nodes[id].e;
         Prim* d = prims.data() + b;
         int l = 0, r = (int)(e - b) - 1;
-        Box lb, rb;
+        Box lb, rb; uint64_t lh = 0, rh = 0;
         while (l <= r) {
             Prim cur = d[l];
-            if (comp(cur.center, axis) < at) { l++; lb.grow(cur.box); }
-            else { std::swap(d[l], d[r]); r--; rb.grow(cur.box); }
+            if (comp(cur.center, axis) < at) { l++; lb.grow(cur.box); fx_prim(&lh, cur); }
+            else { std::swap(d[l], d[r]); r--; rb.grow(cur.box); fx_prim(&rh, cur); }
         }
         uint32_t mid = b + (uint32_t)l;
-        int li = (int)nodes.size(); nodes.push_back(Node{lb, b, mid, -1, -1});
-        int ri = (int)nodes.size(); nodes.push_back(Node{rb, mid, e, -1, -1});
-        nodes[id].left = li; nodes[id].right = ri;
+        int li = (int)nodes.size(); nodes.push_back(Node{lb, b, mid, -1, -1, 0, 0});
+        int ri = (int)nodes.size(); nodes.push_back(Node{rb, mid, e, -1, -1, 0, 0});
+        nodes[id].left = li; nodes[id].right = ri; nodes[id].lhash = lh; nodes[id].rhash = rh;
+    }
+    // builder.rs:321-359 (copy + offset_primitives): node `id` (a fresh leaf over [b, e)) becomes the old subtree `donor`,
+    // shifted to this range, and the range gets the old subtree's primitives in their old order.
+    void graft(int id, int donor) {
+        const Node& src = old_nodes[donor];
+        const uint32_t b = nodes[id].b;
+        for (uint32_t i = src.b; i < src.e; i++) prims[b + (i - src.b)] = old_prims[i];
+        grafted++;
+        struct Pair { int dst, src; };
+        std::vector<Pair> todo; todo.push_back(Pair{id, donor});
+        const int64_t shift = (int64_t)b - (int64_t)src.b;
+        while (!todo.empty()) {
+            Pair pr = todo.back(); todo.pop_back();
+            const Node o = old_nodes[pr.src];
+            Node n = o; n.b = (uint32_t)((int64_t)o.b + shift); n.e = (uint32_t)((int64_t)o.e + shift); n.left = n.right = -1;
+            if (o.left >= 0) {
+                n.left = (int)nodes.size(); nodes.push_back(Node{}); n.right = (int)nodes.size(); nodes.push_back(Node{});
+                todo.push_back(Pair{n.left, o.left}); todo.push_back(Pair{n.right, o.right});
+            }
+            nodes[pr.dst] = n;
+        }
     }
     uint32_t emit(int id, int depth, const std::vector<uint8_t>& alpha, BvhOut* out) const {   // serializer.rs:20-110
         uint32_t at = (uint32_t)out->buf.size();
@@ -367,6 +410,7 @@ struct st_engine {
     int wavelet_cfg = ST_WAVELET_CFG_DEFAULT;       // ST_OPT_WAVELET_TILE_CFG: 4 bits per iteration, tile shape index (kernels.cu wavelet_tiled_cfg)
     DevMem d_tile_errors; uint64_t wavelet_tiled_launches = 0;
     bool fuse_reproject = ST_FUSE_REPROJECT_DEFAULT != 0;   // ST_OPT_FUSE_REPROJECT
+    bool bvh_reuse = true;   // ST_OPT_BVH_REUSE
     bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
     std::vector<CameraSlot*> cameras;
     // timing ---------------------------------------------------------------------------------------
@@ -1023,7 +1067,7 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
         launch_material_derive((const GpuMaterial*)e->d_materials.p, (uint32_t)e->h_materials.size(), (uint32_t*)e->d_matpacked.p, e->stream);
     }
     if (refresh_instances(e)) {   // Bvh::refresh (bvh.rs:48-70)
-        e->bvh.build(e->prims);
+        e->bvh.build(e->prims, e->bvh_reuse);
         std::vector<uint8_t> alpha(e->materials.size());
         for (size_t i = 0; i < alpha.size(); i++) alpha[i] = e->materials[i].alpha_blend ? 1 : 0;
         e->bvh.flatten(alpha, &e->bvh_out);
@@ -1211,13 +1255,48 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
+    if (option == ST_OPT_BVH_REUSE) { e->bvh_reuse = value != 0; return ST_OK; }
     if (option == ST_OPT_FUSE_REPROJECT) { e->fuse_reproject = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILE_CFG) { e->wavelet_cfg = value & 0xfffff; return ST_OK; }
     return fail(ST_ERR_INVALID, "unknown option");
 }
+// ---- host-side BVH builder without a device (test / tool hook; strolle/src/bvh/builder.rs, serializer.rs) ----
+struct st_bvh_builder { BvhBuild b; BvhOut flat; };
+int st_bvh_builder_create(st_bvh_builder** out) { if (!out) return fail(ST_ERR_INVALID, "out is null"); *out = new st_bvh_builder(); return ST_OK; }
+void st_bvh_builder_destroy(st_bvh_builder* b) { delete b; }
+int st_bvh_builder_read(st_bvh_builder* b, float* out, size_t cap_floats) {   // the stream of the last build
+    if (!b || !out) return fail(ST_ERR_INVALID, "null argument");
+    if (cap_floats < b->flat.buf.size() * 4) return fail(ST_ERR_LIMIT, "output buffer too small");
+    std::memcpy(out, b->flat.buf.data(), b->flat.buf.size() * 16);
+    return ST_OK;
+}
+int st_bvh_builder_build(st_bvh_builder* b, const float* prims11, size_t n, int reuse, float* out, size_t cap_floats, size_t* n_floats, uint32_t* grafted, int* depth) {
+    if (!b || (!prims11 && n) || !n_floats) return fail(ST_ERR_INVALID, "null argument");
+    std::vector<Prim> all(n);
+    uint32_t max_mat = 0;
+    for (size_t i = 0; i < n; i++) {
+        const float* f = prims11 + 11 * i;
+        Prim& p = all[i];
+        p.tri = f2bits(f[0]); p.mat = f2bits(f[1]); p.center = h3(f[2], f[3], f[4]);
+        p.box.lo = h3(f[5], f[6], f[7]); p.box.hi = h3(f[8], f[9], f[10]);
+        max_mat = std::max(max_mat, p.mat);
+    }
+    b->b.build(all, reuse != 0);
+    // a grafted subtree may still name a material of an earlier call (quirk C-20): size the flag table for those too
+    for (const Prim& p : b->b.prims) max_mat = std::max(max_mat, p.mat);
+    std::vector<uint8_t> alpha((size_t)max_mat + 1, 0);
+    b->b.flatten(alpha, &b->flat);
+    *n_floats = b->flat.buf.size() * 4;
+    if (grafted) *grafted = b->b.grafted;
+    if (depth) *depth = b->flat.depth;
+    if (out) return st_bvh_builder_read(b, out, cap_floats);
+    return ST_OK;
+}
+
 int st_get_stat(st_engine* e, int stat, uint64_t* value) {
     if (!e || !value) return fail(ST_ERR_INVALID, "null argument");
     if (stat == ST_STAT_WAVELET_TILED_LAUNCHES) { *value = e->wavelet_tiled_launches; return ST_OK; }
+    if (stat == ST_STAT_BVH_GRAFTED_SUBTREES) { *value = e->bvh.grafted; return ST_OK; }
     if (stat == ST_STAT_WAVELET_TILED_ERRORS) {
         CK(cudaSetDevice(e->device));
         CK(cudaStreamSynchronize(e->stream));

@@ -52,10 +52,114 @@ ST_DEV Hit load_hit_lut(const SceneDev& sc, const GpuCamera& c, const float4* __
 
 #define KPARAMS const __grid_constant__ CameraDev cam, const __grid_constant__ SceneDev sc
 
+// Launch bounds per kernel: ST_LB_<KERNEL> is __launch_bounds__(128) (ptxas' own register choice) unless a minimum number
+// of resident CTAs per SM is set (ST_MINB_<KERNEL> = N caps registers at 65536 / (128 N)); values tuned on a B200 with
+// tools/occupancy_tune.py.  -DST_MINB_ALL=N overrides every kernel at once (tuning builds).
+#define ST_LB_N(N) __launch_bounds__(ST_BLOCK, N)
+// measured (profiles/r1j_occupancy_tune.txt): capping these five at 64 registers (8 CTAs/SM) is worth 80 us per 1080p frame
+#if !defined(ST_MINB_ALL)
+#define ST_MINB_GI_PREVIEW 8
+#define ST_MINB_GI_TEMPORAL 8
+#define ST_MINB_GI_SAMPLING_B 8
+#define ST_MINB_GI_SPATIAL_PICK 8
+#define ST_MINB_DI_TEMPORAL 8
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_PRIM_GBUFFER ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_PRIM_GBUFFER)
+#define ST_LB_PRIM_GBUFFER ST_LB_N(ST_MINB_PRIM_GBUFFER)
+#else
+#define ST_LB_PRIM_GBUFFER __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_DI_SAMPLING ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_DI_SAMPLING)
+#define ST_LB_DI_SAMPLING ST_LB_N(ST_MINB_DI_SAMPLING)
+#else
+#define ST_LB_DI_SAMPLING __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_DI_TEMPORAL ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_DI_TEMPORAL)
+#define ST_LB_DI_TEMPORAL ST_LB_N(ST_MINB_DI_TEMPORAL)
+#else
+#define ST_LB_DI_TEMPORAL __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_DI_SPATIAL_PICK ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_DI_SPATIAL_PICK)
+#define ST_LB_DI_SPATIAL_PICK ST_LB_N(ST_MINB_DI_SPATIAL_PICK)
+#else
+#define ST_LB_DI_SPATIAL_PICK __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_SPATIAL_TRACE ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_SPATIAL_TRACE)
+#define ST_LB_SPATIAL_TRACE ST_LB_N(ST_MINB_SPATIAL_TRACE)
+#else
+#define ST_LB_SPATIAL_TRACE __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_DI_RESOLVING ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_DI_RESOLVING)
+#define ST_LB_DI_RESOLVING ST_LB_N(ST_MINB_DI_RESOLVING)
+#else
+#define ST_LB_DI_RESOLVING __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_GI_SAMPLING_A ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_GI_SAMPLING_A)
+#define ST_LB_GI_SAMPLING_A ST_LB_N(ST_MINB_GI_SAMPLING_A)
+#else
+#define ST_LB_GI_SAMPLING_A __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_GI_SAMPLING_B ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_GI_SAMPLING_B)
+#define ST_LB_GI_SAMPLING_B ST_LB_N(ST_MINB_GI_SAMPLING_B)
+#else
+#define ST_LB_GI_SAMPLING_B __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_GI_TEMPORAL ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_GI_TEMPORAL)
+#define ST_LB_GI_TEMPORAL ST_LB_N(ST_MINB_GI_TEMPORAL)
+#else
+#define ST_LB_GI_TEMPORAL __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_GI_SPATIAL_PICK ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_GI_SPATIAL_PICK)
+#define ST_LB_GI_SPATIAL_PICK ST_LB_N(ST_MINB_GI_SPATIAL_PICK)
+#else
+#define ST_LB_GI_SPATIAL_PICK __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_GI_SPATIAL_SAMPLE ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_GI_SPATIAL_SAMPLE)
+#define ST_LB_GI_SPATIAL_SAMPLE ST_LB_N(ST_MINB_GI_SPATIAL_SAMPLE)
+#else
+#define ST_LB_GI_SPATIAL_SAMPLE __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_GI_PREVIEW ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_GI_PREVIEW)
+#define ST_LB_GI_PREVIEW ST_LB_N(ST_MINB_GI_PREVIEW)
+#else
+#define ST_LB_GI_PREVIEW __launch_bounds__(ST_BLOCK)
+#endif
+#if defined(ST_MINB_ALL)
+#define ST_LB_GI_RESOLVING ST_LB_N(ST_MINB_ALL)
+#elif defined(ST_MINB_GI_RESOLVING)
+#define ST_LB_GI_RESOLVING ST_LB_N(ST_MINB_GI_RESOLVING)
+#else
+#define ST_LB_GI_RESOLVING __launch_bounds__(ST_BLOCK)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Primary-visibility G-buffer (stands in for strolle-shaders/src/prim_raster.rs:41-128)
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(ST_BLOCK) k_prim_gbuffer(KPARAMS, int cur) {
+__global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur) {
     ST_TRACE_STACK();
     Px p = pixel_full(cam);
     if (!p.in) return;
@@ -117,7 +221,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_frame_reprojection(KPARAMS, int cu
 }
 
 // K5 di_sampling::main (di_sampling.rs:4-94)
-__global__ void __launch_bounds__(ST_BLOCK) k_di_sampling(KPARAMS, int cur, u32 seed, u32 frame) {
+__global__ void ST_LB_DI_SAMPLING k_di_sampling(KPARAMS, int cur, u32 seed, u32 frame) {
     ST_TRACE_STACK();
     Px p = pixel_full(cam);
     if (!p.in) return;
@@ -137,7 +241,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_sampling(KPARAMS, int cur, u32 
 }
 
 // K6 di_temporal_resampling::main (di_temporal_resampling.rs:4-112)
-__global__ void __launch_bounds__(ST_BLOCK) k_di_temporal(KPARAMS, int cur, u32 seed) {
+__global__ void ST_LB_DI_TEMPORAL k_di_temporal(KPARAMS, int cur, u32 seed) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t npx = (size_t)cam.w * cam.h;
@@ -183,7 +287,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_temporal(KPARAMS, int cur, u32 
 // K7 di_spatial_resampling::pick (di_spatial_resampling.rs:4-147); scratch buf_d0 = di_diff_samples,
 // buf_d1 = di_diff_curr_colors (passes/di_spatial_resampling.rs:24-28).  Sky pixels clear buf_d1
 // (the reference leaves stale texels there and later reads out of bounds — SURVEY Appendix C-15).
-__global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
+__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
     Px g = pixel_half(cam);
     if (!g.in) return;
     uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
@@ -227,7 +331,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_pick(KPARAMS, int cur, 
 }
 
 // K8 / K16 *_spatial_resampling::trace (di_spatial_resampling.rs:150-209, gi_spatial_resampling.rs:163-222)
-__global__ void __launch_bounds__(ST_BLOCK) k_spatial_trace(KPARAMS, const float4* __restrict__ buf_d0, const float4* __restrict__ buf_d1, float4* __restrict__ buf_d2) {
+__global__ void ST_LB_SPATIAL_TRACE k_spatial_trace(KPARAMS, const float4* __restrict__ buf_d0, const float4* __restrict__ buf_d1, float4* __restrict__ buf_d2) {
     ST_TRACE_STACK();
     Px p = pixel_full(cam);
     if (!p.in) return;
@@ -273,7 +377,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 see
 }
 
 // K10 di_resolving::main (di_resolving.rs:4-119)
-__global__ void __launch_bounds__(ST_BLOCK) k_di_resolving(KPARAMS, int cur) {
+__global__ void ST_LB_DI_RESOLVING k_di_resolving(KPARAMS, int cur) {
     ST_TRACE_STACK();
     Px p = pixel_full(cam);
     if (!p.in) return;
@@ -321,7 +425,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) 
 }
 
 // K12 gi_sampling_a::main (gi_sampling_a.rs:4-122)
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_a(KPARAMS, int cur, u32 seed, u32 frame) {
+__global__ void ST_LB_GI_SAMPLING_A k_gi_sampling_a(KPARAMS, int cur, u32 seed, u32 frame) {
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
     if (!g.in) return;
@@ -359,7 +463,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_a(KPARAMS, int cur, u3
 }
 
 // K13 gi_sampling_b::main (gi_sampling_b.rs:4-235)
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_b(KPARAMS, int cur, u32 seed, u32 frame) {
+__global__ void ST_LB_GI_SAMPLING_B k_gi_sampling_b(KPARAMS, int cur, u32 seed, u32 frame) {
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
     if (!g.in) return;
@@ -423,7 +527,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_sampling_b(KPARAMS, int cur, u3
 }
 
 // K14 gi_temporal_resampling::main (gi_temporal_resampling.rs:4-156)
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_temporal(KPARAMS, int cur, u32 seed, u32 frame) {
+__global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 frame) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     bool tracing = gi_tracing_frame(frame);
@@ -475,7 +579,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_temporal(KPARAMS, int cur, u32 
 }
 
 // K15 gi_spatial_resampling::pick (gi_spatial_resampling.rs:4-160); scratch = gi_d0, gi_d1
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
+__global__ void ST_LB_GI_SPATIAL_PICK k_gi_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
     Px g = pixel_half(cam);
     if (!g.in) return;
     uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
@@ -525,7 +629,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_pick(KPARAMS, int cur, 
 }
 
 // K17 gi_spatial_resampling::sample (gi_spatial_resampling.rs:225-314)
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_sample(KPARAMS, u32 seed, u32 frame) {
+__global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u32 frame) {
     Px g = pixel_half(cam);
     if (!g.in) return;
     uint2 sp = checker(g.x, g.y, frame / 2u + 1u);
@@ -561,7 +665,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_spatial_sample(KPARAMS, u32 see
 }
 
 // K18 gi_preview_resampling::main (gi_preview_resampling.rs:4-138)
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_preview(KPARAMS, int cur, u32 seed, u32 nth, const float4* __restrict__ in, float4* __restrict__ out) {
+__global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nth, const float4* __restrict__ in, float4* __restrict__ out) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t cidx = screen_idx(cam, p.x, p.y);
@@ -602,7 +706,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_preview(KPARAMS, int cur, u32 s
 }
 
 // K19 gi_resolving::main (gi_resolving.rs:4-67)
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_resolving(KPARAMS, int cur, const float4* __restrict__ in) {
+__global__ void ST_LB_GI_RESOLVING k_gi_resolving(KPARAMS, int cur, const float4* __restrict__ in) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t idx = screen_idx(cam, p.x, p.y);

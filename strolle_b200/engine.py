@@ -18,8 +18,10 @@ OPT_HALO_NCCL = 3
 OPT_WAVELET_TILED = 4      # bit i = à-trous iteration i runs the tile-staged (TMA) kernel
 OPT_WAVELET_TILE_CFG = 5   # 4 bits per iteration: 0 32x8, 1 32x16, 2 64x4, 3 64x8 output tile
 OPT_FUSE_REPROJECT = 6     # K20 for DI and GI in one launch
+OPT_BVH_REUSE = 7          # graft unchanged subtrees of the previous BVH (reference behaviour)
 STAT_WAVELET_TILED_LAUNCHES = 1
 STAT_WAVELET_TILED_ERRORS = 2
+STAT_BVH_GRAFTED_SUBTREES = 3
 
 
 class StrolleError(RuntimeError):
@@ -27,7 +29,8 @@ class StrolleError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "_lib", "libstrolle_b200.so")
+    # STROLLE_B200_LIB: development aid, selects a tuning build of the same library (tools/occupancy_tune.py)
+    return os.environ.get("STROLLE_B200_LIB") or os.path.join(_HERE, "_lib", "libstrolle_b200.so")
 
 
 class _MeshTriangle(C.Structure):
@@ -93,11 +96,15 @@ def load_library():
         "st_camera_set_strip": [P, i32, C.c_int, C.c_int],
         "st_buffer_device_ptr": [P, i32, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
         "st_frame_schedule": [P, i32, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)], "st_render_range": [P, i32, C.c_int, C.c_int],
+        "st_bvh_builder_create": [C.POINTER(P)], "st_bvh_builder_read": [P, C.c_void_p, C.c_size_t],
+        "st_bvh_builder_build": [P, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(u32), C.POINTER(C.c_int)],
     }
     for name, args in sig.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = None if name == "st_engine_destroy" else C.c_int
+    lib.st_bvh_builder_destroy.argtypes = [P]
+    lib.st_bvh_builder_destroy.restype = None
     lib.st_last_error.restype = C.c_char_p
     lib.st_pass_name.restype = C.c_char_p
     lib.st_pass_name.argtypes = [C.c_int]
@@ -136,6 +143,44 @@ def _f(a, n=None):
     if n is not None and a.size != n:
         raise ValueError(f"expected {n} floats, got {a.size}")
     return a
+
+
+class BvhBuilder:
+    """The host-side BVH builder on its own (strolle/src/bvh/builder.rs + serializer.rs); needs no GPU.
+    `build(prims)` takes an (n, 11) float32 array (triangle id bits, material id bits, centre, bounds min, bounds max)
+    and returns the serialised float4 stream as an (m, 4) float32 array; the object keeps the previous tree, whose
+    unchanged subtrees are grafted when `reuse` is true (`grafted` = how many)."""
+
+    def __init__(self):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        if self.lib.st_bvh_builder_create(C.byref(self._h)) != 0:
+            raise StrolleError(self.lib.st_last_error().decode())
+        self.grafted = 0
+        self.depth = 0
+
+    def build(self, prims, reuse=True):
+        prims = np.ascontiguousarray(prims, dtype=np.float32).reshape(-1, 11)
+        n = C.c_size_t(0); g = C.c_uint32(0); d = C.c_int(0)
+        if self.lib.st_bvh_builder_build(self._h, prims.ctypes.data, prims.shape[0], int(reuse), None, 0, C.byref(n), C.byref(g), C.byref(d)) != 0:
+            raise StrolleError(self.lib.st_last_error().decode())
+        # the size query already built the tree; read it back without rebuilding (a second build would graft everything)
+        out = np.zeros(n.value, dtype=np.float32)
+        if self.lib.st_bvh_builder_read(self._h, out.ctypes.data, out.size) != 0:
+            raise StrolleError(self.lib.st_last_error().decode())
+        self.grafted, self.depth = int(g.value), int(d.value)
+        return out.reshape(-1, 4)
+
+    def close(self):
+        if self._h:
+            self.lib.st_bvh_builder_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine:

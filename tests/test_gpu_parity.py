@@ -343,6 +343,44 @@ def test_moving_instance_rebuilds_bvh_and_velocity(gpu, oracle, blue_noise):
     assert (vel[:, :2] != 0).any(), "the moved box still reports a velocity (stale prev_transform, as in the reference)"
 
 
+@pytest.mark.parametrize("reuse", [True, False])
+def test_bvh_subtree_reuse_and_stale_material_quirk(gpu, oracle, blue_noise, reuse):
+    """BVH refreshes graft the unchanged subtrees of the previous tree (strolle/src/bvh/builder.rs:245-359).
+    Moving a box rebuilds only its side of the tree; giving a box another material without moving it changes no
+    primitive centre, so the reference's centre-only hash (primitive.rs:27-37) reuses the whole tree and the old material id
+    stays in the leaves (quirk C-20).  reuse=False (ST_OPT_BVH_REUSE 0) builds from scratch instead.  Either way the CUDA
+    path and the oracle agree bit for bit."""
+    from strolle_b200.engine import OPT_BVH_REUSE, STAT_BVH_GRAFTED_SUBTREES
+    scene = scenes.cornell(96, 64)
+    eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
+    eg.set_option(OPT_BVH_REUSE, int(reuse)); eo.set_bvh_reuse(reuse)
+    h, mesh, mat, xf = scene["instances"][6]
+    other_mat = scene["instances"][1][2]
+    assert other_mat != mat
+    bvh_before = None
+    for f in range(5):
+        if f == 1:
+            moved = np.array(xf, np.float32).copy(); moved[9] += 0.1
+            for e in (eg, eo):
+                e.insert_instance(h, mesh, mat, moved)
+        if f == 3:
+            for e in (eg, eo):
+                e.insert_instance(h, mesh, other_mat, moved)   # same place, other material
+        eg.tick(); eo.tick()
+        for name in ["triangles", "bvh"]:
+            assert_bits_equal(eg.read_scene(name), eo.read_scene(name), f"frame {f + 1} scene:{name}")
+        if f == 1:
+            assert (eg.get_stat(STAT_BVH_GRAFTED_SUBTREES) > 0) == reuse and (eo.bvh_reused() > 0) == reuse
+        if f == 2:
+            bvh_before = eg.read_scene("bvh").copy()
+        if f == 3:
+            same = bits_equal(eg.read_scene("bvh"), bvh_before)[0]
+            assert same == reuse, "reuse keeps the old material id in the leaves; a fresh build does not"
+        eg.render_camera(cg); eo.render_camera(co)
+        for name in ["prim_gbuffer_d1_a", "prim_gbuffer_d1_b", "di_reservoirs_0", "gi_reservoirs_0", "output"]:
+            assert_bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name), f"frame {f + 1} {name}")
+
+
 DENOISER_BUFFERS = ["di_diff_prev_colors", "di_diff_curr_colors", "di_diff_stash", "di_diff_moments_a", "di_diff_moments_b",
                     "gi_diff_prev_colors", "gi_diff_curr_colors", "gi_diff_stash", "gi_diff_moments_a", "gi_diff_moments_b", "output"]
 

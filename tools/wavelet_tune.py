@@ -37,7 +37,7 @@ def measure(mask, cfg, fuse=0):
     e.synchronize()
     ms, launches = e.pass_times(reset=True)
     e.enable_timing(False)
-    return ms[WAVELET] / FRAMES * 1000.0, ms[REPROJECT] / FRAMES * 1000.0, sum(ms) / FRAMES * 1000.0
+    return float(ms[WAVELET]) / FRAMES * 1000.0, float(ms[REPROJECT]) / FRAMES * 1000.0, float(sum(ms)) / FRAMES * 1000.0
 
 
 for _ in range(12):
