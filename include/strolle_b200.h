@@ -169,7 +169,10 @@ const char* st_pass_name(int pass);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8 };
+/* ST_OPT_VARIANCE_TILED: 1 = K21 frame_denoising::estimate_variance (frame_denoising.rs:81-217) reads its 6x5 window from a
+ * shared-memory tile filled by TMA tensor copies (identical results). */
+#define ST_VARIANCE_TILED_DEFAULT 0
 /* ST_OPT_BVH_REUSE (default 1): a BVH refresh takes over the subtrees of the previous tree whose primitive-centre
  * sequence is unchanged, as the reference does (strolle/src/bvh/builder.rs:245-275, hash = primitive.rs:27-37);
  * 0 = every refresh builds from scratch.  Both give the same tree unless a primitive changed while its centre did
@@ -179,9 +182,9 @@ enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3,
  * shared memory by TMA tensor copies) instead of the per-tap gather kernel; both produce identical bits.
  * ST_OPT_WAVELET_TILE_CFG: 4 bits per iteration, output-tile shape (0: 32x8, 1: 32x16, 2: 64x4, 3: 64x8 pixels). */
 /* Defaults measured on a B200 at 1920x1080 (tools/wavelet_tune.py, profiles/r1i_wavelet_tune.txt): strides 1, 2, 4, 8
- * tile-staged (64x4, 64x4, 32x8, 32x16 output tiles), stride 16 gathers (its jittered 3x3 footprint does not fit a tile). */
+ * tile-staged (32x8, 32x8, 32x8, 32x16 output tiles), stride 16 gathers (its jittered 3x3 footprint does not fit a tile). */
 #define ST_WAVELET_TILED_DEFAULT 15
-#define ST_WAVELET_CFG_DEFAULT 0x01022
+#define ST_WAVELET_CFG_DEFAULT 0x01000
 /* ST_OPT_FUSE_REPROJECT: 1 = K20 frame_denoising::reproject (frame_denoising.rs:4-78) handles the DI and the GI
  * signal in one launch (the reference dispatches it twice, passes/frame_denoising.rs:143-160); identical results. */
 #define ST_FUSE_REPROJECT_DEFAULT 1
@@ -192,7 +195,7 @@ enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3,
 int st_set_option(st_engine* e, int option, int value);
 /* Engine statistics (development / test aid): tile-staged wavelet launches since creation, and how many of its
  * CTAs gave up waiting for their tensor copies (must stay 0). */
-enum { ST_STAT_WAVELET_TILED_LAUNCHES = 1, ST_STAT_WAVELET_TILED_ERRORS = 2, ST_STAT_BVH_GRAFTED_SUBTREES = 3 };
+enum { ST_STAT_WAVELET_TILED_LAUNCHES = 1, ST_STAT_WAVELET_TILED_ERRORS = 2, ST_STAT_BVH_GRAFTED_SUBTREES = 3, ST_STAT_VARIANCE_TILED_LAUNCHES = 4 };
 int st_get_stat(st_engine* e, int stat, uint64_t* value);
 /* The host-side BVH builder on its own (no device needed): binned-SAH build (strolle/src/bvh/builder.rs:17-319) + DFS
  * serialisation (serializer.rs:20-110) over `n` primitives of 11 floats each (triangle id bits, material id bits,

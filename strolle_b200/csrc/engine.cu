@@ -411,6 +411,7 @@ struct st_engine {
     DevMem d_tile_errors; uint64_t wavelet_tiled_launches = 0;
     bool fuse_reproject = ST_FUSE_REPROJECT_DEFAULT != 0;   // ST_OPT_FUSE_REPROJECT
     bool bvh_reuse = true;   // ST_OPT_BVH_REUSE
+    bool variance_tiled = ST_VARIANCE_TILED_DEFAULT != 0; uint64_t variance_tiled_launches = 0;   // ST_OPT_VARIANCE_TILED
     bool luts_static_ready = false, sky_ready = false; float sky_for_altitude = 0.0f;
     std::vector<CameraSlot*> cameras;
     // timing ---------------------------------------------------------------------------------------
@@ -680,7 +681,11 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
             add(P_DENOISE_REPROJECT, [=](cudaStream_t s) { launch_denoise_reproject(cam, sc, cur, cam.gi_diff_prev_colors, cam.gi_diff_moments[cur ^ 1], cam.gi_diff_samples, cam.gi_diff_curr_colors, cam.gi_diff_moments[cur], s); });
         }
         const bool fast = e->svgf_fast;
-        add(P_DENOISE_VARIANCE, [=](cudaStream_t s) { launch_denoise_variance(cam, sc, cur, fast, s); });
+        const bool var_tiled = e->variance_tiled; uint32_t* verr = (uint32_t*)e->d_tile_errors.p;
+        add(P_DENOISE_VARIANCE, [=](cudaStream_t s) {
+            if (var_tiled && launch_denoise_variance_tiled(cam, sc, cur, fast, verr, s)) { e->variance_tiled_launches++; return; }
+            launch_denoise_variance(cam, sc, cur, fast, s);
+        });
         float4* di_io[5][2] = {{cam.di_diff_stash, cam.di_diff_prev_colors}, {cam.di_diff_prev_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors},
                                {cam.di_diff_curr_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors}};
         float4* gi_io[5][2] = {{cam.gi_diff_stash, cam.gi_diff_prev_colors}, {cam.gi_diff_prev_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors},
@@ -1255,6 +1260,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
+    if (option == ST_OPT_VARIANCE_TILED) { e->variance_tiled = value != 0; return ST_OK; }
     if (option == ST_OPT_BVH_REUSE) { e->bvh_reuse = value != 0; return ST_OK; }
     if (option == ST_OPT_FUSE_REPROJECT) { e->fuse_reproject = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILE_CFG) { e->wavelet_cfg = value & 0xfffff; return ST_OK; }
@@ -1296,6 +1302,7 @@ int st_bvh_builder_build(st_bvh_builder* b, const float* prims11, size_t n, int 
 int st_get_stat(st_engine* e, int stat, uint64_t* value) {
     if (!e || !value) return fail(ST_ERR_INVALID, "null argument");
     if (stat == ST_STAT_WAVELET_TILED_LAUNCHES) { *value = e->wavelet_tiled_launches; return ST_OK; }
+    if (stat == ST_STAT_VARIANCE_TILED_LAUNCHES) { *value = e->variance_tiled_launches; return ST_OK; }
     if (stat == ST_STAT_BVH_GRAFTED_SUBTREES) { *value = e->bvh.grafted; return ST_OK; }
     if (stat == ST_STAT_WAVELET_TILED_ERRORS) {
         CK(cudaSetDevice(e->device));

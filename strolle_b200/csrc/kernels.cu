@@ -62,7 +62,7 @@ ST_DEV Hit load_hit_lut(const SceneDev& sc, const GpuCamera& c, const float4* __
 #define ST_MINB_GI_TEMPORAL 8
 #define ST_MINB_GI_SAMPLING_B 8
 #define ST_MINB_GI_SPATIAL_PICK 8
-#define ST_MINB_DI_TEMPORAL 8
+#define ST_MINB_DI_TEMPORAL 12
 #endif
 #if defined(ST_MINB_ALL)
 #define ST_LB_PRIM_GBUFFER ST_LB_N(ST_MINB_ALL)
@@ -945,6 +945,54 @@ ST_DEV void tma_load_2d(u32 dst, const CUtensorMap* tm, int c0, int c1, u32 bar)
                  ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(c0), "r"(c1), "r"(bar) : "memory");
 }
 
+// Per-centre state of K22: the terms of frame_denoising::sample_weight (frame_denoising.rs:363-392) that depend on the centre
+// pixel only are evaluated once (1 / leeway of the depth ramp, sqrt of the centre luminances, the luminance sigmas); `geometry`
+// is the part of a tap's weight shared by the DI and the GI signal, `add` the per-signal luminance term and the accumulation.
+// Same expressions, same order as k_denoise_wavelet (both arithmetic flavours): bit-identical results.
+template <bool FAST> struct WaveletCentre {
+    float3 n; float depth, leeway, rcp_leeway, scdl, scgl, ls_di, ls_gi;
+    float sdw; float3 sdc; float sdv; float sgw; float3 sgc; float sgv;
+    ST_DEV void init(float4 cnd, float4 cdi, float4 cgi, float depth_sigma) {
+        n = xyz(cnd); depth = cnd.w; leeway = cnd.w * depth_sigma; rcp_leeway = FAST ? sfu_rcp(leeway) : 0.0f;
+        float3 cdc = xyz(cdi), cgc = xyz(cgi);
+        scdl = sv_sqrt<FAST>(sv_luma<FAST>(cdc)); scgl = sv_sqrt<FAST>(sv_luma<FAST>(cgc));
+        ls_di = lerpc(2.5f, 0.5f, sv_sqrt<FAST>(cdi.w)); ls_gi = lerpc(1.0f, 0.0f, sv_sqrt<FAST>(cgi.w));
+        sdw = 1.0f; sdc = cdc; sdv = cdi.w; sgw = 1.0f; sgc = cgc; sgv = cgi.w;
+    }
+    // depth ramp and normal^64 of one tap (svgf_depth_weight / svgf_normal_weight); false = the tap cannot contribute
+    ST_DEV bool geometry(float4 nds, float* dw, float* nw) const {
+        float diff = fabs_(nds.w - depth);
+        if (diff >= leeway) return false;
+        *dw = FAST ? __fmaf_rn(-diff, rcp_leeway, 1.0f) : 1.0f - diff / leeway;
+        *nw = svgf_normal_weight<FAST>(n, xyz(nds));
+        return !(*dw == 0.0f || *nw == 0.0f);
+    }
+    ST_DEV void add(float dw, float nw, float4 sdi, float4 sgi) {
+        if (FAST) {
+            float dnw = dw * nw;
+            float wd = svgf_luma_weight<true>(scdl, sv_luma<true>(xyz(sdi)), ls_di) * dnw;
+            if (wd > 0.0f) { sdw += wd; sdc = f3(__fmaf_rn(wd, sdi.x, sdc.x), __fmaf_rn(wd, sdi.y, sdc.y), __fmaf_rn(wd, sdi.z, sdc.z)); sdv = __fmaf_rn(wd * wd, sdi.w, sdv); }
+            float wg = svgf_luma_weight<true>(scgl, sv_luma<true>(xyz(sgi)), ls_gi) * dnw;
+            if (wg > 0.0f) { sgw += wg; sgc = f3(__fmaf_rn(wg, sgi.x, sgc.x), __fmaf_rn(wg, sgi.y, sgc.y), __fmaf_rn(wg, sgi.z, sgc.z)); sgv = __fmaf_rn(wg * wg, sgi.w, sgv); }
+        } else {
+            float wd = svgf_luma_weight<false>(scdl, luma(xyz(sdi)), ls_di) * dw * nw;
+            if (wd > 0.0f) { sdw += wd; sdc = sdc + wd * xyz(sdi); sdv += sq(wd) * sdi.w; }
+            float wg = svgf_luma_weight<false>(scgl, luma(xyz(sgi)), ls_gi) * dw * nw;
+            if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
+        }
+    }
+    ST_DEV void store(float4* __restrict__ di_out, float4* __restrict__ gi_out, size_t i) const {
+        if (FAST) {
+            float rd = sfu_rcp(sdw), rg = sfu_rcp(sgw);
+            di_out[i] = f4(sdc * rd, sdv * (rd * rd));
+            gi_out[i] = f4(sgc * rg, sgv * (rg * rg));
+        } else {
+            di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
+            gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
+        }
+    }
+};
+
 template <int S, int J, int TW, int TH> struct WaveletTile {
     static constexpr int HL = S + J, BW = TW + 2 * HL, BH = TH + 2 * HL;
     static constexpr u32 BOX_BYTES = (u32)(BW * BH * 16);
@@ -952,8 +1000,11 @@ template <int S, int J, int TW, int TH> struct WaveletTile {
     static constexpr u32 SMEM = 3u * PLANE + 128u;   // + slack to align the first plane to 128 B
 };
 
+#ifndef ST_WAVELET_TILED_MINB
+#define ST_WAVELET_TILED_MINB 1
+#endif
 template <bool FAST, int S, int J, int TW, int TH>
-__global__ void __launch_bounds__(TW * TH) k_denoise_wavelet_tiled(KPARAMS, u32 frame, float strength,
+__global__ void __launch_bounds__(TW * TH, (TW * TH <= 256 && S <= 8) ? ST_WAVELET_TILED_MINB : 1) k_denoise_wavelet_tiled(KPARAMS, u32 frame, float strength,
                                                                    const __grid_constant__ CUtensorMap tm_nd, const __grid_constant__ CUtensorMap tm_di,
                                                                    const __grid_constant__ CUtensorMap tm_gi,
                                                                    float4* __restrict__ di_out, float4* __restrict__ gi_out, u32* __restrict__ errors) {
@@ -968,10 +1019,10 @@ __global__ void __launch_bounds__(TW * TH) k_denoise_wavelet_tiled(KPARAMS, u32 
     if (threadIdx.x == 0) { mbar_init(bar, 1u); mbar_fence_init(); }
     __syncthreads();
     if (threadIdx.x == 0) {
-        mbar_expect_tx(bar, 3u * T::BOX_BYTES);
-        tma_load_2d(base, &tm_nd, (x0 - T::HL) * 2, y0 - T::HL, bar);   // x in 8-byte elements (see wavelet_tensor_map)
-        tma_load_2d(base + T::PLANE, &tm_di, (x0 - T::HL) * 2, y0 - T::HL, bar);   // x in 8-byte elements (see wavelet_tensor_map)
-        tma_load_2d(base + 2u * T::PLANE, &tm_gi, (x0 - T::HL) * 2, y0 - T::HL, bar);   // x in 8-byte elements (see wavelet_tensor_map)
+        mbar_expect_tx(bar, 3u * T::BOX_BYTES);   // tensor coordinates: x in 8-byte elements (see wavelet_tensor_map), y in rows
+        tma_load_2d(base, &tm_nd, (x0 - T::HL) * 2, y0 - T::HL, bar);
+        tma_load_2d(base + T::PLANE, &tm_di, (x0 - T::HL) * 2, y0 - T::HL, bar);
+        tma_load_2d(base + 2u * T::PLANE, &tm_gi, (x0 - T::HL) * 2, y0 - T::HL, bar);
     }
     const u32 px = (u32)(x0 + tx), py = (u32)(y0 + ty);
     const bool in = px < (u32)cam.w && py < (u32)cam.y1;
@@ -994,17 +1045,9 @@ __global__ void __launch_bounds__(TW * TH) k_denoise_wavelet_tiled(KPARAMS, u32 
     const size_t i = pix(cam, px, py);
     float4 cnd = t_nd[c];
     float4 cdi = t_di[c];
-    float3 cdc = xyz(cdi); float cdv = cdi.w;
-    if (cnd.w == 0.0f) { di_out[i] = f4(cdc, cdv); return; }
-    float4 cgi = t_gi[c];
-    float3 cgc = xyz(cgi); float cgv = cgi.w;
-    float3 cn = xyz(cnd);
-    float scdl = sv_sqrt<FAST>(sv_luma<FAST>(cdc)), scgl = sv_sqrt<FAST>(sv_luma<FAST>(cgc));
-    float ls_di = lerpc(2.5f, 0.5f, sv_sqrt<FAST>(cdv));
-    float ls_gi = lerpc(1.0f, 0.0f, sv_sqrt<FAST>(cgv));
-    float depth_sigma = 0.33f / strength;
-    float sdw = 1.0f; float3 sdc = cdc; float sdv = cdv;
-    float sgw = 1.0f; float3 sgc = cgc; float sgv = cgv;
+    if (cnd.w == 0.0f) { di_out[i] = f4(xyz(cdi), cdi.w); return; }   // sky: DI passes through, GI is not written (frame_denoising.rs:248-254)
+    WaveletCentre<FAST> ctr;
+    ctr.init(cnd, cdi, t_gi[c], 0.33f / strength);   // depth sigma is the same for DI and GI (frame_denoising.rs:264,267)
     const int cj = c + jo;
 #pragma unroll
     for (int oy = -1; oy <= 1; oy++) {
@@ -1014,33 +1057,12 @@ __global__ void __launch_bounds__(TW * TH) k_denoise_wavelet_tiled(KPARAMS, u32 
             const int k = cj + oy * S * T::BW + ox * S;
             float4 nds = t_nd[k];
             if (nds.w == 0.0f) continue;   // sky, or outside the frame (zero-filled by the tensor copy)
-            float dw = svgf_depth_weight<FAST>(cnd.w, nds.w, depth_sigma);
-            float nw = svgf_normal_weight<FAST>(cn, xyz(nds));
-            if (dw == 0.0f || nw == 0.0f) continue;
-            float dnw = dw * nw;
-            float4 sdi = t_di[k];
-            float4 sgi = t_gi[k];
-            if (FAST) {
-                float wd = svgf_luma_weight<true>(scdl, sv_luma<true>(xyz(sdi)), ls_di) * dnw;
-                if (wd > 0.0f) { sdw += wd; sdc = f3(__fmaf_rn(wd, sdi.x, sdc.x), __fmaf_rn(wd, sdi.y, sdc.y), __fmaf_rn(wd, sdi.z, sdc.z)); sdv = __fmaf_rn(wd * wd, sdi.w, sdv); }
-                float wg = svgf_luma_weight<true>(scgl, sv_luma<true>(xyz(sgi)), ls_gi) * dnw;
-                if (wg > 0.0f) { sgw += wg; sgc = f3(__fmaf_rn(wg, sgi.x, sgc.x), __fmaf_rn(wg, sgi.y, sgc.y), __fmaf_rn(wg, sgi.z, sgc.z)); sgv = __fmaf_rn(wg * wg, sgi.w, sgv); }
-            } else {
-                float wd = svgf_luma_weight<false>(scdl, luma(xyz(sdi)), ls_di) * dw * nw;
-                if (wd > 0.0f) { sdw += wd; sdc = sdc + wd * xyz(sdi); sdv += sq(wd) * sdi.w; }
-                float wg = svgf_luma_weight<false>(scgl, luma(xyz(sgi)), ls_gi) * dw * nw;
-                if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
-            }
+            float dw, nw;
+            if (!ctr.geometry(nds, &dw, &nw)) continue;
+            ctr.add(dw, nw, t_di[k], t_gi[k]);
         }
     }
-    if (FAST) {
-        float rd = sfu_rcp(sdw), rg = sfu_rcp(sgw);
-        di_out[i] = f4(sdc * rd, sdv * (rd * rd));
-        gi_out[i] = f4(sgc * rg, sgv * (rg * rg));
-    } else {
-        di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
-        gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
-    }
+    ctr.store(di_out, gi_out, i);
 }
 
 // R2 frame_composition::fs (frame_composition.rs:19-82), linear HDR out
@@ -1407,6 +1429,87 @@ void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 
     if (fast) k_denoise_wavelet<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
     else k_denoise_wavelet<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
 }
+// K21, tile-staged: the 6x5 window of frame_denoising::estimate_variance (quirk C-3: row -2 spans x in [-2,2], rows -1..2 span
+// x in [-3,2]) is only walked by pixels whose history is shorter than 4 frames, but a warp pays for it as soon as one of its
+// pixels does; with the (TW+6) x (TH+4) neighbourhood in shared memory (three TMA tensor copies, zero fill outside the frame)
+// those 29 taps are LDS.128 at fixed offsets instead of 87 gathered global loads.  Same taps, order and arithmetic as
+// k_denoise_variance.
+template <int TW, int TH> struct VarianceTile {
+    static constexpr int HX = 3, HY = 2, BW = TW + 2 * HX, BH = TH + 2 * HY;
+    static constexpr u32 BOX_BYTES = (u32)(BW * BH * 16);
+    static constexpr u32 PLANE = (BOX_BYTES + 127u) & ~127u;
+    static constexpr u32 SMEM = 3u * PLANE + 128u;
+};
+template <bool FAST, int TW, int TH>
+__global__ void __launch_bounds__(TW * TH) k_denoise_variance_tiled(KPARAMS, int cur, const __grid_constant__ CUtensorMap tm_nd, const __grid_constant__ CUtensorMap tm_di,
+                                                                    const __grid_constant__ CUtensorMap tm_gi, u32* __restrict__ errors) {
+    typedef VarianceTile<TW, TH> T;
+    extern __shared__ unsigned char s_raw[];
+    __shared__ __align__(8) unsigned long long s_bar;
+    const int tx = (int)threadIdx.x % TW, ty = (int)threadIdx.x / TW;
+    const int x0 = (int)blockIdx.x * TW, y0 = cam.y0 + (int)blockIdx.y * TH;
+    const u32 bar = smem_addr(&s_bar);
+    const u32 raw = smem_addr(s_raw);
+    const u32 base = (raw + 127u) & ~127u;
+    if (threadIdx.x == 0) { mbar_init(bar, 1u); mbar_fence_init(); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(bar, 3u * T::BOX_BYTES);
+        tma_load_2d(base, &tm_nd, (x0 - T::HX) * 2, y0 - T::HY, bar);
+        tma_load_2d(base + T::PLANE, &tm_di, (x0 - T::HX) * 2, y0 - T::HY, bar);
+        tma_load_2d(base + 2u * T::PLANE, &tm_gi, (x0 - T::HX) * 2, y0 - T::HY, bar);
+    }
+    const u32 px = (u32)(x0 + tx), py = (u32)(y0 + ty);
+    const bool in = px < (u32)cam.w && py < (u32)cam.y1;
+    const size_t i = in ? pix(cam, px, py) : 0;
+    float4 mdi = f4zero(), mgi = f4zero();
+    if (in) { mdi = cam.di_diff_moments[cur][i]; mgi = cam.gi_diff_moments[cur][i]; }   // in flight together with the tile
+    {
+        bool done = false;
+        for (u32 spin = 0; spin < (1u << 20) && !done; spin++) done = mbar_try_wait(bar, 0u);
+        if (!done) { if (threadIdx.x == 0) atomicAdd(errors, 1u); return; }
+    }
+    if (!in) return;
+    const float4* __restrict__ t_nd = reinterpret_cast<const float4*>(s_raw + (base - raw));
+    const float4* __restrict__ t_di = reinterpret_cast<const float4*>(s_raw + (base - raw) + T::PLANE);
+    const float4* __restrict__ t_gi = reinterpret_cast<const float4*>(s_raw + (base - raw) + 2u * T::PLANE);
+    const int c = (ty + T::HY) * T::BW + (tx + T::HX);
+    float4 cnd = t_nd[c];
+    float4 cdi = t_di[c], cgi = t_gi[c];
+    if (cnd.w == 0.0f) { cam.di_diff_stash[i] = cdi; cam.gi_diff_stash[i] = cgi; return; }
+    float di_var, gi_var;
+    if (mdi.x >= 4.0f) { di_var = mdi.z - sq(mdi.y); gi_var = mgi.z - sq(mgi.y); }
+    else {
+        float3 cn = xyz(cnd);
+        float scdl = sv_sqrt<FAST>(sv_luma<FAST>(xyz(cdi))), scgl = sv_sqrt<FAST>(sv_luma<FAST>(xyz(cgi)));
+        float3 sdi = f3s(0.f), sgi = f3s(0.f);
+#pragma unroll
+        for (int oy = -2; oy <= 2; oy++) {
+#pragma unroll
+            for (int ox = -3; ox <= 2; ox++) {
+                if (oy == -2 && ox == -3) continue;   // quirk C-3: the first row starts at -2
+                const int k = c + oy * T::BW + ox;
+                float4 nds = t_nd[k];
+                if (nds.w != 0.0f) {   // zero = sky, or outside the frame (zero-filled by the tensor copy)
+                    float common = svgf_depth_weight<FAST>(cnd.w, nds.w, 0.2f);
+                    float nw = svgf_normal_weight<FAST>(cn, xyz(nds));
+                    float sl = sv_luma<FAST>(xyz(t_di[k]));
+                    float w = svgf_luma_weight<FAST>(scdl, sl, 1.0f) * common * nw;
+                    sdi = sdi + f3(sl, sl * sl, 1.0f) * f3s(w);
+                    float gl = sv_luma<FAST>(xyz(t_gi[k]));
+                    float wg = svgf_luma_weight<FAST>(scgl, gl, 1.0f) * common * nw;
+                    sgi = sgi + f3(gl, gl * gl, 1.0f) * f3s(wg);
+                }
+            }
+        }
+        { float m1 = sdi.x / sdi.z, m2 = sdi.y / sdi.z; di_var = fabs_(m2 - m1 * m1) * 4.0f; }
+        { float m1 = sgi.x / sgi.z, m2 = sgi.y / sgi.z; gi_var = fabs_(m2 - m1 * m1) * 4.0f; }
+    }
+    di_var = rmax(di_var, 0.0f); gi_var = rmax(gi_var, 0.0f);
+    cam.di_diff_stash[i] = f4(xyz(cdi), di_var);
+    cam.gi_diff_stash[i] = f4(xyz(cgi), gi_var);
+}
+
 // ---- tile-staged K22: tensor maps + launcher --------------------------------------------------
 // A float4 image plane as a 2-D tensor of 8-byte elements (2W x H; the widest element type a tensor map
 // takes, so that a (TW+2·HL)-pixel box row stays under the 256-element box limit), row pitch W·16 B, no
@@ -1484,6 +1587,24 @@ bool launch_denoise_wavelet_tiled(const CameraDev& c, const SceneDev& s, u32 fra
     default: return false;
     }
 #undef ST_WT
+}
+template <bool FAST>
+static bool variance_tiled_go(const CameraDev& c, const SceneDev& s, int cur, u32* errors, cudaStream_t st) {
+    typedef VarianceTile<32, 8> T;
+    CUtensorMap tn, td, tg;
+    if (!wavelet_tensor_map(c.surface_nd, c.w, c.h, T::BW, T::BH, &tn) || !wavelet_tensor_map(c.di_diff_curr_colors, c.w, c.h, T::BW, T::BH, &td) ||
+        !wavelet_tensor_map(c.gi_diff_curr_colors, c.w, c.h, T::BW, T::BH, &tg)) return false;
+    auto kern = k_denoise_variance_tiled<FAST, 32, 8>;
+    static bool attr_set[64] = {};
+    int dev = 0; cudaGetDevice(&dev); dev &= 63;
+    if (!attr_set[dev]) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM) != cudaSuccess) { cudaGetLastError(); return false; } attr_set[dev] = true; }
+    dim3 grid((c.w + 31) / 32, (c.y1 - c.y0 + 7) / 8);
+    kern<<<grid, 256, T::SMEM, st>>>(c, s, cur, tn, td, tg, errors);
+    return true;
+}
+bool launch_denoise_variance_tiled(const CameraDev& c, const SceneDev& s, int cur, bool fast, u32* errors, cudaStream_t st) {
+    if (c.curr.screen.x != (float)c.w || c.curr.screen.y != (float)c.h) return false;   // zero fill == Camera::contains only then
+    return fast ? variance_tiled_go<true>(c, s, cur, errors, st) : variance_tiled_go<false>(c, s, cur, errors, st);
 }
 void launch_composition(const CameraDev& c, const SceneDev& s, int cur, u32 mode, const float4* di_diff, const float4* gi_diff, cudaStream_t st) { k_composition<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, mode, di_diff, gi_diff); }
 void launch_output_rgba8(const CameraDev& c, const SceneDev& s, uchar4* out, cudaStream_t st) { k_output_rgba8<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, out); }

@@ -19,9 +19,11 @@ OPT_WAVELET_TILED = 4      # bit i = à-trous iteration i runs the tile-staged (
 OPT_WAVELET_TILE_CFG = 5   # 4 bits per iteration: 0 32x8, 1 32x16, 2 64x4, 3 64x8 output tile
 OPT_FUSE_REPROJECT = 6     # K20 for DI and GI in one launch
 OPT_BVH_REUSE = 7          # graft unchanged subtrees of the previous BVH (reference behaviour)
+OPT_VARIANCE_TILED = 8     # K21 window from a TMA-filled shared-memory tile
 STAT_WAVELET_TILED_LAUNCHES = 1
 STAT_WAVELET_TILED_ERRORS = 2
 STAT_BVH_GRAFTED_SUBTREES = 3
+STAT_VARIANCE_TILED_LAUNCHES = 4
 
 
 class StrolleError(RuntimeError):

@@ -200,15 +200,15 @@ def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size, til
     from strolle_b200 import multigpu as mg
     w, h = size
     scene = scenes.cornell(w, h)
-    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_FUSE_REPROJECT
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_FUSE_REPROJECT, OPT_VARIANCE_TILED
     ref = gpu.Engine(blue_noise=blue_noise)   # default (fast SVGF weights): strips must match it bit for bit too
-    ref.set_option(OPT_WAVELET_TILED, 0); ref.set_option(OPT_FUSE_REPROJECT, 0)   # the full frame runs the plain kernels ...
+    ref.set_option(OPT_WAVELET_TILED, 0); ref.set_option(OPT_FUSE_REPROJECT, 0); ref.set_option(OPT_VARIANCE_TILED, 0)   # the full frame runs the plain kernels ...
     cref = scenes.apply(ref, scene)
     engines, cams, runners = [], [], []
     lt = _LocalTransport()
     for r in range(world):
         e = gpu.Engine(blue_noise=blue_noise)
-        e.set_option(OPT_WAVELET_TILED, tiled); e.set_option(OPT_FUSE_REPROJECT, 1 if tiled else 0)   # ... the strips also the tile-staged K22 / fused K20
+        e.set_option(OPT_WAVELET_TILED, tiled); e.set_option(OPT_FUSE_REPROJECT, 1 if tiled else 0); e.set_option(OPT_VARIANCE_TILED, 1 if tiled else 0)   # ... the strips also the tile-staged K22 / fused K20
         c = scenes.apply(e, scene)
         rn = mg.StripRunner(e, c, w, h, rank=0, world=1)   # built as single, then configured as a strip by hand
         rn.rank, rn.world = r, world
@@ -404,6 +404,30 @@ def test_tiled_wavelet_matches_gather(gpu, blue_noise, cfg, exact):
                 assert_bits_equal(eb.read_buffer(cb, name), ea.read_buffer(ca, name), f"{size} cfg {cfg} frame {f + 1} {name}")
         assert ea.get_stat(STAT_WAVELET_TILED_LAUNCHES) == 0
         assert eb.get_stat(STAT_WAVELET_TILED_LAUNCHES) == 20, "the tile-staged kernel must be the one that ran"
+        assert eb.get_stat(STAT_WAVELET_TILED_ERRORS) == 0
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_tiled_variance_matches_gather(gpu, oracle, blue_noise, exact):
+    """K21 with its 6x5 window staged in shared memory by TMA == the gather kernel, bit for bit, in both arithmetic flavours;
+    frames 1-3 walk the window for every pixel (history < 4), later frames mix both paths; strict mode also == oracle."""
+    from strolle_b200.engine import OPT_VARIANCE_TILED, STAT_VARIANCE_TILED_LAUNCHES, STAT_WAVELET_TILED_ERRORS
+    for size in [(200, 120), (67, 45)]:
+        scene = scenes.cornell(*size)
+        ea, eb = gpu.Engine(blue_noise=blue_noise, exact=exact), gpu.Engine(blue_noise=blue_noise, exact=exact)
+        ea.set_option(OPT_VARIANCE_TILED, 0); eb.set_option(OPT_VARIANCE_TILED, 1)
+        ca, cb = scenes.apply(ea, scene), scenes.apply(eb, scene)
+        eo = oracle.OracleEngine(blue_noise=blue_noise) if exact else None
+        co = scenes.apply(eo, scene) if exact else None
+        for f in range(6):
+            ea.tick(); eb.tick(); ea.render_camera(ca); eb.render_camera(cb)
+            if exact:
+                eo.tick(); eo.render_camera(co)
+            for name in DENOISER_BUFFERS:
+                assert_bits_equal(eb.read_buffer(cb, name), ea.read_buffer(ca, name), f"{size} frame {f + 1} {name}")
+                if exact:
+                    assert_bits_equal(eb.read_buffer(cb, name), eo.read_buffer(co, name), f"{size} frame {f + 1} {name} vs oracle")
+        assert ea.get_stat(STAT_VARIANCE_TILED_LAUNCHES) == 0 and eb.get_stat(STAT_VARIANCE_TILED_LAUNCHES) == 6
         assert eb.get_stat(STAT_WAVELET_TILED_ERRORS) == 0
 
 

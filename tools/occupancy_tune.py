@@ -38,7 +38,7 @@ if "--child" in sys.argv:
 args = [a for a in sys.argv[1:] if not a.startswith("--")]
 w, h = (args[0], args[1]) if len(args) >= 2 else ("1920", "1080")
 libs = {"base": os.path.join(ROOT, "strolle_b200", "_lib", "libstrolle_b200.so")}
-for p in sorted(glob.glob(os.path.join(ROOT, "strolle_b200", "_lib", "libstrolle_b200_minb*.so"))):
+for p in sorted(glob.glob(os.path.join(ROOT, "strolle_b200", "_lib", "libstrolle_b200_*.so"))):
     libs[os.path.basename(p)[len("libstrolle_b200_"):-3]] = p
 table = {}
 for tag, lib in libs.items():
