@@ -172,7 +172,7 @@ const char* st_pass_name(int pass);
 enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8 };
 /* ST_OPT_VARIANCE_TILED: 1 = K21 frame_denoising::estimate_variance (frame_denoising.rs:81-217) reads its 6x5 window from a
  * shared-memory tile filled by TMA tensor copies (identical results). */
-#define ST_VARIANCE_TILED_DEFAULT 0
+#define ST_VARIANCE_TILED_DEFAULT 1
 /* ST_OPT_BVH_REUSE (default 1): a BVH refresh takes over the subtrees of the previous tree whose primitive-centre
  * sequence is unchanged, as the reference does (strolle/src/bvh/builder.rs:245-275, hash = primitive.rs:27-37);
  * 0 = every refresh builds from scratch.  Both give the same tree unless a primitive changed while its centre did

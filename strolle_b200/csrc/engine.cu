@@ -361,6 +361,9 @@ struct CameraSlot {
     std::vector<std::pair<std::string, size_t>> sizes;      // float4 count per named buffer
     DevMem arena;
     DevMem rgba8; int rgba8_slot = 0;
+    // asynchronous RGBA8 read-back: slot k of the staging buffer is converted on the engine stream (ev_ready[k]) and copied to
+    // the host on the copy stream (ev_copied[k]); the engine stream only waits for ev_copied[k] before reusing slot k
+    cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // peer-memory link of the strip partition: other ranks' arena / flag / rgba8 allocations mapped through CUDA IPC
     struct PeerLink { bool ready = false; std::vector<char*> arena, rgba8; std::vector<uint32_t*> flags; DevMem sync; uint32_t seq = 0; } peer;
 };
@@ -374,6 +377,7 @@ using namespace st;
 struct st_engine {
     int device = 0;
     cudaStream_t stream = nullptr; bool own_stream = true;
+    cudaStream_t copy_stream = nullptr;   // device->host copies of finished frames (ST_OPT_ASYNC_OUTPUT), so that they overlap the next frame
     // meshes / materials / instances / triangles -------------------------------------------------
     std::unordered_map<st_handle, std::vector<st_mesh_triangle>> meshes;
     std::vector<st_material> materials; std::vector<st_handle> material_handles; bool materials_dirty = false;
@@ -862,13 +866,15 @@ void st_engine_destroy(st_engine* e) {
     if (!e) return;
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
-    for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); delete c; }
+    if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
+    for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); for (int k = 0; k < 2; k++) { if (c->ev_ready[k]) cudaEventDestroy(c->ev_ready[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); } delete c; }
     DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb, &e->d_tri_instance, &e->d_instance_xforms, &e->d_tile_errors};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
     for (cudaEvent_t ev : e->event_pool) cudaEventDestroy(ev);
     if (e->comm) g_nccl.CommDestroy(e->comm);
     if (e->own_stream) cudaStreamDestroy(e->stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     delete e;
 }
 
@@ -1033,6 +1039,7 @@ int st_delete_camera(st_engine* e, st_camera_handle h) {
     if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
+    if (e->copy_stream) CK(cudaStreamSynchronize(e->copy_stream));
     cs->alive = false; cs->arena.release(); cs->rgba8.release();
     return ST_OK;
 }
@@ -1163,14 +1170,30 @@ int st_copy_output(st_engine* e, st_camera_handle h, void* host_out, int format)
             int rc2 = cs->rgba8.ensure(2 * n * 4); if (rc2) return rc2;
             cs->rgba8_slot ^= 1;
             SceneDev sc = e->scene(); uchar4* dst8 = (uchar4*)cs->rgba8.p + (cs->rgba8_slot ? n : 0); CameraDev cd = cs->dev;
+            const int k = cs->rgba8_slot;
+            if (e->async_output) {   // conversion on the engine stream, copy on the copy stream: the next frame's passes do not queue behind the copy
+                if (!e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+                if (!cs->ev_ready[k]) { CK(cudaEventCreateWithFlags(&cs->ev_ready[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&cs->ev_copied[k], cudaEventDisableTiming)); }
+                else CK(cudaStreamWaitEvent(e->stream, cs->ev_copied[k], 0));   // slot k's previous copy must have left the staging buffer
+            }
             e->run_timed(P_COMPOSITION, [=](cudaStream_t s) { launch_output_rgba8(cd, sc, dst8, s); });
-            CK(cudaMemcpyAsync(host_out, dst8, n * 4, cudaMemcpyDeviceToHost, e->stream));
+            if (e->async_output) {
+                CK(cudaEventRecord(cs->ev_ready[k], e->stream));
+                CK(cudaStreamWaitEvent(e->copy_stream, cs->ev_ready[k], 0));
+                CK(cudaMemcpyAsync(host_out, dst8, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+                CK(cudaEventRecord(cs->ev_copied[k], e->copy_stream));
+            } else CK(cudaMemcpyAsync(host_out, dst8, n * 4, cudaMemcpyDeviceToHost, e->stream));
         } else return fail(ST_ERR_INVALID, "unsupported output format");
         if (!e->async_output) CK(cudaStreamSynchronize(e->stream));
     }
     return ST_OK;
 }
-int st_synchronize(st_engine* e) { if (!e) return fail(ST_ERR_INVALID, "null engine"); CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream)); return ST_OK; }
+int st_synchronize(st_engine* e) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
+    if (e->copy_stream) CK(cudaStreamSynchronize(e->copy_stream));
+    return ST_OK;
+}
 
 int st_read_buffer(st_engine* e, st_camera_handle h, const char* name, float* dst, size_t cap, size_t* count) {
     CameraSlot* cs = e ? get_camera(e, h) : nullptr;

@@ -459,3 +459,32 @@ def test_fused_reproject_matches_two_launches(gpu, oracle, blue_noise):
         for name in DENOISER_BUFFERS:
             assert_bits_equal(eg.read_buffer(cg, name), e2.read_buffer(c2, name), f"fused vs split frame {f + 1} {name}")
             assert_bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name), f"fused vs oracle frame {f + 1} {name}")
+
+
+def test_async_rgba8_output_pipeline(gpu, blue_noise):
+    """ST_OPT_ASYNC_OUTPUT: the Rgba8UnormSrgb frame is converted on the engine stream and copied to the caller's pinned buffer on
+    a copy stream while the next frame renders; after st_synchronize every buffer holds exactly the frame a blocking read-back
+    returns (two host buffers in flight, three frames deep, then a format the async path does not cover)."""
+    import torch
+    from strolle_b200.engine import OPT_ASYNC_OUTPUT, FORMAT_RGBA8_SRGB, FORMAT_RGBA32F
+    w, h = 160, 90
+    scene = scenes.cornell(w, h)
+    ea, eb = gpu.Engine(blue_noise=blue_noise), gpu.Engine(blue_noise=blue_noise)
+    ca, cb = scenes.apply(ea, scene), scenes.apply(eb, scene)
+    ea.set_option(OPT_ASYNC_OUTPUT, 1)
+    pinned = [torch.zeros((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)]
+    views = [p.numpy() for p in pinned]
+    blocking = np.zeros((h, w, 4), dtype=np.uint8)
+    for f in range(7):
+        ea.tick(); eb.tick()
+        ea.render_camera(ca, out=views[f & 1], fmt=FORMAT_RGBA8_SRGB)
+        eb.render_camera(cb, out=blocking, fmt=FORMAT_RGBA8_SRGB)
+        if f >= 1 and f % 2 == 0:      # buffers are only looked at after a synchronize
+            ea.synchronize()
+            assert (views[f & 1] == blocking).all(), f"async frame {f + 1} differs from the blocking read-back"
+    ea.synchronize()
+    assert (views[0] == blocking).all() and blocking[..., :3].max() > 0 and (blocking[..., 3] == 255).all()
+    f32a, f32b = np.zeros((h, w, 4), np.float32), np.zeros((h, w, 4), np.float32)
+    ea.copy_output(ca, f32a, FORMAT_RGBA32F); eb.copy_output(cb, f32b, FORMAT_RGBA32F)
+    ea.synchronize()
+    assert_bits_equal(f32a, f32b, "float read-back in async mode")
