@@ -236,13 +236,14 @@ def main():
     barrier()
 
     # ---- region A2: the same K frames again with per-pass CUDA events and the ray counter switched on -----
-    eng.enable_timing(True); eng.pass_times(reset=True)
+    eng.enable_timing(True); eng.pass_times(reset=True); eng.wavelet_times(reset=True)
     eng.count_rays(True); eng.ray_count(reset=True)
     barrier()
     for _ in range(args.steps):
         eng.tick(); runner.render()
     barrier()
     pass_ms, launches = eng.pass_times(reset=True)
+    wav_ms, wav_launches = eng.wavelet_times(reset=True)
     rays = eng.ray_count(reset=True)
     eng.enable_timing(False); eng.count_rays(False)
     times = torch.tensor([dev_ms, wall_ms, float(rays), float(launches.sum())], dtype=torch.float64, device="cuda")
@@ -325,6 +326,16 @@ def main():
             roofline["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    # K22 per à-trous iteration: strides 1, 2, 4, 8 run the tile-staged (TMA) kernel, stride 16 the gather kernel (ST_OPT_WAVELET_TILED)
+    tiled_mask = strolle_b200.engine.WAVELET_TILED_DEFAULT
+    wavelet_iterations = []
+    for it in range(5):
+        if wav_launches[it]:
+            dur_s = float(wav_ms[it]) / int(wav_launches[it]) / 1000.0
+            alg = 80 * W * rows
+            wavelet_iterations.append({"stride": 1 << it, "kernel": "k_denoise_wavelet_tiled (TMA tile in shared memory)" if (tiled_mask >> it) & 1 else "k_denoise_wavelet (per-tap gather)",
+                                       "avg_launch_us": dur_s * 1e6, "achieved": alg / dur_s / 1e9, "frac": alg / dur_s / 1e9 / peak})
+    roofline["per_iteration"] = wavelet_iterations
     extra_roof = [r for r in (roof(n) for n in ["prim_gbuffer", "di_spatial_resampling_trace", "gi_spatial_resampling_trace", "frame_denoising_estimate_variance", "frame_denoising_reproject"]) if r]
 
     # ---- CPU baseline (bounded sample) -----------------------------------------------------------------

@@ -165,6 +165,9 @@ int st_device_math(st_engine* e, int op, const float* a, const float* b, float* 
 int st_enable_timing(st_engine* e, int enabled);
 int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset);
 const char* st_pass_name(int pass);
+/* K22 frame_denoising::wavelet per à-trous iteration i (stride 2^i, strolle/src/camera_controller/passes/frame_denoising.rs:161-189):
+ * device time (ms) and launches accumulated while timing is enabled; 5 entries each. */
+int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset);
 /* Engine options.  ST_OPT_SVGF_FAST_MATH (default 1): the SVGF edge-stopping weights (K21/K22) use the
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the

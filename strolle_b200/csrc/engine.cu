@@ -368,7 +368,7 @@ struct CameraSlot {
     struct PeerLink { bool ready = false; std::vector<char*> arena, rgba8; std::vector<uint32_t*> flags; DevMem sync; uint32_t seq = 0; } peer;
 };
 
-struct Step { int pass; std::function<void(cudaStream_t)> run; };
+struct Step { int pass; std::function<void(cudaStream_t)> run; int sub = -1; };   // sub: à-trous iteration of a K22 step
 
 }  // namespace st
 
@@ -421,7 +421,8 @@ struct st_engine {
     // timing ---------------------------------------------------------------------------------------
     bool timing = false;
     float pass_ms[P_COUNT] = {}; uint32_t pass_launches[P_COUNT] = {};
-    struct Timed { int pass; cudaEvent_t a, b; };
+    float wavelet_ms[5] = {}; uint32_t wavelet_launches[5] = {};   // K22 per à-trous iteration (st_wavelet_times)
+    struct Timed { int pass; cudaEvent_t a, b; int sub; };
     std::vector<Timed> pending; std::vector<cudaEvent_t> event_pool;
     cudaEvent_t mark_a = nullptr, mark_b = nullptr;
     // row-strip partition: NCCL communicator over the ranks that share the frame
@@ -442,14 +443,14 @@ struct st_engine {
     }
     uint32_t* light_slot(st_handle h) { for (auto& p : light_slots) if (p.first == h) return &p.second; return nullptr; }
     cudaEvent_t get_event() { if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; } cudaEvent_t e; cudaEventCreate(&e); return e; }
-    void run_timed(int pass, const std::function<void(cudaStream_t)>& fn) {
+    void run_timed(int pass, const std::function<void(cudaStream_t)>& fn, int sub = -1) {
         if (!timing) { fn(stream); pass_launches[pass]++; return; }
-        Timed t; t.pass = pass; t.a = get_event(); t.b = get_event();
+        Timed t; t.pass = pass; t.sub = sub; t.a = get_event(); t.b = get_event();
         cudaEventRecord(t.a, stream); fn(stream); cudaEventRecord(t.b, stream);
         pending.push_back(t); pass_launches[pass]++;
     }
     void collect_timing() {
-        for (Timed& t : pending) { cudaEventSynchronize(t.b); float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b); pass_ms[t.pass] += ms; event_pool.push_back(t.a); event_pool.push_back(t.b); }
+        for (Timed& t : pending) { cudaEventSynchronize(t.b); float ms = 0; cudaEventElapsedTime(&ms, t.a, t.b); pass_ms[t.pass] += ms; if (t.pass == P_DENOISE_WAVELET && t.sub >= 0 && t.sub < 5) { wavelet_ms[t.sub] += ms; wavelet_launches[t.sub]++; } event_pool.push_back(t.a); event_pool.push_back(t.b); }
         pending.clear();
     }
 };
@@ -702,6 +703,7 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
                 if (tiled && launch_denoise_wavelet_tiled(cam, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, cfg, terr, s)) { e->wavelet_tiled_launches++; return; }
                 launch_denoise_wavelet(cam, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s);
             });
+            steps->back().sub = (int)nth;
         }
     }
     uint32_t mode = (uint32_t)d.mode;
@@ -1149,7 +1151,7 @@ int st_render_range(st_engine* e, st_camera_handle h, int first, int last) {
     int rc = ensure_luts(e); if (rc) return rc;
     std::vector<Step> steps; build_schedule(e, cs, &steps);
     if (last < 0 || last >= (int)steps.size()) last = (int)steps.size() - 1;
-    for (int i = std::max(first, 0); i <= last; i++) e->run_timed(steps[i].pass, steps[i].run);
+    for (int i = std::max(first, 0); i <= last; i++) e->run_timed(steps[i].pass, steps[i].run, steps[i].sub);
     CK(cudaGetLastError());
     return ST_OK;
 }
@@ -1450,7 +1452,7 @@ int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int forma
     if (peer && (rc = halo_exchange_peer(e, cs, nullptr))) return rc;   // frame barrier: nobody still reads last frame's rows
     for (int i = 0; i < (int)steps.size(); i++) {
         if (next < plan.size() && plan[next].before_step == i) { if ((rc = peer ? halo_exchange_peer(e, cs, &plan[next]) : halo_exchange(e, cs, plan[next]))) return rc; next++; }
-        e->run_timed(steps[i].pass, steps[i].run);
+        e->run_timed(steps[i].pass, steps[i].run, steps[i].sub);
     }
     CK(cudaGetLastError());
     if (!gather) return ST_OK;
@@ -1513,6 +1515,16 @@ int st_pass_times(st_engine* e, float* ms, uint32_t* launches, int reset) {
     e->collect_timing();
     for (int i = 0; i < P_COUNT; i++) { if (ms) ms[i] = e->pass_ms[i]; if (launches) launches[i] = e->pass_launches[i]; }
     if (reset) { std::memset(e->pass_ms, 0, sizeof e->pass_ms); std::memset(e->pass_launches, 0, sizeof e->pass_launches); }
+    return ST_OK;
+}
+
+/* K22 per à-trous iteration (stride 2^i): device time and launch count since the last reset (timing enabled). */
+int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset) {
+    if (!e) return fail(ST_ERR_INVALID, "null engine");
+    CK(cudaSetDevice(e->device));
+    e->collect_timing();
+    for (int i = 0; i < 5; i++) { if (ms5) ms5[i] = e->wavelet_ms[i]; if (launches5) launches5[i] = e->wavelet_launches[i]; }
+    if (reset) { std::memset(e->wavelet_ms, 0, sizeof e->wavelet_ms); std::memset(e->wavelet_launches, 0, sizeof e->wavelet_launches); }
     return ST_OK;
 }
 

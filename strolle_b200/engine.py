@@ -20,6 +20,7 @@ OPT_WAVELET_TILE_CFG = 5   # 4 bits per iteration: 0 32x8, 1 32x16, 2 64x4, 3 64
 OPT_FUSE_REPROJECT = 6     # K20 for DI and GI in one launch
 OPT_BVH_REUSE = 7          # graft unchanged subtrees of the previous BVH (reference behaviour)
 OPT_VARIANCE_TILED = 8     # K21 window from a TMA-filled shared-memory tile
+WAVELET_TILED_DEFAULT = 15   # include/strolle_b200.h ST_WAVELET_TILED_DEFAULT
 STAT_WAVELET_TILED_LAUNCHES = 1
 STAT_WAVELET_TILED_ERRORS = 2
 STAT_BVH_GRAFTED_SUBTREES = 3
@@ -94,7 +95,7 @@ def load_library():
         "st_peer_export": [P, i32, C.c_void_p], "st_peer_import": [P, i32, C.c_void_p, C.c_int, C.c_int],
         "st_peer_errors": [P, i32, C.POINTER(u32)],
         "st_mark_begin": [P], "st_mark_end": [P, f32p],
-        "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int],
+        "st_enable_timing": [P, C.c_int], "st_pass_times": [P, C.c_void_p, C.c_void_p, C.c_int], "st_wavelet_times": [P, C.c_void_p, C.c_void_p, C.c_int],
         "st_camera_set_strip": [P, i32, C.c_int, C.c_int],
         "st_buffer_device_ptr": [P, i32, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
         "st_frame_schedule": [P, i32, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)], "st_render_range": [P, i32, C.c_int, C.c_int],
@@ -423,6 +424,13 @@ class Engine:
         ms = np.zeros(PASS_COUNT, dtype=np.float32)
         launches = np.zeros(PASS_COUNT, dtype=np.uint32)
         self._check(self.lib.st_pass_times(self._h, ms.ctypes.data, launches.ctypes.data, int(reset)))
+        return ms, launches
+
+    def wavelet_times(self, reset=False):
+        """K22 per à-trous iteration (stride 1, 2, 4, 8, 16): (ms[5], launches[5]) while timing is enabled."""
+        ms = np.zeros(5, dtype=np.float32)
+        launches = np.zeros(5, dtype=np.uint32)
+        self._check(self.lib.st_wavelet_times(self._h, ms.ctypes.data, launches.ctypes.data, int(reset)))
         return ms, launches
 
 
