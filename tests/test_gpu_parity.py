@@ -192,7 +192,8 @@ class _LocalTransport:
         torch.cuda.synchronize()
 
 
-@pytest.mark.parametrize("world,size,tiled", [(2, (160, 96), 0), (4, (128, 160), 0), (2, (160, 96), 31), (3, (200, 150), 31)])
+@pytest.mark.parametrize("world,size,tiled", [(2, (160, 96), 0), (4, (128, 160), 0), (2, (160, 96), 31), (3, (200, 150), 31),
+                                              (4, (1920, 1080), 31)])   # the last one: BASELINE.json's frame size, 270-row strips (config C4's strip height)
 def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size, tiled):
     """Strip-partitioned rendering (SURVEY §8e, config C4's shape) is bit-identical to the single-GPU frame:
     `world` engines each compute one row strip and exchange halo rows according to multigpu.plan_frame."""
@@ -218,7 +219,7 @@ def test_row_strips_reproduce_single_gpu_frame(gpu, blue_noise, world, size, til
         e.set_stream(torch.cuda.current_stream().cuda_stream)
         engines.append(e); cams.append(c); runners.append(rn)
     lt.runners = runners
-    for f in range(7):
+    for f in range(7 if w * h < 500000 else 3):
         ref.tick(); ref.render_camera(cref)
         for e in engines:
             e.tick()
@@ -488,3 +489,46 @@ def test_async_rgba8_output_pipeline(gpu, blue_noise):
     ea.copy_output(ca, f32a, FORMAT_RGBA32F); eb.copy_output(cb, f32b, FORMAT_RGBA32F)
     ea.synchronize()
     assert_bits_equal(f32a, f32b, "float read-back in async mode")
+
+
+def test_full_size_properties(gpu, oracle, blue_noise):
+    """BASELINE.json's full size (Cornell 1920x1080, configs[1]), checked through properties that do not need the oracle to
+    render 2 M pixels per pass: (1) every kernel variant behind an option gives the bits of the plain kernels on all 37
+    buffers; (2) the same seeds give the same bits again (determinism); (3) one closest-hit and one any-hit ray per pixel
+    (2,073,600 each, both scenes) are bit-identical to the oracle's traversal — hit triangle / material ids included — and the
+    Cornell ones to brute force over all triangles; (4) the frame is finite and lit."""
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_FUSE_REPROJECT, OPT_VARIANCE_TILED, OPT_BVH_REUSE
+    w, h = 1920, 1080
+    scene = scenes.cornell(w, h)
+    plain = gpu.Engine(blue_noise=blue_noise, exact=True)
+    for opt in (OPT_WAVELET_TILED, OPT_FUSE_REPROJECT, OPT_VARIANCE_TILED, OPT_BVH_REUSE):
+        plain.set_option(opt, 0)
+    tuned, again = gpu.Engine(blue_noise=blue_noise, exact=True), gpu.Engine(blue_noise=blue_noise, exact=True)
+    cams = [scenes.apply(e, scene) for e in (plain, tuned, again)]
+    for f in range(3):
+        for e, c in zip((plain, tuned, again), cams):
+            e.tick(); e.render_camera(c)
+    for name in CAMERA_BUFFERS:
+        a = plain.read_buffer(cams[0], name)
+        assert_bits_equal(tuned.read_buffer(cams[1], name), a, f"1080p tuned vs plain kernels: {name}")
+        assert_bits_equal(again.read_buffer(cams[2], name), tuned.read_buffer(cams[1], name), f"1080p determinism: {name}")
+    img = tuned.read_buffer(cams[1], "output").reshape(h, w, 4)
+    assert np.isfinite(img).all() and img[..., :3].mean() > 0.01
+    n = w * h
+    for scene_name in ("cornell", "dungeon"):
+        if scene_name == "cornell":
+            sc, lo, hi = scenes.cornell(64, 64), (-1.0, 0.0, -1.0), (1.0, 2.0, 3.2)
+        else:
+            sc, lo, hi = scenes.dungeon(64, 64), (-20.0, 0.1, -40.0), (10.0, 2.9, -5.0)
+        eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, sc)
+        eg.tick(); eo.tick()
+        rays = random_rays(n, 11, lo, hi)
+        hg, ho = eg.trace_closest(rays), eo.trace_closest(rays)
+        assert (hg[:, 9].view(np.uint32) == ho[:, 9].view(np.uint32)).all() and (hg[:, 10].view(np.uint32) == ho[:, 10].view(np.uint32)).all(), f"{scene_name}: hit ids"
+        assert_bits_equal(hg, ho, f"{scene_name}: {n} closest-hit records")
+        rays_any = random_rays(n, 12, lo, hi, max_len=4.0)
+        assert (eg.trace_any(rays_any) == eo.trace_any(rays_any)).all(), f"{scene_name}: {n} any-hit answers"
+        if scene_name == "cornell":
+            dist_brute, tri_brute = eo.trace_brute(rays)
+            hit = ho[:, 8] < 3e38
+            assert (dist_brute[hit].view(np.uint32) == hg[hit, 8].view(np.uint32)).all(), "closest distances == brute force over all triangles"
