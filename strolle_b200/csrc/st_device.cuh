@@ -142,16 +142,23 @@ ST_DEV void count_ray(const SceneDev& sc) {
         if ((threadIdx.x & 31u) == (unsigned)(__ffs(m) - 1)) atomicAdd(sc.ray_counter, (unsigned long long)__popc(m));
     }
 }
+// Both traversals are written "while-while": a lane first walks internal nodes until it stands on a leaf entry (or runs out of
+// work), then the whole run of leaf entries, then pops.  Per lane this is exactly the node sequence of the reference's single
+// loop; across a warp it lets lanes that are still descending catch up before anyone starts triangle tests, so the expensive
+// Möller–Trumbore code runs with more lanes active.
 template <bool COUNT_MEMORY = false>
 ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack& stk, u32* used_memory = nullptr) {
     count_ray(sc);
     TriHit hit = trihit_none();
     float hu = 0.f, hv = 0.f, hid = 0.f;
     u32 ptr = 0u, sp = 0u, used = 0u;
-    for (;;) {
-        if (COUNT_MEMORY) used += 16u;
-        float4 d0 = ldg4(sc.bvh + ptr);
-        if (fbits(d0.w) == 0u) {
+    bool alive = true;
+    while (alive) {
+        float4 d0;
+        for (;;) {   // descend: internal nodes
+            if (COUNT_MEMORY) used += 16u;
+            d0 = ldg4(sc.bvh + ptr);
+            if (fbits(d0.w) != 0u) break;
             if (COUNT_MEMORY) used += 48u;
             float4 d1 = ldg4(sc.bvh + ptr + 1), d2 = ldg4(sc.bvh + ptr + 2), d3 = ldg4(sc.bvh + ptr + 3);
             u32 near_ptr = ptr + 4u, far_ptr = fbits(d1.w);
@@ -160,7 +167,11 @@ ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack
             if (far_d < near_d) { u32 tp = near_ptr; near_ptr = far_ptr; far_ptr = tp; float tf = near_d; near_d = far_d; far_d = tf; }
             if (far_d < hit.t) { stk_push(stk, sp, far_ptr); sp += 1u; }
             if (near_d < hit.t) { ptr = near_ptr; continue; }
-        } else {
+            if (sp > 0u) { sp -= 1u; ptr = stk_get(stk, sp); continue; }
+            alive = false; break;
+        }
+        if (!alive) break;
+        for (;;) {   // the run of leaf entries that starts here (one float4 each, flag bit 0 = another follows)
             if (COUNT_MEMORY) used += 144u;
             u32 flags = fbits(d0.x), tid = fbits(d0.y), mid = fbits(d0.z);
             float t, u, v, inv_det;
@@ -174,10 +185,13 @@ ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack
                 }
                 if (accept) { hit.t = t; hu = u; hv = v; hid = inv_det; hit.triangle_id = tid; hit.material_id = mid; }
             }
-            if (flags & 1u) { ptr += 1u; continue; }
+            if (!(flags & 1u)) break;
+            ptr += 1u;
+            if (COUNT_MEMORY) used += 16u;
+            d0 = ldg4(sc.bvh + ptr);
         }
         if (sp > 0u) { sp -= 1u; ptr = stk_get(stk, sp); }
-        else break;
+        else alive = false;
     }
     if (trihit_some(hit)) {
         tri_shade(sc.triangles + 9u * (size_t)hit.triangle_id, hu, hv, hid, &hit.normal, &hit.uv);
@@ -192,9 +206,12 @@ ST_DEV bool trace_any(const Ray& ray, const SceneDev& sc, const TraceStack& stk)
     count_ray(sc);
     const float best = ray.len;
     u32 ptr = 0u, sp = 0u;
-    for (;;) {
-        float4 d0 = ldg4(sc.bvh + ptr);
-        if (fbits(d0.w) == 0u) {
+    bool found = false, alive = true;
+    while (alive) {
+        float4 d0;
+        for (;;) {
+            d0 = ldg4(sc.bvh + ptr);
+            if (fbits(d0.w) != 0u) break;
             float4 d1 = ldg4(sc.bvh + ptr + 1), d2 = ldg4(sc.bvh + ptr + 2), d3 = ldg4(sc.bvh + ptr + 3);
             u32 near_ptr = ptr + 4u, far_ptr = fbits(d1.w);
             float near_d = box_entry(ray, xyz(d0), xyz(d1));
@@ -202,20 +219,27 @@ ST_DEV bool trace_any(const Ray& ray, const SceneDev& sc, const TraceStack& stk)
             if (far_d < near_d) { u32 tp = near_ptr; near_ptr = far_ptr; far_ptr = tp; float tf = near_d; near_d = far_d; far_d = tf; }
             if (far_d < best) { stk_push(stk, sp, far_ptr); sp += 1u; }
             if (near_d < best) { ptr = near_ptr; continue; }
-        } else {
+            if (sp > 0u) { sp -= 1u; ptr = stk_get(stk, sp); continue; }
+            alive = false; break;
+        }
+        if (!alive) break;
+        for (;;) {
             float t, u, v, inv_det;
             if (tri_test(sc.triangles + 9u * (size_t)fbits(d0.y), ray, best, &t, &u, &v, &inv_det)) {
-                if (!(fbits(d0.x) & 2u)) return true;
+                if (!(fbits(d0.x) & 2u)) { found = true; break; }
                 float3 n_; float2 uv_;
                 tri_shade(sc.triangles + 9u * (size_t)fbits(d0.y), u, v, inv_det, &n_, &uv_);
-                if (!(mat_alpha(sc, fbits(d0.z), uv_) < 1.0f)) return true;
+                if (!(mat_alpha(sc, fbits(d0.z), uv_) < 1.0f)) { found = true; break; }
             }
-            if (fbits(d0.x) & 1u) { ptr += 1u; continue; }
+            if (!(fbits(d0.x) & 1u)) break;
+            ptr += 1u;
+            d0 = ldg4(sc.bvh + ptr);
         }
+        if (found) break;
         if (sp > 0u) { sp -= 1u; ptr = stk_get(stk, sp); }
-        else break;
+        else alive = false;
     }
-    return false;
+    return found;
 }
 
 // ---- G-buffer entry (strolle-gpu/src/gbuffer.rs:19-112) ------------------------
