@@ -338,6 +338,25 @@ def main():
     roofline["per_iteration"] = wavelet_iterations
     extra_roof = [r for r in (roof(n) for n in ["prim_gbuffer", "di_spatial_resampling_trace", "gi_spatial_resampling_trace", "frame_denoising_estimate_variance", "frame_denoising_reproject"]) if r]
 
+    # ---- BVH trace on its own: the ray-stream entry point (the ref_tracing / *_spatial_resampling::trace shape) -------------
+    # 2^20 random rays inside the scene's bounds; `used_memory` is the reference's own traversal-traffic estimate
+    # (strolle-gpu/src/ray.rs:141-214: 16 B per visit + 48 B per internal node + 144 B per leaf entry), i.e. the bytes a
+    # traversal requests from the cache hierarchy, not HBM traffic (the BVH and triangles are L1/L2 resident).
+    traversal = None
+    if world == 1:
+        lo, hi = ((-1.0, 0.0, -1.0), (1.0, 2.0, 3.2)) if args.scene == "cornell" else ((-20.0, 0.1, -40.0), (10.0, 2.9, -5.0))
+        rng = np.random.RandomState(5)
+        nr = 1 << 20
+        rays8 = np.zeros((nr, 8), dtype=np.float32)
+        rays8[:, 0:3] = rng.uniform(lo, hi, size=(nr, 3)); dv = rng.normal(size=(nr, 3)); rays8[:, 4:7] = dv / np.linalg.norm(dv, axis=1, keepdims=True)
+        rays8[:, 3] = np.float32(3.4028234663852886e38)
+        eng.trace_closest(rays8)
+        hits, t_ms = eng.trace_closest(rays8, return_ms=True)
+        used = float(hits[:, 11].astype(np.float64).mean())
+        traversal = {"rays": nr, "kernel_ms": t_ms, "mrays_per_s": nr / (t_ms / 1000.0) / 1e6, "mean_used_memory_bytes_per_ray": used,
+                     "requested_GBps": nr * used / (t_ms / 1000.0) / 1e9, "hit_fraction": float((hits[:, 8] < 3e38).mean()),
+                     "note": "k_trace_stream_closest on random rays in the scene's bounds; requested bytes = the reference's used_memory estimate (cache traffic, not HBM)"}
+
     # ---- CPU baseline (bounded sample) -----------------------------------------------------------------
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -356,7 +375,7 @@ def main():
         "e2e": {"value": e2e_mrays, "unit": "Mrays/s", "fps": e2e_fps, "h2d_bytes_per_step": 148, "d2h_bytes_per_step": W * H * 4,
                 "note": "per step: st_update_camera (148 B host camera struct) + st_tick + st_render_camera(host_out = one of two pinned Rgba8UnormSrgb frames, async D2H); wall clock over K steps incl. all copies, ends with a full sync"},
         "gpu_launches": total_launches,
-        "roofline": roofline, "roofline_other": extra_roof,
+        "roofline": roofline, "roofline_other": extra_roof, "traversal": traversal,
         "cpu_baseline": cpu,
         "pass_ms_per_frame": {names[i]: float(pass_ms[i]) / args.steps for i in range(len(names)) if launches[i]},
     }

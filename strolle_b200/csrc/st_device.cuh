@@ -80,11 +80,13 @@ ST_DEV bool tri_test(const float4* __restrict__ tri, const Ray& ray, float best,
     float3 pvec = cross(ray.d, e2);
     float det = dot(e1, pvec);
     if (fabs_(det) < kF32Eps) return false;
-    float inv_det = 1.0f / det;
     float3 tvec = ray.o - p0;
-    float u = dot(tvec, pvec) * inv_det;
+    float un = dot(tvec, pvec);
     float3 qvec = cross(tvec, e1);
-    float v = dot(ray.d, qvec) * inv_det;
+    float vn = dot(ray.d, qvec);
+    float inv_det = 1.0f / det;
+    float u = un * inv_det;
+    float v = vn * inv_det;
     float t = dot(e2, qvec) * inv_det;
     if ((u < 0.0f) | (u > 1.0f) | (v < 0.0f) | (u + v > 1.0f) | (t <= 0.0f) | (t >= best)) return false;
     *t_out = t; *u_out = u; *v_out = v; *inv_det_out = inv_det;

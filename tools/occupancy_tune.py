@@ -21,7 +21,7 @@ if "--child" in sys.argv:
     from strolle_b200 import scenes
     w, h = int(sys.argv[2]), int(sys.argv[3])
     e = strolle_b200.Engine()
-    cam = scenes.apply(e, scenes.cornell(w, h))
+    cam = scenes.apply(e, scenes.dungeon(w, h) if "--dungeon" in sys.argv else scenes.cornell(w, h))
     for _ in range(12):
         e.tick(); e.render_camera(cam)
     e.synchronize(); e.enable_timing(True); e.pass_times(reset=True)
@@ -43,7 +43,7 @@ for p in sorted(glob.glob(os.path.join(ROOT, "strolle_b200", "_lib", "libstrolle
 table = {}
 for tag, lib in libs.items():
     env = dict(os.environ, STROLLE_B200_LIB=lib)
-    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", w, h], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--child", w, h] + (["--dungeon"] if "--dungeon" in sys.argv else []), env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")]
     if not line:
         print(tag, "FAILED", r.stdout[-400:]); continue
