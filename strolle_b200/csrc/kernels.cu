@@ -8,6 +8,7 @@
 // loads); BVH nodes / triangles go through the read-only path (ld.global.nc.v4.f32) and the
 // traversal stack lives in shared memory, one conflict-free column per thread.
 #include <algorithm>
+#include <cstdio>
 #include <cuda_fp16.h>
 #include <cuda.h>   // CUtensorMap (type only; the encoder is reached through cudaGetDriverEntryPoint)
 #include <map>
@@ -1532,7 +1533,11 @@ static bool wavelet_tensor_map(const float4* plane, int w, int h, int bw, int bh
     auto it = cache.find(key);
     if (it != cache.end()) { *out = it->second; return true; }
     TensorMapEncodeFn enc = tensor_map_encoder();
-    if (!enc) return false;
+    if (!enc) {   // no driver entry point for tensor maps: the callers fall back to the gather kernels; say so once
+        static bool warned = false;
+        if (!warned) { warned = true; std::fprintf(stderr, "strolle_b200: cuTensorMapEncodeTiled is not available from this driver; the tile-staged SVGF kernels are off\n"); }
+        return false;
+    }
     cuuint64_t dims[2] = {(cuuint64_t)w * 2u, (cuuint64_t)h};
     cuuint64_t strides[1] = {(cuuint64_t)w * 16u};
     cuuint32_t box[2] = {(cuuint32_t)bw * 2u, (cuuint32_t)bh};
