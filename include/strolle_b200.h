@@ -157,7 +157,7 @@ int st_set_frame(st_engine* e, uint32_t frame);
  * used_memory).  any: out = n u32 flags.  `device_ms` (optional) receives kernel time. */
 int st_trace_closest(st_engine* e, const float* rays, size_t n, float* out, float* device_ms);
 int st_trace_any(st_engine* e, const float* rays, size_t n, uint32_t* out, float* device_ms);
-/* elementary functions as evaluated on the device (op: 0 sin, 1 cos, 2 acos, 3 atan2, 4 exp, 5 pow) */
+/* elementary functions as evaluated on the device (op: 0 sin, 1 cos, 2 acos, 3 atan2, 4 exp, 5 pow, 6 glam's acos_approx) */
 int st_device_math(st_engine* e, int op, const float* a, const float* b, float* out, size_t n);
 /* Per-pass device time (ms, CUDA events) accumulated since the last reset; `ms`/`launches`
  * have ST_PASS_COUNT entries indexed by st_pass_name(). */

@@ -145,7 +145,7 @@ void orc_trace_brute(void* e, const float* rays, long n, float* out_dist, uint32
     }
 }
 
-// elementary-function hooks: op 0 sin,1 cos,2 acos,3 atan2(a,b),4 exp,5 pow(a,b),6 log(via pow path not exposed) ,7 round_f16
+// elementary-function hooks: op 0 sin,1 cos,2 acos,3 atan2(a,b),4 exp,5 pow(a,b),6 glam acos_approx,7 round_f16
 void orc_math(int op, const float* a, const float* b, float* out, long n) {
     for (long i = 0; i < n; i++) {
         switch (op) {
@@ -155,6 +155,7 @@ void orc_math(int op, const float* a, const float* b, float* out, long n) {
             case 3: out[i] = atan2_(a[i], b[i]); break;
             case 4: out[i] = exp_(a[i]); break;
             case 5: out[i] = pow_(a[i], b[i]); break;
+            case 6: out[i] = acos_approx(a[i]); break;
             case 7: out[i] = round_f16(a[i]); break;
             default: out[i] = 0.0f;
         }

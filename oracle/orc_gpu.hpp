@@ -516,9 +516,20 @@ static inline bool light_contains(const Light& l, V3 p) { return distance(light_
 static inline bool light_is_slot_killed(const Light& l) { return f2u(l.d3.x) == 0xcafebabeu; }
 static inline bool light_is_slot_remapped(const Light& l) { return f2u(l.d3.x) > 0 && f2u(l.d3.x) != 0xcafebabeu; }
 static inline Light light_rollback(Light l) { l.d0 = l.prev_d0; l.d1 = l.prev_d1; l.d2 = l.prev_d2; return l; }
-// glam Vec3::angle_between uses its own acos_approx polynomial (math.rs); only
-// reached for spot lights, which C1–C5 do not exercise.  Restated with acos_.
-static inline float angle_between(V3 a, V3 b) { return acos_(dot(a, b) / sqrt_(length_squared(a) * length_squared(b))); }
+// glam 0.24.2 (crates.io, Cargo.lock; not vendored) `math::acos_approx`, restated from its published definition: DirectXMath's
+// XMScalarACos, a 7th-degree minimax polynomial times sqrt(1 - |x|), mirrored for negative arguments.  `Vec3::angle_between`
+// is acos_approx(dot / sqrt(|a|^2 |b|^2)); the only call site on the path is the spot-light cone (strolle-gpu/src/light.rs:149-152).
+static inline float acos_approx(float v) {
+    bool nonnegative = v >= 0.0f;
+    float x = abs_(v);
+    float omx = 1.0f - x;
+    if (omx < 0.0f) omx = 0.0f;
+    float root = sqrt_(omx);
+    float result = ((((((-0.0012624911f * x + 0.0066700901f) * x - 0.0170881256f) * x + 0.0308918810f) * x - 0.0501743046f) * x + 0.0889789874f) * x - 0.2145988016f) * x + 1.5707963050f;
+    result *= root;
+    return nonnegative ? result : PI - result;
+}
+static inline float angle_between(V3 a, V3 b) { return acos_approx(dot(a, b) / sqrt_(length_squared(a) * length_squared(b))); }
 
 static inline LightRadiance light_radiance(const Light& self, const Hit& hit) {  // light.rs:143-207
     V3 l = light_center(self) - hit.point;

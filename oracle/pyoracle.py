@@ -267,7 +267,7 @@ def ray_count(reset=False, libm=False):
 
 
 def math(op, a, b=None, libm=False):
-    ops = {"sin": 0, "cos": 1, "acos": 2, "atan2": 3, "exp": 4, "pow": 5, "f16": 7}
+    ops = {"sin": 0, "cos": 1, "acos": 2, "atan2": 3, "exp": 4, "pow": 5, "acos_approx": 6, "f16": 7}
     a = _f(a)
     b = _f(b) if b is not None else np.zeros_like(a)
     out = np.empty_like(a)

@@ -1225,6 +1225,7 @@ __global__ void k_math(int op, const float* __restrict__ a, const float* __restr
     switch (op) {
         case 0: r = sin_det(a[i]); break; case 1: r = cos_det(a[i]); break; case 2: r = acos_det(a[i]); break;
         case 3: r = atan2_det(a[i], b[i]); break; case 4: r = exp_det(a[i]); break; case 5: r = pow_det(a[i], b[i]); break;
+        case 6: r = acos_approx_glam(a[i]); break;
     }
     out[i] = r;
 }

@@ -502,7 +502,7 @@ ST_DEV LightRad light_radiance(const GpuLight& self, const Hit& hit) {   // ligh
     else {
         float3 sd = oct_decode(f2(self.d2.y, self.d2.z));
         float3 hv = hit.point - xyz(self.d0);
-        float angle = acos_det(dot(sd, hv) / sqrtf(len2(sd) * len2(hv)));
+        float angle = acos_approx_glam(dot(sd, hv) / sqrtf(len2(sd) * len2(hv)));   // Vec3::angle_between
         f_angle = sat(1.0f - pow_det(angle / self.d2.w, 3.0f));
     }
     float range = self.d1.w, f_dist;

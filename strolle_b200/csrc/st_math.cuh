@@ -73,6 +73,18 @@ ST_DEV float acos_det(float x) {
     if (x >= 0.0f) return kHalfPi - asin_core(x);
     return kHalfPi + asin_core(-x);
 }
+// glam 0.24.2 math::acos_approx (third-party, restated from its published definition = DirectXMath XMScalarACos): what
+// Vec3::angle_between evaluates; on the path only the spot-light cone uses it (strolle-gpu/src/light.rs:149-152).
+ST_DEV float acos_approx_glam(float v) {
+    bool nonnegative = v >= 0.0f;
+    float x = fabs_(v);
+    float omx = 1.0f - x;
+    if (omx < 0.0f) omx = 0.0f;
+    float root = sqrtf(omx);
+    float result = ((((((-0.0012624911f * x + 0.0066700901f) * x - 0.0170881256f) * x + 0.0308918810f) * x - 0.0501743046f) * x + 0.0889789874f) * x - 0.2145988016f) * x + 1.5707963050f;
+    result *= root;
+    return nonnegative ? result : kPi - result;
+}
 ST_DEV float atan_core(float x) {   // x >= 0
     float y;
     if (x > 2.414213562373095f) { y = kHalfPi; x = -(1.0f / x); }

@@ -354,7 +354,7 @@ class Engine:
         return (out, ms.value) if return_ms else out
 
     def device_math(self, op, a, b=None):
-        ops = {"sin": 0, "cos": 1, "acos": 2, "atan2": 3, "exp": 4, "pow": 5}
+        ops = {"sin": 0, "cos": 1, "acos": 2, "atan2": 3, "exp": 4, "pow": 5, "acos_approx": 6}
         a = _f(a)
         b = _f(b) if b is not None else np.zeros_like(a)
         out = np.empty_like(a)

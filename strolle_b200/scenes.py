@@ -59,6 +59,11 @@ def point_light(position, radius, color, rng):
     return np.array(list(position) + [radius] + list(color) + [rng, 0, 0, 0, 0], dtype=np.float32)
 
 
+def spot_light(position, radius, color, rng, direction, angle):
+    """Light::Spot (strolle/src/light.rs:14-22): a point light restricted to a cone of half-angle `angle` around `direction`."""
+    return np.array(list(position) + [radius] + list(color) + [rng] + list(direction) + [angle], dtype=np.float32)
+
+
 def tri36(positions, normals, uvs=None, tangents=None):
     uvs = uvs if uvs is not None else [[0, 0]] * 3
     tangents = tangents if tangents is not None else [[0, 0, 0, 0]] * 3

@@ -36,6 +36,7 @@ def test_device_math_bit_exact(gpu, oracle, blue_noise):
         "cos": (rng.uniform(-20, 20, 200000), None),
         "acos": (np.concatenate([rng.uniform(-1, 1, 200000), [1.0, -1.0, 0.5, -0.5, 0.0, 1.5]]), None),
         "atan2": (rng.normal(size=200000), rng.normal(size=200000)),
+        "acos_approx": (np.concatenate([rng.uniform(-1.2, 1.2, 200000), [1.0, -1.0, 0.0, -0.0, 2.0, -2.0]]), None),   # glam's polynomial (spot-light cone)
         "exp": (np.concatenate([rng.uniform(-110, 90, 200000), [0.0, -1e9, 1e9]]), None),
         "pow": (np.concatenate([rng.uniform(0, 2, 200000), [0.0, 1.0]]), np.concatenate([rng.choice([2.2, 1 / 2.2, 8.0, 5.0, 64.0, 3.0, 1.5, 2.0], 200000), [2.2, 5.0]])),
     }
@@ -532,3 +533,25 @@ def test_full_size_properties(gpu, oracle, blue_noise):
             dist_brute, tri_brute = eo.trace_brute(rays)
             hit = ho[:, 8] < 3e38
             assert (dist_brute[hit].view(np.uint32) == hg[hit, 8].view(np.uint32)).all(), "closest distances == brute force over all triangles"
+
+
+def test_spot_lights_bit_exact(gpu, oracle, blue_noise):
+    """Light::Spot (strolle-gpu/src/light.rs:144-152): the cone factor goes through glam's `angle_between` = acos_approx(...) and
+    powf(3); a narrow and a wide spot next to the point light, one of them moved mid-run (light slot update protocol)."""
+    scene = scenes.cornell(112, 80)
+    h, _, p = scene["lights"][0]
+    scene["lights"].append((h + 1, scenes.LIGHT_SPOT, scenes.spot_light((0.3, 1.8, 0.2), 0.1, (8.0, 6.0, 4.0), 20.0, (0.0, -1.0, 0.0), 0.35)))
+    scene["lights"].append((h + 2, scenes.LIGHT_SPOT, scenes.spot_light((-0.6, 1.2, 1.5), 0.05, (2.0, 3.0, 5.0), 20.0, (0.4, -0.5, -0.77), 1.1)))
+    eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
+    for f in range(5):
+        if f == 3:
+            for e in (eg, eo):
+                e.insert_light(h + 1, scenes.LIGHT_SPOT, scenes.spot_light((0.1, 1.7, 0.4), 0.1, (8.0, 6.0, 4.0), 20.0, (0.1, -1.0, 0.1), 0.5))
+        eg.tick(); eo.tick()
+        assert_bits_equal(eg.read_scene("lights"), eo.read_scene("lights"), f"frame {f + 1} lights")
+        eg.render_camera(cg); eo.render_camera(co)
+        for name in CAMERA_BUFFERS:
+            assert_bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name), f"spot lights frame {f + 1} {name}")
+    di = eo.read_buffer(co, "di_reservoirs_0").reshape(-1, 8)
+    ids = di[:, 7].view(np.uint32)
+    assert len(set(ids.tolist()) & {2, 3}) > 0, "spot lights were sampled"

@@ -157,3 +157,32 @@ def test_textured_scene_oracle(oracle, blue_noise):
         e2.tick(); e2.render_camera(c2)
     img2 = e2.read_buffer(c2, "output").reshape(54, 96, 4)[..., :3]
     assert rel_l2(img, img2) > 0.05
+
+
+def test_glam_acos_approx_and_spot_cone(oracle, blue_noise):
+    """glam's `acos_approx` (what `Vec3::angle_between` evaluates for the spot-light cone, strolle-gpu/src/light.rs:149-152):
+    known answers of the published polynomial (DirectXMath XMScalarACos: exact at +-1, <= 1e-4 rad everywhere, pi-mirrored) and a
+    spot light actually cutting its cone in a rendered frame."""
+    x = np.concatenate([np.linspace(-1, 1, 20001), [1.5, -1.5]]).astype(np.float32)
+    got = oracle.math("acos_approx", x)
+    want = np.arccos(np.clip(x.astype(np.float64), -1, 1))
+    assert np.abs(got - want).max() < 1e-4
+    assert got[20000] == 0.0 and got[0] == np.float32(np.pi)                 # acos_approx(1) = 0, acos_approx(-1) = pi - 0
+    assert got[-2] == 0.0 and got[-1] == np.float32(np.pi)                   # out-of-range arguments clamp through max(1 - |x|, 0)
+    assert abs(float(got[10000]) - 1.5707963050) < 1e-7                       # the polynomial's constant term at x = 0
+    assert np.all(np.diff(got[:20001]) <= 0)                                   # monotone
+    # a downward spot above the Cornell floor: lit inside the cone, dark outside, unlike the point light it replaces
+    from strolle_b200 import scenes
+    lit = {}
+    for kind in ("point", "spot"):
+        scene = scenes.cornell(64, 48)
+        h, _, p = scene["lights"][0]
+        if kind == "spot":
+            scene["lights"][0] = (h, scenes.LIGHT_SPOT, scenes.spot_light(p[0:3], p[3], p[4:7], p[7], (0.0, -1.0, 0.0), 0.35))
+        eo = oracle.OracleEngine(blue_noise=blue_noise)
+        co = scenes.apply(eo, scene)
+        for _ in range(3):
+            eo.tick(); eo.render_camera(co)
+        lit[kind] = eo.read_buffer(co, "di_diff_samples").reshape(48, 64, 4)[..., :3].sum(axis=2)
+    assert np.isfinite(lit["spot"]).all() and lit["spot"].max() > 0
+    assert (lit["spot"] > 0).sum() < 0.7 * (lit["point"] > 0).sum(), "the cone leaves most of the box unlit"
