@@ -101,6 +101,15 @@ def cornell(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, ref_depth=1)
     return dict(name="cornell", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(0.0, -1.0), camera=cam)
 
 
+def cornell_spots(width=160, height=120, **kw):
+    """Cornell box with two Light::Spot lights next to its point light (a narrow one pointing down, a wide oblique one)."""
+    scene = cornell(width, height, **kw)
+    h = scene["lights"][0][0]
+    scene["lights"].append((h + 1, LIGHT_SPOT, spot_light((0.3, 1.8, 0.2), 0.1, (8.0, 6.0, 4.0), 20.0, (0.0, -1.0, 0.0), 0.35)))
+    scene["lights"].append((h + 2, LIGHT_SPOT, spot_light((-0.6, 1.2, 1.5), 0.05, (2.0, 3.0, 5.0), 20.0, (0.4, -0.5, -0.77), 1.1)))
+    return scene
+
+
 def _box(lo, hi):
     lo, hi = np.asarray(lo, np.float32), np.asarray(hi, np.float32)
     c = [np.array([x, y, z], np.float32) for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])]

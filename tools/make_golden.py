@@ -24,6 +24,7 @@ CASES = {
     "cornell_96x54_f13": dict(scene=("cornell", dict(width=96, height=54)), frames=13),
     "cornell_ref_64x48_f4": dict(scene=("cornell", dict(width=64, height=48, mode=scenes.MODE_REFERENCE, ref_depth=1)), frames=4),   # config C5 shape
     "dungeon_96x54_f7": dict(scene=("dungeon", dict(width=96, height=54, cells=6)), frames=7),        # config C3 stand-in
+    "cornell_spots_80x56_f5": dict(scene=("cornell_spots", dict(width=80, height=56)), frames=5),     # Light::Spot cone (glam acos_approx)
 }
 
 
@@ -38,7 +39,7 @@ def digest(a):
 
 def run_case(engine, case):
     kind, kw = case["scene"]
-    sc = scenes.cornell(**kw) if kind == "cornell" else scenes.dungeon(**kw)
+    sc = {"cornell": scenes.cornell, "dungeon": scenes.dungeon, "cornell_spots": scenes.cornell_spots}[kind](**kw)
     cam = scenes.apply(engine, sc)
     for _ in range(case["frames"]):
         engine.tick(); engine.render_camera(cam)
@@ -57,7 +58,10 @@ def run_case(engine, case):
 if __name__ == "__main__":
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
     bn = scenes.blue_noise()
+    only = sys.argv[1:]   # optional: names of the cases to (re)generate
     for name, case in CASES.items():
+        if only and name not in only:
+            continue
         e = pyoracle.OracleEngine(blue_noise=bn)
         res = run_case(e, case)
         with open(os.path.join(ROOT, "tests", "golden", name + ".json"), "w") as f:
