@@ -108,10 +108,17 @@ def test_native_plan_matches_python_plan():
              mg.P_GI_SPATIAL_PICK, mg.P_GI_SPATIAL_TRACE, mg.P_GI_SPATIAL_SAMPLE, mg.P_GI_PREVIEW, mg.P_GI_PREVIEW, mg.P_GI_RESOLVING,
              mg.P_DENOISE_REPROJECT, mg.P_DENOISE_REPROJECT, mg.P_DENOISE_VARIANCE] + [mg.P_DENOISE_WAVELET] * 5 + [mg.P_COMPOSITION])
     gi_spatial = (mg.P_GI_SPATIAL_PICK, mg.P_GI_SPATIAL_TRACE, mg.P_GI_SPATIAL_SAMPLE)
-    schedules = [full, [p for p in full if p not in gi_spatial], [p for p in full if p not in gi_spatial + (mg.P_GI_PREVIEW,)], [mg.P_PRIM_GBUFFER, mg.P_COMPOSITION]]
+    fused = list(full); fused.remove(mg.P_DENOISE_REPROJECT)   # ST_OPT_FUSE_REPROJECT (default): K20 for DI and GI is one step
+    schedules = [full, fused, [p for p in fused if p not in gi_spatial], [p for p in full if p not in gi_spatial], [p for p in full if p not in gi_spatial + (mg.P_GI_PREVIEW,)],
+                 [mg.P_PRIM_GBUFFER, mg.P_COMPOSITION]]
     for sched in schedules:
         for frame in (1, 2, 6, 7):
             for reach in (0, 16):
                 native = plan_frame_native(sched, frame, reach)
                 python = [(ex.before_step, name, r) for ex in mg.plan_frame(sched, frame, reach) for name, r in ex.buffers]
                 assert native == python
+    # the fused schedule shifts every later exchange point by one step and changes nothing else
+    a = [(ex.before_step, tuple(ex.buffers)) for ex in mg.plan_frame(full, 1, 16)]
+    b = [(ex.before_step, tuple(ex.buffers)) for ex in mg.plan_frame(fused, 1, 16)]
+    cut = full.index(mg.P_DENOISE_REPROJECT)
+    assert [(s - 1 if s > cut else s, bufs) for s, bufs in a] == b
