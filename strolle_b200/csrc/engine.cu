@@ -98,6 +98,14 @@ struct Box {   // strolle/src/utils/bounding_box.rs
     Box() : lo(h3(FMAX, FMAX, FMAX)), hi(h3(-FMAX, -FMAX, -FMAX)) {}
     void grow(H3 p) { lo = h3(hmin(lo.x, p.x), hmin(lo.y, p.y), hmin(lo.z, p.z)); hi = h3(hmax(hi.x, p.x), hmax(hi.y, p.y), hmax(hi.z, p.z)); }
     void grow(const Box& b) { grow(b.lo); grow(b.hi); }
+    // same results as grow() when no operand is NaN (the NaN-ignoring min/max of Rust's f32::min/max reduce to these selects)
+    void grow_finite(H3 p) {
+        lo.x = (lo.x < p.x) ? lo.x : p.x; lo.y = (lo.y < p.y) ? lo.y : p.y; lo.z = (lo.z < p.z) ? lo.z : p.z;
+        hi.x = (hi.x > p.x) ? hi.x : p.x; hi.y = (hi.y > p.y) ? hi.y : p.y; hi.z = (hi.z > p.z) ? hi.z : p.z;
+    }
+    void grow_finite(const Box& b) { grow_finite(b.lo); grow_finite(b.hi); }
+    template <bool FINITE> void add(H3 p) { if (FINITE) grow_finite(p); else grow(p); }
+    template <bool FINITE> void add(const Box& b) { if (FINITE) grow_finite(b); else grow(b); }
     bool set() const { return lo.x != FMAX; }
     float half_area() const { H3 e = hi - lo; return e.x * e.y + e.y * e.z + e.z * e.x; }
 };
@@ -184,6 +192,7 @@ public:
     std::vector<Node> old_nodes;
     std::vector<Prim> old_prims;
     uint32_t grafted = 0;   // subtrees taken over by the last build
+    bool finite = true;
 
     // `reuse` = the reference's behaviour.  A grafted subtree is the old one verbatim, including every field of its
     // primitives as they were when it was built: the hash covers the centres only (primitive.rs:27-37), so a primitive
@@ -191,7 +200,12 @@ public:
     void build(const std::vector<Prim>& all, bool reuse = true) {
         old_nodes.swap(nodes); old_prims.swap(prims);
         prims.clear();
-        for (const Prim& p : all) if (p.center.x != FMAX) prims.push_back(p);   // alive only (primitives.rs:58-61)
+        finite = true;   // no NaN anywhere in the live primitives: the bounding-box updates may use plain selects
+        for (const Prim& p : all) if (p.center.x != FMAX) {   // alive only (primitives.rs:58-61)
+            prims.push_back(p);
+            const float v[9] = {p.center.x, p.center.y, p.center.z, p.box.lo.x, p.box.lo.y, p.box.lo.z, p.box.hi.x, p.box.hi.y, p.box.hi.z};
+            for (float f : v) if (f != f) finite = false;
+        }
         nodes.clear(); grafted = 0;
         nodes.push_back(Node{Box(), 0u, (uint32_t)prims.size(), -1, -1, 0, 0});   // root bounds stay unset: SAH cost = +inf (quirk C-8)
         struct Item { int id, donor; };   // donor: node of the old tree at the same position, -1 = none
@@ -199,10 +213,10 @@ public:
         while (!work.empty()) {
             Item it = work.front(); work.pop_front();
             int axis; float at, cost;
-            if (!best_plane(it.id, &axis, &at, &cost)) continue;
+            if (!(finite ? best_plane<true>(it.id, &axis, &at, &cost) : best_plane<false>(it.id, &axis, &at, &cost))) continue;
             float leaf_cost = (float)(nodes[it.id].e - nodes[it.id].b) * nodes[it.id].box.half_area();
             if (!(cost < leaf_cost)) continue;
-            partition(it.id, axis, at);
+            if (finite) partition<true>(it.id, axis, at); else partition<false>(it.id, axis, at);
             const int li = nodes[it.id].left, ri = nodes[it.id].right;
             int ldonor = -1, rdonor = -1; bool lgraft = false, rgraft = false;
             if (it.donor >= 0 && old_nodes[it.donor].left >= 0) {
@@ -218,30 +232,30 @@ public:
 
 private:
     static float comp(H3 v, int a) { return a == 0 ? v.x : (a == 1 ? v.y : v.z); }
-    bool best_plane(int id, int* axis_out, float* at_out, float* cost_out) const {   // builder.rs:70-181
+    template <bool FINITE> bool best_plane(int id, int* axis_out, float* at_out, float* cost_out) const {   // builder.rs:70-181
         const Node& nd = nodes[id];
         uint32_t n = nd.e - nd.b;
         if (n <= 1) return false;
         const Prim* p = prims.data() + nd.b;
         Box cb;
-        for (uint32_t i = 0; i < n; i++) cb.grow(p[i].center);
+        for (uint32_t i = 0; i < n; i++) cb.add<FINITE>(p[i].center);
         H3 ext = cb.hi - cb.lo;
         H3 scale = h3((float)kBins / ext.x, (float)kBins / ext.y, (float)kBins / ext.z);
         Box bb[3][kBins]; uint32_t cnt[3][kBins] = {};
         for (uint32_t i = 0; i < n; i++) {
             H3 f = scale * (p[i].center - cb.lo);
             uint32_t id3[3] = {std::min(to_u32(f.x), (uint32_t)kBins - 1), std::min(to_u32(f.y), (uint32_t)kBins - 1), std::min(to_u32(f.z), (uint32_t)kBins - 1)};
-            for (int a = 0; a < 3; a++) { cnt[a][id3[a]] += 1; bb[a][id3[a]].grow(p[i].box); }
+            for (int a = 0; a < 3; a++) { cnt[a][id3[a]] += 1; bb[a][id3[a]].add<FINITE>(p[i].box); }
         }
         float la[3][kBins - 1], ra[3][kBins - 1]; uint32_t lc[3][kBins - 1], rc[3][kBins - 1];
         for (int a = 0; a < 3; a++) {
             Box lb, rb; uint32_t ln = 0, rn = 0;
             for (int i = 0; i < kBins - 1; i++) {
                 ln += cnt[a][i]; lc[a][i] = ln;
-                if (bb[a][i].set()) lb.grow(bb[a][i]);
+                if (bb[a][i].set()) lb.add<FINITE>(bb[a][i]);
                 la[a][i] = lb.half_area();
                 rn += cnt[a][kBins - 1 - i]; rc[a][kBins - 2 - i] = rn;
-                if (bb[a][kBins - 1 - i].set()) rb.grow(bb[a][kBins - 1 - i]);
+                if (bb[a][kBins - 1 - i].set()) rb.add<FINITE>(bb[a][kBins - 1 - i]);
                 ra[a][kBins - 2 - i] = rb.half_area();
             }
         }
@@ -260,15 +274,15 @@ private:
     // (builder.rs:201-228, primitive.rs:27-37); third-party crate, restated from its published definition.
     static void fx(uint64_t* h, uint32_t w) { *h = (((*h << 5) | (*h >> 59)) ^ (uint64_t)w) * 0x517cc1b727220a95ull; }
     static void fx_prim(uint64_t* h, const Prim& p) { fx(h, f2bits(p.center.x)); fx(h, f2bits(p.center.y)); fx(h, f2bits(p.center.z)); }
-    void partition(int id, int axis, float at) {   // builder.rs:183-319
+    template <bool FINITE> void partition(int id, int axis, float at) {   // builder.rs:183-319
         uint32_t b = nodes[id].b, e = nodes[id].e;
         Prim* d = prims.data() + b;
         int l = 0, r = (int)(e - b) - 1;
         Box lb, rb; uint64_t lh = 0, rh = 0;
         while (l <= r) {
             Prim cur = d[l];
-            if (comp(cur.center, axis) < at) { l++; lb.grow(cur.box); fx_prim(&lh, cur); }
-            else { std::swap(d[l], d[r]); r--; rb.grow(cur.box); fx_prim(&rh, cur); }
+            if (comp(cur.center, axis) < at) { l++; lb.add<FINITE>(cur.box); fx_prim(&lh, cur); }
+            else { std::swap(d[l], d[r]); r--; rb.add<FINITE>(cur.box); fx_prim(&rh, cur); }
         }
         uint32_t mid = b + (uint32_t)l;
         int li = (int)nodes.size(); nodes.push_back(Node{lb, b, mid, -1, -1, 0, 0});

@@ -153,3 +153,32 @@ def test_builder_rejects_bad_arguments():
     assert lib.st_bvh_builder_create(None) != 0
     n = C.c_size_t(0)
     assert lib.st_bvh_builder_build(None, None, 0, 1, None, 0, C.byref(n), None, None) != 0
+
+
+@pytest.mark.parametrize("scene_name", ["cornell", "dungeon"])
+def test_product_builder_reproduces_the_oracle_engine_bvh(oracle, blue_noise, scene_name):
+    """The benchmark scenes themselves: primitives rebuilt from the oracle engine's baked triangle buffer (centre = (p0 + p1 + p2) / 3
+    in f32, strolle/src/triangle.rs:16-22) go through the product's host builder and must give the oracle engine's BVH stream."""
+    from strolle_b200 import scenes
+    from strolle_b200.engine import BvhBuilder
+    scene = scenes.cornell(32, 32) if scene_name == "cornell" else scenes.dungeon(32, 32)
+    eo = oracle.OracleEngine(blue_noise=blue_noise)
+    scenes.apply(eo, scene)
+    eo.tick()
+    tris = eo.read_scene("triangles").reshape(-1, 9, 4)
+    want = eo.read_scene("bvh").reshape(-1, 4)
+    bits = want.view(np.uint32)
+    leaf = bits[:, 3] == 1
+    mat_of = {int(t): int(m) for t, m in zip(bits[leaf, 1], bits[leaf, 2])}
+    p0, p1, p2 = tris[:, 0, :3], tris[:, 3, :3], tris[:, 6, :3]
+    prims = np.zeros((len(tris), 11), dtype=np.float32)
+    prims[:, 0] = np.arange(len(tris), dtype=np.uint32).view(np.float32)
+    prims[:, 1] = np.array([mat_of.get(i, 0) for i in range(len(tris))], dtype=np.uint32).view(np.float32)
+    prims[:, 2:5] = ((p0 + p1) + p2) / np.float32(3.0)
+    prims[:, 5:8] = np.minimum(np.minimum(p0, p1), p2)
+    prims[:, 8:11] = np.maximum(np.maximum(p0, p1), p2)
+    alive = np.array([i in mat_of for i in range(len(tris))])
+    prims[~alive, 2:5] = F32_MAX
+    got = BvhBuilder().build(prims, reuse=False)
+    assert same_bits(got, want), f"{scene_name}: host builder stream differs from the oracle engine's BVH"
+    assert alive.sum() > 30
