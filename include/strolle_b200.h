@@ -172,7 +172,13 @@ int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9 };
+/* ST_OPT_SHADING_FAST_MATH (default 1): the ReSTIR DI/GI kernels K5-K19 (strolle-shaders/src/di_*.rs, gi_*.rs) run in their
+ * fast-shading build: FMA contraction, approximate division / square root and SFU sin/cos/ex2/lg2 for radiance, BRDF, pdf
+ * and MIS evaluation - the arithmetic a GPU shader compiler emits for the reference's SPIR-V.  BVH traversal, the ray/box and
+ * ray/triangle tests, the alpha test and the RNG are identical in both builds (same hit for the same ray, bit for bit); the
+ * frame stays inside the 1e-3 relative per-channel L2 tolerance.  0 = strict IEEE everywhere (bit-identical to the oracle). */
+#define ST_SHADING_FAST_DEFAULT 1
 /* ST_OPT_VARIANCE_TILED: 1 = K21 frame_denoising::estimate_variance (frame_denoising.rs:81-217) reads its 6x5 window from a
  * shared-memory tile filled by TMA tensor copies (identical results). */
 #define ST_VARIANCE_TILED_DEFAULT 1

@@ -33,6 +33,8 @@ struct Lut {   // a sampled Rgba16Float texture with a linear, clamp-to-edge sam
 struct Scene {
     const V4* triangles;  // 9 vec4 per triangle (strolle-gpu/src/triangle.rs:8-21)
     const V4* bvh;        // strolle/src/bvh/serializer.rs:53-104
+    size_t bvh_len = 0;   // vec4 count; 0 = no primitive alive: the serialiser emits nothing (serializer.rs:20-110) and the
+                          // reference's rasteriser draws nothing (passes/prim_raster.rs:134-246), so every ray misses
     const Material* materials;
     const Light* lights;
     World world;
@@ -203,6 +205,7 @@ static inline void count_ray() {
 // (strolle-gpu/src/lib.rs:72-76); both oracle and product assert at upload.
 static inline size_t ray_traverse(const Ray& self, const Scene& sc, Tracing tracing, TriangleHit* hit, u32* visited_nodes = nullptr) {
     count_ray();
+    if (sc.bvh_len == 0) { if (visited_nodes) *visited_nodes = 0; return 0; }   // empty scene: a miss, nothing touched
     size_t used_memory = 0;
     u32 bvh_ptr = 0;
     u32 stack[BVH_STACK_SIZE];

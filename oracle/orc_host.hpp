@@ -727,7 +727,7 @@ struct Engine {
         if (inval) { Camera a = c->st.curr_camera, b = c->st.prev_camera; c->st.init(hc.w, hc.h); c->st.curr_camera = a; c->st.prev_camera = b; }
     }
     Scene scene() {
-        Scene sc; sc.triangles = gpu_triangles.data(); sc.bvh = gpu_bvh.data(); sc.materials = gpu_materials.data(); sc.lights = gpu_lights.data();
+        Scene sc; sc.triangles = gpu_triangles.data(); sc.bvh = gpu_bvh.data(); sc.bvh_len = gpu_bvh.size(); sc.materials = gpu_materials.data(); sc.lights = gpu_lights.data();
         sc.world = world; sc.blue_noise = blue_noise.data();
         sc.transmittance_lut.w = 256; sc.transmittance_lut.h = 64; sc.transmittance_lut.texels = luts.transmittance.data();
         sc.sky_lut.w = 256; sc.sky_lut.h = 256; sc.sky_lut.texels = luts.sky.data();

@@ -13,10 +13,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libstrolle_b200.so")
-SOURCES = ["kernels.cu", "engine.cu"]
+# (source, object stem, extra flags): kernels.cu is built twice — strict IEEE (namespace st) and the fast-shading flavour of the
+# ReSTIR kernels (namespace stf: FMA contraction, approximate div/sqrt, SFU transcendentals; traversal stays bit-exact, st_math.cuh)
+UNITS = [("kernels.cu", "kernels", ["-fmad=false"]),
+         ("kernels.cu", "kernels_fast", ["-DST_FAST=1", "-fmad=true", "-prec-div=false", "-prec-sqrt=false"]),
+         ("engine.cu", "engine", ["-fmad=false"])]
 HEADERS = ["st_math.cuh", "st_device.cuh", "st_types.h", "kernels.h", os.path.join("..", "..", "include", "strolle_b200.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-fmad=false",
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo",
          "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "-Xptxas", "-v"]
 
 
@@ -36,19 +40,19 @@ def build(force=False, verbose=False, defines=(), tag=""):
     suffix = ("_" + tag) if tag else ""
     lib = LIB.replace(".so", suffix + ".so")
     flags = FLAGS + ["-D" + d for d in defines]
-    for src in SOURCES:
-        obj = os.path.join(OUT_DIR, src.replace(".cu", suffix + ".o"))
+    for src, stem, extra in UNITS:
+        obj = os.path.join(OUT_DIR, stem + suffix + ".o")
         objs.append(obj)
         if force or _stale(obj, deps + [os.path.join(CSRC, src)]):
-            cmd = [NVCC] + flags + ["-c", os.path.join(CSRC, src), "-o", obj]
-            procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for src, p in procs:
+            cmd = [NVCC] + flags + extra + ["-c", os.path.join(CSRC, src), "-o", obj]
+            procs.append((stem, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for stem, p in procs:
         out, _ = p.communicate()
-        with open(os.path.join(OUT_DIR, src + suffix + ".ptxas.log"), "w") as f:
+        with open(os.path.join(OUT_DIR, stem + suffix + ".ptxas.log"), "w") as f:
             f.write(out)
         if p.returncode != 0:
             sys.stderr.write(out)
-            raise RuntimeError("nvcc failed for " + src)
+            raise RuntimeError("nvcc failed for " + stem)
         if verbose:
             print(out)
     if force or procs or _stale(lib, objs):

@@ -422,6 +422,7 @@ struct st_engine {
     DevMem d_triangles, d_bvh, d_materials, d_matpacked, d_unpacklut, d_lights, d_noise, d_tlut, d_slut, d_skylut, d_scratch, d_raycount;
     bool count_rays = false;
     bool svgf_fast = true;   // ST_OPT_SVGF_FAST_MATH
+    bool shading_fast = ST_SHADING_FAST_DEFAULT != 0;   // ST_OPT_SHADING_FAST_MATH
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
     int wavelet_tiled = ST_WAVELET_TILED_DEFAULT;   // ST_OPT_WAVELET_TILED: bit i = à-trous iteration i (stride 2^i) runs the tile-staged (TMA) kernel
@@ -445,7 +446,7 @@ struct st_engine {
 
     SceneDev scene() const {
         SceneDev s;
-        s.triangles = (const float4*)d_triangles.p; s.bvh = (const float4*)d_bvh.p; s.materials = (const GpuMaterial*)d_materials.p;
+        s.triangles = (const float4*)d_triangles.p; s.bvh = (const float4*)d_bvh.p; s.bvh_len = (uint32_t)bvh_out.buf.size(); s.materials = (const GpuMaterial*)d_materials.p;
         s.lights = (const GpuLight*)d_lights.p; s.blue_noise = (const uchar4*)d_noise.p;
         s.transmittance_lut = (const float4*)d_tlut.p; s.scattering_lut = (const float4*)d_slut.p; s.sky_lut = (const float4*)d_skylut.p;
         s.world = world;
@@ -573,10 +574,10 @@ static int ensure_luts(st_engine* e) {   // AtmospherePass::run (passes/atmosphe
         e->run_timed(P_ATMOSPHERE, [&](cudaStream_t s) { launch_atm_transmittance((float4*)e->d_tlut.p, s); launch_atm_scattering((const float4*)e->d_tlut.p, (float4*)e->d_slut.p, s); });
         e->luts_static_ready = true;
     }
-    if (!e->sky_ready || e->sky_for_altitude != e->sun_altitude) {
+    if (!e->sky_ready || e->sky_for_altitude != e->world.sun_altitude) {   // one source of truth: the altitude st_tick published in `world`
         float alt = e->world.sun_altitude;
         e->run_timed(P_ATMOSPHERE, [&](cudaStream_t s) { launch_atm_sky((const float4*)e->d_tlut.p, (const float4*)e->d_slut.p, alt, (float4*)e->d_skylut.p, s); });
-        e->sky_ready = true; e->sky_for_altitude = e->sun_altitude;
+        e->sky_ready = true; e->sky_for_altitude = alt;
     }
     return ST_OK;
 }
@@ -631,6 +632,7 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
     const uint32_t f = cs->frame;
     const int cur = (f % 2u) == 1u ? 1 : 0;   // is_alternate (camera_controller.rs:185-187)
     const st_camera& d = cs->desc;
+    const bool fs = e->shading_fast;   // ReSTIR kernels from the fast-shading build (ST_OPT_SHADING_FAST_MATH)
     auto seed = [&](uint32_t k) { return dispatch_seed(e->seed_base, f, k); };
     auto add = [&](int pass, std::function<void(cudaStream_t)> fn) { steps->push_back(Step{pass, std::move(fn)}); };
     const float4* di_final = (d.denoise && (d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_DI_DIFFUSE)) ? cam.di_diff_curr_colors : cam.di_diff_samples;
@@ -657,39 +659,39 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
         add(P_FRAME_REPROJECTION, [=](cudaStream_t s) { launch_frame_reprojection(cam, sc, cur, s); });
         if (needs_di) {
             uint32_t s1 = seed(P_DI_SAMPLING), s2 = seed(P_DI_TEMPORAL), s3 = seed(P_DI_SPATIAL_PICK), s5 = seed(P_DI_SPATIAL_SAMPLE);
-            add(P_DI_SAMPLING, [=](cudaStream_t s) { launch_di_sampling(cam, sc, cur, s1, f, s); });
-            add(P_DI_TEMPORAL, [=](cudaStream_t s) { launch_di_temporal(cam, sc, cur, s2, s); });
-            add(P_DI_SPATIAL_PICK, [=](cudaStream_t s) { launch_di_spatial_pick(cam, sc, cur, s3, f, s); });
-            add(P_DI_SPATIAL_TRACE, [=](cudaStream_t s) { launch_spatial_trace(cam, sc, cam.di_diff_samples, cam.di_diff_curr_colors, cam.di_diff_stash, s); });
-            add(P_DI_SPATIAL_SAMPLE, [=](cudaStream_t s) { launch_di_spatial_sample(cam, sc, s5, f, s); });
-            add(P_DI_RESOLVING, [=](cudaStream_t s) { launch_di_resolving(cam, sc, cur, s); });
+            add(P_DI_SAMPLING, [=](cudaStream_t s) { (fs ? stf::launch_di_sampling : st::launch_di_sampling)(cam, sc, cur, s1, f, s); });
+            add(P_DI_TEMPORAL, [=](cudaStream_t s) { (fs ? stf::launch_di_temporal : st::launch_di_temporal)(cam, sc, cur, s2, s); });
+            add(P_DI_SPATIAL_PICK, [=](cudaStream_t s) { (fs ? stf::launch_di_spatial_pick : st::launch_di_spatial_pick)(cam, sc, cur, s3, f, s); });
+            add(P_DI_SPATIAL_TRACE, [=](cudaStream_t s) { (fs ? stf::launch_spatial_trace : st::launch_spatial_trace)(cam, sc, cam.di_diff_samples, cam.di_diff_curr_colors, cam.di_diff_stash, s); });
+            add(P_DI_SPATIAL_SAMPLE, [=](cudaStream_t s) { (fs ? stf::launch_di_spatial_sample : st::launch_di_spatial_sample)(cam, sc, s5, f, s); });
+            add(P_DI_RESOLVING, [=](cudaStream_t s) { (fs ? stf::launch_di_resolving : st::launch_di_resolving)(cam, sc, cur, s); });
         }
         if (needs_gi) {
             uint32_t sa = seed(P_GI_SAMPLING_A), sb = seed(P_GI_SAMPLING_B), st_ = seed(P_GI_TEMPORAL), sp = seed(P_GI_SPATIAL_PICK), ss = seed(P_GI_SPATIAL_SAMPLE), sv = seed(P_GI_PREVIEW);
             uint32_t source;
-            add(P_GI_REPROJECTION, [=](cudaStream_t s) { launch_gi_reprojection(cam, sc, cur, s); });
+            add(P_GI_REPROJECTION, [=](cudaStream_t s) { (fs ? stf::launch_gi_reprojection : st::launch_gi_reprojection)(cam, sc, cur, s); });
             auto sampling = [&]() {
-                add(P_GI_SAMPLING_A, [=](cudaStream_t s) { launch_gi_sampling_a(cam, sc, cur, sa, f, s); });
-                add(P_GI_SAMPLING_B, [=](cudaStream_t s) { launch_gi_sampling_b(cam, sc, cur, sb, f, s); });
+                add(P_GI_SAMPLING_A, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_a : st::launch_gi_sampling_a)(cam, sc, cur, sa, f, s); });
+                add(P_GI_SAMPLING_B, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_b : st::launch_gi_sampling_b)(cam, sc, cur, sb, f, s); });
             };
             if (f % 6u < 4u) {
                 if (f % 2u == 0u) sampling();
-                add(P_GI_TEMPORAL, [=](cudaStream_t s) { launch_gi_temporal(cam, sc, cur, st_, f, s); });
+                add(P_GI_TEMPORAL, [=](cudaStream_t s) { (fs ? stf::launch_gi_temporal : st::launch_gi_temporal)(cam, sc, cur, st_, f, s); });
                 if (f % 2u == 1u) {
-                    add(P_GI_SPATIAL_PICK, [=](cudaStream_t s) { launch_gi_spatial_pick(cam, sc, cur, sp, f, s); });
-                    add(P_GI_SPATIAL_TRACE, [=](cudaStream_t s) { launch_spatial_trace(cam, sc, cam.gi_d0, cam.gi_d1, cam.gi_d2, s); });
-                    add(P_GI_SPATIAL_SAMPLE, [=](cudaStream_t s) { launch_gi_spatial_sample(cam, sc, ss, f, s); });
+                    add(P_GI_SPATIAL_PICK, [=](cudaStream_t s) { (fs ? stf::launch_gi_spatial_pick : st::launch_gi_spatial_pick)(cam, sc, cur, sp, f, s); });
+                    add(P_GI_SPATIAL_TRACE, [=](cudaStream_t s) { (fs ? stf::launch_spatial_trace : st::launch_spatial_trace)(cam, sc, cam.gi_d0, cam.gi_d1, cam.gi_d2, s); });
+                    add(P_GI_SPATIAL_SAMPLE, [=](cudaStream_t s) { (fs ? stf::launch_gi_spatial_sample : st::launch_gi_spatial_sample)(cam, sc, ss, f, s); });
                     source = 1;
                 } else source = 0;
             } else {
                 sampling();
-                add(P_GI_TEMPORAL, [=](cudaStream_t s) { launch_gi_temporal(cam, sc, cur, st_, f, s); });
+                add(P_GI_TEMPORAL, [=](cudaStream_t s) { (fs ? stf::launch_gi_temporal : st::launch_gi_temporal)(cam, sc, cur, st_, f, s); });
                 source = 0;
             }
             const float4* src0 = source == 0 ? cam.gi_reservoirs[1] : cam.gi_reservoirs[2];
-            add(P_GI_PREVIEW, [=](cudaStream_t s) { launch_gi_preview(cam, sc, cur, sv, 0u, src0, cam.gi_reservoirs[3], s); });
-            add(P_GI_PREVIEW, [=](cudaStream_t s) { launch_gi_preview(cam, sc, cur, sv, 1u, cam.gi_reservoirs[3], cam.gi_reservoirs[0], s); });
-            add(P_GI_RESOLVING, [=](cudaStream_t s) { launch_gi_resolving(cam, sc, cur, src0, s); });
+            add(P_GI_PREVIEW, [=](cudaStream_t s) { (fs ? stf::launch_gi_preview : st::launch_gi_preview)(cam, sc, cur, sv, 0u, src0, cam.gi_reservoirs[3], s); });
+            add(P_GI_PREVIEW, [=](cudaStream_t s) { (fs ? stf::launch_gi_preview : st::launch_gi_preview)(cam, sc, cur, sv, 1u, cam.gi_reservoirs[3], cam.gi_reservoirs[0], s); });
+            add(P_GI_RESOLVING, [=](cudaStream_t s) { (fs ? stf::launch_gi_resolving : st::launch_gi_resolving)(cam, sc, cur, src0, s); });
         }
     }
     if (d.denoise) {   // FrameDenoisingPass::run (passes/frame_denoising.rs:143-190)
@@ -1070,7 +1072,7 @@ int st_camera_set_strip(st_engine* e, st_camera_handle h, int y0, int y1) {
 int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     CK(cudaSetDevice(e->device));
-    int rc;
+    int rc; bool too_deep = false;
     if (e->materials_dirty || e->images_dirty) {   // Materials::refresh + Material::serialize (materials.rs:79-85, material.rs:29-50)
         e->materials_dirty = false; e->images_dirty = false;
         auto rect = [&](const st_engine::MatTex& mt, int k) {   // Images::lookup (images.rs:114-127)
@@ -1099,7 +1101,10 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
         std::vector<uint8_t> alpha(e->materials.size());
         for (size_t i = 0; i < alpha.size(); i++) alpha[i] = e->materials[i].alpha_blend ? 1 : 0;
         e->bvh.flatten(alpha, &e->bvh_out);
-        if (e->bvh_out.depth - 1 > 24) return fail(ST_ERR_LIMIT, "BVH deeper than the 24-entry traversal stack (strolle-gpu/src/lib.rs:72-76)");
+        // A tree deeper than the traversal stack cannot be walked (the reference silently corrupts a neighbour's stack,
+        // strolle-gpu/src/lib.rs:72-76).  The tick still completes — with an EMPTY tree, so that the device never pairs the
+        // new triangles with the old BVH — and reports ST_ERR_LIMIT at its end; nothing is drawn until the scene changes.
+        if (e->bvh_out.depth - 1 > 24) { e->bvh_out.buf.clear(); too_deep = true; }
         if ((rc = upload(e, e->d_bvh, e->bvh_out.buf.data(), e->bvh_out.buf.size() * 16))) return rc;
     }
     if (e->motion_dirty) {   // per-instance curr_xform_inv / prev_transform for the velocity map (passes/prim_raster.rs:198-223)
@@ -1146,6 +1151,7 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
     }
     for (CameraSlot* c : e->cameras) if (c->alive) c->frame = e->frame;   // CameraController::flush (camera_controller.rs:81-85)
     e->frame += 1;
+    if (too_deep) return fail(ST_ERR_LIMIT, "BVH deeper than the 24-entry traversal stack (strolle-gpu/src/lib.rs:72-76): the scene is not drawn until it changes");
     return ST_OK;
 }
 
@@ -1254,7 +1260,7 @@ int st_bvh_depth(st_engine* e, int* depth) { if (!e || !depth) return fail(ST_ER
 
 static int trace_stream(st_engine* e, const float* rays, size_t n, void* out, bool closest, float* device_ms) {
     if (!e || !rays || !out) return fail(ST_ERR_INVALID, "null argument");
-    if (!e->d_bvh.p) return fail(ST_ERR_INVALID, "no scene uploaded: call st_tick first");
+    if (e->frame <= 1) return fail(ST_ERR_INVALID, "no scene uploaded: call st_tick first");
     CK(cudaSetDevice(e->device));
     size_t out_bytes = closest ? n * 48 : n * 4;
     DevMem d_in, d_out; int rc;
@@ -1296,6 +1302,7 @@ int st_device_math(st_engine* e, int op, const float* a, const float* b, float* 
 int st_set_option(st_engine* e, int option, int value) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     if (option == ST_OPT_SVGF_FAST_MATH) { e->svgf_fast = value != 0; return ST_OK; }
+    if (option == ST_OPT_SHADING_FAST_MATH) { e->shading_fast = value != 0; return ST_OK; }
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }

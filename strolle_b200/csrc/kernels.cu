@@ -17,7 +17,15 @@
 #include "st_device.cuh"
 #include "kernels.h"
 
-namespace st {
+// Compiled twice (strolle_b200/build.py): as namespace st with strict IEEE arithmetic (every kernel), and with -DST_FAST=1 as
+// namespace stf, the fast-shading flavour of the ReSTIR kernels K5-K19 only (see st_math.cuh).
+#if defined(ST_FAST) && ST_FAST
+#define ST_EXACT_ONLY 0
+#else
+#define ST_EXACT_ONLY 1
+#endif
+
+namespace ST_NS {
 
 #define TILE_W 16
 #define TILE_H 8
@@ -157,6 +165,7 @@ ST_DEV Hit load_hit_lut(const SceneDev& sc, const GpuCamera& c, const float4* __
 #define ST_LB_GI_RESOLVING __launch_bounds__(ST_BLOCK)
 #endif
 
+#if ST_EXACT_ONLY
 // ---------------------------------------------------------------------------------------------
 // Primary-visibility G-buffer (stands in for strolle-shaders/src/prim_raster.rs:41-128)
 // ---------------------------------------------------------------------------------------------
@@ -220,6 +229,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_frame_reprojection(KPARAMS, int cu
     }
     cam.reprojection_map[i] = reproj_encode(rp);
 }
+#endif   // ST_EXACT_ONLY
 
 // K5 di_sampling::main (di_sampling.rs:4-94)
 __global__ void ST_LB_DI_SAMPLING k_di_sampling(KPARAMS, int cur, u32 seed, u32 frame) {
@@ -725,6 +735,7 @@ __global__ void ST_LB_GI_RESOLVING k_gi_resolving(KPARAMS, int cur, const float4
     gi_store(gi_load(in, idx), out, idx);
 }
 
+#if ST_EXACT_ONLY
 // K20 frame_denoising::reproject (frame_denoising.rs:4-78)
 __global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject(KPARAMS, int cur, const float4* __restrict__ prev_colors, const float4* __restrict__ prev_moments,
                                                                 const float4* __restrict__ samples, float4* __restrict__ colors, float4* __restrict__ moments) {
@@ -1395,6 +1406,8 @@ __global__ void k_atm_sky(const float4* __restrict__ tl, const float4* __restric
     out[y * 256 + x] = f4(round_f16(lum.x), round_f16(lum.y), round_f16(lum.z), 1.0f);
 }
 
+#endif   // ST_EXACT_ONLY
+
 // ---------------------------------------------------------------------------------------------
 // Host-side launchers
 // ---------------------------------------------------------------------------------------------
@@ -1402,8 +1415,6 @@ static dim3 grid_full(const CameraDev& cam) { return dim3((cam.w + TILE_W - 1) /
 static dim3 grid_half(const CameraDev& cam) { int hw = 8 * (((cam.w + 7) / 8) / 2); return dim3((hw + TILE_W - 1) / TILE_W, (cam.y1 - cam.y0 + TILE_H - 1) / TILE_H); }
 #define HALF_LAUNCH(kernel, c, st, ...) do { dim3 g_ = grid_half(c); if (g_.x > 0 && g_.y > 0) kernel<<<g_, ST_BLOCK, 0, st>>>(__VA_ARGS__); } while (0)
 
-void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
-void launch_frame_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_frame_reprojection<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
 void launch_di_sampling(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_di_sampling<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
 void launch_di_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, cudaStream_t st) { k_di_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed); }
 void launch_di_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_di_spatial_pick, c, st, c, s, cur, seed, frame); }
@@ -1418,6 +1429,9 @@ void launch_gi_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 
 void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_sample, c, st, c, s, seed, frame); }
 void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out); }
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
+#if ST_EXACT_ONLY
+void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
+void launch_frame_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_frame_reprojection<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
 void launch_denoise_reproject(const CameraDev& c, const SceneDev& s, int cur, const float4* pc, const float4* pm, const float4* smp, float4* col, float4* mom, cudaStream_t st) { k_denoise_reproject<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, pc, pm, smp, col, mom); }
 void launch_denoise_reproject_pair(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) {
     ReprojectSignal di{c.di_diff_prev_colors, c.di_diff_moments[cur ^ 1], c.di_diff_samples, c.di_diff_curr_colors, c.di_diff_moments[cur]};
@@ -1665,4 +1679,5 @@ void launch_atm_scattering(const float4* tl, float4* out, cudaStream_t st) { k_a
 void launch_atm_sky(const float4* tl, const float4* sl, float sun_altitude, float4* out, cudaStream_t st) { k_atm_sky<<<256, 256, 0, st>>>(tl, sl, sun_altitude, out); }
 void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st) { k_atm_sun_color<<<1, 1, 0, st>>>(out2, world); }
 
-}  // namespace st
+#endif   // ST_EXACT_ONLY
+}  // namespace ST_NS

@@ -5,7 +5,10 @@
 #include "st_math.cuh"
 #include "st_types.h"
 
-namespace st {
+namespace ST_NS {
+#if defined(ST_FAST) && ST_FAST
+using namespace st;   // the POD layouts of st_types.h
+#endif
 
 #define ST_BVH_STACK 24          // strolle-gpu/src/lib.rs:76
 #define ST_BLOCK 128             // threads per CTA for all per-pixel kernels (16 x 8 pixel tile)
@@ -32,7 +35,7 @@ ST_DEV float3 oct_decode(float2 e) {
 // ---- Ray (strolle-gpu/src/ray.rs) --------------------------------------------
 struct Ray { float3 o, d, inv; float len; };
 ST_DEV Ray ray_zero() { Ray r; r.o = f3s(0.f); r.d = f3s(0.f); r.inv = f3s(0.f); r.len = 0.f; return r; }
-ST_DEV Ray ray_make(float3 o, float3 d) { Ray r; r.o = o; r.d = d; r.inv = 1.0f / d; r.len = kF32Max; return r; }   // ray.rs:22-30
+ST_DEV Ray ray_make(float3 o, float3 d) { Ray r; r.o = o; r.d = d; r.inv = f3(xdiv(1.0f, d.x), xdiv(1.0f, d.y), xdiv(1.0f, d.z)); r.len = kF32Max; return r; }   // ray.rs:22-30
 ST_DEV Ray ray_make(float3 o, float3 d, float len) { Ray r = ray_make(o, d); r.len = len; return r; }
 ST_DEV float3 ray_at(const Ray& r, float t) { return r.o + r.d * t; }
 ST_DEV float ray_sphere(const Ray& r, float radius) {   // ray.rs:304-322
@@ -62,9 +65,9 @@ ST_DEV TriHit trihit_unpack(float4 d0, float4 d1) {   // hit.rs:95-110
 // slab test (ray.rs:273-302); fminf/fmaxf are NaN-ignoring like Rust's f32::min/max and only
 // ordering of the result is consumed here, so the hardware min/max is used.
 ST_DEV float box_entry(const Ray& r, float3 bmin, float3 bmax) {
-    float t1x = (bmin.x - r.o.x) * r.inv.x, t2x = (bmax.x - r.o.x) * r.inv.x;
-    float t1y = (bmin.y - r.o.y) * r.inv.y, t2y = (bmax.y - r.o.y) * r.inv.y;
-    float t1z = (bmin.z - r.o.z) * r.inv.z, t2z = (bmax.z - r.o.z) * r.inv.z;
+    float t1x = xmul(xsub(bmin.x, r.o.x), r.inv.x), t2x = xmul(xsub(bmax.x, r.o.x), r.inv.x);
+    float t1y = xmul(xsub(bmin.y, r.o.y), r.inv.y), t2y = xmul(xsub(bmax.y, r.o.y), r.inv.y);
+    float t1z = xmul(xsub(bmin.z, r.o.z), r.inv.z), t2z = xmul(xsub(bmax.z, r.o.z), r.inv.z);
     float tmin = fmaxf(0.0f, fminf(t1x, t2x)), tmax = fminf(kF32Max, fmaxf(t1x, t2x));
     tmin = fmaxf(tmin, fminf(t1y, t2y)); tmax = fminf(tmax, fmaxf(t1y, t2y));
     tmin = fmaxf(tmin, fminf(t1z, t2z)); tmax = fminf(tmax, fmaxf(t1z, t2z));
@@ -76,44 +79,45 @@ ST_DEV float box_entry(const Ray& r, float3 bmin, float3 bmax) {
 ST_DEV bool tri_test(const float4* __restrict__ tri, const Ray& ray, float best, float* t_out, float* u_out, float* v_out, float* inv_det_out) {
     float4 a0 = ldg4(tri), a3 = ldg4(tri + 3), a6 = ldg4(tri + 6);
     float3 p0 = xyz(a0);
-    float3 e1 = xyz(a3) - p0, e2 = xyz(a6) - p0;
-    float3 pvec = cross(ray.d, e2);
-    float det = dot(e1, pvec);
+    float3 e1 = xsub3(xyz(a3), p0), e2 = xsub3(xyz(a6), p0);
+    float3 pvec = xcross(ray.d, e2);
+    float det = xdot(e1, pvec);
     if (fabs_(det) < kF32Eps) return false;
-    float3 tvec = ray.o - p0;
-    float un = dot(tvec, pvec);
-    float3 qvec = cross(tvec, e1);
-    float vn = dot(ray.d, qvec);
-    float inv_det = 1.0f / det;
-    float u = un * inv_det;
-    float v = vn * inv_det;
-    float t = dot(e2, qvec) * inv_det;
-    if ((u < 0.0f) | (u > 1.0f) | (v < 0.0f) | (u + v > 1.0f) | (t <= 0.0f) | (t >= best)) return false;
+    float3 tvec = xsub3(ray.o, p0);
+    float un = xdot(tvec, pvec);
+    float3 qvec = xcross(tvec, e1);
+    float vn = xdot(ray.d, qvec);
+    float inv_det = xdiv(1.0f, det);
+    float u = xmul(un, inv_det);
+    float v = xmul(vn, inv_det);
+    float t = xmul(xdot(e2, qvec), inv_det);
+    if ((u < 0.0f) | (u > 1.0f) | (v < 0.0f) | (xadd(u, v) > 1.0f) | (t <= 0.0f) | (t >= best)) return false;
     *t_out = t; *u_out = u; *v_out = v; *inv_det_out = inv_det;
     return true;
 }
 ST_DEV void tri_shade(const float4* __restrict__ tri, float u, float v, float inv_det, float3* normal, float2* uv) {
     float4 a0 = ldg4(tri), a1 = ldg4(tri + 1), a3 = ldg4(tri + 3), a4 = ldg4(tri + 4), a6 = ldg4(tri + 6), a7 = ldg4(tri + 7);
-    float3 n = u * xyz(a4) + v * xyz(a7) + (1.0f - u - v) * xyz(a1);
-    *normal = norm(n) * cpsign(1.0f, inv_det);
+    float3 n = xadd3(xadd3(xscale(xyz(a4), u), xscale(xyz(a7), v)), xscale(xyz(a1), xsub(xsub(1.0f, u), v)));
+    *normal = xscale(xnorm(n), cpsign(1.0f, inv_det));
     float2 uv0 = f2(a0.w, a1.w), uv1 = f2(a3.w, a4.w), uv2 = f2(a6.w, a7.w);
-    *uv = uv0 + (uv1 - uv0) * u + (uv2 - uv0) * v;
+    *uv = f2(xadd(xadd(uv0.x, xmul(xsub(uv1.x, uv0.x), u)), xmul(xsub(uv2.x, uv0.x), v)), xadd(xadd(uv0.y, xmul(xsub(uv1.y, uv0.y), u)), xmul(xsub(uv2.y, uv0.y), v)));
 }
 
 // Material::sample_atlas (strolle-gpu/src/material.rs:76-104): repeat-wrap the hit uv, map it into the
 // image's atlas rect, nearest-texel fetch (wgpu default sampler, clamp-to-edge), sRGB decode of r,g,b.
-ST_DEV float wrap_uv(float t) { return (t > 0.0f) ? fmodf(t, 1.0f) : 1.0f - fmodf(-t, 1.0f); }
+ST_DEV float wrap_uv(float t) { return (t > 0.0f) ? fmodf(t, 1.0f) : xsub(1.0f, fmodf(-t, 1.0f)); }
 ST_DEV float4 atlas_fetch(const SceneDev& sc, float2 uv) {
     if (!sc.atlas) return f4zero();
-    int x = to_i32_sat(floorf(uv.x * (float)kAtlasSize)), y = to_i32_sat(floorf(uv.y * (float)kAtlasSize));
+    int x = to_i32_sat(floorf(xmul(uv.x, (float)kAtlasSize))), y = to_i32_sat(floorf(xmul(uv.y, (float)kAtlasSize)));
     x = max(0, min(x, (int)kAtlasSize - 1)); y = max(0, min(y, (int)kAtlasSize - 1));
     uchar4 t = __ldg(sc.atlas + (size_t)y * kAtlasSize + (size_t)x);
-    return f4(__ldg(sc.srgb_lut + t.x), __ldg(sc.srgb_lut + t.y), __ldg(sc.srgb_lut + t.z), (float)t.w / 255.0f);
+    return f4(__ldg(sc.srgb_lut + t.x), __ldg(sc.srgb_lut + t.y), __ldg(sc.srgb_lut + t.z), xdiv((float)t.w, 255.0f));
 }
 ST_DEV float4 sample_atlas(const SceneDev& sc, float2 hit_uv, float4 multiplier, float4 texture) {
     if (all_zero(texture)) return multiplier;
-    float2 uv = f2(texture.x, texture.y) + f2(wrap_uv(hit_uv.x), wrap_uv(hit_uv.y)) * f2(texture.z, texture.w);
-    return multiplier * atlas_fetch(sc, uv);
+    float2 uv = f2(xadd(texture.x, xmul(wrap_uv(hit_uv.x), texture.z)), xadd(texture.y, xmul(wrap_uv(hit_uv.y), texture.w)));
+    float4 t = atlas_fetch(sc, uv);
+    return f4(xmul(multiplier.x, t.x), xmul(multiplier.y, t.y), xmul(multiplier.z, t.z), xmul(multiplier.w, t.w));
 }
 ST_DEV float4 mat_base_color(const SceneDev& sc, const GpuMaterial& m, float2 uv) { return sample_atlas(sc, uv, m.base_color, m.base_color_texture); }
 ST_DEV float3 mat_emissive(const SceneDev& sc, const GpuMaterial& m, float2 uv) { return xyz(sample_atlas(sc, uv, m.emissive, m.emissive_texture)); }
@@ -152,6 +156,7 @@ template <bool COUNT_MEMORY = false>
 ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack& stk, u32* used_memory = nullptr) {
     count_ray(sc);
     TriHit hit = trihit_none();
+    if (sc.bvh_len == 0u) { if (COUNT_MEMORY && used_memory) *used_memory = 0u; return hit; }   // empty scene (no instance alive)
     float hu = 0.f, hv = 0.f, hid = 0.f;
     u32 ptr = 0u, sp = 0u, used = 0u;
     bool alive = true;
@@ -206,6 +211,7 @@ ST_DEV TriHit trace_closest(const Ray& ray, const SceneDev& sc, const TraceStack
 // The answer does not depend on visiting order; the reference's order is kept anyway.
 ST_DEV bool trace_any(const Ray& ray, const SceneDev& sc, const TraceStack& stk) {
     count_ray(sc);
+    if (sc.bvh_len == 0u) return false;
     const float best = ray.len;
     u32 ptr = 0u, sp = 0u;
     bool found = false, alive = true;
@@ -402,7 +408,7 @@ ST_DEV u32 rng_u32(Rng& r) {
     u32 word = ((r.s >> ((r.s >> 28) + 4u)) ^ r.s) * 277803737u;
     return (word >> 22) ^ word;
 }
-ST_DEV float rng_f(Rng& r) { return (float)rng_u32(r) / 4294967296.0f; }
+ST_DEV float rng_f(Rng& r) { return xmul((float)rng_u32(r), 2.3283064365386963e-10f); }   // / 2^32 (white.rs:44-46), exact as a product
 ST_DEV float2 rng_disk(Rng& r) {
     float radius = sqrtf(rng_f(r));
     float a = rng_f(r) * kPi * 2.0f;
@@ -745,4 +751,4 @@ ST_DEV uint2 checker(u32 gx, u32 gy, u32 frame) { return make_uint2(gx * 2u + ((
 ST_DEV bool checker_at(u32 px, u32 py, u32 frame) { uint2 r = checker(px / 2u, py, frame); return r.x == px && r.y == py; }
 ST_DEV bool gi_tracing_frame(u32 frame) { return frame % 6u < 4u; }
 
-}  // namespace st
+}  // namespace ST_NS

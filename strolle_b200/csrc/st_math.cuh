@@ -9,11 +9,26 @@
 // acos, atan2, exp, pow) are explicit Cephes-style polynomial kernels instead of
 // libdevice calls so that a frame is reproducible bit-for-bit against a CPU run
 // of the same formulas.
+//
+// This header (and st_device.cuh, kernels.cu) is compiled TWICE:
+//   ST_FAST undefined  -> namespace st : the strict flavour described above (nvcc -fmad=false).
+//   ST_FAST = 1        -> namespace stf: the "fast shading" flavour of the ReSTIR kernels (nvcc -fmad=true -prec-div=false
+//                         -prec-sqrt=false): FMA contraction, div/sqrt/rcp approximations and SFU sin/cos/ex2/lg2 for radiance,
+//                         BRDF, pdf and MIS evaluation — what a GPU shader compiler emits for the reference's rust-gpu SPIR-V.
+// Everything that DECIDES something discrete is written with the x*() primitives below (explicit round-to-nearest
+// intrinsics that no compiler flag contracts or approximates): BVH traversal, ray/box and ray/triangle tests, the alpha test's
+// texel address, RNG draws.  Both flavours therefore return the same hit for the same ray, bit for bit.
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
 
-namespace st {
+#if defined(ST_FAST) && ST_FAST
+#define ST_NS stf
+#else
+#define ST_NS st
+#endif
+
+namespace ST_NS {
 
 typedef uint32_t u32;
 typedef int32_t i32;
@@ -24,6 +39,13 @@ static const float kPi = 3.14159265358979323846f;
 static const float kHalfPi = 1.5707963267948966f;
 static const float kF32Max = 3.40282347e+38f;
 static const float kF32Eps = 1.1920929e-7f;
+
+// flag-independent IEEE-754 primitives: one correctly rounded operation each, never contracted into an FMA
+ST_DEV float xadd(float a, float b) { return __fadd_rn(a, b); }
+ST_DEV float xsub(float a, float b) { return __fsub_rn(a, b); }
+ST_DEV float xmul(float a, float b) { return __fmul_rn(a, b); }
+ST_DEV float xdiv(float a, float b) { return __fdiv_rn(a, b); }
+ST_DEV float xsqrt(float a) { return __fsqrt_rn(a); }
 
 ST_DEV u32 fbits(float f) { return __float_as_uint(f); }
 ST_DEV float bitsf(u32 u) { return __uint_as_float(u); }
@@ -43,6 +65,10 @@ ST_DEV u32 to_u32_sat(float f) { return __float2uint_rz(f); }   // truncating, s
 ST_DEV i32 to_i32_sat(float f) { return __float2int_rz(f); }
 
 // ---- elementary functions ---------------------------------------------------
+#if defined(ST_FAST) && ST_FAST
+// SFU flavour: sin.approx / cos.approx (arguments on this path are within a few multiples of pi), ex2/lg2.approx.
+ST_DEV void sincos_det(float x, float* s_out, float* c_out) { __sincosf(x, s_out, c_out); }
+#else
 ST_DEV void sincos_det(float xx, float* s_out, float* c_out) {
     float x = fabs_(xx);
     u32 j = (u32)(1.27323954473516f * x);
@@ -58,6 +84,7 @@ ST_DEV void sincos_det(float xx, float* s_out, float* c_out) {
     if (fbits(xx) & 0x80000000u) s = -s;
     *s_out = s; *c_out = c;
 }
+#endif
 ST_DEV float sin_det(float x) { float s, c; sincos_det(x, &s, &c); return s; }
 ST_DEV float cos_det(float x) { float s, c; sincos_det(x, &s, &c); return c; }
 
@@ -110,6 +137,10 @@ ST_DEV float ldexp_det(float m, int n) {
     else if (n < -126) { m = m * bitsf(0x00800000u); n += 126; if (n < -126) n = -126; }
     return m * bitsf((u32)(n + 127) << 23);
 }
+#if defined(ST_FAST) && ST_FAST
+ST_DEV float exp_det(float x) { return __expf(x); }
+ST_DEV float log_det(float x) { return __logf(x); }
+#else
 ST_DEV float exp_det(float x) {
     if (!(x == x)) return x;
     if (x > 88.72283905206835f) return finf();
@@ -137,6 +168,7 @@ ST_DEV float log_det(float x) {   // x > 0 finite
     r += 0.693359375f * fe;
     return r;
 }
+#endif
 ST_DEV float pow_det(float x, float y) {
     if (y == 0.0f) return 1.0f;
     if (!(x == x) || !(y == y)) return fnan();
@@ -151,7 +183,11 @@ ST_DEV float pow_det(float x, float y) {
     if (y == 8.0f) { float x2 = x * x; float x4 = x2 * x2; return x4 * x4; }
     if (y == 64.0f) { float x2 = x * x; float x4 = x2 * x2; float x8 = x4 * x4; float x16 = x8 * x8; float x32 = x16 * x16; return x32 * x32; }
     if (y == 1.5f) return x * sqrtf(x);
+#if defined(ST_FAST) && ST_FAST
+    return __powf(x, y);   // ex2.approx(y * lg2.approx(x))
+#else
     return exp_det(y * log_det(x));
+#endif
 }
 
 // ---- vectors ----------------------------------------------------------------
@@ -191,6 +227,13 @@ ST_DEV float dot(float2 a, float2 b) { return (a.x * b.x) + (a.y * b.y); }
 ST_DEV float dot(float3 a, float3 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z); }
 ST_DEV float dot(float4 a, float4 b) { return (a.x * b.x) + (a.y * b.y) + (a.z * b.z) + (a.w * b.w); }
 ST_DEV float3 cross(float3 a, float3 b) { return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+// the same formulas through the flag-independent primitives (traversal, intersection tests)
+ST_DEV float3 xsub3(float3 a, float3 b) { return f3(xsub(a.x, b.x), xsub(a.y, b.y), xsub(a.z, b.z)); }
+ST_DEV float xdot(float3 a, float3 b) { return xadd(xadd(xmul(a.x, b.x), xmul(a.y, b.y)), xmul(a.z, b.z)); }
+ST_DEV float3 xcross(float3 a, float3 b) { return f3(xsub(xmul(a.y, b.z), xmul(b.y, a.z)), xsub(xmul(a.z, b.x), xmul(b.z, a.x)), xsub(xmul(a.x, b.y), xmul(b.x, a.y))); }
+ST_DEV float3 xscale(float3 a, float s) { return f3(xmul(a.x, s), xmul(a.y, s), xmul(a.z, s)); }
+ST_DEV float3 xadd3(float3 a, float3 b) { return f3(xadd(a.x, b.x), xadd(a.y, b.y), xadd(a.z, b.z)); }
+ST_DEV float3 xnorm(float3 a) { return xscale(a, xdiv(1.0f, xsqrt(xdot(a, a)))); }
 ST_DEV float len2(float3 a) { return dot(a, a); }
 ST_DEV float len2(float2 a) { return dot(a, a); }
 ST_DEV float len(float3 a) { return sqrtf(dot(a, a)); }
@@ -230,4 +273,4 @@ ST_DEV float3 project_point(const Mat4& m, float3 p) {
 }
 ST_DEV u32 pack_bytes(u32 a, u32 b, u32 c, u32 d) { return a | (b << 8) | (c << 16) | (d << 24); }
 
-}  // namespace st
+}  // namespace ST_NS

@@ -31,6 +31,7 @@ static const uint32_t kAtlasSize = 8192;   // strolle/src/images.rs:29-30
 struct SceneDev {
     const float4* triangles;   // 9 float4 per triangle (strolle-gpu/src/triangle.rs:8-21)
     const float4* bvh;         // strolle/src/bvh/serializer.rs:53-104
+    uint32_t bvh_len;          // float4 count of `bvh`; 0 = no primitive alive (empty stream, serializer.rs:20-110): every ray misses
     const GpuMaterial* materials;
     const GpuLight* lights;
     const uchar4* blue_noise;  // 256x256 RGBA8

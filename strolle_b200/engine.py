@@ -20,6 +20,7 @@ OPT_WAVELET_TILE_CFG = 5   # 4 bits per iteration: 0 32x8, 1 32x16, 2 64x4, 3 64
 OPT_FUSE_REPROJECT = 6     # K20 for DI and GI in one launch
 OPT_BVH_REUSE = 7          # graft unchanged subtrees of the previous BVH (reference behaviour)
 OPT_VARIANCE_TILED = 8     # K21 window from a TMA-filled shared-memory tile
+OPT_SHADING_FAST_MATH = 9  # ReSTIR kernels K5-K19 from the fast-shading build (FMA + SFU approximations; traversal unchanged)
 WAVELET_TILED_DEFAULT = 15   # include/strolle_b200.h ST_WAVELET_TILED_DEFAULT
 STAT_WAVELET_TILED_LAUNCHES = 1
 STAT_WAVELET_TILED_ERRORS = 2
@@ -190,7 +191,7 @@ class Engine:
     """strolle::Engine on one B200 (CUDA device `device`)."""
 
     def __init__(self, device=0, blue_noise=None, seed_base=0xC0FFEE, exact=False):
-        """`exact=True` switches the SVGF weights to strict IEEE arithmetic (bit-identical to the CPU oracle)."""
+        """`exact=True` switches the SVGF weights and the ReSTIR shading kernels to strict IEEE arithmetic (bit-identical to the CPU oracle)."""
         self.lib = load_library()
         h = C.c_void_p()
         self._h = None
@@ -204,6 +205,7 @@ class Engine:
         self._check(self.lib.st_set_seed_base(self._h, seed_base))
         if exact:
             self.set_option(OPT_SVGF_FAST_MATH, 0)
+            self.set_option(OPT_SHADING_FAST_MATH, 0)
         self._cams = {}
 
     def _check(self, rc):

@@ -139,7 +139,7 @@ def _torus(major=0.5, minor=0.25, nu=24, nv=12):
 
 
 def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cells=13):
-    """Config C3 stand-in: a *synthetic* dungeon (BASELINE.json: "synthetic Cornell and dungeon scenes").
+    """A *synthetic* dungeon (small parity cases and golden fixtures; the benchmark's C3 is `demo_level` below).
 
     The reference's demo level (bevy-strolle/assets/demo.zip, 8,393 triangles + 3 emissive tori, 6 point
     lights, sun az 3.0 / alt 0.35, bevy-strolle/examples/demo.rs:150-237) needs the texture atlas (SURVEY
@@ -210,6 +210,77 @@ def dungeon(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, seed=7, cell
                transform=look_at_transform(tuple(eye), (eye[0], eye[1], eye[2] - 0.2)),
                projection=perspective_infinite_reverse_rh(math.pi / 4.0, width / height, 0.1))
     return dict(name="dungeon_synthetic", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(3.0, 0.35), camera=cam)
+
+
+def _bevy_torus(radius=1.0, ring_radius=0.5, segments=32, sides=24):
+    """bevy 0.12.1 `shape::Torus::default()` (third-party crate pinned in Cargo.toml:16, not vendored under /root/reference; restated
+    from its published mesh generator): (segments+1) x (sides+1) vertices, two triangles (lt, rt, lb), (rt, rb, lb) per face."""
+    pos, nor, uvs = [], [], []
+    seg_stride, side_stride = np.float32(2.0 * math.pi) / np.float32(segments), np.float32(2.0 * math.pi) / np.float32(sides)
+    for seg in range(segments + 1):
+        theta = float(seg_stride * np.float32(seg))
+        for side in range(sides + 1):
+            phi = float(side_stride * np.float32(side))
+            p = np.array([math.cos(theta) * (radius + ring_radius * math.cos(phi)), ring_radius * math.sin(phi),
+                          math.sin(theta) * (radius + ring_radius * math.cos(phi))], np.float64)
+            c = np.array([radius * math.cos(theta), 0.0, radius * math.sin(theta)], np.float64)
+            n = (p - c) / np.linalg.norm(p - c)
+            pos.append(p.astype(np.float32)); nor.append(n.astype(np.float32)); uvs.append([seg / segments, side / sides])
+    tris = []
+    row = sides + 1
+    for seg in range(segments):
+        for side in range(sides):
+            lt, rt, lb, rb = side + seg * row, side + 1 + seg * row, side + (seg + 1) * row, side + 1 + (seg + 1) * row
+            for a, b, c in ((lt, rt, lb), (rt, rb, lb)):
+                tris.append(tri36([pos[a], pos[b], pos[c]], [nor[a], nor[b], nor[c]], [uvs[a], uvs[b], uvs[c]]))
+    return tris
+
+
+def demo_level(width=1920, height=1080, mode=MODE_IMAGE, denoise=True, textures=True):
+    """BASELINE config C3: the reference's dungeon demo (bevy-strolle/examples/demo.rs).
+
+    Geometry, materials and textures come from the reference's own asset (assets/demo.zip -> demo/level.glb, extracted
+    by tools/make_assets.py into assets/dungeon.npz: 45 meshes, 8,393 triangles, 45 64x64 base-colour textures); the
+    rest follows demo.rs: every material re-lit with reflectance 0 / perceptual_roughness 1 (`adjust_materials`,
+    demo.rs:246-261 — it walks ALL StandardMaterials, the tori's included), three emissive tori
+    (shape::Torus::default(), rotation_z(1.0), scale 0.5, emissive 10 x (0.9, 0.6, 0.3), demo.rs:195-219), six point
+    lights of intensity 5000 (x 1/4pi in bevy-strolle/src/stages/extract.rs:285), range 35, radius 0.15 (demo.rs:169-191), the
+    flashlight dropped for its zero intensity (extract.rs:306-311), camera eye (-5.75, 0.5, -16.8) -> (-5.75, 0.5, -17.0)
+    (demo.rs:150-152), sun azimuth 3.0 (_common.rs:166-173) and strolle::Sun's default altitude 0.35 (strolle/src/sun.rs:7-13).
+    `textures=False` is demo.rs's T key (base_color_texture = None on every material)."""
+    d = np.load(os.path.join(_ASSETS, "dungeon.npz"))
+    meshes, materials, instances, lights, images, material_textures = {}, {}, [], [], {}, {}
+    nmesh = len(d["mesh_material"])
+    zeros_t = np.zeros((3, 4), np.float32)
+    for k in range(nmesh):
+        pos, nor, uv = d[f"pos{k}"], d[f"nor{k}"], d[f"uv{k}"]
+        tris = np.concatenate([pos.reshape(-1, 9), nor.reshape(-1, 9), uv.reshape(-1, 6), np.tile(zeros_t.reshape(1, 12), (len(pos), 1))], axis=1).astype(np.float32)
+        meshes[1000 + k] = tris
+        instances.append((5000 + k, 1000 + k, 100 + int(d["mesh_material"][k]), affine_from_colmajor4x4(d["mesh_transform_colmajor"][k])))
+    for i, bmr in enumerate(d["material_base_metallic_roughness"]):
+        # bevy_gltf StandardMaterial (base colour factor, metallic factor) then demo.rs::adjust_materials: reflectance 0, roughness 1
+        materials[100 + i] = (material(tuple(float(v) for v in bmr[:4]), perceptual_roughness=1.0, metallic=float(bmr[4]), reflectance=0.0), False)
+        t = int(d["material_texture"][i])
+        if textures and t >= 0:
+            material_textures[100 + i] = dict(base_color=700 + t)
+    if textures:
+        for t, img in enumerate(d["images_rgba8"]):
+            images[700 + t] = np.ascontiguousarray(img)
+    torus = np.stack(_bevy_torus())
+    meshes[2000] = torus
+    c1, s1 = math.cos(1.0), math.sin(1.0)   # Quat::from_rotation_z(1.0) * scale 0.5
+    for k, (tx, ty, tz) in enumerate([(-0.5, 0.33, -5.5), (-11.0, 0.33, 28.0), (-11.5, 0.33, 13.5)]):
+        materials[160 + k] = (material((0.9, 0.6, 0.3, 1.0), emissive=(9.0, 6.0, 3.0, 1.0), perceptual_roughness=1.0, reflectance=0.0), False)
+        xf = np.array([0.5 * c1, 0.5 * s1, 0.0, -0.5 * s1, 0.5 * c1, 0.0, 0.0, 0.0, 0.5, tx, ty, tz], np.float32)
+        instances.append((6000 + k, 2000, 160 + k, xf))
+    inten = 5000.0 / (4.0 * math.pi)
+    for k, p in enumerate([(-3.0, 0.75, -23.0), (-23.5, 0.75, -31.0), (1.25, 0.75, -10.5), (-3.15, 0.75, 1.25), (-3.25, 0.75, 20.25), (13.25, 0.75, -28.25)]):
+        lights.append((9000 + k, LIGHT_POINT, point_light(p, 0.15, (inten,) * 3, 35.0)))
+    cam = dict(mode=mode, denoise=denoise, ref_depth=1, w=width, h=height,
+               transform=look_at_transform((-5.75, 0.5, -16.8), (-5.75, 0.5, -17.0)),
+               projection=perspective_infinite_reverse_rh(math.pi / 4.0, width / height, 0.1))
+    return dict(name="dungeon_demo_level", meshes=meshes, materials=materials, instances=instances, lights=lights, sun=(3.0, 0.35), camera=cam,
+                images=images, material_textures=material_textures)
 
 
 def _quad(p0, p1, p2, p3, normal, uv_lo=(0.0, 0.0), uv_hi=(1.0, 1.0)):

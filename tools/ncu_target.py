@@ -17,7 +17,7 @@ frames = int(sys.argv[4]) if len(sys.argv) > 4 else 14
 w, h = (int(sys.argv[5]), int(sys.argv[6])) if len(sys.argv) > 6 else (1920, 1080)
 e = strolle_b200.Engine()
 e.set_option(OPT_WAVELET_TILED, mask); e.set_option(OPT_WAVELET_TILE_CFG, cfg); e.set_option(OPT_FUSE_REPROJECT, fuse)
-cam = scenes.apply(e, scenes.dungeon(w, h) if os.environ.get("ST_SCENE") == "dungeon" else scenes.cornell(w, h))
+cam = scenes.apply(e, {"dungeon": scenes.dungeon, "demo": scenes.demo_level}.get(os.environ.get("ST_SCENE", ""), scenes.cornell)(w, h))
 for _ in range(frames):
     e.tick(); e.render_camera(cam)
 e.synchronize()

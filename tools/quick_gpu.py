@@ -7,8 +7,8 @@ from strolle_b200 import scenes
 
 w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
 name = sys.argv[3] if len(sys.argv) > 3 else "cornell"
-e = strolle_b200.Engine()
-sc = scenes.cornell(w, h) if name == "cornell" else scenes.dungeon(w, h)
+e = strolle_b200.Engine(exact=bool(int(os.environ.get('ST_EXACT', '0'))))
+sc = {"cornell": scenes.cornell, "dungeon": scenes.dungeon, "demo": scenes.demo_level}[name](w, h)
 cam = scenes.apply(e, sc)
 for f in range(12):
     e.tick(); e.render_camera(cam)
