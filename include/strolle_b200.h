@@ -172,7 +172,11 @@ int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9, ST_OPT_STRIP_FUSED = 10 };
+/* ST_OPT_STRIP_FUSED (default 1): strip-partitioned frames use the fused transport (producer kernels store boundary rows straight
+ * into the neighbours' buffers, neighbour-only sequence flags, halo rows of the G-buffer and of the SVGF chain recomputed instead of
+ * shipped, DI / GI chains interleaved so that rows in flight overlap compute, temporal rows pulled on demand); 0 = one push +
+ * all-rank barrier kernel per exchange point.  Needs strips of >= 128 rows. */
 /* ST_OPT_SHADING_FAST_MATH (default 1): the ReSTIR DI/GI kernels K5-K19 (strolle-shaders/src/di_*.rs, gi_*.rs) run in their
  * fast-shading build: FMA contraction, approximate division / square root and SFU sin/cos/ex2/lg2 for radiance, BRDF, pdf
  * and MIS evaluation - the arithmetic a GPU shader compiler emits for the reference's SPIR-V.  BVH traversal, the ray/box and
@@ -259,6 +263,47 @@ int st_buffer_device_ptr(st_engine* e, st_camera_handle camera, const char* name
  * schedule (indices into the schedule returned by st_frame_schedule). */
 int st_frame_schedule(st_engine* e, st_camera_handle camera, int* pass_ids, int cap, int* count);
 int st_render_range(st_engine* e, st_camera_handle camera, int first, int last);
+
+/* Links engines of THIS process into one strip group (rank = index): enables peer access between their devices and maps every
+ * member's per-camera buffers into the others (what st_peer_export / st_peer_import do between processes).  Members may share a
+ * device (the whole protocol then runs on one GPU: how single-GPU boxes test it). */
+int st_link_local(st_engine* const* engines, const st_camera_handle* cameras, int n);
+
+/* ---- st_multi: one process, several devices (`Engine::new` over a list of device ordinals) --------------------------
+ * The strolle::Engine surface for a row-strip group: scene verbs are replayed on every member (the scene is replicated), a camera
+ * exists on every member, st_multi_render_camera renders every member's strip of ONE frame with the fused transport and copies
+ * each strip into the caller's frame.  Mirrors the st_* verbs one to one (lib.rs:132-301). */
+typedef struct st_multi st_multi;
+int st_multi_create(const int* device_ordinals, int n, st_multi** out);
+void st_multi_destroy(st_multi* m);
+int st_multi_size(st_multi* m);
+st_engine* st_multi_engine(st_multi* m, int rank);   /* member access (statistics, options, st_read_buffer on one strip) */
+st_camera_handle st_multi_member_camera(st_multi* m, st_camera_handle camera, int rank);
+int st_multi_insert_mesh(st_multi* m, st_handle mesh, const st_mesh_triangle* triangles, size_t count);
+int st_multi_remove_mesh(st_multi* m, st_handle mesh);
+int st_multi_insert_material(st_multi* m, st_handle material, const st_material* mat);
+int st_multi_has_material(st_multi* m, st_handle material);
+int st_multi_remove_material(st_multi* m, st_handle material);
+int st_multi_insert_image(st_multi* m, st_handle image, const uint8_t* rgba8, uint32_t width, uint32_t height);
+int st_multi_remove_image(st_multi* m, st_handle image);
+int st_multi_set_material_textures(st_multi* m, st_handle material, const st_material_textures* textures);
+int st_multi_insert_instance(st_multi* m, st_handle instance, st_handle mesh, st_handle material, const float affine[12]);
+int st_multi_remove_instance(st_multi* m, st_handle instance);
+int st_multi_insert_light(st_multi* m, st_handle light, const st_light* l);
+int st_multi_remove_light(st_multi* m, st_handle light);
+int st_multi_update_sun(st_multi* m, float azimuth, float altitude);
+int st_multi_create_camera(st_multi* m, const st_camera* camera, st_camera_handle* out);
+int st_multi_update_camera(st_multi* m, st_camera_handle camera, const st_camera* desc);
+int st_multi_delete_camera(st_multi* m, st_camera_handle camera);
+int st_multi_tick(st_multi* m);
+/* host_out: the full frame (width*height pixels of `format`); every member fills its own rows.  NULL = enqueue only. */
+int st_multi_render_camera(st_multi* m, st_camera_handle camera, void* host_out, int format);
+int st_multi_synchronize(st_multi* m);
+int st_multi_set_option(st_multi* m, int option, int value);
+int st_multi_set_seed_base(st_multi* m, uint32_t base);
+int st_multi_set_blue_noise(st_multi* m, const uint8_t* rgba8_256x256);
+int st_multi_read_buffer(st_multi* m, st_camera_handle camera, const char* name, float* dst, size_t cap_floats, size_t* count);
+int st_multi_peer_errors(st_multi* m, st_camera_handle camera, uint32_t* count);
 
 #ifdef __cplusplus
 }

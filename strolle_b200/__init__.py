@@ -5,5 +5,5 @@ BVH traversal + ray/triangle intersection, ReSTIR DI / GI temporal + spatial res
 (include/strolle_b200.h).  `strolle_b200.Engine` is a thin ctypes mirror of `strolle::Engine`.
 There is no CPU fallback: without the built library or without a CUDA device, construction fails.
 """
-from .engine import Engine, StrolleError, lib_path, load_library, PASS_NAMES  # noqa: F401
+from .engine import Engine, MultiEngine, StrolleError, lib_path, load_library, PASS_NAMES  # noqa: F401
 from . import scenes  # noqa: F401

@@ -379,7 +379,9 @@ struct CameraSlot {
     // the host on the copy stream (ev_copied[k]); the engine stream only waits for ev_copied[k] before reusing slot k
     cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // peer-memory link of the strip partition: other ranks' arena / flag / rgba8 allocations mapped through CUDA IPC
-    struct PeerLink { bool ready = false; std::vector<char*> arena, rgba8; std::vector<uint32_t*> flags; DevMem sync; uint32_t seq = 0; } peer;
+    // sync words: [0, 128) fused-transport flags (slot * 16 + source rank), 128.. legacy k_peer_exchange flags, 144 its block counter,
+    // 145 its time-outs, 200/201 need_rows {min, max}, 202 fused-transport wait time-outs, 204 (u64) rows pulled
+    struct PeerLink { bool ready = false; bool ipc = false; std::vector<char*> arena, rgba8; std::vector<uint32_t*> flags; DevMem sync; uint32_t seq = 0, fseq = 0; } peer;
 };
 
 struct Step { int pass; std::function<void(cudaStream_t)> run; int sub = -1; };   // sub: à-trous iteration of a K22 step
@@ -425,6 +427,8 @@ struct st_engine {
     bool shading_fast = ST_SHADING_FAST_DEFAULT != 0;   // ST_OPT_SHADING_FAST_MATH
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
+    bool strip_fused = true;     // ST_OPT_STRIP_FUSED: mirror stores + neighbour flags + recompute instead of stand-alone exchanges
+    bool last_frame_fused = false;
     int wavelet_tiled = ST_WAVELET_TILED_DEFAULT;   // ST_OPT_WAVELET_TILED: bit i = à-trous iteration i (stride 2^i) runs the tile-staged (TMA) kernel
     int wavelet_cfg = ST_WAVELET_CFG_DEFAULT;       // ST_OPT_WAVELET_TILE_CFG: 4 bits per iteration, tile shape index (kernels.cu wavelet_tiled_cfg)
     DevMem d_tile_errors; uint64_t wavelet_tiled_launches = 0;
@@ -622,12 +626,21 @@ static int allocate_camera(st_engine* e, CameraSlot* cs) {
     size_t off = 0;
     for (size_t i = 0; i < cs->named.size(); i++) { *cs->named[i].second = (float4*)((char*)cs->arena.p + off); off += (cs->sizes[i].second * 16 + 255) / 256 * 256; }
     d.w = (int)cs->desc.width; d.h = (int)cs->desc.height; d.y0 = 0; d.y1 = d.h;
+    d.own_y0 = 0; d.own_y1 = d.h; d.mirror_up = 0; d.mirror_dn = 0; d.need_rows = nullptr;
     return ST_OK;
 }
 
 // CameraController::render (strolle/src/camera_controller.rs:87-174) as an explicit step list
-static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* steps) {
+// Rows a pass computes beyond the owned strip [y0, y1) in a strip-partitioned frame (fused transport): the G-buffer pass recomputes the
+// rows its neighbours' spatial taps reach, K21 / K22 recompute the rows the following à-trous iterations read, so that none of
+// those buffers has to travel.  All zero = every pass runs on [y0, y1).
+struct StripExt { int gbuffer = 0, variance = 0, wavelet[5] = {0, 0, 0, 0, 0}; int preview_mirror[2] = {0, 0}; };
+static CameraDev grown(const CameraDev& c, int rows) { CameraDev g = c; g.y0 = std::max(0, c.y0 - rows); g.y1 = std::min(c.h, c.y1 + rows); return g; }
+static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* steps, const StripExt* ext = nullptr) {
     const CameraDev cam = cs->dev;   // snapshot (pointers + cameras)
+    const StripExt no_ext; const StripExt& x = ext ? *ext : no_ext;
+    const CameraDev camG = grown(cam, x.gbuffer), camV = grown(cam, x.variance);
+    const int pm0 = x.preview_mirror[0], pm1 = x.preview_mirror[1];
     const SceneDev sc = e->scene();
     const uint32_t f = cs->frame;
     const int cur = (f % 2u) == 1u ? 1 : 0;   // is_alternate (camera_controller.rs:185-187)
@@ -654,7 +667,7 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
     }
     const bool needs_di = d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_DI_DIFFUSE || d.mode == ST_MODE_DI_SPECULAR;
     const bool needs_gi = d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_GI_DIFFUSE || d.mode == ST_MODE_GI_SPECULAR;
-    add(P_PRIM_GBUFFER, [=](cudaStream_t s) { launch_prim_gbuffer(cam, sc, cur, s); });
+    add(P_PRIM_GBUFFER, [=](cudaStream_t s) { launch_prim_gbuffer(camG, sc, cur, s); });
     if (!e->instances.empty()) {
         add(P_FRAME_REPROJECTION, [=](cudaStream_t s) { launch_frame_reprojection(cam, sc, cur, s); });
         if (needs_di) {
@@ -689,8 +702,8 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
                 source = 0;
             }
             const float4* src0 = source == 0 ? cam.gi_reservoirs[1] : cam.gi_reservoirs[2];
-            add(P_GI_PREVIEW, [=](cudaStream_t s) { (fs ? stf::launch_gi_preview : st::launch_gi_preview)(cam, sc, cur, sv, 0u, src0, cam.gi_reservoirs[3], s); });
-            add(P_GI_PREVIEW, [=](cudaStream_t s) { (fs ? stf::launch_gi_preview : st::launch_gi_preview)(cam, sc, cur, sv, 1u, cam.gi_reservoirs[3], cam.gi_reservoirs[0], s); });
+            add(P_GI_PREVIEW, [=](cudaStream_t s) { (fs ? stf::launch_gi_preview : st::launch_gi_preview)(cam, sc, cur, sv, 0u, src0, cam.gi_reservoirs[3], pm0, s); });
+            add(P_GI_PREVIEW, [=](cudaStream_t s) { (fs ? stf::launch_gi_preview : st::launch_gi_preview)(cam, sc, cur, sv, 1u, cam.gi_reservoirs[3], cam.gi_reservoirs[0], pm1, s); });
             add(P_GI_RESOLVING, [=](cudaStream_t s) { (fs ? stf::launch_gi_resolving : st::launch_gi_resolving)(cam, sc, cur, src0, s); });
         }
     }
@@ -704,8 +717,8 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
         const bool fast = e->svgf_fast;
         const bool var_tiled = e->variance_tiled; uint32_t* verr = (uint32_t*)e->d_tile_errors.p;
         add(P_DENOISE_VARIANCE, [=](cudaStream_t s) {
-            if (var_tiled && launch_denoise_variance_tiled(cam, sc, cur, fast, verr, s)) { e->variance_tiled_launches++; return; }
-            launch_denoise_variance(cam, sc, cur, fast, s);
+            if (var_tiled && launch_denoise_variance_tiled(camV, sc, cur, fast, verr, s)) { e->variance_tiled_launches++; return; }
+            launch_denoise_variance(camV, sc, cur, fast, s);
         });
         float4* di_io[5][2] = {{cam.di_diff_stash, cam.di_diff_prev_colors}, {cam.di_diff_prev_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors},
                                {cam.di_diff_curr_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors}};
@@ -715,9 +728,10 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
             float4 *a = di_io[nth][0], *b = di_io[nth][1], *c = gi_io[nth][0], *g = gi_io[nth][1];
             const bool tiled = ((e->wavelet_tiled >> nth) & 1) != 0; const int cfg = (e->wavelet_cfg >> (4 * nth)) & 15;
             uint32_t* terr = (uint32_t*)e->d_tile_errors.p;
+            const CameraDev camW = grown(cam, x.wavelet[nth]);
             add(P_DENOISE_WAVELET, [=](cudaStream_t s) {
-                if (tiled && launch_denoise_wavelet_tiled(cam, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, cfg, terr, s)) { e->wavelet_tiled_launches++; return; }
-                launch_denoise_wavelet(cam, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s);
+                if (tiled && launch_denoise_wavelet_tiled(camW, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, cfg, terr, s)) { e->wavelet_tiled_launches++; return; }
+                launch_denoise_wavelet(camW, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s);
             });
             steps->back().sub = (int)nth;
         }
@@ -808,11 +822,12 @@ static int halo_exchange(st_engine* e, CameraSlot* cs, const HaloExchange& ex) {
     return ST_OK;
 }
 
+static const int kLegacyFlagWord = 128, kNeedRowsWord = 200, kStripErrorWord = 202, kPulledRowsWord = 204, kSyncBytes = 4096;
 // the same exchange over mapped peer memory: one kernel stores my rows into every neighbour and runs the barrier
 static void peer_fill(st_engine* e, CameraSlot* cs, PeerExchange* x) {
-    uint32_t* sync = (uint32_t*)cs->peer.sync.p;   // [0..16) flags, [16] completion counter, [17] time-outs
+    uint32_t* sync = (uint32_t*)cs->peer.sync.p + kLegacyFlagWord;   // [0..16) flags, [16] completion counter, [17] time-outs
     x->nseg = 0; x->n_ranks = e->n_ranks; x->rank = e->rank; x->my_flags = sync; x->counter = sync + 16; x->errors = sync + 17; x->signal = 0; x->seq = 0;
-    for (int r = 0; r < ST_PEER_MAX_RANKS; r++) x->peer_flags[r] = (r < e->n_ranks && r != e->rank) ? cs->peer.flags[r] + e->rank : nullptr;
+    for (int r = 0; r < ST_PEER_MAX_RANKS; r++) x->peer_flags[r] = (r < e->n_ranks && r != e->rank) ? cs->peer.flags[r] + kLegacyFlagWord + e->rank : nullptr;
 }
 static void peer_flush(st_engine* e, CameraSlot* cs, PeerExchange* x, bool last) {
     if (last) { x->signal = 1; x->seq = ++cs->peer.seq; }
@@ -844,6 +859,111 @@ static int halo_exchange_peer(st_engine* e, CameraSlot* cs, const HaloExchange* 
         }
     }
     peer_flush(e, cs, &x, true);
+    return ST_OK;
+}
+
+// ---- strip partition, fused transport ----------------------------------------------------------------------------------------
+// One frame of this rank's strip with no stand-alone exchange step ("overlap with interior compute"):
+//  * nothing the rank can recompute travels: the G-buffer pass runs on the strip grown by the spatial reach (primary rays are
+//    deterministic), K21 / K22 run on rows grown by what the following à-trous iterations read (35 rows recomputed instead of six
+//    exchanges);
+//  * what must travel is stored straight into the neighbours' buffers by the kernel that produces it (CameraDev::mirror_up/dn:
+//    di[1], gi[1], gi[2], gi[3], the K20 colours and moments), and only the two neighbours are involved: a sequence flag per
+//    producer (k_strip_signal after the kernel) and a wait in front of the first consumer (k_strip_wait);
+//  * the DI and GI chains are independent until K20, so their passes are interleaved: while one chain's rows are in flight the
+//    other chain computes (same kernels, same seeds, same results as the reference order);
+//  * last frame's outputs that the temporal passes read at reprojected positions are pulled by the reader (k_strip_pull), sized
+//    on the device from this frame's velocities: nothing for a static camera, exact for any motion.
+// Every remote access of frame f happens after the rank has seen FRAME_DONE(f-1) from every rank, and a rank overwrites buffers
+// others may pull only after every rank signalled PULL_DONE(f).
+static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<std::pair<int, int>>& bounds) {
+    const int R = e->rank, N = e->n_ranks, H = (int)cs->desc.height;
+    const uint32_t seq = ++cs->peer.fseq;
+    uint32_t* sync = (uint32_t*)cs->peer.sync.p;
+    CameraDev& d = cs->dev;
+    d.y0 = d.own_y0 = bounds[R].first; d.y1 = d.own_y1 = bounds[R].second;
+    d.mirror_up = R > 0 ? (long long)(cs->peer.arena[R - 1] - cs->peer.arena[R]) : 0;
+    d.mirror_dn = R + 1 < N ? (long long)(cs->peer.arena[R + 1] - cs->peer.arena[R]) : 0;
+    d.need_rows = (int*)(sync + kNeedRowsWord);
+    StripExt ext; ext.gbuffer = kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
+    for (int i = 0; i < 5; i++) ext.wavelet[i] = wext[i];
+    ext.preview_mirror[0] = kPreview2Reach; ext.preview_mirror[1] = 0;
+    std::vector<Step> steps; build_schedule(e, cs, &steps, &ext);
+
+    StripSync ss; ss.my_flags = sync; ss.errors = sync + kStripErrorWord; ss.n_ranks = N; ss.rank = R;
+    for (int r = 0; r < ST_PEER_MAX_RANKS; r++) ss.peer_flags[r] = (r < N && r != R) ? cs->peer.flags[r] : nullptr;
+    const uint32_t all = (N >= 32 ? 0xffffffffu : ((1u << N) - 1u)) & ~(1u << R);
+    const uint32_t nb = ((R > 0 ? (1u << (R - 1)) : 0u) | (R + 1 < N ? (1u << (R + 1)) : 0u));
+    auto signal = [&](int slot, uint32_t mask, bool reset_need = false) {
+        int* rn = reset_need ? (int*)(sync + kNeedRowsWord) : nullptr;
+        e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_signal(ss, slot, seq, mask, rn, H, s); });
+    };
+    auto wait = [&](int slot, uint32_t mask, uint32_t value) { e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_wait(ss, slot, value, mask, s); }); };
+    auto emit = [&](const Step& st) { e->run_timed(st.pass, st.run, st.sub); };
+
+    // split the reference order into the blocks the interleaving moves around
+    std::vector<const Step*> pre, di1, di_pick, di_rest, gi1, gi_sp, pv1, gi_tail, post;
+    int nth_preview = 0;
+    for (const Step& st : steps) {
+        switch (st.pass) {
+        case P_PRIM_GBUFFER: case P_FRAME_REPROJECTION: case P_BVH_HEATMAP: case P_REF_TRACING: case P_REF_SHADING: pre.push_back(&st); break;
+        case P_DI_SAMPLING: case P_DI_TEMPORAL: di1.push_back(&st); break;
+        case P_DI_SPATIAL_PICK: case P_DI_SPATIAL_TRACE: di_pick.push_back(&st); break;
+        case P_DI_SPATIAL_SAMPLE: case P_DI_RESOLVING: di_rest.push_back(&st); break;
+        case P_GI_REPROJECTION: case P_GI_SAMPLING_A: case P_GI_SAMPLING_B: case P_GI_TEMPORAL: gi1.push_back(&st); break;
+        case P_GI_SPATIAL_PICK: case P_GI_SPATIAL_TRACE: case P_GI_SPATIAL_SAMPLE: gi_sp.push_back(&st); break;
+        case P_GI_PREVIEW: (nth_preview++ == 0 ? pv1 : gi_tail).push_back(&st); break;
+        case P_GI_RESOLVING: gi_tail.push_back(&st); break;
+        default: post.push_back(&st); break;
+        }
+    }
+    // frame start: the primary pass needs nobody; then wait until every rank has finished the previous frame, pull, tell everybody
+    size_t k = 0;
+    if (!pre.empty() && pre[0]->pass == P_PRIM_GBUFFER) { emit(*pre[0]); k = 1; }
+    wait(SLOT_FRAME_DONE, all, seq - 1u);
+    {
+        StripPull pl; std::memset(&pl, 0, sizeof pl);
+        for (int r = 0; r < N; r++) { pl.arena[r] = cs->peer.arena[r]; pl.bounds[r] = bounds[r].first; }
+        pl.bounds[N] = H; pl.n_ranks = N; pl.rank = R; pl.w = (int)cs->desc.width; pl.h = H; pl.own_y0 = d.own_y0; pl.own_y1 = d.own_y1;
+        pl.need_rows = (const int*)(sync + kNeedRowsWord); pl.pulled_rows = (unsigned long long*)(sync + kPulledRowsWord);
+        const char* prv = (cs->frame % 2u == 1u) ? "a" : "b";
+        struct { std::string name; int local; } items[] = {
+            {std::string("prim_surface_map_") + prv, kSpatialReach}, {std::string("prim_gbuffer_d0_") + prv, kSpatialReach}, {std::string("prim_gbuffer_d1_") + prv, kSpatialReach},
+            {"di_reservoirs_0", 0}, {"gi_reservoirs_0", 0}, {"di_diff_prev_colors", 0}, {"gi_diff_prev_colors", 0},
+            {std::string("di_diff_moments_") + prv, 0}, {std::string("gi_diff_moments_") + prv, 0}};
+        for (auto& it : items) {
+            size_t kk = 0; float4* base = camera_buffer(cs, it.name, &kk);
+            if (!base) return fail(ST_ERR_NOT_FOUND, "pull list names unknown buffer " + it.name);
+            pl.items[pl.nitems++] = StripPullItem{(size_t)((char*)base - (char*)cs->arena.p), (int)kk, it.local};
+        }
+        e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_pull(pl, s); });
+    }
+    signal(SLOT_PULL_DONE, all, true);
+    for (; k < pre.size(); k++) emit(*pre[k]);
+    // DI and GI up to their first gathering pass
+    for (auto* st : di1) emit(*st);
+    if (!di1.empty()) signal(SLOT_DI1, nb);
+    for (auto* st : gi1) emit(*st);
+    if (!gi1.empty()) signal(SLOT_GI1, nb);
+    if (!di_pick.empty()) { wait(SLOT_DI1, nb, seq); for (auto* st : di_pick) emit(*st); }
+    if (!gi1.empty()) wait(SLOT_GI1, nb, seq);
+    if (!gi_sp.empty()) { for (auto* st : gi_sp) emit(*st); signal(SLOT_GI2, nb); }
+    wait(SLOT_PULL_DONE, all, seq);   // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
+    if (!di_rest.empty()) emit(*di_rest[0]);
+    if (!gi_sp.empty()) wait(SLOT_GI2, nb, seq);
+    for (auto* st : pv1) emit(*st);
+    if (!pv1.empty()) signal(SLOT_GI3, nb);
+    for (size_t i = 1; i < di_rest.size(); i++) emit(*di_rest[i]);
+    if (!pv1.empty()) wait(SLOT_GI3, nb, seq);
+    for (auto* st : gi_tail) emit(*st);
+    // SVGF: K20 mirrors its rows, then everything downstream is recomputed locally
+    bool svgf_waited = false;
+    for (auto* st : post) {
+        if ((st->pass == P_DENOISE_VARIANCE) && !svgf_waited) { signal(SLOT_SVGF, nb); wait(SLOT_SVGF, nb, seq); svgf_waited = true; }
+        emit(*st);
+    }
+    signal(SLOT_FRAME_DONE, all);
+    d.y0 = d.own_y0; d.y1 = d.own_y1;
     return ST_OK;
 }
 
@@ -1065,7 +1185,7 @@ int st_camera_set_strip(st_engine* e, st_camera_handle h, int y0, int y1) {
     CameraSlot* cs = e ? get_camera(e, h) : nullptr;
     if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
     if (y0 < 0 || y1 > (int)cs->desc.height || y0 >= y1) return fail(ST_ERR_INVALID, "bad strip");
-    cs->dev.y0 = y0; cs->dev.y1 = y1;
+    cs->dev.y0 = y0; cs->dev.y1 = y1; cs->dev.own_y0 = y0; cs->dev.own_y1 = y1;
     return ST_OK;
 }
 
@@ -1180,34 +1300,37 @@ int st_render_camera(st_engine* e, st_camera_handle h, void* host_out, int forma
     if (host_out) return st_copy_output(e, h, host_out, format);
     return ST_OK;
 }
+// Converts rows [y0, y1) of the composed frame to `format` and copies them to the same rows of `host_out` (a full-frame buffer).
+static int copy_rows_out(st_engine* e, CameraSlot* cs, void* host_out, int format, int y0, int y1) {
+    const size_t W = cs->desc.width, n = W * cs->desc.height;
+    const size_t first = (size_t)y0 * W, count = (size_t)(y1 - y0) * W;
+    if (format == ST_FORMAT_RGBA32F) CK(cudaMemcpyAsync((char*)host_out + first * 16, cs->dev.output + first, count * 16, cudaMemcpyDeviceToHost, e->stream));
+    else if (format == ST_FORMAT_RGBA8_SRGB) {
+        int rc2 = cs->rgba8.ensure(2 * n * 4); if (rc2) return rc2;
+        cs->rgba8_slot ^= 1;
+        SceneDev sc = e->scene(); uchar4* dst8 = (uchar4*)cs->rgba8.p + (cs->rgba8_slot ? n : 0); CameraDev cd = cs->dev; cd.y0 = y0; cd.y1 = y1;
+        const int k = cs->rgba8_slot;
+        if (e->async_output) {   // conversion on the engine stream, copy on the copy stream: the next frame's passes do not queue behind the copy
+            if (!e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+            if (!cs->ev_ready[k]) { CK(cudaEventCreateWithFlags(&cs->ev_ready[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&cs->ev_copied[k], cudaEventDisableTiming)); }
+            else CK(cudaStreamWaitEvent(e->stream, cs->ev_copied[k], 0));   // slot k's previous copy must have left the staging buffer
+        }
+        e->run_timed(P_COMPOSITION, [=](cudaStream_t s) { launch_output_rgba8(cd, sc, dst8, s); });
+        if (e->async_output) {
+            CK(cudaEventRecord(cs->ev_ready[k], e->stream));
+            CK(cudaStreamWaitEvent(e->copy_stream, cs->ev_ready[k], 0));
+            CK(cudaMemcpyAsync((char*)host_out + first * 4, dst8 + first, count * 4, cudaMemcpyDeviceToHost, e->copy_stream));
+            CK(cudaEventRecord(cs->ev_copied[k], e->copy_stream));
+        } else CK(cudaMemcpyAsync((char*)host_out + first * 4, dst8 + first, count * 4, cudaMemcpyDeviceToHost, e->stream));
+    } else return fail(ST_ERR_INVALID, "unsupported output format");
+    return ST_OK;
+}
 int st_copy_output(st_engine* e, st_camera_handle h, void* host_out, int format) {
-    CameraSlot* cs0 = e ? get_camera(e, h) : nullptr;
-    if (!cs0 || !host_out) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    CameraSlot* cs = e ? get_camera(e, h) : nullptr;
+    if (!cs || !host_out) return fail(ST_ERR_NOT_FOUND, "unknown camera");
     CK(cudaSetDevice(e->device));
-    {
-        CameraSlot* cs = cs0;
-        size_t n = (size_t)cs->desc.width * cs->desc.height;
-        if (format == ST_FORMAT_RGBA32F) CK(cudaMemcpyAsync(host_out, cs->dev.output, n * 16, cudaMemcpyDeviceToHost, e->stream));
-        else if (format == ST_FORMAT_RGBA8_SRGB) {
-            int rc2 = cs->rgba8.ensure(2 * n * 4); if (rc2) return rc2;
-            cs->rgba8_slot ^= 1;
-            SceneDev sc = e->scene(); uchar4* dst8 = (uchar4*)cs->rgba8.p + (cs->rgba8_slot ? n : 0); CameraDev cd = cs->dev;
-            const int k = cs->rgba8_slot;
-            if (e->async_output) {   // conversion on the engine stream, copy on the copy stream: the next frame's passes do not queue behind the copy
-                if (!e->copy_stream) CK(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-                if (!cs->ev_ready[k]) { CK(cudaEventCreateWithFlags(&cs->ev_ready[k], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&cs->ev_copied[k], cudaEventDisableTiming)); }
-                else CK(cudaStreamWaitEvent(e->stream, cs->ev_copied[k], 0));   // slot k's previous copy must have left the staging buffer
-            }
-            e->run_timed(P_COMPOSITION, [=](cudaStream_t s) { launch_output_rgba8(cd, sc, dst8, s); });
-            if (e->async_output) {
-                CK(cudaEventRecord(cs->ev_ready[k], e->stream));
-                CK(cudaStreamWaitEvent(e->copy_stream, cs->ev_ready[k], 0));
-                CK(cudaMemcpyAsync(host_out, dst8, n * 4, cudaMemcpyDeviceToHost, e->copy_stream));
-                CK(cudaEventRecord(cs->ev_copied[k], e->copy_stream));
-            } else CK(cudaMemcpyAsync(host_out, dst8, n * 4, cudaMemcpyDeviceToHost, e->stream));
-        } else return fail(ST_ERR_INVALID, "unsupported output format");
-        if (!e->async_output) CK(cudaStreamSynchronize(e->stream));
-    }
+    int rc = copy_rows_out(e, cs, host_out, format, 0, (int)cs->desc.height); if (rc) return rc;
+    if (!e->async_output) CK(cudaStreamSynchronize(e->stream));
     return ST_OK;
 }
 int st_synchronize(st_engine* e) {
@@ -1305,6 +1428,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_SHADING_FAST_MATH) { e->shading_fast = value != 0; return ST_OK; }
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
+    if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
     if (option == ST_OPT_VARIANCE_TILED) { e->variance_tiled = value != 0; return ST_OK; }
     if (option == ST_OPT_BVH_REUSE) { e->bvh_reuse = value != 0; return ST_OK; }
@@ -1411,7 +1535,8 @@ int st_peer_export(st_engine* e, st_camera_handle h, uint8_t* out192) {
     CK(cudaSetDevice(e->device));
     size_t n = (size_t)cs->desc.width * cs->desc.height;
     int rc = cs->rgba8.ensure(2 * n * 4); if (rc) return rc;
-    if ((rc = cs->peer.sync.ensure(256))) return rc;
+    if ((rc = cs->peer.sync.ensure(kSyncBytes))) return rc;
+    { const int need0[2] = {(int)cs->desc.height, -1}; CK(cudaMemcpy((uint32_t*)cs->peer.sync.p + kNeedRowsWord, need0, 8, cudaMemcpyHostToDevice)); }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "ipc handle size");
     cudaIpcMemHandle_t hs[3];
     CK(cudaIpcGetMemHandle(&hs[0], cs->arena.p)); CK(cudaIpcGetMemHandle(&hs[1], cs->peer.sync.p)); CK(cudaIpcGetMemHandle(&hs[2], cs->rgba8.p));
@@ -1433,7 +1558,7 @@ int st_peer_import(st_engine* e, st_camera_handle h, const uint8_t* all, int ran
         CK(cudaIpcOpenMemHandle(&p, hs[1], cudaIpcMemLazyEnablePeerAccess)); cs->peer.flags[r] = (uint32_t*)p;
         CK(cudaIpcOpenMemHandle(&p, hs[2], cudaIpcMemLazyEnablePeerAccess)); cs->peer.rgba8[r] = (char*)p;
     }
-    e->rank = rank; e->n_ranks = world; cs->peer.seq = 0; cs->peer.ready = true;
+    e->rank = rank; e->n_ranks = world; cs->peer.seq = 0; cs->peer.fseq = 0; cs->peer.ready = true; cs->peer.ipc = true;
     return ST_OK;
 }
 int st_peer_errors(st_engine* e, st_camera_handle h, uint32_t* count) {
@@ -1442,7 +1567,10 @@ int st_peer_errors(st_engine* e, st_camera_handle h, uint32_t* count) {
     *count = 0;
     if (!cs->peer.sync.p) return ST_OK;
     CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
-    CK(cudaMemcpy(count, (uint32_t*)cs->peer.sync.p + 17, 4, cudaMemcpyDeviceToHost));
+    uint32_t both[2] = {0, 0};
+    CK(cudaMemcpy(&both[0], (uint32_t*)cs->peer.sync.p + kLegacyFlagWord + 17, 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&both[1], (uint32_t*)cs->peer.sync.p + kStripErrorWord, 4, cudaMemcpyDeviceToHost));
+    *count = both[0] + both[1];
     return ST_OK;
 }
 int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap) {
@@ -1454,29 +1582,65 @@ int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach
     std::memcpy(out, text.c_str(), text.size() + 1);
     return ST_OK;
 }
+// enqueues this rank's strip of the frame (no output handling)
+static int enqueue_strip_frame(st_engine* e, CameraSlot* cs, int temporal_reach) {
+    const bool peer = e->n_ranks > 1 && cs->peer.ready && !e->halo_nccl;
+    if (e->n_ranks > 1 && !peer && !e->comm) return fail(ST_ERR_INVALID, "st_nccl_init, st_peer_import or st_link_local first");
+    if (cs->frame == 0) return fail(ST_ERR_INVALID, "st_tick must precede rendering");
+    int rc = ensure_luts(e); if (rc) return rc;
+    std::vector<std::pair<int, int>> bounds; strip_bounds((int)cs->desc.height, e->n_ranks, &bounds);
+    cs->dev.y0 = cs->dev.own_y0 = bounds[e->rank].first; cs->dev.y1 = cs->dev.own_y1 = bounds[e->rank].second;
+    int min_rows = (int)cs->desc.height;
+    for (auto& bd : bounds) min_rows = std::min(min_rows, bd.second - bd.first);
+    // the fused transport sends to the two neighbours only: every strip must cover the largest reach
+    const bool fused = peer && e->strip_fused && min_rows >= kSpatialReach;
+    e->last_frame_fused = fused;
+    e->halo_bytes_last_frame = 0;
+    if (fused) {
+        if ((rc = render_strips_fused(e, cs, bounds))) return rc;
+        // rows mirrored into this rank by its neighbours (the K6 / K14 / K17 / K18 / K20 stores); the temporal pull is counted on the device
+        const uint64_t W = cs->desc.width; const int nbs = (e->rank > 0 ? 1 : 0) + (e->rank + 1 < e->n_ranks ? 1 : 0);
+        std::vector<Step> steps; build_schedule(e, cs, &steps);
+        bool di = false, gi = false, sp = false, dn = cs->desc.denoise != 0;
+        for (const Step& st : steps) { di |= st.pass == P_DI_TEMPORAL; gi |= st.pass == P_GI_TEMPORAL; sp |= st.pass == P_GI_SPATIAL_SAMPLE; }
+        uint64_t per_nb = 0;
+        if (di) per_nb += (uint64_t)kSpatialReach * 32;
+        if (gi) per_nb += (uint64_t)kSpatialReach * 64 * (sp ? 2 : 1) + (uint64_t)kPreview2Reach * 64;
+        if (dn) per_nb += 38ull * 64;
+        e->halo_bytes_last_frame = per_nb * W * nbs;
+    } else {
+        cs->dev.mirror_up = cs->dev.mirror_dn = 0; cs->dev.need_rows = nullptr;
+        std::vector<Step> steps; build_schedule(e, cs, &steps);
+        std::vector<int> ids; for (const Step& st : steps) ids.push_back(st.pass);
+        std::vector<HaloExchange> plan;
+        if (e->n_ranks > 1) plan_frame(ids.data(), (int)ids.size(), cs->frame, temporal_reach, &plan);
+        size_t next = 0;
+        if (peer && (rc = halo_exchange_peer(e, cs, nullptr))) return rc;   // frame barrier: nobody still reads last frame's rows
+        for (int i = 0; i < (int)steps.size(); i++) {
+            if (next < plan.size() && plan[next].before_step == i) { if ((rc = peer ? halo_exchange_peer(e, cs, &plan[next]) : halo_exchange(e, cs, plan[next]))) return rc; next++; }
+            e->run_timed(steps[i].pass, steps[i].run, steps[i].sub);
+        }
+    }
+    CK(cudaGetLastError());
+    return ST_OK;
+}
+// `gather`: 0 = render only; 1 = assemble the composed frame on rank 0 (strips travel in `format`; rank 0 copies it to `host_out`);
+// 2 = every rank converts its OWN rows and copies them into rows [y0, y1) of `host_out`, a full-frame host buffer that the ranks
+// share (one buffer in a single-process host, a shared-memory segment between processes): no funnel through rank 0.
 int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int format, int temporal_reach, int gather) {
     CameraSlot* cs = e ? get_camera(e, h) : nullptr;
     if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
-    const bool peer = e->n_ranks > 1 && cs->peer.ready && !e->halo_nccl;
-    if (e->n_ranks > 1 && !peer && !e->comm) return fail(ST_ERR_INVALID, "st_nccl_init or st_peer_import first");
-    if (cs->frame == 0) return fail(ST_ERR_INVALID, "st_tick must precede rendering");
     CK(cudaSetDevice(e->device));
-    int rc = ensure_luts(e); if (rc) return rc;
-    std::vector<std::pair<int, int>> bounds; strip_bounds((int)cs->desc.height, e->n_ranks, &bounds);
-    cs->dev.y0 = bounds[e->rank].first; cs->dev.y1 = bounds[e->rank].second;
-    std::vector<Step> steps; build_schedule(e, cs, &steps);
-    std::vector<int> ids; for (const Step& s : steps) ids.push_back(s.pass);
-    std::vector<HaloExchange> plan;
-    if (e->n_ranks > 1) plan_frame(ids.data(), (int)ids.size(), cs->frame, temporal_reach, &plan);
-    e->halo_bytes_last_frame = 0;
-    size_t next = 0;
-    if (peer && (rc = halo_exchange_peer(e, cs, nullptr))) return rc;   // frame barrier: nobody still reads last frame's rows
-    for (int i = 0; i < (int)steps.size(); i++) {
-        if (next < plan.size() && plan[next].before_step == i) { if ((rc = peer ? halo_exchange_peer(e, cs, &plan[next]) : halo_exchange(e, cs, plan[next]))) return rc; next++; }
-        e->run_timed(steps[i].pass, steps[i].run, steps[i].sub);
-    }
-    CK(cudaGetLastError());
+    int rc = enqueue_strip_frame(e, cs, temporal_reach); if (rc) return rc;
     if (!gather) return ST_OK;
+    const bool peer = e->n_ranks > 1 && cs->peer.ready && !e->halo_nccl;
+    std::vector<std::pair<int, int>> bounds; strip_bounds((int)cs->desc.height, e->n_ranks, &bounds);
+    if (gather == 2) {
+        if (!host_out) return fail(ST_ERR_INVALID, "gather 2 needs the shared host frame");
+        if ((rc = copy_rows_out(e, cs, host_out, format, bounds[e->rank].first, bounds[e->rank].second))) return rc;
+        if (!e->async_output) CK(cudaStreamSynchronize(e->stream));
+        return ST_OK;
+    }
     // assemble the composed frame on rank 0 (strips travel in the requested output format)
     const size_t W = cs->desc.width, n = W * cs->desc.height;
     char* base; size_t px_bytes; ncclDataType_t dt; size_t per_px;
@@ -1513,6 +1677,44 @@ int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int forma
     }
     return ST_OK;
 }
+// Links engines that live in THIS process into a strip group (rank = index): enables peer access between their devices and hands every
+// engine the others' buffers directly (the multi-process route is st_peer_export / st_peer_import over CUDA IPC).  Two ranks may share
+// a device, which is how a single-GPU box exercises the whole protocol.
+static int link_prepare(st_engine* e, CameraSlot* cs) {
+    CK(cudaSetDevice(e->device));
+    size_t n = (size_t)cs->desc.width * cs->desc.height;
+    int rc = cs->rgba8.ensure(2 * n * 4); if (rc) return rc;
+    if ((rc = cs->peer.sync.ensure(kSyncBytes))) return rc;
+    const int need0[2] = {(int)cs->desc.height, -1};
+    CK(cudaMemcpy((uint32_t*)cs->peer.sync.p + kNeedRowsWord, need0, 8, cudaMemcpyHostToDevice));
+    return ST_OK;
+}
+int st_link_local(st_engine* const* engines, const st_camera_handle* cameras, int n) {
+    if (!engines || !cameras || n < 1 || n > ST_PEER_MAX_RANKS) return fail(ST_ERR_LIMIT, "1..16 engines");
+    std::vector<CameraSlot*> cams(n);
+    for (int r = 0; r < n; r++) {
+        cams[r] = engines[r] ? get_camera(engines[r], cameras[r]) : nullptr;
+        if (!cams[r]) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+        if (cams[r]->desc.width != cams[0]->desc.width || cams[r]->desc.height != cams[0]->desc.height) return fail(ST_ERR_INVALID, "linked cameras must have one size");
+        int rc = link_prepare(engines[r], cams[r]); if (rc) return rc;
+    }
+    for (int a = 0; a < n; a++) for (int b = 0; b < n; b++) {
+        if (engines[a]->device == engines[b]->device) continue;
+        int can = 0; CK(cudaDeviceCanAccessPeer(&can, engines[a]->device, engines[b]->device));
+        if (!can) return fail(ST_ERR_CUDA, "devices cannot access each other's memory");
+        CK(cudaSetDevice(engines[a]->device));
+        cudaError_t ce = cudaDeviceEnablePeerAccess(engines[b]->device, 0);
+        if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return fail(ST_ERR_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(ce));
+        cudaGetLastError();
+    }
+    for (int r = 0; r < n; r++) {
+        CameraSlot* cs = cams[r];
+        cs->peer.arena.assign(n, nullptr); cs->peer.rgba8.assign(n, nullptr); cs->peer.flags.assign(n, nullptr);
+        for (int q = 0; q < n; q++) { cs->peer.arena[q] = (char*)cams[q]->arena.p; cs->peer.flags[q] = (uint32_t*)cams[q]->peer.sync.p; cs->peer.rgba8[q] = (char*)cams[q]->rgba8.p; }
+        engines[r]->rank = r; engines[r]->n_ranks = n; cs->peer.seq = 0; cs->peer.fseq = 0; cs->peer.ready = true; cs->peer.ipc = false;
+    }
+    return ST_OK;
+}
 int st_halo_bytes(st_engine* e, uint64_t* bytes) { if (!e || !bytes) return fail(ST_ERR_INVALID, "null argument"); *bytes = e->halo_bytes_last_frame; return ST_OK; }
 int st_mark_begin(st_engine* e) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
@@ -1546,6 +1748,117 @@ int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset) {
     e->collect_timing();
     for (int i = 0; i < 5; i++) { if (ms5) ms5[i] = e->wavelet_ms[i]; if (launches5) launches5[i] = e->wavelet_launches[i]; }
     if (reset) { std::memset(e->wavelet_ms, 0, sizeof e->wavelet_ms); std::memset(e->wavelet_launches, 0, sizeof e->wavelet_launches); }
+    return ST_OK;
+}
+
+// =================================================================================================
+// st_multi: ONE host process driving several devices ("st_engine_create(device_ordinals[], n)").
+// A thin group over n engines: scene verbs are replayed on every member (the scene is replicated), a camera is created on
+// every member and linked (st_link_local), st_multi_render_camera enqueues every rank's strip of the frame (fused transport) and then
+// lets every rank copy its own rows into the caller's frame.  What a single-process host (the Bevy plugin) binds instead of st_engine.
+// =================================================================================================
+struct st_multi { std::vector<st_engine*> e; std::vector<std::vector<st_camera_handle>> cams; };   // cams[c][rank]
+#define ST_MULTI_ALL(call) do { if (!m) return fail(ST_ERR_INVALID, "null group"); for (st_engine* e : m->e) { int rc_ = (call); if (rc_) return rc_; } return ST_OK; } while (0)
+int st_multi_create(const int* devices, int n, st_multi** out) {
+    if (!devices || !out || n < 1 || n > ST_PEER_MAX_RANKS) return fail(ST_ERR_LIMIT, "1..16 devices");
+    st_multi* m = new st_multi();
+    for (int i = 0; i < n; i++) { st_engine* e = nullptr; int rc = st_engine_create(devices[i], &e); if (rc) { for (st_engine* x : m->e) st_engine_destroy(x); delete m; return rc; } m->e.push_back(e); }
+    *out = m;
+    return ST_OK;
+}
+void st_multi_destroy(st_multi* m) { if (!m) return; for (st_engine* e : m->e) { cudaSetDevice(e->device); cudaStreamSynchronize(e->stream); } for (st_engine* e : m->e) st_engine_destroy(e); delete m; }
+int st_multi_size(st_multi* m) { return m ? (int)m->e.size() : 0; }
+st_engine* st_multi_engine(st_multi* m, int rank) { return (m && rank >= 0 && rank < (int)m->e.size()) ? m->e[rank] : nullptr; }
+int st_multi_insert_mesh(st_multi* m, st_handle mesh, const st_mesh_triangle* t, size_t count) { ST_MULTI_ALL(st_insert_mesh(e, mesh, t, count)); }
+int st_multi_remove_mesh(st_multi* m, st_handle mesh) { ST_MULTI_ALL(st_remove_mesh(e, mesh)); }
+int st_multi_insert_material(st_multi* m, st_handle h, const st_material* mat) { ST_MULTI_ALL(st_insert_material(e, h, mat)); }
+int st_multi_has_material(st_multi* m, st_handle h) { return (m && !m->e.empty()) ? st_has_material(m->e[0], h) : 0; }
+int st_multi_remove_material(st_multi* m, st_handle h) { ST_MULTI_ALL(st_remove_material(e, h)); }
+int st_multi_insert_image(st_multi* m, st_handle h, const uint8_t* rgba8, uint32_t w, uint32_t hgt) { ST_MULTI_ALL(st_insert_image(e, h, rgba8, w, hgt)); }
+int st_multi_remove_image(st_multi* m, st_handle h) { ST_MULTI_ALL(st_remove_image(e, h)); }
+int st_multi_set_material_textures(st_multi* m, st_handle h, const st_material_textures* t) { ST_MULTI_ALL(st_set_material_textures(e, h, t)); }
+int st_multi_insert_instance(st_multi* m, st_handle h, st_handle mesh, st_handle material, const float a[12]) { ST_MULTI_ALL(st_insert_instance(e, h, mesh, material, a)); }
+int st_multi_remove_instance(st_multi* m, st_handle h) { ST_MULTI_ALL(st_remove_instance(e, h)); }
+int st_multi_insert_light(st_multi* m, st_handle h, const st_light* l) { ST_MULTI_ALL(st_insert_light(e, h, l)); }
+int st_multi_remove_light(st_multi* m, st_handle h) { ST_MULTI_ALL(st_remove_light(e, h)); }
+int st_multi_update_sun(st_multi* m, float az, float alt) { ST_MULTI_ALL(st_update_sun(e, az, alt)); }
+int st_multi_set_option(st_multi* m, int option, int value) { ST_MULTI_ALL(st_set_option(e, option, value)); }
+int st_multi_set_seed_base(st_multi* m, uint32_t base) { ST_MULTI_ALL(st_set_seed_base(e, base)); }
+int st_multi_set_blue_noise(st_multi* m, const uint8_t* rgba) { ST_MULTI_ALL(st_set_blue_noise(e, rgba)); }
+int st_multi_tick(st_multi* m) { ST_MULTI_ALL(st_tick(e)); }
+int st_multi_synchronize(st_multi* m) { ST_MULTI_ALL(st_synchronize(e)); }
+int st_multi_create_camera(st_multi* m, const st_camera* c, st_camera_handle* out) {
+    if (!m || !c || !out) return fail(ST_ERR_INVALID, "null argument");
+    std::vector<st_camera_handle> hs(m->e.size());
+    for (size_t i = 0; i < m->e.size(); i++) { int rc = st_create_camera(m->e[i], c, &hs[i]); if (rc) return rc; }
+    if (m->e.size() > 1) { int rc = st_link_local(m->e.data(), hs.data(), (int)m->e.size()); if (rc) return rc; }
+    m->cams.push_back(hs);
+    *out = (st_camera_handle)m->cams.size() - 1;
+    return ST_OK;
+}
+int st_multi_update_camera(st_multi* m, st_camera_handle h, const st_camera* c) {
+    if (!m || h < 0 || (size_t)h >= m->cams.size() || !c) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    bool relink = false;
+    for (size_t i = 0; i < m->e.size(); i++) {
+        CameraSlot* cs = get_camera(m->e[i], m->cams[h][i]);
+        if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+        relink |= cs->desc.mode != c->mode || cs->desc.denoise != c->denoise || cs->desc.ref_depth != c->ref_depth || cs->desc.width != c->width || cs->desc.height != c->height;
+    }
+    if (relink) for (st_engine* e : m->e) { cudaSetDevice(e->device); cudaStreamSynchronize(e->stream); }   // buffers are re-created: nobody may still be writing into them
+    for (size_t i = 0; i < m->e.size(); i++) { int rc = st_update_camera(m->e[i], m->cams[h][i], c); if (rc) return rc; }
+    if (relink && m->e.size() > 1) return st_link_local(m->e.data(), m->cams[h].data(), (int)m->e.size());
+    return ST_OK;
+}
+int st_multi_delete_camera(st_multi* m, st_camera_handle h) {
+    if (!m || h < 0 || (size_t)h >= m->cams.size()) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    for (st_engine* e : m->e) { cudaSetDevice(e->device); cudaStreamSynchronize(e->stream); }
+    for (size_t i = 0; i < m->e.size(); i++) { int rc = st_delete_camera(m->e[i], m->cams[h][i]); if (rc) return rc; }
+    return ST_OK;
+}
+st_camera_handle st_multi_member_camera(st_multi* m, st_camera_handle h, int rank) { return (m && h >= 0 && (size_t)h < m->cams.size() && rank >= 0 && (size_t)rank < m->e.size()) ? m->cams[h][rank] : -1; }
+// Engine::render_camera for the group.  All ranks' frames are enqueued before any output copy is issued and nothing in between
+// synchronises: the ranks wait for each other on the device (sequence flags), never on the host.
+int st_multi_render_camera(st_multi* m, st_camera_handle h, void* host_out, int format) {
+    if (!m || h < 0 || (size_t)h >= m->cams.size()) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    const size_t n = m->e.size();
+    if (n == 1) return st_render_camera(m->e[0], m->cams[h][0], host_out, format);
+    std::vector<CameraSlot*> cs(n);
+    for (size_t i = 0; i < n; i++) {   // first-use allocations and LUT generation synchronise their device: do them before anything can wait on a peer
+        cs[i] = get_camera(m->e[i], m->cams[h][i]);
+        if (!cs[i]) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+        CK(cudaSetDevice(m->e[i]->device));
+        int rc = ensure_luts(m->e[i]); if (rc) return rc;
+    }
+    for (size_t i = 0; i < n; i++) { CK(cudaSetDevice(m->e[i]->device)); int rc = enqueue_strip_frame(m->e[i], cs[i], 16); if (rc) return rc; }
+    if (!host_out) return ST_OK;
+    std::vector<std::pair<int, int>> bounds; strip_bounds((int)cs[0]->desc.height, (int)n, &bounds);
+    for (size_t i = 0; i < n; i++) { CK(cudaSetDevice(m->e[i]->device)); int rc = copy_rows_out(m->e[i], cs[i], host_out, format, bounds[i].first, bounds[i].second); if (rc) return rc; }
+    for (size_t i = 0; i < n; i++) if (!m->e[i]->async_output) { CK(cudaSetDevice(m->e[i]->device)); CK(cudaStreamSynchronize(m->e[i]->stream)); }
+    return ST_OK;
+}
+// per-camera buffer of the whole frame, assembled from the members' strips (test hook, cf. st_read_buffer)
+int st_multi_read_buffer(st_multi* m, st_camera_handle h, const char* name, float* dst, size_t cap, size_t* count) {
+    if (!m || h < 0 || (size_t)h >= m->cams.size() || !name || !count) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    const size_t n = m->e.size();
+    int rc = st_read_buffer(m->e[0], m->cams[h][0], name, nullptr, 0, count); if (rc) return rc;
+    if (!dst) return ST_OK;
+    if (cap < *count) return fail(ST_ERR_LIMIT, "buffer too small");
+    CameraSlot* c0 = get_camera(m->e[0], m->cams[h][0]);
+    std::vector<std::pair<int, int>> bounds; strip_bounds((int)c0->desc.height, (int)n, &bounds);
+    const size_t per_row = *count / c0->desc.height;
+    for (size_t i = 0; i < n; i++) {
+        void* p = nullptr; size_t bytes = 0;
+        if ((rc = st_buffer_device_ptr(m->e[i], m->cams[h][i], name, &p, &bytes))) return rc;
+        CK(cudaSetDevice(m->e[i]->device)); CK(cudaStreamSynchronize(m->e[i]->stream));
+        size_t a = (size_t)bounds[i].first * per_row, b = (size_t)bounds[i].second * per_row;
+        CK(cudaMemcpy(dst + a, (const float*)p + a, (b - a) * 4, cudaMemcpyDeviceToHost));
+    }
+    return ST_OK;
+}
+int st_multi_peer_errors(st_multi* m, st_camera_handle h, uint32_t* count) {
+    if (!m || h < 0 || (size_t)h >= m->cams.size() || !count) return fail(ST_ERR_NOT_FOUND, "unknown camera");
+    *count = 0;
+    for (size_t i = 0; i < m->e.size(); i++) { uint32_t c = 0; int rc = st_peer_errors(m->e[i], m->cams[h][i], &c); if (rc) return rc; *count += c; }
     return ST_OK;
 }
 

@@ -195,6 +195,15 @@ __global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur) {
         float2 v = cam_world_to_screen(cam.curr, th.point) - cam_world_to_screen(cam.prev, prev_point);
         if (len2(v) >= 0.001f) vel = f4(v.x, v.y, 0.f, 0.f);
         tid.x = bitsf(th.triangle_id);
+        // strip partition: which rows of LAST frame's buffers the temporal passes (K4, K6, K11, K14, K20) of this strip will read:
+        // they fetch at prev = pixel - velocity (rounded, or its floor/ceil corners).  Only pixels whose reprojection leaves the
+        // owned rows report; the pull kernel that follows brings exactly those rows in from their owners.
+        if (cam.need_rows != nullptr && vel.y != 0.0f && (int)p.y >= cam.own_y0 && (int)p.y < cam.own_y1) {
+            float py = (float)p.y - vel.y;
+            int lo = max(0, min(cam.h - 1, to_i32_sat(floorf(py)))), hi = max(0, min(cam.h - 1, to_i32_sat(ceilf(py))));
+            if (lo < cam.own_y0) atomicMin(cam.need_rows, lo);
+            if (hi >= cam.own_y1) atomicMax(cam.need_rows + 1, hi);
+        }
     }
     size_t i = pix(cam, p.x, p.y);
     cam.prim_gbuffer_d0[cur][i] = g0; cam.prim_gbuffer_d1[cur][i] = g1; cam.prim_surface_map[cur][i] = surf;
@@ -292,7 +301,7 @@ __global__ void ST_LB_DI_TEMPORAL k_di_temporal(KPARAMS, int cur, u32 seed) {
     main_.pdf = main_pdf;
     main_.confidence = killed ? 0.0f : 1.0f;
     main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
-    di_store(main_, cam.di_reservoirs[1], lhs_idx);
+    di_store_m(cam, main_, cam.di_reservoirs[1], lhs_idx, p.y, ST_REACH_SPATIAL);
 }
 
 // K7 di_spatial_resampling::pick (di_spatial_resampling.rs:4-147); scratch buf_d0 = di_diff_samples,
@@ -546,7 +555,7 @@ __global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 
     Rng rng = rng_make(seed, p.x, p.y);
     Hit lhs_hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     float4* curr = cam.gi_reservoirs[1];
-    if (!hit_some(lhs_hit)) { gi_store(gi_zero(), curr, lhs_idx); return; }
+    if (!hit_some(lhs_hit)) { gi_store_m(cam, gi_zero(), curr, lhs_idx, p.y, ST_REACH_SPATIAL); return; }
     bool got = tracing ? (frame % 2u == 0u && checker_at(p.x, p.y, frame / 2u)) : checker_at(p.x, p.y, frame);
     GiRes lhs = got ? gi_load(curr, lhs_idx) : gi_zero();
     GiRes rhs = gi_zero();
@@ -586,7 +595,7 @@ __global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 
     main_.pdf = main_pdf;
     main_.v1 = lhs_hit.point;
     main_.w = rmin(main_.w, 5.0f);
-    gi_store(main_, curr, lhs_idx);
+    gi_store_m(cam, main_, curr, lhs_idx, p.y, ST_REACH_SPATIAL);
 }
 
 // K15 gi_spatial_resampling::pick (gi_spatial_resampling.rs:4-160); scratch = gi_d0, gi_d1
@@ -669,20 +678,20 @@ __global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u
         main_.v1 = lhs.v1;
         main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
         main_.w = rmin(main_.w, 5.0f);
-        gi_store(main_, out, idx);
-    } else gi_store(lhs, out, idx);
+        gi_store_m(cam, main_, out, idx, sp.y, ST_REACH_SPATIAL);
+    } else gi_store_m(cam, lhs, out, idx, sp.y, ST_REACH_SPATIAL);
     uint2 op = checker(g.x, g.y, frame / 2u);
-    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); gi_store(gi_load(in, oi), out, oi); }
+    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); gi_store_m(cam, gi_load(in, oi), out, oi, op.y, ST_REACH_SPATIAL); }
 }
 
 // K18 gi_preview_resampling::main (gi_preview_resampling.rs:4-138)
-__global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nth, const float4* __restrict__ in, float4* __restrict__ out) {
+__global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nth, const float4* __restrict__ in, float4* __restrict__ out, int reach) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t cidx = screen_idx(cam, p.x, p.y);
     Rng rng = rng_make(seed, p.x, p.y);
     Hit chit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    if (!hit_some(chit)) { gi_store(gi_zero(), out, cidx); return; }
+    if (!hit_some(chit)) { gi_store_m(cam, gi_zero(), out, cidx, p.y, reach); return; }
     GiRes main_ = gi_zero();
     float main_pdf = 0.0f;
     GiRes center = gi_load(in, cidx);
@@ -713,7 +722,7 @@ __global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nt
     main_.v1 = center.v1;
     main_.w = res_norm(main_.w, main_pdf, 1.0f, main_.m);
     main_.w = rmin(main_.w, 5.0f);
-    gi_store(main_, out, cidx);
+    gi_store_m(cam, main_, out, cidx, p.y, reach);
 }
 
 // K19 gi_resolving::main (gi_resolving.rs:4-67)
@@ -743,7 +752,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject(KPARAMS, int cur
     if (!p.in) return;
     size_t i = pix(cam, p.x, p.y);
     float4 sample = samples[i];
-    if (cam.prim_surface_map[cur][i].z == 0.0f) { colors[i] = sample; return; }
+    if (cam.prim_surface_map[cur][i].z == 0.0f) { store4m(cam, colors + i, sample, p.y, ST_REACH_SVGF); return; }
     float sl = luma(xyz(sample));
     Reproj rp = reproj_decode(cam.reprojection_map[i]);
     float3 color, moment;
@@ -755,14 +764,14 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject(KPARAMS, int cur
         color = lerpc(xyz(pc), xyz(sample), alpha);
         moment = f3(hist, lerpc(pm.y, sl, alpha), lerpc(pm.z, sl * sl, alpha));
     } else { color = xyz(sample); moment = f3(1.0f, sl, sl * sl); }
-    colors[i] = f4(color, 0.0f);
-    moments[i] = f4(moment, 0.0f);
+    store4m(cam, colors + i, f4(color, 0.0f), p.y, ST_REACH_SVGF);
+    store4m(cam, moments + i, f4(moment, 0.0f), p.y, ST_REACH_SVGF);
 }
 
 // K20 for the DI and the GI signal in one launch: the surface depth and the reprojection entry are read once
 // (192 instead of 2 x 112 B/px); per signal exactly the arithmetic of k_denoise_reproject.
 struct ReprojectSignal { const float4* prev_colors; const float4* prev_moments; const float4* samples; float4* colors; float4* moments; };
-ST_DEV void denoise_reproject_signal(const CameraDev& cam, size_t i, float4 sample, const Reproj& rp, bool has_rp, const ReprojectSignal& g) {
+ST_DEV void denoise_reproject_signal(const CameraDev& cam, size_t i, u32 y, float4 sample, const Reproj& rp, bool has_rp, const ReprojectSignal& g) {
     float sl = luma(xyz(sample));
     float3 color, moment;
     if (has_rp && sample.w > 0.0f) {
@@ -773,19 +782,19 @@ ST_DEV void denoise_reproject_signal(const CameraDev& cam, size_t i, float4 samp
         color = lerpc(xyz(pc), xyz(sample), alpha);
         moment = f3(hist, lerpc(pm.y, sl, alpha), lerpc(pm.z, sl * sl, alpha));
     } else { color = xyz(sample); moment = f3(1.0f, sl, sl * sl); }
-    g.colors[i] = f4(color, 0.0f);
-    g.moments[i] = f4(moment, 0.0f);
+    store4m(cam, g.colors + i, f4(color, 0.0f), y, ST_REACH_SVGF);
+    store4m(cam, g.moments + i, f4(moment, 0.0f), y, ST_REACH_SVGF);
 }
 __global__ void __launch_bounds__(ST_BLOCK) k_denoise_reproject_pair(KPARAMS, int cur, const __grid_constant__ ReprojectSignal di, const __grid_constant__ ReprojectSignal gi) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t i = pix(cam, p.x, p.y);
     float4 sd = di.samples[i], sg = gi.samples[i];
-    if (cam.prim_surface_map[cur][i].z == 0.0f) { di.colors[i] = sd; gi.colors[i] = sg; return; }
+    if (cam.prim_surface_map[cur][i].z == 0.0f) { store4m(cam, di.colors + i, sd, p.y, ST_REACH_SVGF); store4m(cam, gi.colors + i, sg, p.y, ST_REACH_SVGF); return; }
     Reproj rp = reproj_decode(cam.reprojection_map[i]);
     bool has_rp = reproj_some(rp);
-    denoise_reproject_signal(cam, i, sd, rp, has_rp, di);
-    denoise_reproject_signal(cam, i, sg, rp, has_rp, gi);
+    denoise_reproject_signal(cam, i, p.y, sd, rp, has_rp, di);
+    denoise_reproject_signal(cam, i, p.y, sg, rp, has_rp, gi);
 }
 
 // frame_denoising::sample_weight (frame_denoising.rs:363-392), split into the part that is common to
@@ -1427,7 +1436,7 @@ void launch_gi_sampling_b(const CameraDev& c, const SceneDev& s, int cur, u32 se
 void launch_gi_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_gi_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
 void launch_gi_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_pick, c, st, c, s, cur, seed, frame); }
 void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_sample, c, st, c, s, seed, frame); }
-void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out); }
+void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, int mirror_reach, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out, mirror_reach); }
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
 #if ST_EXACT_ONLY
 void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
@@ -1637,6 +1646,57 @@ void launch_math(int op, const float* a, const float* b, float* out, long n, cud
 void launch_material_derive(const GpuMaterial* mats, u32 n, u32* packed, cudaStream_t st) { if (n) k_material_derive<<<(n + 127) / 128, 128, 0, st>>>(mats, n, packed); }
 void launch_srgb_lut(float* lut, cudaStream_t st) { k_srgb_lut<<<1, 256, 0, st>>>(lut); }
 void launch_unpack_lut(float* lut, cudaStream_t st) { k_unpack_lut<<<1, 256, 0, st>>>(lut); }
+// ---- strips, fused transport: sequence flags between ranks + the temporal pull -------------------------------------------
+// Flags live in each rank's own memory, word [slot * ST_PEER_MAX_RANKS + source rank]; a rank raises its word in a peer's array to
+// the frame's sequence number with a system-scope release store after the kernels that produced the rows have completed
+// (stream order + fence), and a consumer spins on its local words with acquire loads.  One warp, lane r <-> rank r.
+ST_DEV void st_release_sys(u32* p, u32 v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+ST_DEV u32 ld_acquire_sys(const u32* p) { u32 v; asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v; }
+__global__ void __launch_bounds__(32) k_strip_signal(const __grid_constant__ StripSync s, int slot, u32 seq, u32 dst_mask, int* reset_need, int h) {
+    __threadfence_system();
+    int r = (int)threadIdx.x;
+    if (r < s.n_ranks && r != s.rank && ((dst_mask >> r) & 1u) && s.peer_flags[r] != nullptr) st_release_sys(s.peer_flags[r] + slot * ST_PEER_MAX_RANKS + s.rank, seq);
+    if (reset_need != nullptr && r == 0) { reset_need[0] = h; reset_need[1] = -1; }
+}
+__global__ void __launch_bounds__(32) k_strip_wait(const __grid_constant__ StripSync s, int slot, u32 seq, u32 src_mask) {
+    int r = (int)threadIdx.x;
+    if (r < s.n_ranks && r != s.rank && ((src_mask >> r) & 1u)) {
+        const u32* f = s.my_flags + slot * ST_PEER_MAX_RANKS + r;
+        long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - seq) < 0) {
+            if (clock64() - t0 > 20000000000ll) { atomicAdd(s.errors, 1u); break; }   // ~10 s: a peer died; do not hang the GPU
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+// Temporal pull: rows [need_lo, own_y0) and [own_y1, need_hi] of last frame's outputs, read from their owners' arenas over NVLink
+// (P2P loads).  The row range was measured on the device by this frame's G-buffer pass, so a static camera pulls nothing and
+// any amount of motion is covered exactly.  blockIdx.y = buffer.
+__global__ void __launch_bounds__(256) k_strip_pull(const __grid_constant__ StripPull p) {
+    const int lo = max(0, min(p.need_rows[0], p.own_y0)), hi = min(p.h - 1, max(p.need_rows[1], p.own_y1 - 1));
+    const StripPullItem it = p.items[blockIdx.y];
+    // rows this rank already holds because it computes them itself (the extended G-buffer rows of the previous frame)
+    const int have_lo = max(0, p.own_y0 - it.local_rows), have_hi = min(p.h, p.own_y1 + it.local_rows);
+    const int up0 = lo, up1 = min(p.own_y0, have_lo), dn0 = max(p.own_y1, have_hi), dn1 = hi + 1;
+    const int nup = max(0, up1 - up0), ndn = max(0, dn1 - dn0);
+    const unsigned long long per_row = (unsigned long long)p.w * (unsigned long long)it.vec4_per_px;
+    const unsigned long long total = (unsigned long long)(nup + ndn) * per_row;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (unsigned long long)gridDim.x * blockDim.x) {
+        int ri = (int)(i / per_row);
+        unsigned long long col = i - (unsigned long long)ri * per_row;
+        int row = ri < nup ? up0 + ri : dn0 + (ri - nup);
+        int owner = 0;
+        while (owner + 1 < p.n_ranks && row >= p.bounds[owner + 1]) owner++;
+        size_t off = it.offset + ((size_t)row * per_row + col) * 16;
+        *reinterpret_cast<uint4*>(p.arena[p.rank] + off) = *reinterpret_cast<const uint4*>(p.arena[owner] + off);
+    }
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (nup + ndn) > 0) atomicAdd(p.pulled_rows, (unsigned long long)(nup + ndn));
+}
+void launch_strip_signal(const StripSync& s, int slot, u32 seq, u32 dst_mask, int* reset_need, int h, cudaStream_t st) { k_strip_signal<<<1, 32, 0, st>>>(s, slot, seq, dst_mask, reset_need, h); }
+void launch_strip_wait(const StripSync& s, int slot, u32 seq, u32 src_mask, cudaStream_t st) { k_strip_wait<<<1, 32, 0, st>>>(s, slot, seq, src_mask); }
+void launch_strip_pull(const StripPull& p, cudaStream_t st) { if (p.nitems > 0) k_strip_pull<<<dim3(48, (unsigned)p.nitems), 256, 0, st>>>(p); }
+
 // ---- strips: push boundary rows into the neighbours' buffers, then barrier --------------------------------------
 // One launch per exchange point.  blockIdx.y = segment (a run of rows of one buffer for one peer), blockIdx.x strides
 // it with 16-byte stores that land in the peer's HBM through NVLink.  The last block to finish (completion counter)

@@ -20,7 +20,7 @@ void launch_gi_sampling_b(const CameraDev& c, const SceneDev& s, int cur, u32 se
 void launch_gi_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
 void launch_gi_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
 void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st);
-void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st);
+void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, int mirror_reach, cudaStream_t st);
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st);
 void launch_denoise_reproject(const CameraDev& c, const SceneDev& s, int cur, const float4* pc, const float4* pm, const float4* smp, float4* col, float4* mom, cudaStream_t st);
 void launch_denoise_reproject_pair(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
@@ -55,6 +55,25 @@ struct PeerExchange {
     int n_ranks, rank; u32 seq; int signal;
 };
 void launch_peer_exchange(const PeerExchange& x, cudaStream_t st);
+
+// Fused strip transport (engine.cu render_strips_fused): sequence flags between ranks and the temporal pull
+enum StripSlot { SLOT_FRAME_DONE = 0, SLOT_PULL_DONE = 1, SLOT_DI1 = 2, SLOT_GI1 = 3, SLOT_GI2 = 4, SLOT_GI3 = 5, SLOT_SVGF = 6, SLOT_OUTPUT = 7, SLOT_COUNT = 8 };
+struct StripSync {
+    const u32* my_flags;                  // this rank's flag words, [slot * ST_PEER_MAX_RANKS + source rank]
+    u32* peer_flags[ST_PEER_MAX_RANKS];   // every other rank's flag array (mapped peer memory); null for self
+    u32* errors;                          // wait time-outs
+    int n_ranks, rank;
+};
+struct StripPullItem { size_t offset; int vec4_per_px; int local_rows; };   // arena byte offset of the buffer, float4 per pixel, rows beyond the strip this rank holds itself
+struct StripPull {
+    char* arena[ST_PEER_MAX_RANKS]; int bounds[ST_PEER_MAX_RANKS + 1];
+    int n_ranks, rank, w, h, own_y0, own_y1;
+    const int* need_rows; unsigned long long* pulled_rows;
+    StripPullItem items[12]; int nitems;
+};
+void launch_strip_signal(const StripSync& s, int slot, u32 seq, u32 dst_mask, int* reset_need, int h, cudaStream_t st);
+void launch_strip_wait(const StripSync& s, int slot, u32 seq, u32 src_mask, cudaStream_t st);
+void launch_strip_pull(const StripPull& p, cudaStream_t st);
 void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st);
 
 }  // namespace st
@@ -75,6 +94,6 @@ void launch_gi_sampling_b(const CameraDev& c, const SceneDev& s, int cur, u32 se
 void launch_gi_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
 void launch_gi_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
 void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st);
-void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, cudaStream_t st);
+void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, int mirror_reach, cudaStream_t st);
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st);
 }  // namespace stf

@@ -12,6 +12,10 @@ using namespace st;   // the POD layouts of st_types.h
 
 #define ST_BVH_STACK 24          // strolle-gpu/src/lib.rs:76
 #define ST_BLOCK 128             // threads per CTA for all per-pixel kernels (16 x 8 pixel tile)
+// rows of a neighbouring strip that a gathering pass reads (strip partition)
+#define ST_REACH_SPATIAL 128     // ReSTIR spatial taps (di_spatial_resampling.rs:55-56, gi_spatial_resampling.rs, gi_preview_resampling.rs pass 1)
+#define ST_REACH_PREVIEW2 64     // gi_preview_resampling.rs:64-70, pass 2
+#define ST_REACH_SVGF 38         // K21 (3 rows) + the five K22 iterations (1 + 2 + 4 + 9 + 19 = 35) recomputed on the receiving side
 
 ST_DEV float4 ldg4(const float4* p) { return __ldg(p); }
 
@@ -649,6 +653,16 @@ ST_DEV void di_store(const DiRes& r, float4* __restrict__ buf, size_t id) {   //
     buf[2 * id] = f4(r.m, r.w, r.pdf, bitsf(pack_bytes(r.occluded ? 1u : 0u, to_u32_sat(r.confidence), 0u, 0u)));
     buf[2 * id + 1] = f4(r.light_point, bitsf(r.light_id));
 }
+// ---- strip partition: a store that also lands in the neighbouring strips' copy when the row is within `reach` of an edge ----
+ST_DEV void mirror4(const CameraDev& cam, float4* p, float4 v, u32 y, int reach) {
+    if (cam.mirror_up != 0 && (int)y < cam.own_y0 + reach) *reinterpret_cast<float4*>(reinterpret_cast<char*>(p) + cam.mirror_up) = v;
+    if (cam.mirror_dn != 0 && (int)y >= cam.own_y1 - reach) *reinterpret_cast<float4*>(reinterpret_cast<char*>(p) + cam.mirror_dn) = v;
+}
+ST_DEV void store4m(const CameraDev& cam, float4* p, float4 v, u32 y, int reach) { *p = v; mirror4(cam, p, v, y, reach); }
+ST_DEV void di_store_m(const CameraDev& cam, const DiRes& r, float4* __restrict__ buf, size_t id, u32 y, int reach) {
+    store4m(cam, buf + 2 * id, f4(r.m, r.w, r.pdf, bitsf(pack_bytes(r.occluded ? 1u : 0u, to_u32_sat(r.confidence), 0u, 0u))), y, reach);
+    store4m(cam, buf + 2 * id + 1, f4(r.light_point, bitsf(r.light_id)), y, reach);
+}
 // Reservoir::update specialised: copies sample fields of `s` into `dst` on acceptance (reservoir.rs:24-39)
 ST_DEV bool di_update(DiRes& dst, Rng& rng, const DiRes& s, float weight) {
     dst.m += 1.0f; dst.w += weight;
@@ -677,6 +691,13 @@ ST_DEV void gi_store(const GiRes& r, float4* __restrict__ buf, size_t id) {   //
     buf[4 * id + 1] = f4(r.v1, r.w);
     buf[4 * id + 2] = f4(r.v2, r.pdf);
     buf[4 * id + 3] = f4(n.x, n.y, r.confidence, bitsf(r.rng));
+}
+ST_DEV void gi_store_m(const CameraDev& cam, const GiRes& r, float4* __restrict__ buf, size_t id, u32 y, int reach) {
+    float2 n = oct_encode(r.v2n);
+    store4m(cam, buf + 4 * id, f4(r.radiance, r.m), y, reach);
+    store4m(cam, buf + 4 * id + 1, f4(r.v1, r.w), y, reach);
+    store4m(cam, buf + 4 * id + 2, f4(r.v2, r.pdf), y, reach);
+    store4m(cam, buf + 4 * id + 3, f4(n.x, n.y, r.confidence, bitsf(r.rng)), y, reach);
 }
 ST_DEV void gi_take_sample(GiRes& dst, const GiRes& s) { dst.pdf = s.pdf; dst.rng = s.rng; dst.radiance = s.radiance; dst.v1 = s.v1; dst.v2 = s.v2; dst.v2n = s.v2n; }
 ST_DEV bool gi_update(GiRes& dst, Rng& rng, const GiRes& s, float weight) {

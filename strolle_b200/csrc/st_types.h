@@ -66,6 +66,13 @@ struct CameraDev {
     float4* prim_triangle_ids;
     float4* surface_nd;          // derived: (decoded surface normal.xyz, depth) of the current frame, written with the G-buffer
     float4* output;
+    // Row-strip partition, fused transport (engine.cu render_strips_fused): the kernels that produce a buffer a neighbouring
+    // strip gathers from (K6 di[1], K14 gi[1], K17 gi[2], K18#1 gi[3], K20 colours + moments) store the rows within reach of
+    // the strip's edges a second time, straight into the neighbour's copy of the buffer over NVLink.  Arenas have the same
+    // layout on every rank, so the remote address is the local one plus a constant byte offset.  0 = no neighbour there.
+    long long mirror_up, mirror_dn;
+    int own_y0, own_y1;          // the rows this rank owns (mirror decisions); [y0, y1) may be wider when a pass recomputes halo rows
+    int* need_rows;              // device: {min, max} previous-frame row the reprojection of the owned rows reaches (K0 -> temporal pull); null = off
 };
 
 // Kernel ids (also the explicit-seed dispatch ids and the timing slots).

@@ -20,6 +20,7 @@ OPT_WAVELET_TILE_CFG = 5   # 4 bits per iteration: 0 32x8, 1 32x16, 2 64x4, 3 64
 OPT_FUSE_REPROJECT = 6     # K20 for DI and GI in one launch
 OPT_BVH_REUSE = 7          # graft unchanged subtrees of the previous BVH (reference behaviour)
 OPT_VARIANCE_TILED = 8     # K21 window from a TMA-filled shared-memory tile
+OPT_STRIP_FUSED = 10         # strips: fused transport (mirror stores, neighbour flags, recompute) instead of push+barrier exchanges
 OPT_SHADING_FAST_MATH = 9  # ReSTIR kernels K5-K19 from the fast-shading build (FMA + SFU approximations; traversal unchanged)
 WAVELET_TILED_DEFAULT = 15   # include/strolle_b200.h ST_WAVELET_TILED_DEFAULT
 STAT_WAVELET_TILED_LAUNCHES = 1
@@ -100,6 +101,18 @@ def load_library():
         "st_camera_set_strip": [P, i32, C.c_int, C.c_int],
         "st_buffer_device_ptr": [P, i32, C.c_char_p, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
         "st_frame_schedule": [P, i32, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)], "st_render_range": [P, i32, C.c_int, C.c_int],
+        "st_link_local": [C.POINTER(P), C.POINTER(i32), C.c_int],
+        "st_multi_create": [C.POINTER(C.c_int), C.c_int, C.POINTER(P)],
+        "st_multi_insert_mesh": [P, u64, C.POINTER(_MeshTriangle), C.c_size_t], "st_multi_remove_mesh": [P, u64],
+        "st_multi_insert_material": [P, u64, C.POINTER(_Material)], "st_multi_has_material": [P, u64], "st_multi_remove_material": [P, u64],
+        "st_multi_insert_image": [P, u64, C.c_void_p, u32, u32], "st_multi_remove_image": [P, u64], "st_multi_set_material_textures": [P, u64, C.POINTER(_MaterialTextures)],
+        "st_multi_insert_instance": [P, u64, u64, u64, f32p], "st_multi_remove_instance": [P, u64],
+        "st_multi_insert_light": [P, u64, C.POINTER(_Light)], "st_multi_remove_light": [P, u64], "st_multi_update_sun": [P, C.c_float, C.c_float],
+        "st_multi_create_camera": [P, C.POINTER(_Camera), C.POINTER(i32)], "st_multi_update_camera": [P, i32, C.POINTER(_Camera)], "st_multi_delete_camera": [P, i32],
+        "st_multi_tick": [P], "st_multi_render_camera": [P, i32, P, C.c_int], "st_multi_synchronize": [P],
+        "st_multi_set_option": [P, C.c_int, C.c_int], "st_multi_set_seed_base": [P, u32], "st_multi_set_blue_noise": [P, C.c_void_p],
+        "st_multi_read_buffer": [P, i32, C.c_char_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)], "st_multi_peer_errors": [P, i32, C.POINTER(u32)],
+        "st_multi_size": [P], "st_multi_member_camera": [P, i32, C.c_int],
         "st_bvh_builder_create": [C.POINTER(P)], "st_bvh_builder_read": [P, C.c_void_p, C.c_size_t],
         "st_bvh_builder_build": [P, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(u32), C.POINTER(C.c_int)],
     }
@@ -109,6 +122,10 @@ def load_library():
         fn.restype = None if name == "st_engine_destroy" else C.c_int
     lib.st_bvh_builder_destroy.argtypes = [P]
     lib.st_bvh_builder_destroy.restype = None
+    lib.st_multi_destroy.argtypes = [P]
+    lib.st_multi_destroy.restype = None
+    lib.st_multi_engine.argtypes = [P, C.c_int]
+    lib.st_multi_engine.restype = P
     lib.st_last_error.restype = C.c_char_p
     lib.st_pass_name.restype = C.c_char_p
     lib.st_pass_name.argtypes = [C.c_int]
@@ -434,6 +451,126 @@ class Engine:
         launches = np.zeros(5, dtype=np.uint32)
         self._check(self.lib.st_wavelet_times(self._h, ms.ctypes.data, launches.ctypes.data, int(reset)))
         return ms, launches
+
+
+class MultiEngine:
+    """strolle::Engine over several devices of ONE process (st_multi_*): the frame is partitioned into row strips, one per
+    device; same method names as `Engine`, so `scenes.apply` and the tests drive it unchanged.  `devices` may repeat an
+    ordinal (several strips on one GPU: exercises the whole strip protocol on a single-GPU box)."""
+
+    def __init__(self, devices=(0, 1), blue_noise=None, seed_base=0xC0FFEE, exact=False):
+        self.lib = load_library()
+        self._h = None
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        self._check(self.lib.st_multi_create(arr, len(devices), C.byref(h)))
+        self._h = h
+        self.n = len(devices)
+        if blue_noise is None:
+            from . import scenes
+            blue_noise = scenes.blue_noise()
+        bn = np.ascontiguousarray(blue_noise, dtype=np.uint8).reshape(-1)
+        self._check(self.lib.st_multi_set_blue_noise(self._h, bn.ctypes.data))
+        self._check(self.lib.st_multi_set_seed_base(self._h, seed_base))
+        if exact:
+            self.set_option(OPT_SVGF_FAST_MATH, 0)
+            self.set_option(OPT_SHADING_FAST_MATH, 0)
+
+    _check = Engine._check
+
+    def close(self):
+        if self._h:
+            self.lib.st_multi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def member(self, rank):
+        """Borrowed `Engine` view of member `rank` (statistics, per-strip buffers); do not close it."""
+        e = Engine.__new__(Engine)
+        e.lib, e._h, e._cams = self.lib, C.c_void_p(self.lib.st_multi_engine(self._h, rank)), {}
+        e.close = lambda: None
+        return e
+
+    def member_camera(self, cam, rank):
+        return self.lib.st_multi_member_camera(self._h, cam, rank)
+
+    def insert_mesh(self, handle, triangles36):
+        t = _f(triangles36)
+        self._check(self.lib.st_multi_insert_mesh(self._h, handle, t.ctypes.data_as(C.POINTER(_MeshTriangle)), t.size // 36))
+
+    def insert_material(self, handle, params12, alpha_blend=False):
+        p = _f(params12, 12)
+        m = _Material((C.c_float * 4)(*p[0:4]), (C.c_float * 4)(*p[4:8]), p[8], p[9], p[10], p[11], int(alpha_blend))
+        self._check(self.lib.st_multi_insert_material(self._h, handle, C.byref(m)))
+
+    def insert_image(self, handle, rgba8):
+        a = np.ascontiguousarray(rgba8, dtype=np.uint8)
+        self._check(self.lib.st_multi_insert_image(self._h, handle, a.ctypes.data, a.shape[1], a.shape[0]))
+
+    def set_material_textures(self, handle, base_color=None, emissive=None, metallic_roughness=None, normal_map=None):
+        t = [base_color, emissive, metallic_roughness, normal_map]
+        mask = sum((1 << i) for i, v in enumerate(t) if v is not None)
+        mt = _MaterialTextures(*[v or 0 for v in t], mask)
+        self._check(self.lib.st_multi_set_material_textures(self._h, handle, C.byref(mt)))
+
+    def insert_instance(self, handle, mesh, material, affine12):
+        a = _f(affine12, 12)
+        self._check(self.lib.st_multi_insert_instance(self._h, handle, mesh, material, a.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def remove_instance(self, handle):
+        self._check(self.lib.st_multi_remove_instance(self._h, handle))
+
+    def insert_light(self, handle, kind, params12):
+        p = _f(params12, 12)
+        l = _Light(kind, (C.c_float * 3)(*p[0:3]), p[3], (C.c_float * 3)(*p[4:7]), p[7], (C.c_float * 3)(*p[8:11]), p[11])
+        self._check(self.lib.st_multi_insert_light(self._h, handle, C.byref(l)))
+
+    def remove_light(self, handle):
+        self._check(self.lib.st_multi_remove_light(self._h, handle))
+
+    def update_sun(self, azimuth, altitude):
+        self._check(self.lib.st_multi_update_sun(self._h, azimuth, altitude))
+
+    def create_camera(self, mode, denoise, ref_depth, w, h, transform16, projection16):
+        c = Engine._cam(mode, denoise, ref_depth, w, h, transform16, projection16)
+        out = C.c_int32()
+        self._check(self.lib.st_multi_create_camera(self._h, C.byref(c), C.byref(out)))
+        return out.value
+
+    def update_camera(self, cam, mode, denoise, ref_depth, w, h, transform16, projection16):
+        c = Engine._cam(mode, denoise, ref_depth, w, h, transform16, projection16)
+        self._check(self.lib.st_multi_update_camera(self._h, cam, C.byref(c)))
+
+    def tick(self):
+        self._check(self.lib.st_multi_tick(self._h))
+
+    def render_camera(self, cam, out=None, fmt=FORMAT_RGBA32F):
+        ptr = out.ctypes.data if out is not None else None
+        self._check(self.lib.st_multi_render_camera(self._h, cam, ptr, fmt))
+
+    def synchronize(self):
+        self._check(self.lib.st_multi_synchronize(self._h))
+
+    def set_option(self, option, value):
+        self._check(self.lib.st_multi_set_option(self._h, option, int(value)))
+
+    def read_buffer(self, cam, name):
+        """The whole frame's buffer, each strip read from the member that owns it."""
+        n = C.c_size_t()
+        self._check(self.lib.st_multi_read_buffer(self._h, cam, name.encode(), None, 0, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        self._check(self.lib.st_multi_read_buffer(self._h, cam, name.encode(), out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+    def peer_errors(self, cam):
+        n = C.c_uint32()
+        self._check(self.lib.st_multi_peer_errors(self._h, cam, C.byref(n)))
+        return n.value
 
 
 def nccl_unique_id():

@@ -731,3 +731,61 @@ def test_fast_shading_traversal_is_the_exact_traversal(gpu, blue_noise):
         ea.render_range(ca, k + 1, len(sched) - 1); eb.render_range(cb, k + 1, len(sched) - 1)
     vis = ea.read_buffer(ca, "di_reservoirs_0").reshape(-1, 8)[:, 3].view(np.uint32) & 0xff
     assert 0.02 < (vis > 0).mean() < 0.98
+
+
+# ---- row strips across devices of one process (st_multi_*, fused transport) --------------------------------------------------------
+
+def _devices(n):
+    import torch
+    have = max(torch.cuda.device_count(), 1)
+    return [k % have for k in range(n)]   # a single-GPU box runs every strip on device 0: same protocol, same kernels
+
+
+@pytest.mark.parametrize("n,size,exact,fused", [(2, (320, 288), True, True), (3, (256, 400), True, True), (2, (320, 288), False, True),
+                                                (4, (200, 520), False, True), (2, (320, 288), True, False)])
+def test_multi_device_group_matches_single_gpu(gpu, blue_noise, n, size, exact, fused):
+    """st_multi_* (one process, n devices): the frame rendered as n row strips — producer kernels mirroring their
+    boundary rows into the neighbours, neighbour-only sequence flags, G-buffer / SVGF halo rows recomputed, temporal rows pulled on
+    demand — is the single-GPU frame, bit for bit, in every per-camera buffer, through two GI cycles with the camera first still,
+    then drifting, then jumping by more rows than any fixed temporal halo would cover."""
+    from strolle_b200.engine import OPT_STRIP_FUSED, FORMAT_RGBA8_SRGB
+    w, h = size
+    scene = scenes.cornell(w, h)
+    one = gpu.Engine(blue_noise=blue_noise, exact=exact)
+    grp = gpu.MultiEngine(_devices(n), blue_noise=blue_noise, exact=exact)
+    grp.set_option(OPT_STRIP_FUSED, int(fused))
+    c1, cn = scenes.apply(one, scene), scenes.apply(grp, scene)
+    c = scene["camera"]
+    for f in range(13):
+        eye = (0.0, 1.0, 3.2)
+        if 4 <= f < 9:
+            eye = (0.01 * (f - 3), 1.0 + 0.03 * (f - 3), 3.2)           # drifting up: reprojection crosses strip edges
+        if f >= 9:
+            eye = (0.05, 1.0 + 0.15 + (0.35 if f % 2 else 0.0), 3.15)   # jumping up and down by tens of rows
+        t = scenes.look_at_transform(eye, (0.0, 1.0 + (eye[1] - 1.0), 0.0))
+        for e, cam in ((one, c1), (grp, cn)):
+            e.update_camera(cam, c["mode"], c["denoise"], c["ref_depth"], w, h, t, c["projection"])
+            e.tick(); e.render_camera(cam)
+        for name in CAMERA_BUFFERS:
+            assert_bits_equal(grp.read_buffer(cn, name), one.read_buffer(c1, name), f"{n} strips frame {f + 1} {name}")
+    assert grp.peer_errors(cn) == 0
+    vel = one.read_buffer(c1, "velocity_map").reshape(h, w, 4)
+    assert np.abs(vel[..., 1]).max() > 16.0, "the jump moved pixels by more than 16 rows"
+    a, b = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 4), np.uint8)
+    one.tick(); grp.tick()
+    one.render_camera(c1, a, FORMAT_RGBA8_SRGB); grp.render_camera(cn, b, FORMAT_RGBA8_SRGB)
+    assert (a == b).all() and a[..., :3].max() > 0
+
+
+def test_multi_device_group_demo_level_and_modes(gpu, blue_noise):
+    """The same on the reference's dungeon (textures, atmosphere, 6 lights) and for a DI-only / GI-only camera mode (chains that are
+    interleaved in Image mode run alone there)."""
+    for scene in (scenes.demo_level(288, 300), scenes.cornell(256, 272, mode=scenes.MODE_DI_DIFFUSE), scenes.cornell(256, 272, mode=scenes.MODE_GI_DIFFUSE, denoise=False)):
+        one = gpu.Engine(blue_noise=blue_noise)
+        grp = gpu.MultiEngine(_devices(2), blue_noise=blue_noise)
+        c1, cn = scenes.apply(one, scene), scenes.apply(grp, scene)
+        for f in range(7):
+            one.tick(); grp.tick(); one.render_camera(c1); grp.render_camera(cn)
+            for name in ["output", "di_reservoirs_0", "gi_reservoirs_0", "gi_reservoirs_3", "di_diff_curr_colors", "gi_diff_curr_colors", "di_diff_prev_colors", "gi_diff_moments_a"]:
+                assert_bits_equal(grp.read_buffer(cn, name), one.read_buffer(c1, name), f"{scene['name']} mode {scene['camera']['mode']} frame {f + 1} {name}")
+        assert grp.peer_errors(cn) == 0
