@@ -405,6 +405,7 @@ struct st_engine {
     std::vector<ImageRect> images; uint32_t shelf_x = 0, shelf_y = 0, shelf_h = 0; bool images_dirty = false;
     DevMem d_atlas, d_srgb, d_tri_instance, d_instance_xforms;
     bool motion_dirty = true;
+    bool moved_last_tick = false;   // an instance was inserted / moved / removed in the tick that prepared the current frame
     struct Inst { st_handle handle, mesh, material; Affine3 xf, xf_inv, prev_xf; bool dirty; };
     std::vector<Inst> instances; bool instances_dirty = false;
     struct Range { st_handle handle; size_t b, e; };
@@ -1227,6 +1228,7 @@ int st_tick(st_engine* e) {   // Engine::tick (lib.rs:301-395)
         if (e->bvh_out.depth - 1 > 24) { e->bvh_out.buf.clear(); too_deep = true; }
         if ((rc = upload(e, e->d_bvh, e->bvh_out.buf.data(), e->bvh_out.buf.size() * 16))) return rc;
     }
+    e->moved_last_tick = e->motion_dirty;
     if (e->motion_dirty) {   // per-instance curr_xform_inv / prev_transform for the velocity map (passes/prim_raster.rs:198-223)
         e->motion_dirty = false;
         std::vector<uint32_t> tri_inst(e->h_triangles.size() / 9, 0u);
@@ -1613,7 +1615,11 @@ static int enqueue_strip_frame(st_engine* e, CameraSlot* cs, int temporal_reach)
         std::vector<Step> steps; build_schedule(e, cs, &steps);
         std::vector<int> ids; for (const Step& st : steps) ids.push_back(st.pass);
         std::vector<HaloExchange> plan;
-        if (e->n_ranks > 1) plan_frame(ids.data(), (int)ids.size(), cs->frame, temporal_reach, &plan);
+        // The exchange-point transports ship a FIXED number of last frame's rows.  That is only enough while nothing moves: with a moving
+        // camera or instance the reprojected reads can land anywhere, so the whole of last frame's buffers is exchanged then (correct for
+        // any motion, and slow: the fused transport sizes this on the device instead).
+        const bool moving = e->moved_last_tick || std::memcmp(&cs->dev.curr, &cs->dev.prev, sizeof(GpuCamera)) != 0;
+        if (e->n_ranks > 1) plan_frame(ids.data(), (int)ids.size(), cs->frame, moving ? (int)cs->desc.height : temporal_reach, &plan);
         size_t next = 0;
         if (peer && (rc = halo_exchange_peer(e, cs, nullptr))) return rc;   // frame barrier: nobody still reads last frame's rows
         for (int i = 0; i < (int)steps.size(); i++) {
