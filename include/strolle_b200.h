@@ -172,7 +172,14 @@ int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9, ST_OPT_STRIP_FUSED = 10 };
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9, ST_OPT_STRIP_FUSED = 10, ST_OPT_FUSED_PASSES = 11 };
+/* ST_OPT_FUSED_PASSES (default 1): reference passes whose hand-over is private to a pixel or to a checkerboard pair run as ONE launch:
+ * K5+K6 (di_sampling + di_temporal_resampling), K7+K8+K9 (di_spatial_resampling pick / trace / sample), K12+K13 (gi_sampling a + b),
+ * K11 inside K14 on tracing frames (gi_reprojection + gi_temporal_resampling), K15+K16+K17 (gi_spatial_resampling) and the second
+ * gi_preview_resampling pass + K19 gi_resolving.  Reservoirs, samples and every later buffer are bit-identical to the one-launch-per-
+ * pass schedule; only the scratch textures between the fused members (and the intermediate gi_reservoirs entries they replaced) are no
+ * longer written.  0 = one launch per reference dispatch (every buffer comparable with the oracle). */
+#define ST_FUSED_PASSES_DEFAULT 1
 /* ST_OPT_STRIP_FUSED (default 1): strip-partitioned frames use the fused transport (producer kernels store boundary rows straight
  * into the neighbours' buffers, neighbour-only sequence flags, halo rows of the G-buffer and of the SVGF chain recomputed instead of
  * shipped, DI / GI chains interleaved so that rows in flight overlap compute, temporal rows pulled on demand); 0 = one push +

@@ -240,14 +240,9 @@ __global__ void __launch_bounds__(ST_BLOCK) k_frame_reprojection(KPARAMS, int cu
 }
 #endif   // ST_EXACT_ONLY
 
-// K5 di_sampling::main (di_sampling.rs:4-94)
-__global__ void ST_LB_DI_SAMPLING k_di_sampling(KPARAMS, int cur, u32 seed, u32 frame) {
-    ST_TRACE_STACK();
-    Px p = pixel_full(cam);
-    if (!p.in) return;
+// K5 di_sampling::main (di_sampling.rs:4-94): the initial sample of a pixel whose primary hit is `hit`
+ST_DEV DiRes di_sampling_px(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, const Hit& hit, u32 seed, u32 frame, Px p) {
     Rng rng = rng_make(seed, p.x, p.y);
-    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    if (!hit_some(hit)) return;
     EphRes res = ephemeral_build(rng, sc, hit);
     DiRes out = di_zero();
     if (res.m > 0.0f) {
@@ -257,19 +252,22 @@ __global__ void ST_LB_DI_SAMPLING k_di_sampling(KPARAMS, int cur, u32 seed, u32 
         if (occ) res.w = 0.0f;
         out.pdf = 0.f; out.confidence = 0.f; out.light_id = res.light_id; out.light_point = ray.o; out.occluded = occ; out.m = 1.0f; out.w = res.w;
     }
-    di_store(out, cam.di_reservoirs[1], screen_idx(cam, p.x, p.y));
+    return out;
 }
-
-// K6 di_temporal_resampling::main (di_temporal_resampling.rs:4-112)
-__global__ void ST_LB_DI_TEMPORAL k_di_temporal(KPARAMS, int cur, u32 seed) {
+__global__ void ST_LB_DI_SAMPLING k_di_sampling(KPARAMS, int cur, u32 seed, u32 frame) {
+    ST_TRACE_STACK();
     Px p = pixel_full(cam);
     if (!p.in) return;
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(hit)) return;
+    di_store(di_sampling_px(cam, sc, stk, hit, seed, frame, p), cam.di_reservoirs[1], screen_idx(cam, p.x, p.y));
+}
+
+// K6 di_temporal_resampling::main (di_temporal_resampling.rs:4-112): merges this frame's sample `lhs` with last frame's reservoir at
+// the reprojected position
+ST_DEV DiRes di_temporal_px(const CameraDev& cam, const SceneDev& sc, int cur, u32 seed, Px p, const Hit& lhs_hit, DiRes lhs) {
     size_t npx = (size_t)cam.w * cam.h;
-    size_t lhs_idx = screen_idx(cam, p.x, p.y);
     Rng rng = rng_make(seed, p.x, p.y);
-    Hit lhs_hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    if (!hit_some(lhs_hit)) return;
-    DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
     if (lhs.m != 0.0f) lhs.pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), lhs_hit);
     DiRes rhs = di_zero();
     Hit rhs_hit = hit_zero();
@@ -301,24 +299,46 @@ __global__ void ST_LB_DI_TEMPORAL k_di_temporal(KPARAMS, int cur, u32 seed) {
     main_.pdf = main_pdf;
     main_.confidence = killed ? 0.0f : 1.0f;
     main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
-    di_store_m(cam, main_, cam.di_reservoirs[1], lhs_idx, p.y, ST_REACH_SPATIAL);
+    return main_;
 }
+__global__ void ST_LB_DI_TEMPORAL k_di_temporal(KPARAMS, int cur, u32 seed) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t lhs_idx = screen_idx(cam, p.x, p.y);
+    Hit lhs_hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(lhs_hit)) return;
+    di_store_m(cam, di_temporal_px(cam, sc, cur, seed, p, lhs_hit, di_load(cam.di_reservoirs[1], lhs_idx)), cam.di_reservoirs[1], lhs_idx, p.y, ST_REACH_SPATIAL);
+}
+// K5 + K6 in one launch (ST_OPT_FUSED_PASSES): the pixel's fresh sample goes from K5 to K6 in registers instead of through di_reservoirs[1]
+// (the hit is decoded once).  What di_store / di_load would do to the sample on the way (confidence -> byte) is the identity for K5's
+// output (confidence 0), so the result is the two-launch result bit for bit.
+__global__ void ST_LB_DI_SAMPLING k_di_sample_temporal(KPARAMS, int cur, u32 seed_sampling, u32 seed_temporal, u32 frame) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(hit)) return;
+    DiRes fresh = di_sampling_px(cam, sc, stk, hit, seed_sampling, frame, p);
+    di_store_m(cam, di_temporal_px(cam, sc, cur, seed_temporal, p, hit, fresh), cam.di_reservoirs[1], screen_idx(cam, p.x, p.y), p.y, ST_REACH_SPATIAL);
+}
+
+// The four scratch texels of one checkerboard pair: (d0, d1) of texel a = (2gx, gy) and texel b = (2gx + 1, gy).
+// state 0: the pair has no left-hand pixel on the screen, nothing is written; 1: only the two d1 texels are cleared; 2: all four.
+struct PairTexels { float4 a0, a1, b0, b1; int state; };
 
 // K7 di_spatial_resampling::pick (di_spatial_resampling.rs:4-147); scratch buf_d0 = di_diff_samples,
 // buf_d1 = di_diff_curr_colors (passes/di_spatial_resampling.rs:24-28).  Sky pixels clear buf_d1
 // (the reference leaves stale texels there and later reads out of bounds — SURVEY Appendix C-15).
-__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
-    Px g = pixel_half(cam);
-    if (!g.in) return;
+ST_DEV PairTexels di_spatial_pick_pair(const CameraDev& cam, const SceneDev& sc, int cur, u32 seed, u32 frame, Px g) {
+    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
     uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
-    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
+    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return o;
+    o.state = 1;
     size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
     Rng rng = rng_make(seed, lp.x, lp.y);
-    float4* buf_d0 = cam.di_diff_samples; float4* buf_d1 = cam.di_diff_curr_colors;
     const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
-    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
     Hit lhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, lp.x, lp.y);
-    if (!hit_some(lhs_hit)) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    if (!hit_some(lhs_hit)) return o;
     DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
     DiRes rhs = di_zero();
     size_t rhs_idx = 0;
@@ -338,42 +358,58 @@ __global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_pick(KPARAMS, int cur, u32 se
         rhs = di_load(cam.di_reservoirs[1], rhs_idx);
         if (rhs.m != 0.0f) { rhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, rpos.x, rpos.y); break; }
     }
-    if (rhs.m == 0.0f) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    if (rhs.m == 0.0f) return o;
     float lhs_rhs_pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), rhs_hit);
     float rhs_lhs_pdf = di_pdf_with(rhs, light_load(sc, rhs.light_id), lhs_hit);
     Ray ra = (lhs_rhs_pdf > 0.0f) ? di_ray(lhs, rhs_hit.point) : ray_zero();
     Ray rb = (rhs_lhs_pdf > 0.0f) ? di_ray(rhs, lhs_hit.point) : ray_zero();
     float2 na = oct_encode(ra.d), nb = oct_encode(rb.d);
-    tex_store(buf_d0, cam, ax, g.y, f4(ra.o, ra.len));
-    tex_store(buf_d1, cam, ax, g.y, f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), 0.0f));
-    tex_store(buf_d0, cam, bx, g.y, f4(rb.o, rb.len));
-    tex_store(buf_d1, cam, bx, g.y, f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf));
+    o.a0 = f4(ra.o, ra.len); o.a1 = f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), 0.0f);
+    o.b0 = f4(rb.o, rb.len); o.b1 = f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf);
+    o.state = 2;
+    return o;
+}
+ST_DEV void store_pair_texels(const CameraDev& cam, const PairTexels& o, float4* buf_d0, float4* buf_d1, Px g) {
+    if (o.state == 0) return;
+    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
+    if (o.state == 2) { tex_store(buf_d0, cam, ax, g.y, o.a0); tex_store(buf_d0, cam, bx, g.y, o.b0); }
+    tex_store(buf_d1, cam, ax, g.y, o.a1); tex_store(buf_d1, cam, bx, g.y, o.b1);
+}
+__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    store_pair_texels(cam, di_spatial_pick_pair(cam, sc, cur, seed, frame, g), cam.di_diff_samples, cam.di_diff_curr_colors, g);
 }
 
-// K8 / K16 *_spatial_resampling::trace (di_spatial_resampling.rs:150-209, gi_spatial_resampling.rs:163-222)
+// K8 / K16 *_spatial_resampling::trace (di_spatial_resampling.rs:150-209, gi_spatial_resampling.rs:163-222): one scratch texel
+ST_DEV float4 spatial_trace_texel(const SceneDev& sc, const TraceStack& stk, float4 d0, float4 d1) {
+    if (all_zero(d1)) return f4zero();
+    Ray ray = ray_make(xyz(d0), oct_decode(f2(d1.x, d1.y)), d0.w);
+    bool occ = trace_any(ray, sc, stk);
+    return f4(occ ? 0.0f : 1.0f, d1.z, d1.w, 0.0f);
+}
 __global__ void ST_LB_SPATIAL_TRACE k_spatial_trace(KPARAMS, const float4* __restrict__ buf_d0, const float4* __restrict__ buf_d1, float4* __restrict__ buf_d2) {
     ST_TRACE_STACK();
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t i = pix(cam, p.x, p.y);
-    float4 d0 = buf_d0[i], d1 = buf_d1[i];
-    if (all_zero(d1)) { buf_d2[i] = f4zero(); return; }
-    Ray ray = ray_make(xyz(d0), oct_decode(f2(d1.x, d1.y)), d0.w);
-    bool occ = trace_any(ray, sc, stk);
-    buf_d2[i] = f4(occ ? 0.0f : 1.0f, d1.z, d1.w, 0.0f);
+    buf_d2[i] = spatial_trace_texel(sc, stk, buf_d0[i], buf_d1[i]);
+}
+// the two visibility texels of a pair as K8 / K16 would leave them for K9 / K17 (a texel outside the texture reads as zero)
+ST_DEV void trace_pair_texels(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, const PairTexels& o, Px g, float4* d2a, float4* d2b) {
+    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
+    *d2a = (o.state == 2 && in_tex(cam, ax, g.y)) ? spatial_trace_texel(sc, stk, o.a0, o.a1) : f4zero();
+    *d2b = (o.state == 2 && in_tex(cam, bx, g.y)) ? spatial_trace_texel(sc, stk, o.b0, o.b1) : f4zero();
 }
 
-// K9 di_spatial_resampling::sample (di_spatial_resampling.rs:212-297)
-__global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 seed, u32 frame) {
-    Px g = pixel_half(cam);
-    if (!g.in) return;
+// K9 di_spatial_resampling::sample (di_spatial_resampling.rs:212-297); d0 / d1 = the pair's two visibility texels
+ST_DEV void di_spatial_sample_pair(const CameraDev& cam, u32 seed, u32 frame, Px g, float4 d0, float4 d1) {
     uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
     if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
     size_t npx = (size_t)cam.w * cam.h;
     size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
     Rng rng = rng_make(seed, lp.x, lp.y);
     const float4* in = cam.di_reservoirs[1]; float4* out = cam.di_reservoirs[2];
-    float4 d0 = tex_or_zero(cam.di_diff_stash, cam, g.x * 2u, g.y), d1 = tex_or_zero(cam.di_diff_stash, cam, g.x * 2u + 1u, g.y);
     float lhs_rhs_vis = d0.x; u32 rhs_idx = fbits(d0.y);
     float rhs_lhs_vis = d1.x, lhs_rhs_pdf = d1.y, rhs_lhs_pdf = d1.z;
     DiRes lhs = di_load(in, lhs_idx);
@@ -394,6 +430,23 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 see
     } else di_store(lhs, out, lhs_idx);
     uint2 op = checker(g.x, g.y, frame / 2u);
     if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); di_store(di_load(in, oi), out, oi); }
+}
+__global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    di_spatial_sample_pair(cam, seed, frame, g, tex_or_zero(cam.di_diff_stash, cam, g.x * 2u, g.y), tex_or_zero(cam.di_diff_stash, cam, g.x * 2u + 1u, g.y));
+}
+// K7 + K8 + K9 in one launch (ST_OPT_FUSED_PASSES): one thread per checkerboard pair picks the neighbour, traces the pair's two shadow
+// rays and merges — the three scratch textures (48 B per pixel written and read back) never leave the registers.  Same draws, same rays
+// (direction through the same octahedral round trip), same merge as the three-launch sequence.
+__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_fused(KPARAMS, int cur, u32 seed_pick, u32 seed_sample, u32 frame) {
+    ST_TRACE_STACK();
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    PairTexels o = di_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+    if (o.state == 0) return;
+    float4 d2a, d2b; trace_pair_texels(cam, sc, stk, o, g, &d2a, &d2b);
+    di_spatial_sample_pair(cam, seed_sample, frame, g, d2a, d2b);
 }
 
 // K10 di_resolving::main (di_resolving.rs:4-119)
@@ -426,13 +479,8 @@ __global__ void ST_LB_DI_RESOLVING k_di_resolving(KPARAMS, int cur) {
 }
 
 // K11 gi_reprojection::main (gi_reprojection.rs:4-51)
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) {
-    Px p = pixel_full(cam);
-    if (!p.in) return;
+ST_DEV GiRes gi_reprojection_px(const CameraDev& cam, const Hit& hit, const Reproj& rp) {
     size_t npx = (size_t)cam.w * cam.h;
-    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    if (!hit_some(hit)) return;
-    Reproj rp = reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)]);
     GiRes res = gi_zero();
     if (reproj_some(rp)) {
         uint2 rpos = reproj_round(rp);
@@ -441,29 +489,38 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) 
     }
     res.confidence = 1.0f;
     res.v1 = hit.point;
-    gi_store(res, cam.gi_reservoirs[2], screen_idx(cam, p.x, p.y));
+    return res;
+}
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(hit)) return;
+    // strips: the columns the checkerboard passes do not cover (widths whose (W + 7) / 8 is odd) keep this entry as the spatial pass's
+    // output, so there it is one of the rows a neighbouring strip's preview pass gathers
+    gi_store_m(cam, gi_reprojection_px(cam, hit, reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)])), cam.gi_reservoirs[2], screen_idx(cam, p.x, p.y), p.y,
+               (int)p.x >= 2 * half_grid_w(cam.w) ? ST_REACH_SPATIAL : 0);
 }
 
 // K12 gi_sampling_a::main (gi_sampling_a.rs:4-122)
-__global__ void ST_LB_GI_SAMPLING_A k_gi_sampling_a(KPARAMS, int cur, u32 seed, u32 frame) {
-    ST_TRACE_STACK();
-    Px g = pixel_half(cam);
-    if (!g.in) return;
+// returns false where the kernel leaves without writing its three scratch texels (gi_d0: ray direction + pdf, gi_d1/gi_d2: the packed
+// G-buffer entry of what the ray hit)
+ST_DEV bool gi_sampling_a_pair(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, int cur, u32 seed, u32 frame, Px g, float4* t0, float4* t1, float4* t2) {
     bool tracing = gi_tracing_frame(frame);
     uint2 sp = tracing ? checker(g.x, g.y, frame / 2u) : checker(g.x, g.y, frame);
-    if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
+    if (!cam_contains_u(cam.curr, sp.x, sp.y)) return false;
     size_t idx = screen_idx(cam, sp.x, sp.y);
     Ray gi_r; float gi_pdf_;
     if (tracing) {
         Rng rng = rng_make(seed, sp.x, sp.y);
         Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
-        if (!hit_some(hit)) return;
+        if (!hit_some(hit)) return false;
         BrdfS s = brdf_layered_sample(hit.g, rng, -hit.dir);
         gi_r = ray_make(hit.point, s.dir);
         gi_pdf_ = s.pdf;
     } else {
         GiRes res = gi_load(cam.gi_reservoirs[2], idx);
-        if (res.m == 0.0f) return;
+        if (res.m == 0.0f) return false;
         gi_r = ray_make(res.v1, gi_dir(res, res.v1));
         gi_pdf_ = 1.0f;
     }
@@ -477,24 +534,28 @@ __global__ void ST_LB_GI_SAMPLING_A k_gi_sampling_a(KPARAMS, int cur, u32 seed, 
         gi_color_bits = all_zero(m.base_color_texture) ? __ldg(sc.material_packed + gh.material_id) : gbuf_pack_color(gg.base_color);
         gg.roughness = m.roughness; gg.reflectance = m.reflectance; gg.depth = dist(gi_r.o, gh.point);
     }
-    float4 d1, d2; gbuf_pack_pre(gg, gi_color_bits, &d1, &d2);
-    size_t gi = pix(cam, g.x, g.y);
-    cam.gi_d0[gi] = f4(gi_r.d, gi_pdf_); cam.gi_d1[gi] = d1; cam.gi_d2[gi] = d2;
+    gbuf_pack_pre(gg, gi_color_bits, t1, t2);
+    *t0 = f4(gi_r.d, gi_pdf_);
+    return true;
 }
-
-// K13 gi_sampling_b::main (gi_sampling_b.rs:4-235)
-__global__ void ST_LB_GI_SAMPLING_B k_gi_sampling_b(KPARAMS, int cur, u32 seed, u32 frame) {
+__global__ void ST_LB_GI_SAMPLING_A k_gi_sampling_a(KPARAMS, int cur, u32 seed, u32 frame) {
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
     if (!g.in) return;
+    float4 t0, t1, t2;
+    if (!gi_sampling_a_pair(cam, sc, stk, cur, seed, frame, g, &t0, &t1, &t2)) return;
+    size_t gi = pix(cam, g.x, g.y);
+    cam.gi_d0[gi] = t0; cam.gi_d1[gi] = t1; cam.gi_d2[gi] = t2;
+}
+
+// K13 gi_sampling_b::main (gi_sampling_b.rs:4-235)
+ST_DEV void gi_sampling_b_pair(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, int cur, u32 seed, u32 frame, Px g, float4 d0, float4 d1, float4 d2) {
     bool tracing = gi_tracing_frame(frame);
     uint2 sp = tracing ? checker(g.x, g.y, frame / 2u) : checker(g.x, g.y, frame);
     if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
     size_t idx = screen_idx(cam, sp.x, sp.y);
     Hit prim = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
     if (!hit_some(prim)) return;
-    size_t gi = pix(cam, g.x, g.y);
-    float4 d0 = cam.gi_d0[gi], d1 = cam.gi_d1[gi], d2 = cam.gi_d2[gi];
     Rng rng; Hit gh; float gi_pdf_;
     if (tracing) {
         rng = rng_make(seed, sp.x, sp.y);
@@ -545,9 +606,30 @@ __global__ void ST_LB_GI_SAMPLING_B k_gi_sampling_b(KPARAMS, int cur, u32 seed, 
     }
     gi_store(res, cam.gi_reservoirs[1], idx);
 }
+__global__ void ST_LB_GI_SAMPLING_B k_gi_sampling_b(KPARAMS, int cur, u32 seed, u32 frame) {
+    ST_TRACE_STACK();
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    size_t gi = pix(cam, g.x, g.y);
+    gi_sampling_b_pair(cam, sc, stk, cur, seed, frame, g, cam.gi_d0[gi], cam.gi_d1[gi], cam.gi_d2[gi]);
+}
+// K12 + K13 in one launch (ST_OPT_FUSED_PASSES): the bounce ray is traced and shaded by the same thread; the hit still goes through
+// GBufferEntry's pack / unpack (its 8-bit quantisation is part of the result), just not through memory.
+__global__ void ST_LB_GI_SAMPLING_B k_gi_sampling_fused(KPARAMS, int cur, u32 seed_a, u32 seed_b, u32 frame) {
+    ST_TRACE_STACK();
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    float4 t0, t1, t2;
+    if (!gi_sampling_a_pair(cam, sc, stk, cur, seed_a, frame, g, &t0, &t1, &t2)) return;
+    gi_sampling_b_pair(cam, sc, stk, cur, seed_b, frame, g, t0, t1, t2);
+}
 
 // K14 gi_temporal_resampling::main (gi_temporal_resampling.rs:4-156)
-__global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 frame) {
+// `inline_reprojection` (ST_OPT_FUSED_PASSES, tracing frames): K11 is evaluated here instead of in its own launch — last frame's
+// reservoir is fetched from gi_reservoirs[0] at the reprojected position directly, and handed on as K11 would have left it in
+// gi_reservoirs[2] (its normal goes through the same octahedral store / load round trip).  gi_reservoirs[2] itself is then only written
+// for the columns a later pass still reads there (those the checkerboard passes do not cover when the width is odd).
+__global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 frame, int inline_reprojection) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     bool tracing = gi_tracing_frame(frame);
@@ -561,8 +643,12 @@ __global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 
     GiRes rhs = gi_zero();
     Hit rhs_hit = hit_zero();
     Reproj rp = reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)]);
+    if (inline_reprojection) {
+        GiRes r11 = gi_reprojection_px(cam, lhs_hit, rp);
+        if ((int)p.x >= 2 * half_grid_w(cam.w)) gi_store_m(cam, r11, cam.gi_reservoirs[2], lhs_idx, p.y, ST_REACH_SPATIAL);
+        if (reproj_some(rp)) { rhs = r11; rhs.v2n = oct_decode(oct_encode(r11.v2n)); }
+    } else if (reproj_some(rp)) rhs = gi_load(cam.gi_reservoirs[2], lhs_idx);
     if (reproj_some(rp)) {
-        rhs = gi_load(cam.gi_reservoirs[2], lhs_idx);
         rhs.confidence = 1.0f;
         rhs.m = rmin(rhs.m, 128.0f);
         if (!tracing && lhs.m != 0.0f && rhs.m != 0.0f && gi_exists(rhs)) {
@@ -599,20 +685,18 @@ __global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 
 }
 
 // K15 gi_spatial_resampling::pick (gi_spatial_resampling.rs:4-160); scratch = gi_d0, gi_d1
-__global__ void ST_LB_GI_SPATIAL_PICK k_gi_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
-    Px g = pixel_half(cam);
-    if (!g.in) return;
+ST_DEV PairTexels gi_spatial_pick_pair(const CameraDev& cam, const SceneDev& sc, int cur, u32 seed, u32 frame, Px g) {
+    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
     uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
-    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
+    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return o;
+    o.state = 1;
     size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
     Rng rng = rng_make(seed, lp.x, lp.y);
-    float4* buf_d0 = cam.gi_d0; float4* buf_d1 = cam.gi_d1;
     const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
     const float4* reservoirs = cam.gi_reservoirs[1];
-    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
     Hit lhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, lp.x, lp.y);
     GiRes lhs = gi_load(reservoirs, lhs_idx);
-    if (!hit_some(lhs_hit) || lhs.m == 0.0f) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    if (!hit_some(lhs_hit) || lhs.m == 0.0f) return o;
     GiRes rhs = gi_zero();
     size_t rhs_idx = 0;
     Hit rhs_hit = hit_zero();
@@ -636,29 +720,31 @@ __global__ void ST_LB_GI_SPATIAL_PICK k_gi_spatial_pick(KPARAMS, int cur, u32 se
         rhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, rpos.x, rpos.y);
         break;
     }
-    if (rhs.m == 0.0f || !hit_some(rhs_hit)) { tex_store(buf_d1, cam, ax, g.y, f4zero()); tex_store(buf_d1, cam, bx, g.y, f4zero()); return; }
+    if (rhs.m == 0.0f || !hit_some(rhs_hit)) return o;
     float lhs_rhs_pdf = gi_pdf(lhs, rhs_hit);
     float rhs_lhs_pdf = gi_pdf(rhs, lhs_hit);
     Ray ra = (lhs_rhs_pdf > 0.0f) ? gi_ray(lhs, rhs_hit.point) : ray_zero();
     Ray rb = (rhs_lhs_pdf > 0.0f) ? gi_ray(rhs, lhs_hit.point) : ray_zero();
     float2 na = oct_encode(ra.d), nb = oct_encode(rb.d);
-    tex_store(buf_d0, cam, ax, g.y, f4(ra.o, ra.len));
-    tex_store(buf_d1, cam, ax, g.y, f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), rhs_jac));
-    tex_store(buf_d0, cam, bx, g.y, f4(rb.o, rb.len));
-    tex_store(buf_d1, cam, bx, g.y, f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf));
+    o.a0 = f4(ra.o, ra.len); o.a1 = f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), rhs_jac);
+    o.b0 = f4(rb.o, rb.len); o.b1 = f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf);
+    o.state = 2;
+    return o;
+}
+__global__ void ST_LB_GI_SPATIAL_PICK k_gi_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    store_pair_texels(cam, gi_spatial_pick_pair(cam, sc, cur, seed, frame, g), cam.gi_d0, cam.gi_d1, g);
 }
 
 // K17 gi_spatial_resampling::sample (gi_spatial_resampling.rs:225-314)
-__global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u32 frame) {
-    Px g = pixel_half(cam);
-    if (!g.in) return;
+ST_DEV void gi_spatial_sample_pair(const CameraDev& cam, u32 seed, u32 frame, Px g, float4 d0, float4 d1) {
     uint2 sp = checker(g.x, g.y, frame / 2u + 1u);
     if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
     size_t npx = (size_t)cam.w * cam.h;
     size_t idx = screen_idx(cam, sp.x, sp.y);
     Rng rng = rng_make(seed, sp.x, sp.y);
     const float4* in = cam.gi_reservoirs[1]; float4* out = cam.gi_reservoirs[2];
-    float4 d0 = tex_or_zero(cam.gi_d2, cam, g.x * 2u, g.y), d1 = tex_or_zero(cam.gi_d2, cam, g.x * 2u + 1u, g.y);
     float lhs_rhs_vis = d0.x; u32 rhs_idx = fbits(d0.y); float rhs_jac = d0.z;
     float rhs_lhs_vis = d1.x, lhs_rhs_pdf = d1.y, rhs_lhs_pdf = d1.z;
     GiRes lhs = gi_load(in, idx);
@@ -683,15 +769,27 @@ __global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u
     uint2 op = checker(g.x, g.y, frame / 2u);
     if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); gi_store_m(cam, gi_load(in, oi), out, oi, op.y, ST_REACH_SPATIAL); }
 }
+__global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    gi_spatial_sample_pair(cam, seed, frame, g, tex_or_zero(cam.gi_d2, cam, g.x * 2u, g.y), tex_or_zero(cam.gi_d2, cam, g.x * 2u + 1u, g.y));
+}
+// K15 + K16 + K17 in one launch (ST_OPT_FUSED_PASSES), like k_di_spatial_fused
+__global__ void ST_LB_GI_SPATIAL_PICK k_gi_spatial_fused(KPARAMS, int cur, u32 seed_pick, u32 seed_sample, u32 frame) {
+    ST_TRACE_STACK();
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    PairTexels o = gi_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+    if (o.state == 0) return;
+    float4 d2a, d2b; trace_pair_texels(cam, sc, stk, o, g, &d2a, &d2b);
+    gi_spatial_sample_pair(cam, seed_sample, frame, g, d2a, d2b);
+}
 
-// K18 gi_preview_resampling::main (gi_preview_resampling.rs:4-138)
-__global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nth, const float4* __restrict__ in, float4* __restrict__ out, int reach) {
-    Px p = pixel_full(cam);
-    if (!p.in) return;
+// K18 gi_preview_resampling::main (gi_preview_resampling.rs:4-138).  Returns false where the kernel exits without writing (quirk C-6).
+ST_DEV bool gi_preview_px(const CameraDev& cam, const SceneDev& sc, const Hit& chit, u32 seed, u32 nth, const float4* __restrict__ in, Px p, GiRes* result) {
     size_t cidx = screen_idx(cam, p.x, p.y);
     Rng rng = rng_make(seed, p.x, p.y);
-    Hit chit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    if (!hit_some(chit)) { gi_store_m(cam, gi_zero(), out, cidx, p.y, reach); return; }
+    if (!hit_some(chit)) { *result = gi_zero(); return true; }
     GiRes main_ = gi_zero();
     float main_pdf = 0.0f;
     GiRes center = gi_load(in, cidx);
@@ -703,7 +801,7 @@ __global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nt
         float2 off = rng_disk(rng) * max_radius;
         float2 fp = f2((float)p.x, (float)p.y) + off;
         uint2 sp = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
-        if (sp.x == p.x && sp.y == p.y) return;   // quirk C-6: the kernel exits without writing
+        if (sp.x == p.x && sp.y == p.y) return false;   // quirk C-6: the kernel exits without writing
         if (!cam_contains_u(cam.curr, sp.x, sp.y)) continue;
         float4 nd = surf[pix(cam, sp.x, sp.y)];
         if (nd.w == 0.0f) continue;
@@ -722,17 +820,21 @@ __global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nt
     main_.v1 = center.v1;
     main_.w = res_norm(main_.w, main_pdf, 1.0f, main_.m);
     main_.w = rmin(main_.w, 5.0f);
-    gi_store_m(cam, main_, out, cidx, p.y, reach);
+    *result = main_;
+    return true;
 }
-
-// K19 gi_resolving::main (gi_resolving.rs:4-67)
-__global__ void ST_LB_GI_RESOLVING k_gi_resolving(KPARAMS, int cur, const float4* __restrict__ in) {
+__global__ void ST_LB_GI_PREVIEW k_gi_preview(KPARAMS, int cur, u32 seed, u32 nth, const float4* __restrict__ in, float4* __restrict__ out, int reach) {
     Px p = pixel_full(cam);
     if (!p.in) return;
+    Hit chit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    GiRes r;
+    if (gi_preview_px(cam, sc, chit, seed, nth, in, p, &r)) gi_store_m(cam, r, out, screen_idx(cam, p.x, p.y), p.y, reach);
+}
+
+// K19 gi_resolving::main (gi_resolving.rs:4-67): shades the pixel from `res` (the entry the second preview pass left in gi_reservoirs[0]),
+// then replaces that entry with the frame's source reservoir
+ST_DEV void gi_resolving_px(const CameraDev& cam, const Hit& hit, const GiRes& res, const float4* __restrict__ in, Px p) {
     size_t idx = screen_idx(cam, p.x, p.y);
-    float4* out = cam.gi_reservoirs[0];
-    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    GiRes res = gi_load(out, idx);
     float confidence; float3 radiance;
     if (hit_some(hit)) { confidence = res.confidence; radiance = res.w * gi_cosine(res, hit) * res.radiance; }
     else { confidence = 1.0f; radiance = f3s(0.f); }
@@ -741,7 +843,24 @@ __global__ void ST_LB_GI_RESOLVING k_gi_resolving(KPARAMS, int cur, const float4
     size_t i = pix(cam, p.x, p.y);
     cam.gi_diff_samples[i] = f4(radiance * diff_brdf, confidence);
     cam.gi_spec_samples[i] = f4(radiance * spec, confidence);
-    gi_store(gi_load(in, idx), out, idx);
+    gi_store(gi_load(in, idx), cam.gi_reservoirs[0], idx);
+}
+__global__ void ST_LB_GI_RESOLVING k_gi_resolving(KPARAMS, int cur, const float4* __restrict__ in) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    gi_resolving_px(cam, hit, gi_load(cam.gi_reservoirs[0], screen_idx(cam, p.x, p.y)), in, p);
+}
+// second preview pass + K19 in one launch (ST_OPT_FUSED_PASSES): the pass's result is shaded straight away instead of going through
+// gi_reservoirs[0] (K19 only consumes fields that a store / load leaves untouched); where the pass exits without writing (quirk C-6) K19
+// sees last frame's entry, which is what is loaded here then.
+__global__ void ST_LB_GI_PREVIEW k_gi_preview_resolve(KPARAMS, int cur, u32 seed, const float4* __restrict__ in, const float4* __restrict__ source) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    Hit chit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    GiRes r;
+    if (!gi_preview_px(cam, sc, chit, seed, 1u, in, p, &r)) r = gi_load(cam.gi_reservoirs[0], screen_idx(cam, p.x, p.y));
+    gi_resolving_px(cam, chit, r, source, p);
 }
 
 #if ST_EXACT_ONLY
@@ -1433,11 +1552,16 @@ void launch_di_resolving(const CameraDev& c, const SceneDev& s, int cur, cudaStr
 void launch_gi_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_gi_reprojection<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
 void launch_gi_sampling_a(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_sampling_a, c, st, c, s, cur, seed, frame); }
 void launch_gi_sampling_b(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_sampling_b, c, st, c, s, cur, seed, frame); }
-void launch_gi_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { k_gi_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame); }
+void launch_gi_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, int inline_reprojection, cudaStream_t st) { k_gi_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, frame, inline_reprojection); }
 void launch_gi_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_pick, c, st, c, s, cur, seed, frame); }
 void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_sample, c, st, c, s, seed, frame); }
 void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, int mirror_reach, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out, mirror_reach); }
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
+void launch_di_sample_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed_sampling, u32 seed_temporal, u32 frame, cudaStream_t st) { k_di_sample_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed_sampling, seed_temporal, frame); }
+void launch_di_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_di_spatial_fused, c, st, c, s, cur, seed_pick, seed_sample, frame); }
+void launch_gi_sampling_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_a, u32 seed_b, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_sampling_fused, c, st, c, s, cur, seed_a, seed_b, frame); }
+void launch_gi_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_fused, c, st, c, s, cur, seed_pick, seed_sample, frame); }
+void launch_gi_preview_resolve(const CameraDev& c, const SceneDev& s, int cur, u32 seed, const float4* in, const float4* source, cudaStream_t st) { k_gi_preview_resolve<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, in, source); }
 #if ST_EXACT_ONLY
 void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
 void launch_frame_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_frame_reprojection<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }

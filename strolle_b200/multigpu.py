@@ -54,7 +54,7 @@ def plan_frame(schedule: Sequence[int], frame: int, temporal_reach: int = 16) ->
     wavelet_inputs = ["stash", "prev_colors", "stash", "curr_colors", "stash"]
     gi_source = None
     if P_GI_PREVIEW in schedule:
-        gi_source = 2 if P_GI_SPATIAL_SAMPLE in schedule else 1
+        gi_source = 2 if P_GI_SPATIAL_PICK in schedule else 1
     for i, p in enumerate(schedule):
         bufs: List[Tuple[str, int]] = []
         if i == 0 and temporal_reach > 0:

@@ -792,3 +792,31 @@ def test_multi_device_group_demo_level_and_modes(gpu, blue_noise):
             for name in ["output", "di_reservoirs_0", "gi_reservoirs_0", "gi_reservoirs_3", "di_diff_curr_colors", "gi_diff_curr_colors", "di_diff_prev_colors", "gi_diff_moments_a"]:
                 assert_bits_equal(grp.read_buffer(cn, name), one.read_buffer(c1, name), f"{scene['name']} mode {scene['camera']['mode']} frame {f + 1} {name}")
         assert grp.peer_errors(cn) == 0
+
+
+NOT_WRITTEN_WHEN_FUSED = {"gi_d0", "gi_d1", "gi_d2", "gi_reservoirs_2"}   # scratch between fused members / K11's entry when it runs inside K14
+
+
+@pytest.mark.parametrize("scene_name,size", [("cornell", (200, 120)), ("cornell", (121, 67)), ("textured_room", (192, 108)), ("demo_level", (176, 99))])
+def test_fused_passes_bit_exact(gpu, oracle, blue_noise, scene_name, size):
+    """ST_OPT_FUSED_PASSES with strict arithmetic: K5+K6, K7+K8+K9, K12+K13, K11-in-K14, K15+K16+K17 and preview#2+K19 as single launches
+    leave every reservoir, sample, colour, moment and the composed frame bit-identical to the oracle's one-dispatch-per-pass frame, over
+    two GI cycles with a moving camera (widths 200 and 121 have columns the checkerboard passes do not cover; the textured room has
+    alpha-tested and metallic surfaces)."""
+    from strolle_b200.engine import OPT_FUSED_PASSES
+    scene = {"cornell": scenes.cornell, "demo_level": scenes.demo_level, "textured_room": scenes.textured_room}[scene_name](*size)
+    eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
+    eg.set_option(OPT_FUSED_PASSES, 1)
+    c = scene["camera"]
+    base = np.asarray(c["transform"], np.float32).copy()
+    names = [n for n in CAMERA_BUFFERS if n not in NOT_WRITTEN_WHEN_FUSED]
+    for f in range(13):
+        t = base.copy()
+        if f >= 5:
+            t[12] += 0.01 * (f - 4); t[13] += 0.006 * (f - 4)   # translate the eye
+        for e, cam in ((eg, cg), (eo, co)):
+            e.update_camera(cam, c["mode"], c["denoise"], c["ref_depth"], c["w"], c["h"], t, c["projection"])
+            e.tick(); e.render_camera(cam)
+        assert len(eg.frame_schedule(cg)) <= 18, "fused schedule"
+        for name in names:
+            assert_bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name), f"fused passes {scene_name} {size} frame {f + 1} {name}")
