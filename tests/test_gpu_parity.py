@@ -820,3 +820,19 @@ def test_fused_passes_bit_exact(gpu, oracle, blue_noise, scene_name, size):
         assert len(eg.frame_schedule(cg)) <= 18, "fused schedule"
         for name in names:
             assert_bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name), f"fused passes {scene_name} {size} frame {f + 1} {name}")
+
+
+@pytest.mark.parametrize("exact", [True, False])
+def test_batched_wavelet_matches_gather(gpu, blue_noise, exact):
+    """K22's batched-gather kernel (ST_OPT_WAVELET_BATCHED: all tap addresses first, then 8-16 gathers in flight) gives the bits of the
+    per-tap gather kernel for every stride, in both arithmetic flavours, on sizes with partial tiles and mirrored borders."""
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_WAVELET_BATCHED
+    for size in [(200, 120), (67, 45)]:
+        scene = scenes.cornell(*size)
+        ea, eb = gpu.Engine(blue_noise=blue_noise, exact=exact), gpu.Engine(blue_noise=blue_noise, exact=exact)
+        ea.set_option(OPT_WAVELET_TILED, 0); eb.set_option(OPT_WAVELET_BATCHED, 31)
+        ca, cb = scenes.apply(ea, scene), scenes.apply(eb, scene)
+        for f in range(4):
+            ea.tick(); eb.tick(); ea.render_camera(ca); eb.render_camera(cb)
+            for name in DENOISER_BUFFERS:
+                assert_bits_equal(eb.read_buffer(cb, name), ea.read_buffer(ca, name), f"{size} frame {f + 1} {name}")
