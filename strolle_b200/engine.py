@@ -424,7 +424,7 @@ class Engine:
 
     def render_strips(self, cam, out=None, fmt=FORMAT_RGBA32F, temporal_reach=16, gather=False):
         ptr = out.ctypes.data if out is not None else None
-        self._check(self.lib.st_render_strips(self._h, cam, ptr, fmt, temporal_reach, 1 if (gather or out is not None) else 0))
+        self._check(self.lib.st_render_strips(self._h, cam, ptr, fmt, temporal_reach, int(gather) if gather else (1 if out is not None else 0)))
 
     def halo_bytes(self):
         n = C.c_uint64()

@@ -152,22 +152,25 @@ class StripRunner:
         if world > 1:
             import torch
             engine.set_strip(cam, self.y0, self.y1)
-            engine.set_stream(torch.cuda.current_stream().cuda_stream)
             self.native = (transport is None) if native is None else native
             if self.native:
                 import torch.distributed as dist
-                from .engine import nccl_unique_id
-                box = [nccl_unique_id() if rank == 0 else None]
-                dist.broadcast_object_list(box, src=0)
-                engine.nccl_init(box[0], rank, world)
                 self.peer = bool(peer)
-                if self.peer:   # map every rank's camera buffers (CUDA IPC): halo rows then travel as peer stores, not NCCL
+                if self.peer:   # map every rank's camera buffers (CUDA IPC): rows then travel as peer stores / loads on the engine's own stream
                     handles = [None] * world
                     dist.all_gather_object(handles, engine.peer_export(cam))
                     engine.peer_import(cam, handles, rank, world)
                     dist.barrier()
-            elif transport is None:
-                self.transport = TorchDistTransport(rank)
+                else:           # engine-owned NCCL communicator, ordered against torch's stream
+                    from .engine import nccl_unique_id
+                    engine.set_stream(torch.cuda.current_stream().cuda_stream)
+                    box = [nccl_unique_id() if rank == 0 else None]
+                    dist.broadcast_object_list(box, src=0)
+                    engine.nccl_init(box[0], rank, world)
+            else:
+                engine.set_stream(torch.cuda.current_stream().cuda_stream)
+                if transport is None:
+                    self.transport = TorchDistTransport(rank)
 
     def _view(self, name):
         """(H, floats_per_row) torch view of an engine buffer."""
@@ -191,18 +194,30 @@ class StripRunner:
         self.halo_bytes_last_frame += nbytes
         self.transport.run(ops)
 
-    def render(self, out=None, fmt=0):
+    def transport_name(self):
+        if self.world == 1:
+            return "single GPU"
+        if self.native and self.peer:
+            return ("fused peer-memory transport over NVLink (CUDA IPC): producer kernels store boundary rows into the neighbours' buffers, neighbour-only "
+                    "sequence flags, G-buffer / SVGF halo rows recomputed, temporal rows pulled on demand; no NCCL on the data path")
+        return "engine-owned NCCL send/recv per exchange point" if self.native else "torch.distributed P2P between st_render_range calls"
+
+    def render(self, out=None, fmt=0, gather=None, moving=False):
+        """`out` (world > 1): a host frame shared by all ranks (gather 2, default: every rank copies its own rows), or rank 0's
+        private buffer with gather=1 (strips assembled on rank 0 first)."""
         eng, cam = self.engine, self.cam
         if self.world == 1:
             eng.render_camera(cam, out, fmt)
             return
         if self.native:
-            eng.render_strips(cam, out, fmt, self.temporal_reach, gather=out is not None)
+            g = 0 if out is None else (2 if gather is None else gather)
+            eng.render_strips(cam, out, fmt, self.temporal_reach, gather=g)
             self.halo_bytes_last_frame = eng.halo_bytes()
             return
         schedule = eng.frame_schedule(cam)
         frame = eng.frame() - 1   # tick() already advanced the engine's counter; the camera renders frame-1
-        plan = plan_frame(schedule, frame, self.temporal_reach)
+        # a fixed temporal halo is only enough while nothing moves (ADVICE r1): under motion the whole of last frame's buffers is exchanged
+        plan = plan_frame(schedule, frame, self.h if moving else self.temporal_reach)
         self.halo_bytes_last_frame = 0
         first = 0
         for ex in plan:

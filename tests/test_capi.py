@@ -54,3 +54,32 @@ def test_product_does_not_touch_the_oracle():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for pat in banned:
                     assert not re.search(pat, text), f"{f} references the oracle ({pat})"
+
+
+def test_rust_sys_crate_matches_the_header():
+    """rust/strolle-b200-sys/src/lib.rs is generated from include/strolle_b200.h (tools/gen_rust_sys.py): the committed file must be
+    what the generator produces now, and must declare every C entry point exactly once."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("gen_rust_sys", os.path.join(ROOT, "tools", "gen_rust_sys.py"))
+    gen = importlib.util.module_from_spec(spec); spec.loader.exec_module(gen)
+    text, names = gen.generate()
+    assert open(gen.OUT).read() == text, "run python tools/gen_rust_sys.py"
+    assert sorted(names) == declared_symbols()
+
+
+def test_rust_engine_forwards_every_reference_method():
+    """The safe crate has every public method of strolle::Engine (strolle/src/lib.rs:132-301) and each one calls into the C ABI."""
+    src = open(os.path.join(ROOT, "rust", "strolle-b200", "src", "lib.rs")).read()
+    src = src[src.index("impl<P: Params> Engine<P> {"):]
+    for method, ffi in [("new", "st_multi_create"), ("insert_mesh", "st_multi_insert_mesh"), ("remove_mesh", "st_multi_remove_mesh"), ("insert_material", "st_multi_insert_material"),
+                        ("has_material", "st_multi_has_material"), ("remove_material", "st_multi_remove_material"), ("insert_image", "st_multi_insert_image"),
+                        ("remove_image", "st_multi_remove_image"), ("insert_instance", "st_multi_insert_instance"), ("remove_instance", "st_multi_remove_instance"),
+                        ("insert_light", "st_multi_insert_light"), ("remove_light", "st_multi_remove_light"), ("update_sun", "st_multi_update_sun"),
+                        ("create_camera", "st_multi_create_camera"), ("update_camera", "st_multi_update_camera"), ("render_camera", "st_multi_render_camera"),
+                        ("delete_camera", "st_multi_delete_camera"), ("tick", "st_multi_tick")]:
+        m = re.search(r"pub fn %s\b.*?\n    }\n" % method, src, flags=re.S)
+        assert m, f"Engine::{method} missing"
+        assert ffi in m.group(0), f"Engine::{method} does not call {ffi}"
+    sys_src = open(os.path.join(ROOT, "rust", "strolle-b200-sys", "src", "lib.rs")).read()
+    for ffi in set(re.findall(r"sys::(st_\w+)\(", src)):
+        assert f"pub fn {ffi}(" in sys_src, f"{ffi} used by the safe crate but not declared by the sys crate"

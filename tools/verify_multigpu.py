@@ -41,9 +41,9 @@ def check_strips(native, peer=False):
         last = f == FRAMES - 1
         eng.tick()
         if last:
-            runner.render(out=out8, fmt=strolle_b200.engine.FORMAT_RGBA8_SRGB)
+            runner.render(out=out8, fmt=strolle_b200.engine.FORMAT_RGBA8_SRGB, gather=1)
         else:
-            runner.render(out=out, fmt=strolle_b200.engine.FORMAT_RGBA32F)
+            runner.render(out=out, fmt=strolle_b200.engine.FORMAT_RGBA32F, gather=1)
         if rank == 0:
             full.tick(); full.render_camera(cfull, want8 if last else None, strolle_b200.engine.FORMAT_RGBA8_SRGB)
             if last:
