@@ -432,7 +432,6 @@ struct st_engine {
     bool strip_fused = true;     // ST_OPT_STRIP_FUSED: mirror stores + neighbour flags + recompute instead of stand-alone exchanges
     bool last_frame_fused = false;
     int wavelet_tiled = ST_WAVELET_TILED_DEFAULT;   // ST_OPT_WAVELET_TILED: bit i = à-trous iteration i (stride 2^i) runs the tile-staged (TMA) kernel
-    int wavelet_batched = ST_WAVELET_BATCHED_DEFAULT;   // ST_OPT_WAVELET_BATCHED: bit i = iteration i runs the batched-gather kernel (wins over the tiled bit)
     int wavelet_cfg = ST_WAVELET_CFG_DEFAULT;       // ST_OPT_WAVELET_TILE_CFG: 4 bits per iteration, tile shape index (kernels.cu wavelet_tiled_cfg)
     DevMem d_tile_errors; uint64_t wavelet_tiled_launches = 0;
     bool fuse_reproject = ST_FUSE_REPROJECT_DEFAULT != 0;   // ST_OPT_FUSE_REPROJECT
@@ -746,12 +745,10 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
                                {cam.gi_diff_curr_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors}};
         for (uint32_t nth = 0; nth < 5; nth++) {
             float4 *a = di_io[nth][0], *b = di_io[nth][1], *c = gi_io[nth][0], *g = gi_io[nth][1];
-            const bool batched = ((e->wavelet_batched >> nth) & 1) != 0;
-            const bool tiled = !batched && ((e->wavelet_tiled >> nth) & 1) != 0; const int cfg = (e->wavelet_cfg >> (4 * nth)) & 15;
+            const bool tiled = ((e->wavelet_tiled >> nth) & 1) != 0; const int cfg = (e->wavelet_cfg >> (4 * nth)) & 15;
             uint32_t* terr = (uint32_t*)e->d_tile_errors.p;
             const CameraDev camW = grown(cam, x.wavelet[nth]);
             add(P_DENOISE_WAVELET, [=](cudaStream_t s) {
-                if (batched && camW.curr.screen.x == (float)camW.w && camW.curr.screen.y == (float)camW.h) { launch_denoise_wavelet_batched(camW, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s); return; }
                 if (tiled && launch_denoise_wavelet_tiled(camW, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, cfg, terr, s)) { e->wavelet_tiled_launches++; return; }
                 launch_denoise_wavelet(camW, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s);
             });
@@ -1454,7 +1451,6 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
     if (option == ST_OPT_FUSED_PASSES) { e->fused_passes = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
-    if (option == ST_OPT_WAVELET_BATCHED) { e->wavelet_batched = value & 31; return ST_OK; }
     if (option == ST_OPT_VARIANCE_TILED) { e->variance_tiled = value != 0; return ST_OK; }
     if (option == ST_OPT_BVH_REUSE) { e->bvh_reuse = value != 0; return ST_OK; }
     if (option == ST_OPT_FUSE_REPROJECT) { e->fuse_reproject = value != 0; return ST_OK; }
@@ -1499,6 +1495,13 @@ int st_get_stat(st_engine* e, int stat, uint64_t* value) {
     if (stat == ST_STAT_WAVELET_TILED_LAUNCHES) { *value = e->wavelet_tiled_launches; return ST_OK; }
     if (stat == ST_STAT_VARIANCE_TILED_LAUNCHES) { *value = e->variance_tiled_launches; return ST_OK; }
     if (stat == ST_STAT_BVH_GRAFTED_SUBTREES) { *value = e->bvh.grafted; return ST_OK; }
+    if (stat == ST_STAT_STRIP_PULLED_ROWS) {   // rows of last frame's buffers this rank fetched from their owners so far (fused strip transport, all cameras)
+        CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
+        uint64_t total = 0;
+        for (CameraSlot* c : e->cameras) if (c->alive && c->peer.sync.p) { uint64_t v = 0; CK(cudaMemcpy(&v, (uint32_t*)c->peer.sync.p + kPulledRowsWord, 8, cudaMemcpyDeviceToHost)); total += v; }
+        *value = total; return ST_OK;
+    }
+    if (stat == ST_STAT_LAST_FRAME_FUSED_STRIPS) { *value = e->last_frame_fused ? 1 : 0; return ST_OK; }
     if (stat == ST_STAT_WAVELET_TILED_ERRORS) {
         CK(cudaSetDevice(e->device));
         CK(cudaStreamSynchronize(e->stream));

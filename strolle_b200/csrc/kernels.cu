@@ -1205,62 +1205,6 @@ __global__ void __launch_bounds__(TW * TH, (TW * TH <= 256 && S <= 8) ? ST_WAVEL
     ctr.store(di_out, gi_out, i);
 }
 
-// ---------------------------------------------------------------------------------------------
-// K22, batched-gather variant (large strides, where a tile of the jittered 3x3 footprint does not pay): the eight tap addresses are
-// known before anything is loaded (jitter from the blue-noise texel), so all eight (normal, depth) loads are issued back to back,
-// then the colour loads of the taps that survived the geometry test, four taps at a time — 8 to 16 independent 16-byte gathers in
-// flight per thread instead of one dependent chain per tap.  Same taps, order and arithmetic as k_denoise_wavelet (WaveletCentre).
-// ---------------------------------------------------------------------------------------------
-#ifndef ST_WAVELET_BATCHED_MINB
-#define ST_WAVELET_BATCHED_MINB 8
-#endif
-template <bool FAST>
-__global__ void __launch_bounds__(ST_BLOCK, ST_WAVELET_BATCHED_MINB) k_denoise_wavelet_batched(KPARAMS, u32 frame, u32 stride, float strength,
-                                                                       const float4* __restrict__ di_in, float4* __restrict__ di_out,
-                                                                       const float4* __restrict__ gi_in, float4* __restrict__ gi_out) {
-    Px p = pixel_full(cam);
-    if (!p.in) return;
-    const size_t i = pix(cam, p.x, p.y);
-    const float4* __restrict__ snd = cam.surface_nd;
-    float4 cnd = snd[i];
-    float4 cdi = di_in[i];
-    if (cnd.w == 0.0f) { di_out[i] = f4(xyz(cdi), cdi.w); return; }
-    float4 bn = blue_noise(sc, p.x, p.y, frame);
-    float4 cgi = gi_in[i];
-    float2 jf = (f2(bn.z, bn.w) - f2(0.5f, 0.5f)) * ((float)stride - 1.0f) * 0.5f;
-    const int jx = to_i32_sat(jf.x), jy = to_i32_sat(jf.y);
-    const int sw = to_i32_sat(cam.curr.screen.x), sh = to_i32_sat(cam.curr.screen.y);
-    int at[8]; u32 live = 0u;
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-        const int k = t < 4 ? t : t + 1, ox = k % 3 - 1, oy = k / 3 - 1;   // row-major 3x3 without the centre
-        int sx = (int)p.x + jx + ox * (int)stride, sy = (int)p.y + jy + oy * (int)stride;
-        if (sx >= 0 && sy >= 0 && sx < sw && sy < sh) live |= 1u << t;      // Camera::contains (camera.rs:43-55)
-        sx = max(0, min(sx, cam.w - 1)); sy = max(0, min(sy, cam.h - 1));   // an address that is always valid; the value is ignored when !live
-        at[t] = sy * cam.w + sx;
-    }
-    float4 nd[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) nd[t] = snd[at[t]];
-    WaveletCentre<FAST> ctr;
-    ctr.init(cnd, cdi, cgi, 0.33f / strength);
-    float dw[8], nw[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) {
-        dw[t] = 0.0f; nw[t] = 0.0f;
-        if (!((live >> t) & 1u) || nd[t].w == 0.0f || !ctr.geometry(nd[t], &dw[t], &nw[t])) live &= ~(1u << t);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        float4 a[4], b[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int t = 4 * h + k; if ((live >> t) & 1u) { a[k] = di_in[at[t]]; b[k] = gi_in[at[t]]; } else { a[k] = f4zero(); b[k] = f4zero(); } }
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int t = 4 * h + k; if ((live >> t) & 1u) ctr.add(dw[t], nw[t], a[k], b[k]); }
-    }
-    ctr.store(di_out, gi_out, i);
-}
-
 // R2 frame_composition::fs (frame_composition.rs:19-82), linear HDR out
 __global__ void __launch_bounds__(ST_BLOCK) k_composition(KPARAMS, int cur, u32 mode, const float4* __restrict__ di_diff, const float4* __restrict__ gi_diff) {
     Px p = pixel_full(cam);
@@ -1633,10 +1577,6 @@ void launch_denoise_variance(const CameraDev& c, const SceneDev& s, int cur, boo
 void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, bool fast, cudaStream_t st) {
     if (fast) k_denoise_wavelet<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
     else k_denoise_wavelet<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
-}
-void launch_denoise_wavelet_batched(const CameraDev& c, const SceneDev& s, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, bool fast, cudaStream_t st) {
-    if (fast) k_denoise_wavelet_batched<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, frame, stride, strength, di_in, di_out, gi_in, gi_out);
-    else k_denoise_wavelet_batched<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, frame, stride, strength, di_in, di_out, gi_in, gi_out);
 }
 // K21, tile-staged: the 6x5 window of frame_denoising::estimate_variance (quirk C-3: row -2 spans x in [-2,2], rows -1..2 span
 // x in [-3,2]) is only walked by pixels whose history is shorter than 4 frames, but a warp pays for it as soon as one of its

@@ -774,6 +774,10 @@ def test_multi_device_group_matches_single_gpu(gpu, blue_noise, n, size, exact, 
     assert grp.peer_errors(cn) == 0
     vel = one.read_buffer(c1, "velocity_map").reshape(h, w, 4)
     assert np.abs(vel[..., 1]).max() > 16.0, "the jump moved pixels by more than 16 rows"
+    if fused:
+        from strolle_b200.engine import STAT_STRIP_PULLED_ROWS, STAT_LAST_FRAME_FUSED_STRIPS
+        assert all(grp.member(r).get_stat(STAT_LAST_FRAME_FUSED_STRIPS) == 1 for r in range(n)), "the fused transport is what ran"
+        assert sum(grp.member(r).get_stat(STAT_STRIP_PULLED_ROWS) for r in range(n)) > 0, "the moving frames pulled rows from their owners"
     a, b = np.zeros((h, w, 4), np.uint8), np.zeros((h, w, 4), np.uint8)
     one.tick(); grp.tick()
     one.render_camera(c1, a, FORMAT_RGBA8_SRGB); grp.render_camera(cn, b, FORMAT_RGBA8_SRGB)
@@ -820,19 +824,3 @@ def test_fused_passes_bit_exact(gpu, oracle, blue_noise, scene_name, size):
         assert len(eg.frame_schedule(cg)) <= 18, "fused schedule"
         for name in names:
             assert_bits_equal(eg.read_buffer(cg, name), eo.read_buffer(co, name), f"fused passes {scene_name} {size} frame {f + 1} {name}")
-
-
-@pytest.mark.parametrize("exact", [True, False])
-def test_batched_wavelet_matches_gather(gpu, blue_noise, exact):
-    """K22's batched-gather kernel (ST_OPT_WAVELET_BATCHED: all tap addresses first, then 8-16 gathers in flight) gives the bits of the
-    per-tap gather kernel for every stride, in both arithmetic flavours, on sizes with partial tiles and mirrored borders."""
-    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_WAVELET_BATCHED
-    for size in [(200, 120), (67, 45)]:
-        scene = scenes.cornell(*size)
-        ea, eb = gpu.Engine(blue_noise=blue_noise, exact=exact), gpu.Engine(blue_noise=blue_noise, exact=exact)
-        ea.set_option(OPT_WAVELET_TILED, 0); eb.set_option(OPT_WAVELET_BATCHED, 31)
-        ca, cb = scenes.apply(ea, scene), scenes.apply(eb, scene)
-        for f in range(4):
-            ea.tick(); eb.tick(); ea.render_camera(ca); eb.render_camera(cb)
-            for name in DENOISER_BUFFERS:
-                assert_bits_equal(eb.read_buffer(cb, name), ea.read_buffer(ca, name), f"{size} frame {f + 1} {name}")
