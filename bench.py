@@ -325,26 +325,43 @@ def measure(ctx, scene, steps, warmup, detail=False, e2e=False, clocks=None):
         eng.set_option(OPT_ASYNC_OUTPUT, 0)
         out["e2e_fps"] = steps * 1000.0 / e2e_ms
         out["e2e_frame_mean"] = float(host[(steps - 1) & 1][..., :3].mean()) if ctx.rank == 0 else None
-        if ctx.world > 1:   # strip parity: the frame the ranks just delivered vs a single-GPU render of the same frame id on rank 0
-            eng.tick(); runner.render(out=host[0], fmt=FORMAT_RGBA8_SRGB); ctx.barrier(eng)
-            ok = None
-            if ctx.rank == 0:
-                solo = strolle_b200.Engine(device=ctx.local)
-                scam = scenes.apply(solo, scene)
-                want = np.zeros((H, W, 4), np.uint8)
-                n_frames = eng.frame() - 1
-                for _ in range(n_frames):
-                    solo.tick()
-                    solo.render_camera(scam)
-                solo.copy_output(scam, want, FORMAT_RGBA8_SRGB)
-                ok = bool((want == host[0]).all())
-                solo.close()
-            out["strip_parity_ok"] = ok
+        if ctx.world > 1:
             out["peer_errors"] = eng.peer_errors(cam) if runner.peer else 0
-            ctx.barrier(eng)
     out["engine"] = eng
     out["cam"] = cam
     return out
+
+
+def strip_parity(ctx, scene, frames=8):
+    """N > 1: fresh strip engines render `frames` frames and deliver the last one into the shared host frame; rank 0 renders the same
+    frames on ONE GPU from the same initial state.  True iff the two Rgba8UnormSrgb frames are identical (outside any timed region)."""
+    import numpy as np
+    import strolle_b200
+    from strolle_b200 import scenes
+    from strolle_b200.engine import FORMAT_RGBA8_SRGB
+    from strolle_b200.multigpu import StripRunner
+    c = scene["camera"]
+    W, H = c["w"], c["h"]
+    eng = strolle_b200.Engine(device=ctx.local)
+    cam = scenes.apply(eng, scene)
+    runner = StripRunner(eng, cam, W, H, ctx.rank, ctx.world)
+    host = ctx.host_frame(H, W, 1)[0]
+    for f in range(frames):
+        eng.tick(); runner.render(out=host if f == frames - 1 else None, fmt=FORMAT_RGBA8_SRGB)
+    ctx.barrier(eng)
+    ok = None
+    if ctx.rank == 0:
+        solo = strolle_b200.Engine(device=ctx.local)
+        scam = scenes.apply(solo, scene)
+        want = np.zeros((H, W, 4), np.uint8)
+        for f in range(frames):
+            solo.tick(); solo.render_camera(scam, want if f == frames - 1 else None, FORMAT_RGBA8_SRGB)
+        ok = bool((want == host).all()) and int(want[..., :3].max()) > 0
+        solo.close()
+    errors = eng.peer_errors(cam) if runner.peer else 0
+    ctx.barrier(eng)
+    eng.close()
+    return ok, errors
 
 
 def c5_reference_mode(ctx, spp):
@@ -391,6 +408,9 @@ def main():
     main_m = measure(ctx, build_scene(args.scene, W, H), args.steps, args.warmup, detail=True, e2e=True, clocks=clocks)
     clk = clocks.stop() if rank == 0 else None
     eng = main_m["engine"]
+    if world > 1:
+        main_m["strip_parity_ok"], perr = strip_parity(ctx, build_scene(args.scene, W, H))
+        main_m["peer_errors"] = (main_m.get("peer_errors") or 0) + perr
 
     # ---- BVH trace on its own (rank 0 engine; the ray-stream entry point) ------------------------------------------------------
     traversal = None

@@ -918,6 +918,9 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
         e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_signal(ss, slot, seq, mask, rn, H, s); });
     };
     auto wait = [&](int slot, uint32_t mask, uint32_t value) { e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_wait(ss, slot, value, mask, s); }); };
+    auto signal_wait = [&](int sig_slot, uint32_t sig_mask, int wait_slot, uint32_t wait_mask, uint32_t value) {
+        e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_signal_wait(ss, sig_slot, seq, sig_mask, wait_slot, value, wait_mask, s); });
+    };
     auto emit = [&](const Step& st) { e->run_timed(st.pass, st.run, st.sub); };
 
     // split the reference order into the blocks the interleaving moves around
@@ -963,11 +966,15 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     for (auto* st : di1) emit(*st);
     if (!di1.empty()) signal(SLOT_DI1, nb);
     for (auto* st : gi1) emit(*st);
-    if (!gi1.empty()) signal(SLOT_GI1, nb);
-    if (!di_pick.empty()) { wait(SLOT_DI1, nb, seq); for (auto* st : di_pick) emit(*st); }
+    if (!gi1.empty() && !di_pick.empty()) signal_wait(SLOT_GI1, nb, SLOT_DI1, nb, seq);
+    else if (!gi1.empty()) signal(SLOT_GI1, nb);
+    else if (!di_pick.empty()) wait(SLOT_DI1, nb, seq);
+    for (auto* st : di_pick) emit(*st);
     if (!gi1.empty()) wait(SLOT_GI1, nb, seq);
-    if (!gi_sp.empty()) { for (auto* st : gi_sp) emit(*st); signal(SLOT_GI2, nb); }
-    wait(SLOT_PULL_DONE, all, seq);   // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
+    for (auto* st : gi_sp) emit(*st);
+    // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
+    if (!gi_sp.empty()) signal_wait(SLOT_GI2, nb, SLOT_PULL_DONE, all, seq);
+    else wait(SLOT_PULL_DONE, all, seq);
     if (!di_rest.empty()) emit(*di_rest[0]);
     if (!gi_sp.empty()) wait(SLOT_GI2, nb, seq);
     for (auto* st : pv1) emit(*st);
@@ -978,7 +985,7 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     // SVGF: K20 mirrors its rows, then everything downstream is recomputed locally
     bool svgf_waited = false;
     for (auto* st : post) {
-        if ((st->pass == P_DENOISE_VARIANCE) && !svgf_waited) { signal(SLOT_SVGF, nb); wait(SLOT_SVGF, nb, seq); svgf_waited = true; }
+        if ((st->pass == P_DENOISE_VARIANCE) && !svgf_waited) { signal_wait(SLOT_SVGF, nb, SLOT_SVGF, nb, seq); svgf_waited = true; }
         emit(*st);
     }
     signal(SLOT_FRAME_DONE, all);

@@ -1815,8 +1815,25 @@ __global__ void __launch_bounds__(256) k_strip_pull(const __grid_constant__ Stri
         size_t off = it.offset + ((size_t)row * per_row + col) * 16;
         *reinterpret_cast<uint4*>(p.arena[p.rank] + off) = *reinterpret_cast<const uint4*>(p.arena[owner] + off);
     }
-    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && (nup + ndn) > 0) atomicAdd(p.pulled_rows, (unsigned long long)(nup + ndn));
+    // statistics: rows of last frame this strip reached into, beyond its own (whatever part of them a buffer then had to fetch)
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) { int reach = max(0, p.own_y0 - lo) + max(0, hi + 1 - p.own_y1); if (reach > 0) atomicAdd(p.pulled_rows, (unsigned long long)reach); }
 }
+// a signal and a wait that follow each other on the stream, as one launch
+__global__ void __launch_bounds__(32) k_strip_signal_wait(const __grid_constant__ StripSync s, int sig_slot, u32 seq, u32 dst_mask, int wait_slot, u32 wait_seq, u32 src_mask) {
+    __threadfence_system();
+    int r = (int)threadIdx.x;
+    if (r < s.n_ranks && r != s.rank && ((dst_mask >> r) & 1u) && s.peer_flags[r] != nullptr) st_release_sys(s.peer_flags[r] + sig_slot * ST_PEER_MAX_RANKS + s.rank, seq);
+    if (r < s.n_ranks && r != s.rank && ((src_mask >> r) & 1u)) {
+        const u32* f = s.my_flags + wait_slot * ST_PEER_MAX_RANKS + r;
+        long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - wait_seq) < 0) {
+            if (clock64() - t0 > 20000000000ll) { atomicAdd(s.errors, 1u); break; }
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
+}
+void launch_strip_signal_wait(const StripSync& s, int sig_slot, u32 seq, u32 dst_mask, int wait_slot, u32 wait_seq, u32 src_mask, cudaStream_t st) { k_strip_signal_wait<<<1, 32, 0, st>>>(s, sig_slot, seq, dst_mask, wait_slot, wait_seq, src_mask); }
 void launch_strip_signal(const StripSync& s, int slot, u32 seq, u32 dst_mask, int* reset_need, int h, cudaStream_t st) { k_strip_signal<<<1, 32, 0, st>>>(s, slot, seq, dst_mask, reset_need, h); }
 void launch_strip_wait(const StripSync& s, int slot, u32 seq, u32 src_mask, cudaStream_t st) { k_strip_wait<<<1, 32, 0, st>>>(s, slot, seq, src_mask); }
 void launch_strip_pull(const StripPull& p, cudaStream_t st) { if (p.nitems > 0) k_strip_pull<<<dim3(48, (unsigned)p.nitems), 256, 0, st>>>(p); }

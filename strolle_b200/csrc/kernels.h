@@ -78,6 +78,7 @@ struct StripPull {
 };
 void launch_strip_signal(const StripSync& s, int slot, u32 seq, u32 dst_mask, int* reset_need, int h, cudaStream_t st);
 void launch_strip_wait(const StripSync& s, int slot, u32 seq, u32 src_mask, cudaStream_t st);
+void launch_strip_signal_wait(const StripSync& s, int sig_slot, u32 seq, u32 dst_mask, int wait_slot, u32 wait_seq, u32 src_mask, cudaStream_t st);
 void launch_strip_pull(const StripPull& p, cudaStream_t st);
 void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st);
 

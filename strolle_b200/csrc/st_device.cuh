@@ -18,6 +18,11 @@ using namespace st;   // the POD layouts of st_types.h
 #define ST_REACH_SVGF 38         // K21 (3 rows) + the five K22 iterations (1 + 2 + 4 + 9 + 19 = 35) recomputed on the receiving side
 
 ST_DEV float4 ldg4(const float4* p) { return __ldg(p); }
+// Reservoir entries are 32 B (DI) / 64 B (GI), 32-byte aligned: moved with 256-bit accesses (LDG / STG.E.ENL2.256 on sm_100a), which halves
+// the requests of the scattered reservoir gathers and makes the mirrored stores to a neighbouring GPU full 32-byte sectors on NVLink.
+struct __align__(32) F8 { float4 a, b; };
+ST_DEV F8 ld8(const float4* p) { return *reinterpret_cast<const F8*>(p); }
+ST_DEV void st8(float4* p, float4 a, float4 b) { F8 v; v.a = a; v.b = b; *reinterpret_cast<F8*>(p) = v; }
 
 // ---- Normal (strolle-gpu/src/normal.rs:9-34) --------------------------------
 ST_DEV float2 oct_encode(float3 n) {
@@ -643,15 +648,15 @@ ST_DEV float3 atmosphere_sample(const SceneDev& sc, float3 sun_dir, float3 ray_d
 struct DiRes { float m, w; float pdf, confidence; u32 light_id; float3 light_point; bool occluded; };
 ST_DEV DiRes di_zero() { DiRes r; r.m = 0.f; r.w = 0.f; r.pdf = 0.f; r.confidence = 0.f; r.light_id = 0u; r.light_point = f3s(0.f); r.occluded = false; return r; }
 ST_DEV DiRes di_load(const float4* __restrict__ buf, size_t id) {   // di.rs:17-35
-    float4 d0 = buf[2 * id], d1 = buf[2 * id + 1];
+    F8 e = ld8(buf + 2 * id);
+    float4 d0 = e.a, d1 = e.b;
     u32 b = fbits(d0.w);
     DiRes r; r.m = d0.x; r.w = d0.y; r.pdf = d0.z; r.confidence = (float)((b >> 8) & 0xffu); r.occluded = (b & 0xffu) > 0u;
     r.light_point = xyz(d1); r.light_id = fbits(d1.w);
     return r;
 }
 ST_DEV void di_store(const DiRes& r, float4* __restrict__ buf, size_t id) {   // di.rs:37-59
-    buf[2 * id] = f4(r.m, r.w, r.pdf, bitsf(pack_bytes(r.occluded ? 1u : 0u, to_u32_sat(r.confidence), 0u, 0u)));
-    buf[2 * id + 1] = f4(r.light_point, bitsf(r.light_id));
+    st8(buf + 2 * id, f4(r.m, r.w, r.pdf, bitsf(pack_bytes(r.occluded ? 1u : 0u, to_u32_sat(r.confidence), 0u, 0u))), f4(r.light_point, bitsf(r.light_id)));
 }
 // ---- strip partition: a store that also lands in the neighbouring strips' copy when the row is within `reach` of an edge ----
 ST_DEV void mirror4(const CameraDev& cam, float4* p, float4 v, u32 y, int reach) {
@@ -659,9 +664,13 @@ ST_DEV void mirror4(const CameraDev& cam, float4* p, float4 v, u32 y, int reach)
     if (cam.mirror_dn != 0 && (int)y >= cam.own_y1 - reach) *reinterpret_cast<float4*>(reinterpret_cast<char*>(p) + cam.mirror_dn) = v;
 }
 ST_DEV void store4m(const CameraDev& cam, float4* p, float4 v, u32 y, int reach) { *p = v; mirror4(cam, p, v, y, reach); }
+ST_DEV void store8m(const CameraDev& cam, float4* p, float4 a, float4 b, u32 y, int reach) {
+    st8(p, a, b);
+    if (cam.mirror_up != 0 && (int)y < cam.own_y0 + reach) st8(reinterpret_cast<float4*>(reinterpret_cast<char*>(p) + cam.mirror_up), a, b);
+    if (cam.mirror_dn != 0 && (int)y >= cam.own_y1 - reach) st8(reinterpret_cast<float4*>(reinterpret_cast<char*>(p) + cam.mirror_dn), a, b);
+}
 ST_DEV void di_store_m(const CameraDev& cam, const DiRes& r, float4* __restrict__ buf, size_t id, u32 y, int reach) {
-    store4m(cam, buf + 2 * id, f4(r.m, r.w, r.pdf, bitsf(pack_bytes(r.occluded ? 1u : 0u, to_u32_sat(r.confidence), 0u, 0u))), y, reach);
-    store4m(cam, buf + 2 * id + 1, f4(r.light_point, bitsf(r.light_id)), y, reach);
+    store8m(cam, buf + 2 * id, f4(r.m, r.w, r.pdf, bitsf(pack_bytes(r.occluded ? 1u : 0u, to_u32_sat(r.confidence), 0u, 0u))), f4(r.light_point, bitsf(r.light_id)), y, reach);
 }
 // Reservoir::update specialised: copies sample fields of `s` into `dst` on acceptance (reservoir.rs:24-39)
 ST_DEV bool di_update(DiRes& dst, Rng& rng, const DiRes& s, float weight) {
@@ -680,24 +689,21 @@ ST_DEV Ray di_ray(const DiRes& s, float3 hit_point) { float3 d = hit_point - s.l
 struct GiRes { float m, w, confidence; float pdf; u32 rng; float3 radiance, v1, v2, v2n; };
 ST_DEV GiRes gi_zero() { GiRes r; r.m = 0.f; r.w = 0.f; r.confidence = 0.f; r.pdf = 0.f; r.rng = 0u; r.radiance = f3s(0.f); r.v1 = f3s(0.f); r.v2 = f3s(0.f); r.v2n = f3s(0.f); return r; }
 ST_DEV GiRes gi_load(const float4* __restrict__ buf, size_t id) {   // gi.rs:19-40
-    float4 d0 = buf[4 * id], d1 = buf[4 * id + 1], d2 = buf[4 * id + 2], d3 = buf[4 * id + 3];
+    F8 e0 = ld8(buf + 4 * id), e1 = ld8(buf + 4 * id + 2);
+    float4 d0 = e0.a, d1 = e0.b, d2 = e1.a, d3 = e1.b;
     GiRes r; r.radiance = xyz(d0); r.m = d0.w; r.v1 = xyz(d1); r.w = d1.w; r.v2 = xyz(d2); r.pdf = d2.w;
     r.v2n = oct_decode(f2(d3.x, d3.y)); r.confidence = d3.z; r.rng = fbits(d3.w);
     return r;
 }
 ST_DEV void gi_store(const GiRes& r, float4* __restrict__ buf, size_t id) {   // gi.rs:42-57
     float2 n = oct_encode(r.v2n);
-    buf[4 * id] = f4(r.radiance, r.m);
-    buf[4 * id + 1] = f4(r.v1, r.w);
-    buf[4 * id + 2] = f4(r.v2, r.pdf);
-    buf[4 * id + 3] = f4(n.x, n.y, r.confidence, bitsf(r.rng));
+    st8(buf + 4 * id, f4(r.radiance, r.m), f4(r.v1, r.w));
+    st8(buf + 4 * id + 2, f4(r.v2, r.pdf), f4(n.x, n.y, r.confidence, bitsf(r.rng)));
 }
 ST_DEV void gi_store_m(const CameraDev& cam, const GiRes& r, float4* __restrict__ buf, size_t id, u32 y, int reach) {
     float2 n = oct_encode(r.v2n);
-    store4m(cam, buf + 4 * id, f4(r.radiance, r.m), y, reach);
-    store4m(cam, buf + 4 * id + 1, f4(r.v1, r.w), y, reach);
-    store4m(cam, buf + 4 * id + 2, f4(r.v2, r.pdf), y, reach);
-    store4m(cam, buf + 4 * id + 3, f4(n.x, n.y, r.confidence, bitsf(r.rng)), y, reach);
+    store8m(cam, buf + 4 * id, f4(r.radiance, r.m), f4(r.v1, r.w), y, reach);
+    store8m(cam, buf + 4 * id + 2, f4(r.v2, r.pdf), f4(n.x, n.y, r.confidence, bitsf(r.rng)), y, reach);
 }
 ST_DEV void gi_take_sample(GiRes& dst, const GiRes& s) { dst.pdf = s.pdf; dst.rng = s.rng; dst.radiance = s.radiance; dst.v1 = s.v1; dst.v2 = s.v2; dst.v2n = s.v2n; }
 ST_DEV bool gi_update(GiRes& dst, Rng& rng, const GiRes& s, float weight) {
