@@ -287,11 +287,16 @@ def measure(ctx, scene, steps, warmup, detail=False, e2e=False, clocks=None):
     wav_ms, wav_launches = eng.wavelet_times(reset=True)
     rays = eng.ray_count(reset=True)
     eng.enable_timing(False); eng.count_rays(False)
+    per_rank = None
+    if ctx.dist:   # every rank's own per-pass times: shows how much of the exchange time is waiting for a slower neighbour (content imbalance between strips)
+        mine = {"compute_ms_per_frame": float(pass_ms.sum() - pass_ms[26]) / steps, "halo_exchange_ms_per_frame": float(pass_ms[26]) / steps}
+        per_rank = [None] * ctx.world
+        ctx.dist.all_gather_object(per_rank, mine)
     dev_ms, wall_ms = ctx.reduce([dev_ms, wall_ms], "max")
     rays, total_launches = ctx.reduce([float(rays), float(launches.sum())], "sum")
     out = {"w": W, "h": H, "rows": runner.y1 - runner.y0, "ms_per_step": dev_ms / steps, "fps": 1000.0 * steps / dev_ms, "wall_ms_per_step": wall_ms / steps,
            "rays_per_frame": rays / steps, "mrays": rays / (dev_ms / 1000.0) / 1e6, "launches": int(total_launches), "pass_ms": pass_ms, "pass_launches": launches,
-           "wav_ms": wav_ms, "wav_launches": wav_launches, "halo_bytes": runner.halo_bytes_last_frame, "transport": runner.transport_name()}
+           "wav_ms": wav_ms, "wav_launches": wav_launches, "halo_bytes": runner.halo_bytes_last_frame, "transport": runner.transport_name(), "per_rank": per_rank}
     if detail:   # every kernel strict IEEE, one launch per reference dispatch: the configuration that is bit-identical to the oracle
         for opt in (OPT_SVGF_FAST_MATH, OPT_SHADING_FAST_MATH, OPT_FUSED_PASSES):
             eng.set_option(opt, 0)
@@ -516,7 +521,7 @@ def main():
         "arithmetic": "product default: ReSTIR shading (K5-K19) and SVGF weights with FMA + SFU approximations inside north_star's 1e-3 tolerance, fused launches; traversal / primary pass / "
                       "reprojection strict IEEE.  exact_ms_per_step = every kernel strict IEEE, one launch per reference dispatch, bit-identical to the oracle",
         "rays_per_frame": main_m["rays_per_frame"], "wall_ms_per_step": main_m["wall_ms_per_step"], "halo_bytes_per_frame_rank0": main_m["halo_bytes"],
-        "strip_parity_ok": main_m.get("strip_parity_ok"), "peer_errors": main_m.get("peer_errors"),
+        "strip_parity_ok": main_m.get("strip_parity_ok"), "peer_errors": main_m.get("peer_errors"), "per_rank": main_m.get("per_rank"),
         "clocks": clk,
         "e2e": {"value": main_m["rays_per_frame"] * e2e_fps / 1e6, "unit": "Mrays/s", "fps": e2e_fps, "h2d_bytes_per_step": 148 * world, "d2h_bytes_per_step": W * H * 4,
                 "note": "per step: st_update_camera (148 B host camera struct per rank) + st_tick + st_render_strips(host frame, gather 2): every rank converts its own rows to Rgba8UnormSrgb and "

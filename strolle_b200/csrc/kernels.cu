@@ -31,15 +31,23 @@ namespace ST_NS {
 #define TILE_H 8
 
 struct Px { u32 x, y; bool in; };
+// Row tile of this CTA.  In a strip that mirrors rows into the strip below it, the CTAs are rotated so that the bottom boundary rows are
+// computed FIRST (the top boundary rows follow, the interior last): the remote stores of both boundaries drain over NVLink while the
+// interior is still computing, instead of at the very end of the kernel.
+ST_DEV u32 row_tile(const CameraDev& cam) {
+    if (cam.mirror_dn == 0) return blockIdx.y;
+    const u32 lead = (u32)(ST_REACH_SPATIAL / TILE_H);
+    return gridDim.y > lead ? (blockIdx.y + gridDim.y - lead) % gridDim.y : blockIdx.y;
+}
 ST_DEV Px pixel_full(const CameraDev& cam) {
-    Px p; p.x = blockIdx.x * TILE_W + (threadIdx.x % TILE_W); p.y = (u32)cam.y0 + blockIdx.y * TILE_H + (threadIdx.x / TILE_W);
+    Px p; p.x = blockIdx.x * TILE_W + (threadIdx.x % TILE_W); p.y = (u32)cam.y0 + row_tile(cam) * TILE_H + (threadIdx.x / TILE_W);
     p.in = p.x < (u32)cam.w && p.y < (u32)cam.y1;
     return p;
 }
 // half-width checkerboard dispatch of the reference: gid.x < 8*(((W+7)/8)/2), gid.y < 8*((H+7)/8)
 ST_DEV int half_grid_w(int w) { return 8 * (((w + 7) / 8) / 2); }
 ST_DEV Px pixel_half(const CameraDev& cam) {
-    Px p; p.x = blockIdx.x * TILE_W + (threadIdx.x % TILE_W); p.y = (u32)cam.y0 + blockIdx.y * TILE_H + (threadIdx.x / TILE_W);
+    Px p; p.x = blockIdx.x * TILE_W + (threadIdx.x % TILE_W); p.y = (u32)cam.y0 + row_tile(cam) * TILE_H + (threadIdx.x / TILE_W);
     p.in = p.x < (u32)half_grid_w(cam.w) && p.y < (u32)cam.y1;
     return p;
 }
@@ -73,97 +81,68 @@ ST_DEV Hit load_hit_lut(const SceneDev& sc, const GpuCamera& c, const float4* __
 #define ST_MINB_GI_SPATIAL_PICK 8
 #define ST_MINB_DI_TEMPORAL 12
 #endif
+// ST_LB_<K>: -DST_MINB_ALL=N beats a per-kernel ST_MINB_<K>, which beats ptxas' own choice.  The preprocessor cannot test a macro whose
+// name is pasted together, so the three-way choice is spelled once per kernel through ST_LB_PICK (0 = "no minimum").
+#define ST_LB_PICK(per_kernel) ST_LB_CHOOSE(ST_MINB_ALL_OR_0, per_kernel)
 #if defined(ST_MINB_ALL)
-#define ST_LB_PRIM_GBUFFER ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_PRIM_GBUFFER)
-#define ST_LB_PRIM_GBUFFER ST_LB_N(ST_MINB_PRIM_GBUFFER)
+#define ST_MINB_ALL_OR_0 ST_MINB_ALL
 #else
-#define ST_LB_PRIM_GBUFFER __launch_bounds__(ST_BLOCK)
+#define ST_MINB_ALL_OR_0 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_DI_SAMPLING ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_DI_SAMPLING)
-#define ST_LB_DI_SAMPLING ST_LB_N(ST_MINB_DI_SAMPLING)
-#else
-#define ST_LB_DI_SAMPLING __launch_bounds__(ST_BLOCK)
+template <int ALL, int ONE> struct LbMin { static constexpr int value = ALL > 0 ? ALL : ONE; };
+#define ST_LB_CHOOSE(all, one) __launch_bounds__(ST_BLOCK, (LbMin<all, one>::value > 0 ? LbMin<all, one>::value : 1))
+#ifndef ST_MINB_PRIM_GBUFFER
+#define ST_MINB_PRIM_GBUFFER 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_DI_TEMPORAL ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_DI_TEMPORAL)
-#define ST_LB_DI_TEMPORAL ST_LB_N(ST_MINB_DI_TEMPORAL)
-#else
-#define ST_LB_DI_TEMPORAL __launch_bounds__(ST_BLOCK)
+#define ST_LB_PRIM_GBUFFER ST_LB_PICK(ST_MINB_PRIM_GBUFFER)
+#ifndef ST_MINB_DI_SAMPLING
+#define ST_MINB_DI_SAMPLING 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_DI_SPATIAL_PICK ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_DI_SPATIAL_PICK)
-#define ST_LB_DI_SPATIAL_PICK ST_LB_N(ST_MINB_DI_SPATIAL_PICK)
-#else
-#define ST_LB_DI_SPATIAL_PICK __launch_bounds__(ST_BLOCK)
+#define ST_LB_DI_SAMPLING ST_LB_PICK(ST_MINB_DI_SAMPLING)
+#ifndef ST_MINB_DI_TEMPORAL
+#define ST_MINB_DI_TEMPORAL 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_SPATIAL_TRACE ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_SPATIAL_TRACE)
-#define ST_LB_SPATIAL_TRACE ST_LB_N(ST_MINB_SPATIAL_TRACE)
-#else
-#define ST_LB_SPATIAL_TRACE __launch_bounds__(ST_BLOCK)
+#define ST_LB_DI_TEMPORAL ST_LB_PICK(ST_MINB_DI_TEMPORAL)
+#ifndef ST_MINB_DI_SPATIAL_PICK
+#define ST_MINB_DI_SPATIAL_PICK 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_DI_RESOLVING ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_DI_RESOLVING)
-#define ST_LB_DI_RESOLVING ST_LB_N(ST_MINB_DI_RESOLVING)
-#else
-#define ST_LB_DI_RESOLVING __launch_bounds__(ST_BLOCK)
+#define ST_LB_DI_SPATIAL_PICK ST_LB_PICK(ST_MINB_DI_SPATIAL_PICK)
+#ifndef ST_MINB_SPATIAL_TRACE
+#define ST_MINB_SPATIAL_TRACE 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_GI_SAMPLING_A ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_GI_SAMPLING_A)
-#define ST_LB_GI_SAMPLING_A ST_LB_N(ST_MINB_GI_SAMPLING_A)
-#else
-#define ST_LB_GI_SAMPLING_A __launch_bounds__(ST_BLOCK)
+#define ST_LB_SPATIAL_TRACE ST_LB_PICK(ST_MINB_SPATIAL_TRACE)
+#ifndef ST_MINB_DI_RESOLVING
+#define ST_MINB_DI_RESOLVING 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_GI_SAMPLING_B ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_GI_SAMPLING_B)
-#define ST_LB_GI_SAMPLING_B ST_LB_N(ST_MINB_GI_SAMPLING_B)
-#else
-#define ST_LB_GI_SAMPLING_B __launch_bounds__(ST_BLOCK)
+#define ST_LB_DI_RESOLVING ST_LB_PICK(ST_MINB_DI_RESOLVING)
+#ifndef ST_MINB_GI_SAMPLING_A
+#define ST_MINB_GI_SAMPLING_A 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_GI_TEMPORAL ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_GI_TEMPORAL)
-#define ST_LB_GI_TEMPORAL ST_LB_N(ST_MINB_GI_TEMPORAL)
-#else
-#define ST_LB_GI_TEMPORAL __launch_bounds__(ST_BLOCK)
+#define ST_LB_GI_SAMPLING_A ST_LB_PICK(ST_MINB_GI_SAMPLING_A)
+#ifndef ST_MINB_GI_SAMPLING_B
+#define ST_MINB_GI_SAMPLING_B 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_GI_SPATIAL_PICK ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_GI_SPATIAL_PICK)
-#define ST_LB_GI_SPATIAL_PICK ST_LB_N(ST_MINB_GI_SPATIAL_PICK)
-#else
-#define ST_LB_GI_SPATIAL_PICK __launch_bounds__(ST_BLOCK)
+#define ST_LB_GI_SAMPLING_B ST_LB_PICK(ST_MINB_GI_SAMPLING_B)
+#ifndef ST_MINB_GI_TEMPORAL
+#define ST_MINB_GI_TEMPORAL 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_GI_SPATIAL_SAMPLE ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_GI_SPATIAL_SAMPLE)
-#define ST_LB_GI_SPATIAL_SAMPLE ST_LB_N(ST_MINB_GI_SPATIAL_SAMPLE)
-#else
-#define ST_LB_GI_SPATIAL_SAMPLE __launch_bounds__(ST_BLOCK)
+#define ST_LB_GI_TEMPORAL ST_LB_PICK(ST_MINB_GI_TEMPORAL)
+#ifndef ST_MINB_GI_SPATIAL_PICK
+#define ST_MINB_GI_SPATIAL_PICK 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_GI_PREVIEW ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_GI_PREVIEW)
-#define ST_LB_GI_PREVIEW ST_LB_N(ST_MINB_GI_PREVIEW)
-#else
-#define ST_LB_GI_PREVIEW __launch_bounds__(ST_BLOCK)
+#define ST_LB_GI_SPATIAL_PICK ST_LB_PICK(ST_MINB_GI_SPATIAL_PICK)
+#ifndef ST_MINB_GI_SPATIAL_SAMPLE
+#define ST_MINB_GI_SPATIAL_SAMPLE 0
 #endif
-#if defined(ST_MINB_ALL)
-#define ST_LB_GI_RESOLVING ST_LB_N(ST_MINB_ALL)
-#elif defined(ST_MINB_GI_RESOLVING)
-#define ST_LB_GI_RESOLVING ST_LB_N(ST_MINB_GI_RESOLVING)
-#else
-#define ST_LB_GI_RESOLVING __launch_bounds__(ST_BLOCK)
+#define ST_LB_GI_SPATIAL_SAMPLE ST_LB_PICK(ST_MINB_GI_SPATIAL_SAMPLE)
+#ifndef ST_MINB_GI_PREVIEW
+#define ST_MINB_GI_PREVIEW 0
 #endif
+#define ST_LB_GI_PREVIEW ST_LB_PICK(ST_MINB_GI_PREVIEW)
+#ifndef ST_MINB_GI_RESOLVING
+#define ST_MINB_GI_RESOLVING 0
+#endif
+#define ST_LB_GI_RESOLVING ST_LB_PICK(ST_MINB_GI_RESOLVING)
 
 #if ST_EXACT_ONLY
 // ---------------------------------------------------------------------------------------------
