@@ -381,6 +381,8 @@ struct CameraSlot {
     // peer-memory link of the strip partition: other ranks' arena / flag / rgba8 allocations mapped through CUDA IPC
     // sync words: [0, 128) fused-transport flags (slot * 16 + source rank), 128.. legacy k_peer_exchange flags, 144 its block counter,
     // 145 its time-outs, 200/201 need_rows {min, max}, 202 fused-transport wait time-outs, 204 (u64) rows pulled
+    // copy-engine pushes of the large GI halos (ST_OPT_STRIP_DMA): one side stream per neighbour (0 = up, 1 = down), `pushed` = the last push issued there
+    cudaStream_t side[2] = {nullptr, nullptr}; cudaEvent_t ev_produced = nullptr, ev_pushed[2] = {nullptr, nullptr}; bool pushed_pending[2] = {false, false};
     struct PeerLink { bool ready = false; bool ipc = false; std::vector<char*> arena, rgba8; std::vector<uint32_t*> flags; DevMem sync; uint32_t seq = 0, fseq = 0; } peer;
 };
 
@@ -429,6 +431,7 @@ struct st_engine {
     bool fused_passes = ST_FUSED_PASSES_DEFAULT != 0;   // ST_OPT_FUSED_PASSES
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
+    bool strip_dma = ST_STRIP_DMA_DEFAULT != 0;   // ST_OPT_STRIP_DMA: gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores
     bool strip_fused = true;     // ST_OPT_STRIP_FUSED: mirror stores + neighbour flags + recompute instead of stand-alone exchanges
     bool last_frame_fused = false;
     int wavelet_tiled = ST_WAVELET_TILED_DEFAULT;   // ST_OPT_WAVELET_TILED: bit i = à-trous iteration i (stride 2^i) runs the tile-staged (TMA) kernel
@@ -628,7 +631,7 @@ static int allocate_camera(st_engine* e, CameraSlot* cs) {
     size_t off = 0;
     for (size_t i = 0; i < cs->named.size(); i++) { *cs->named[i].second = (float4*)((char*)cs->arena.p + off); off += (cs->sizes[i].second * 16 + 255) / 256 * 256; }
     d.w = (int)cs->desc.width; d.h = (int)cs->desc.height; d.y0 = 0; d.y1 = d.h;
-    d.own_y0 = 0; d.own_y1 = d.h; d.mirror_up = 0; d.mirror_dn = 0; d.need_rows = nullptr;
+    d.own_y0 = 0; d.own_y1 = d.h; d.mirror_up = 0; d.mirror_dn = 0; d.need_rows = nullptr; d.gi_mirror_reach = 128;
     return ST_OK;
 }
 
@@ -904,6 +907,14 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     d.mirror_up = R > 0 ? (long long)(cs->peer.arena[R - 1] - cs->peer.arena[R]) : 0;
     d.mirror_dn = R + 1 < N ? (long long)(cs->peer.arena[R + 1] - cs->peer.arena[R]) : 0;
     d.need_rows = (int*)(sync + kNeedRowsWord);
+    const bool dma = e->strip_dma;
+    d.gi_mirror_reach = dma ? 0 : kSpatialReach;
+    if (dma && !cs->ev_produced) {
+        CK(cudaEventCreateWithFlags(&cs->ev_produced, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) { CK(cudaStreamCreateWithFlags(&cs->side[k], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&cs->ev_pushed[k], cudaEventDisableTiming)); }
+    }
+    // the copy engines of last frame have long finished; this orders this frame's writes of the pushed rows after them formally
+    for (int k = 0; k < 2; k++) if (cs->pushed_pending[k]) { CK(cudaStreamWaitEvent(e->stream, cs->ev_pushed[k], 0)); cs->pushed_pending[k] = false; }
     StripExt ext; ext.gbuffer = kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
     for (int i = 0; i < 5; i++) ext.wavelet[i] = wext[i];
     ext.preview_mirror[0] = kPreview2Reach; ext.preview_mirror[1] = 0;
@@ -922,6 +933,25 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
         e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_signal_wait(ss, sig_slot, seq, sig_mask, wait_slot, value, wait_mask, s); });
     };
     auto emit = [&](const Step& st) { e->run_timed(st.pass, st.run, st.sub); };
+    // The 128-row halos of gi_reservoirs[1] / [2] are the bulk of what travels (64 B per pixel).  With ST_OPT_STRIP_DMA they are not
+    // mirrored by the producing kernel (whose own time they would stretch) but pushed by the copy engines right after it, one side
+    // stream per neighbour, while this stream goes on with the other chain's passes; the flag is raised on the side stream behind the copy.
+    int push_rc = ST_OK;
+    auto push_rows = [&](const char* name, int reach, int slot) {
+        size_t kk = 0; float4* base = camera_buffer(cs, name, &kk);
+        if (!base) { push_rc = fail(ST_ERR_NOT_FOUND, std::string("unknown buffer ") + name); return; }
+        const size_t W = cs->desc.width, row_bytes = W * kk * 16, off = (size_t)((char*)base - (char*)cs->arena.p);
+        cudaEventRecord(cs->ev_produced, e->stream);
+        for (int k = 0; k < 2; k++) {
+            const int nbr = k == 0 ? R - 1 : R + 1;
+            if (nbr < 0 || nbr >= N) continue;
+            const int r0 = k == 0 ? d.own_y0 : std::max(d.own_y0, d.own_y1 - reach), r1 = k == 0 ? std::min(d.own_y1, d.own_y0 + reach) : d.own_y1;
+            cudaStreamWaitEvent(cs->side[k], cs->ev_produced, 0);
+            cudaMemcpyAsync(cs->peer.arena[nbr] + off + (size_t)r0 * row_bytes, (char*)base + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDefault, cs->side[k]);
+            launch_strip_signal(ss, slot, seq, 1u << nbr, nullptr, H, cs->side[k]);
+            cudaEventRecord(cs->ev_pushed[k], cs->side[k]); cs->pushed_pending[k] = true;
+        }
+    };
 
     // split the reference order into the blocks the interleaving moves around
     std::vector<const Step*> pre, di1, di_pick, di_rest, gi1, gi_sp, pv1, gi_tail, post;
@@ -966,14 +996,18 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     for (auto* st : di1) emit(*st);
     if (!di1.empty()) signal(SLOT_DI1, nb);
     for (auto* st : gi1) emit(*st);
-    if (!gi1.empty() && !di_pick.empty()) signal_wait(SLOT_GI1, nb, SLOT_DI1, nb, seq);
+    if (dma) {   // the flags of the GI halos are raised by the side streams, behind their copies
+        if (!gi1.empty()) push_rows("gi_reservoirs_1", kSpatialReach, SLOT_GI1);
+        if (!di_pick.empty()) wait(SLOT_DI1, nb, seq);
+    } else if (!gi1.empty() && !di_pick.empty()) signal_wait(SLOT_GI1, nb, SLOT_DI1, nb, seq);
     else if (!gi1.empty()) signal(SLOT_GI1, nb);
     else if (!di_pick.empty()) wait(SLOT_DI1, nb, seq);
     for (auto* st : di_pick) emit(*st);
     if (!gi1.empty()) wait(SLOT_GI1, nb, seq);
     for (auto* st : gi_sp) emit(*st);
     // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
-    if (!gi_sp.empty()) signal_wait(SLOT_GI2, nb, SLOT_PULL_DONE, all, seq);
+    if (!gi_sp.empty() && dma) { push_rows("gi_reservoirs_2", kSpatialReach, SLOT_GI2); wait(SLOT_PULL_DONE, all, seq); }
+    else if (!gi_sp.empty()) signal_wait(SLOT_GI2, nb, SLOT_PULL_DONE, all, seq);
     else wait(SLOT_PULL_DONE, all, seq);
     if (!di_rest.empty()) emit(*di_rest[0]);
     if (!gi_sp.empty()) wait(SLOT_GI2, nb, seq);
@@ -990,6 +1024,8 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     }
     signal(SLOT_FRAME_DONE, all);
     d.y0 = d.own_y0; d.y1 = d.own_y1;
+    if (push_rc) return push_rc;
+    CK(cudaGetLastError());
     return ST_OK;
 }
 
@@ -1031,7 +1067,8 @@ void st_engine_destroy(st_engine* e) {
     cudaSetDevice(e->device);
     cudaStreamSynchronize(e->stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
-    for (CameraSlot* c : e->cameras) { c->arena.release(); c->rgba8.release(); for (int k = 0; k < 2; k++) { if (c->ev_ready[k]) cudaEventDestroy(c->ev_ready[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); } delete c; }
+    for (CameraSlot* c : e->cameras) { for (int k = 0; k < 2; k++) { if (c->side[k]) { cudaStreamSynchronize(c->side[k]); cudaStreamDestroy(c->side[k]); } if (c->ev_pushed[k]) cudaEventDestroy(c->ev_pushed[k]); } if (c->ev_produced) cudaEventDestroy(c->ev_produced);
+        c->arena.release(); c->rgba8.release(); for (int k = 0; k < 2; k++) { if (c->ev_ready[k]) cudaEventDestroy(c->ev_ready[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); } delete c; }
     DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb, &e->d_tri_instance, &e->d_instance_xforms, &e->d_tile_errors};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -1456,6 +1493,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
+    if (option == ST_OPT_STRIP_DMA) { e->strip_dma = value != 0; return ST_OK; }
     if (option == ST_OPT_FUSED_PASSES) { e->fused_passes = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
     if (option == ST_OPT_VARIANCE_TILED) { e->variance_tiled = value != 0; return ST_OK; }

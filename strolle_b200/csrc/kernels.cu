@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) 
     // strips: the columns the checkerboard passes do not cover (widths whose (W + 7) / 8 is odd) keep this entry as the spatial pass's
     // output, so there it is one of the rows a neighbouring strip's preview pass gathers
     gi_store_m(cam, gi_reprojection_px(cam, hit, reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)])), cam.gi_reservoirs[2], screen_idx(cam, p.x, p.y), p.y,
-               (int)p.x >= 2 * half_grid_w(cam.w) ? ST_REACH_SPATIAL : 0);
+               (int)p.x >= 2 * half_grid_w(cam.w) ? cam.gi_mirror_reach : 0);
 }
 
 // K12 gi_sampling_a::main (gi_sampling_a.rs:4-122)
@@ -616,7 +616,7 @@ __global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 
     Rng rng = rng_make(seed, p.x, p.y);
     Hit lhs_hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     float4* curr = cam.gi_reservoirs[1];
-    if (!hit_some(lhs_hit)) { gi_store_m(cam, gi_zero(), curr, lhs_idx, p.y, ST_REACH_SPATIAL); return; }
+    if (!hit_some(lhs_hit)) { gi_store_m(cam, gi_zero(), curr, lhs_idx, p.y, cam.gi_mirror_reach); return; }
     bool got = tracing ? (frame % 2u == 0u && checker_at(p.x, p.y, frame / 2u)) : checker_at(p.x, p.y, frame);
     GiRes lhs = got ? gi_load(curr, lhs_idx) : gi_zero();
     GiRes rhs = gi_zero();
@@ -624,7 +624,7 @@ __global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 
     Reproj rp = reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)]);
     if (inline_reprojection) {
         GiRes r11 = gi_reprojection_px(cam, lhs_hit, rp);
-        if ((int)p.x >= 2 * half_grid_w(cam.w)) gi_store_m(cam, r11, cam.gi_reservoirs[2], lhs_idx, p.y, ST_REACH_SPATIAL);
+        if ((int)p.x >= 2 * half_grid_w(cam.w)) gi_store_m(cam, r11, cam.gi_reservoirs[2], lhs_idx, p.y, cam.gi_mirror_reach);
         if (reproj_some(rp)) { rhs = r11; rhs.v2n = oct_decode(oct_encode(r11.v2n)); }
     } else if (reproj_some(rp)) rhs = gi_load(cam.gi_reservoirs[2], lhs_idx);
     if (reproj_some(rp)) {
@@ -660,7 +660,7 @@ __global__ void ST_LB_GI_TEMPORAL k_gi_temporal(KPARAMS, int cur, u32 seed, u32 
     main_.pdf = main_pdf;
     main_.v1 = lhs_hit.point;
     main_.w = rmin(main_.w, 5.0f);
-    gi_store_m(cam, main_, curr, lhs_idx, p.y, ST_REACH_SPATIAL);
+    gi_store_m(cam, main_, curr, lhs_idx, p.y, cam.gi_mirror_reach);
 }
 
 // K15 gi_spatial_resampling::pick (gi_spatial_resampling.rs:4-160); scratch = gi_d0, gi_d1
@@ -743,10 +743,10 @@ ST_DEV void gi_spatial_sample_pair(const CameraDev& cam, u32 seed, u32 frame, Px
         main_.v1 = lhs.v1;
         main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
         main_.w = rmin(main_.w, 5.0f);
-        gi_store_m(cam, main_, out, idx, sp.y, ST_REACH_SPATIAL);
-    } else gi_store_m(cam, lhs, out, idx, sp.y, ST_REACH_SPATIAL);
+        gi_store_m(cam, main_, out, idx, sp.y, cam.gi_mirror_reach);
+    } else gi_store_m(cam, lhs, out, idx, sp.y, cam.gi_mirror_reach);
     uint2 op = checker(g.x, g.y, frame / 2u);
-    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); gi_store_m(cam, gi_load(in, oi), out, oi, op.y, ST_REACH_SPATIAL); }
+    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); gi_store_m(cam, gi_load(in, oi), out, oi, op.y, cam.gi_mirror_reach); }
 }
 __global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u32 frame) {
     Px g = pixel_half(cam);

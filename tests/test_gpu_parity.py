@@ -745,18 +745,19 @@ def _devices(n):
 
 
 @pytest.mark.parametrize("n,size,exact,fused", [(2, (320, 288), True, True), (3, (256, 400), True, True), (2, (320, 288), False, True),
-                                                (4, (200, 520), False, True), (2, (320, 288), True, False)])
+                                                (4, (200, 520), False, True), (2, (320, 288), True, False), (3, (200, 400), False, "mirror")])
 def test_multi_device_group_matches_single_gpu(gpu, blue_noise, n, size, exact, fused):
     """st_multi_* (one process, n devices): the frame rendered as n row strips — producer kernels mirroring their
     boundary rows into the neighbours, neighbour-only sequence flags, G-buffer / SVGF halo rows recomputed, temporal rows pulled on
     demand — is the single-GPU frame, bit for bit, in every per-camera buffer, through two GI cycles with the camera first still,
     then drifting, then jumping by more rows than any fixed temporal halo would cover."""
-    from strolle_b200.engine import OPT_STRIP_FUSED, FORMAT_RGBA8_SRGB
+    from strolle_b200.engine import OPT_STRIP_FUSED, OPT_STRIP_DMA, FORMAT_RGBA8_SRGB
     w, h = size
     scene = scenes.cornell(w, h)
     one = gpu.Engine(blue_noise=blue_noise, exact=exact)
     grp = gpu.MultiEngine(_devices(n), blue_noise=blue_noise, exact=exact)
-    grp.set_option(OPT_STRIP_FUSED, int(fused))
+    grp.set_option(OPT_STRIP_FUSED, int(bool(fused)))
+    grp.set_option(OPT_STRIP_DMA, 0 if fused == "mirror" else 1)   # "mirror": the GI halos also by in-kernel stores instead of the copy engines
     c1, cn = scenes.apply(one, scene), scenes.apply(grp, scene)
     c = scene["camera"]
     for f in range(13):
