@@ -429,6 +429,7 @@ struct st_engine {
     bool svgf_fast = true;   // ST_OPT_SVGF_FAST_MATH
     bool shading_fast = ST_SHADING_FAST_DEFAULT != 0;   // ST_OPT_SHADING_FAST_MATH
     bool fused_passes = ST_FUSED_PASSES_DEFAULT != 0;   // ST_OPT_FUSED_PASSES
+    bool binned_trace = ST_BINNED_TRACE_DEFAULT != 0;   // ST_OPT_BINNED_TRACE
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
     bool strip_dma = ST_STRIP_DMA_DEFAULT != 0;   // ST_OPT_STRIP_DMA: gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores
@@ -676,6 +677,7 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
     // ST_OPT_FUSED_PASSES: passes whose hand-over is private to a pixel (or to a checkerboard pair) run as one launch; the step keeps
     // the pass id of the member that gathers from other pixels, which is what the strip plans key on.
     const bool fp = e->fused_passes;
+    const bool binned = e->binned_trace;
     if (!e->instances.empty()) {
         add(P_FRAME_REPROJECTION, [=](cudaStream_t s) { launch_frame_reprojection(cam, sc, cur, s); });
         if (needs_di) {
@@ -699,7 +701,7 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
             const int inline_rp = (fp && tracing) ? 1 : 0;   // K11 inside K14; validation frames keep K11 (K12 / K13 read its output)
             if (!inline_rp) add(P_GI_REPROJECTION, [=](cudaStream_t s) { (fs ? stf::launch_gi_reprojection : st::launch_gi_reprojection)(cam, sc, cur, s); });
             auto sampling = [&]() {
-                if (fp) { add(P_GI_SAMPLING_B, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_fused : st::launch_gi_sampling_fused)(cam, sc, cur, sa, sb, f, s); }); return; }
+                if (fp) { add(P_GI_SAMPLING_B, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_fused : st::launch_gi_sampling_fused)(cam, sc, cur, sa, sb, f, binned, s); }); return; }
                 add(P_GI_SAMPLING_A, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_a : st::launch_gi_sampling_a)(cam, sc, cur, sa, f, s); });
                 add(P_GI_SAMPLING_B, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_b : st::launch_gi_sampling_b)(cam, sc, cur, sb, f, s); });
             };
@@ -1495,6 +1497,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
     if (option == ST_OPT_STRIP_DMA) { e->strip_dma = value != 0; return ST_OK; }
     if (option == ST_OPT_FUSED_PASSES) { e->fused_passes = value != 0; return ST_OK; }
+    if (option == ST_OPT_BINNED_TRACE) { e->binned_trace = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
     if (option == ST_OPT_VARIANCE_TILED) { e->variance_tiled = value != 0; return ST_OK; }
     if (option == ST_OPT_BVH_REUSE) { e->bvh_reuse = value != 0; return ST_OK; }

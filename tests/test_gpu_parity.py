@@ -808,10 +808,11 @@ def test_fused_passes_bit_exact(gpu, oracle, blue_noise, scene_name, size):
     leave every reservoir, sample, colour, moment and the composed frame bit-identical to the oracle's one-dispatch-per-pass frame, over
     two GI cycles with a moving camera (widths 200 and 121 have columns the checkerboard passes do not cover; the textured room has
     alpha-tested and metallic surfaces)."""
-    from strolle_b200.engine import OPT_FUSED_PASSES
+    from strolle_b200.engine import OPT_FUSED_PASSES, OPT_BINNED_TRACE
     scene = {"cornell": scenes.cornell, "demo_level": scenes.demo_level, "textured_room": scenes.textured_room}[scene_name](*size)
     eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
     eg.set_option(OPT_FUSED_PASSES, 1)
+    eg.set_option(OPT_BINNED_TRACE, 0 if size == (121, 67) else 1)   # the fused GI sampling launch with and without its direction-sorted tracer
     c = scene["camera"]
     base = np.asarray(c["transform"], np.float32).copy()
     names = [n for n in CAMERA_BUFFERS if n not in NOT_WRITTEN_WHEN_FUSED]
