@@ -148,7 +148,9 @@ template <int ALL, int ONE> struct LbMin { static constexpr int value = ALL > 0 
 // ---------------------------------------------------------------------------------------------
 // Primary-visibility G-buffer (stands in for strolle-shaders/src/prim_raster.rs:41-128)
 // ---------------------------------------------------------------------------------------------
-__global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur) {
+ST_DEV float4 frame_reprojection_px(const CameraDev& cam, int cur, Px p, float4 surface_texel, float4 vel);
+// `with_reprojection` (ST_OPT_FUSED_PASSES, single GPU): K4 runs in this launch too — its inputs for the pixel are still in registers
+__global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur, int with_reprojection) {
     ST_TRACE_STACK();
     Px p = pixel_full(cam);
     if (!p.in) return;
@@ -187,18 +189,15 @@ __global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur) {
     size_t i = pix(cam, p.x, p.y);
     cam.prim_gbuffer_d0[cur][i] = g0; cam.prim_gbuffer_d1[cur][i] = g1; cam.prim_surface_map[cur][i] = surf;
     cam.velocity_map[i] = vel; cam.prim_triangle_ids[i] = tid; cam.surface_nd[i] = nd;
+    if (with_reprojection) cam.reprojection_map[i] = frame_reprojection_px(cam, cur, p, surf, vel);
 }
 
-// K4 frame_reprojection::main (frame_reprojection.rs:7-95)
-__global__ void __launch_bounds__(ST_BLOCK) k_frame_reprojection(KPARAMS, int cur) {
-    Px p = pixel_full(cam);
-    if (!p.in) return;
-    const float4* sc_ = cam.prim_surface_map[cur]; const float4* sp_ = cam.prim_surface_map[cur ^ 1];
-    size_t i = pix(cam, p.x, p.y);
+// K4 frame_reprojection::main (frame_reprojection.rs:7-95): where the pixel was last frame and how far that can be trusted
+ST_DEV float4 frame_reprojection_px(const CameraDev& cam, int cur, Px p, float4 surface_texel, float4 vel) {
+    const float4* sp_ = cam.prim_surface_map[cur ^ 1];
     Reproj rp; rp.px = 0.f; rp.py = 0.f; rp.confidence = 0.f; rp.validity = 0u;
-    Surf surface = surf_decode(sc_[i]);
-    if (surface.depth == 0.0f) { cam.reprojection_map[i] = reproj_encode(rp); return; }
-    float4 vel = cam.velocity_map[i];
+    Surf surface = surf_decode(surface_texel);
+    if (surface.depth == 0.0f) return reproj_encode(rp);
     float2 prev = f2((float)p.x, (float)p.y) - f2(vel.x, vel.y);
     float2 pr = f2(roundf(prev.x), roundf(prev.y));
     if (cam_contains_f(cam.prev, pr)) {
@@ -215,7 +214,13 @@ __global__ void __launch_bounds__(ST_BLOCK) k_frame_reprojection(KPARAMS, int cu
             if (surf_similarity(surf_decode(sp_[pix(cam, (u32)xs[k], (u32)ys[k])]), surface) >= 0.25f) rp.validity |= (1u << k);
         }
     }
-    cam.reprojection_map[i] = reproj_encode(rp);
+    return reproj_encode(rp);
+}
+__global__ void __launch_bounds__(ST_BLOCK) k_frame_reprojection(KPARAMS, int cur) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    cam.reprojection_map[i] = frame_reprojection_px(cam, cur, p, cam.prim_surface_map[cur][i], cam.velocity_map[i]);
 }
 #endif   // ST_EXACT_ONLY
 
@@ -1649,7 +1654,7 @@ void launch_gi_sampling_fused(const CameraDev& c, const SceneDev& s, int cur, u3
 void launch_gi_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_fused, c, st, c, s, cur, seed_pick, seed_sample, frame); }
 void launch_gi_preview_resolve(const CameraDev& c, const SceneDev& s, int cur, u32 seed, const float4* in, const float4* source, cudaStream_t st) { k_gi_preview_resolve<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, in, source); }
 #if ST_EXACT_ONLY
-void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
+void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, int with_reprojection, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, with_reprojection); }
 void launch_frame_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) { k_frame_reprojection<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); }
 void launch_denoise_reproject(const CameraDev& c, const SceneDev& s, int cur, const float4* pc, const float4* pm, const float4* smp, float4* col, float4* mom, cudaStream_t st) { k_denoise_reproject<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, pc, pm, smp, col, mom); }
 void launch_denoise_reproject_pair(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st) {

@@ -6,7 +6,7 @@
 namespace st {
 typedef uint32_t u32;
 
-void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
+void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, int with_reprojection, cudaStream_t st);
 void launch_frame_reprojection(const CameraDev& c, const SceneDev& s, int cur, cudaStream_t st);
 void launch_di_sampling(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
 void launch_di_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, cudaStream_t st);
