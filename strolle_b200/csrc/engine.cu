@@ -1245,6 +1245,7 @@ int st_delete_camera(st_engine* e, st_camera_handle h) {
     CK(cudaSetDevice(e->device));
     CK(cudaStreamSynchronize(e->stream));
     if (e->copy_stream) CK(cudaStreamSynchronize(e->copy_stream));
+    for (int k = 0; k < 2; k++) if (cs->side[k]) CK(cudaStreamSynchronize(cs->side[k]));
     cs->alive = false; cs->arena.release(); cs->rgba8.release();
     return ST_OK;
 }
@@ -1405,6 +1406,7 @@ int st_synchronize(st_engine* e) {
     if (!e) return fail(ST_ERR_INVALID, "null engine");
     CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
     if (e->copy_stream) CK(cudaStreamSynchronize(e->copy_stream));
+    for (CameraSlot* c : e->cameras) for (int k = 0; k < 2; k++) if (c->side[k]) CK(cudaStreamSynchronize(c->side[k]));   // copy-engine pushes of strip halos
     return ST_OK;
 }
 
