@@ -255,6 +255,9 @@ int st_nccl_unique_id(uint8_t* out128);
 int st_nccl_init(st_engine* e, const uint8_t* id128, int rank, int world);
 int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap);
 int st_render_strips(st_engine* e, st_camera_handle camera, void* host_out, int format, int temporal_reach, int gather);
+/* The fused strip transport's order of one frame for a given pass schedule (st_frame_schedule), as text for tests:
+ * "step:i;signal:SLOT:nb|all;wait:SLOT:nb|all[:prev];pull;push:buffer:SLOT;..." (no device needed). */
+int st_plan_strip_order(const int* schedule, int n, int dma, char* out, size_t cap);
 int st_halo_bytes(st_engine* e, uint64_t* bytes);
 /* Peer-memory halo transport (default once linked): every rank exports CUDA IPC handles of the camera's buffers
  * (st_peer_export, ST_PEER_HANDLE_BYTES bytes), the host runtime all-gathers them, st_peer_import maps the other

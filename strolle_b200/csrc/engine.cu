@@ -888,6 +888,77 @@ static int halo_exchange_peer(st_engine* e, CameraSlot* cs, const HaloExchange* 
     return ST_OK;
 }
 
+// ---- strip partition, fused transport: the order of one frame (pure; exported as text by st_plan_strip_order for CPU tests) ----
+struct StripOp {
+    enum Kind { STEP, SIGNAL, WAIT, SIGNAL_WAIT, PULL, PUSH } kind = STEP;
+    int step = -1;                                   // STEP: index into the frame schedule
+    int sig_slot = -1, wait_slot = -1;               // StripSlot
+    bool sig_all = false, wait_all = false;          // every rank instead of the two neighbours
+    bool wait_prev_frame = false, reset_need = false;
+    const char* buffer = nullptr;                    // PUSH: rows of this buffer go to the neighbours by copy engine, then sig_slot is raised there
+};
+static void plan_strip_order(const std::vector<int>& pass, bool dma, std::vector<StripOp>* out) {
+    auto step = [&](int i) { StripOp o; o.kind = StripOp::STEP; o.step = i; out->push_back(o); };
+    auto signal = [&](int slot, bool all_ranks = false, bool reset_need = false) { StripOp o; o.kind = StripOp::SIGNAL; o.sig_slot = slot; o.sig_all = all_ranks; o.reset_need = reset_need; out->push_back(o); };
+    auto wait = [&](int slot, bool all_ranks = false, bool prev = false) { StripOp o; o.kind = StripOp::WAIT; o.wait_slot = slot; o.wait_all = all_ranks; o.wait_prev_frame = prev; out->push_back(o); };
+    auto signal_wait = [&](int sslot, int wslot, bool wall = false) { StripOp o; o.kind = StripOp::SIGNAL_WAIT; o.sig_slot = sslot; o.wait_slot = wslot; o.wait_all = wall; out->push_back(o); };
+    auto push = [&](const char* buffer, int slot) { StripOp o; o.kind = StripOp::PUSH; o.buffer = buffer; o.sig_slot = slot; out->push_back(o); };
+    // split the reference order into the blocks the interleaving moves around
+    std::vector<int> pre, di1, di_pick, di_rest, gi1, gi_sp, pv1, gi_tail, post;
+    int nth_preview = 0;
+    for (int i = 0; i < (int)pass.size(); i++) {
+        switch (pass[i]) {
+        case P_PRIM_GBUFFER: case P_FRAME_REPROJECTION: case P_BVH_HEATMAP: case P_REF_TRACING: case P_REF_SHADING: pre.push_back(i); break;
+        case P_DI_SAMPLING: case P_DI_TEMPORAL: di1.push_back(i); break;
+        case P_DI_SPATIAL_PICK: case P_DI_SPATIAL_TRACE: di_pick.push_back(i); break;
+        case P_DI_SPATIAL_SAMPLE: case P_DI_RESOLVING: di_rest.push_back(i); break;
+        case P_GI_REPROJECTION: case P_GI_SAMPLING_A: case P_GI_SAMPLING_B: case P_GI_TEMPORAL: gi1.push_back(i); break;
+        case P_GI_SPATIAL_PICK: case P_GI_SPATIAL_TRACE: case P_GI_SPATIAL_SAMPLE: gi_sp.push_back(i); break;
+        case P_GI_PREVIEW: (nth_preview++ == 0 ? pv1 : gi_tail).push_back(i); break;
+        case P_GI_RESOLVING: gi_tail.push_back(i); break;
+        default: post.push_back(i); break;
+        }
+    }
+    // frame start: the primary pass needs nobody; then wait until every rank has finished the previous frame, pull, tell everybody
+    size_t k = 0;
+    if (!pre.empty() && pass[pre[0]] == P_PRIM_GBUFFER) { step(pre[0]); k = 1; }
+    wait(SLOT_FRAME_DONE, true, true);
+    { StripOp o; o.kind = StripOp::PULL; out->push_back(o); }
+    signal(SLOT_PULL_DONE, true, true);
+    for (; k < pre.size(); k++) step(pre[k]);
+    // DI and GI up to their first gathering pass
+    for (int i : di1) step(i);
+    if (!di1.empty()) signal(SLOT_DI1);
+    for (int i : gi1) step(i);
+    if (dma) {   // the flags of the GI halos are raised by the side streams, behind their copies
+        if (!gi1.empty()) push("gi_reservoirs_1", SLOT_GI1);
+        if (!di_pick.empty()) wait(SLOT_DI1);
+    } else if (!gi1.empty() && !di_pick.empty()) signal_wait(SLOT_GI1, SLOT_DI1);
+    else if (!gi1.empty()) signal(SLOT_GI1);
+    else if (!di_pick.empty()) wait(SLOT_DI1);
+    for (int i : di_pick) step(i);
+    if (!gi1.empty()) wait(SLOT_GI1);
+    for (int i : gi_sp) step(i);
+    // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
+    if (!gi_sp.empty() && dma) { push("gi_reservoirs_2", SLOT_GI2); wait(SLOT_PULL_DONE, true); }
+    else if (!gi_sp.empty()) signal_wait(SLOT_GI2, SLOT_PULL_DONE, true);
+    else wait(SLOT_PULL_DONE, true);
+    if (!di_rest.empty()) step(di_rest[0]);
+    if (!gi_sp.empty()) wait(SLOT_GI2);
+    for (int i : pv1) step(i);
+    if (!pv1.empty()) signal(SLOT_GI3);
+    for (size_t i = 1; i < di_rest.size(); i++) step(di_rest[i]);
+    if (!pv1.empty()) wait(SLOT_GI3);
+    for (int i : gi_tail) step(i);
+    // SVGF: K20 mirrors its rows, then everything downstream is recomputed locally
+    bool svgf_waited = false;
+    for (int i : post) {
+        if (pass[i] == P_DENOISE_VARIANCE && !svgf_waited) { signal_wait(SLOT_SVGF, SLOT_SVGF); svgf_waited = true; }
+        step(i);
+    }
+    signal(SLOT_FRAME_DONE, true);
+}
+
 // ---- strip partition, fused transport ----------------------------------------------------------------------------------------
 // One frame of this rank's strip with no stand-alone exchange step ("overlap with interior compute"):
 //  * nothing the rank can recompute travels: the G-buffer pass runs on the strip grown by the spatial reach (primary rays are
@@ -957,76 +1028,38 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
         }
     };
 
-    // split the reference order into the blocks the interleaving moves around
-    std::vector<const Step*> pre, di1, di_pick, di_rest, gi1, gi_sp, pv1, gi_tail, post;
-    int nth_preview = 0;
-    for (const Step& st : steps) {
-        switch (st.pass) {
-        case P_PRIM_GBUFFER: case P_FRAME_REPROJECTION: case P_BVH_HEATMAP: case P_REF_TRACING: case P_REF_SHADING: pre.push_back(&st); break;
-        case P_DI_SAMPLING: case P_DI_TEMPORAL: di1.push_back(&st); break;
-        case P_DI_SPATIAL_PICK: case P_DI_SPATIAL_TRACE: di_pick.push_back(&st); break;
-        case P_DI_SPATIAL_SAMPLE: case P_DI_RESOLVING: di_rest.push_back(&st); break;
-        case P_GI_REPROJECTION: case P_GI_SAMPLING_A: case P_GI_SAMPLING_B: case P_GI_TEMPORAL: gi1.push_back(&st); break;
-        case P_GI_SPATIAL_PICK: case P_GI_SPATIAL_TRACE: case P_GI_SPATIAL_SAMPLE: gi_sp.push_back(&st); break;
-        case P_GI_PREVIEW: (nth_preview++ == 0 ? pv1 : gi_tail).push_back(&st); break;
-        case P_GI_RESOLVING: gi_tail.push_back(&st); break;
-        default: post.push_back(&st); break;
+    // the order of passes, flags, pulls and pushes is planned by a pure function (CPU-testable: st_plan_strip_order); execute it
+    std::vector<int> ids; for (const Step& st : steps) ids.push_back(st.pass);
+    std::vector<StripOp> ops; plan_strip_order(ids, dma, &ops);
+    const char* prv = (cs->frame % 2u == 1u) ? "a" : "b";
+    for (const StripOp& op : ops) {
+        const uint32_t smask = op.sig_all ? all : nb, wmask = op.wait_all ? all : nb;
+        const uint32_t wseq = op.wait_prev_frame ? seq - 1u : seq;
+        switch (op.kind) {
+        case StripOp::STEP: emit(steps[op.step]); break;
+        case StripOp::SIGNAL: signal(op.sig_slot, smask, op.reset_need); break;
+        case StripOp::WAIT: wait(op.wait_slot, wmask, wseq); break;
+        case StripOp::SIGNAL_WAIT: signal_wait(op.sig_slot, smask, op.wait_slot, wmask, wseq); break;
+        case StripOp::PUSH: push_rows(op.buffer, kSpatialReach, op.sig_slot); break;
+        case StripOp::PULL: {
+            StripPull pl; std::memset(&pl, 0, sizeof pl);
+            for (int r = 0; r < N; r++) { pl.arena[r] = cs->peer.arena[r]; pl.bounds[r] = bounds[r].first; }
+            pl.bounds[N] = H; pl.n_ranks = N; pl.rank = R; pl.w = (int)cs->desc.width; pl.h = H; pl.own_y0 = d.own_y0; pl.own_y1 = d.own_y1;
+            pl.need_rows = (const int*)(sync + kNeedRowsWord); pl.pulled_rows = (unsigned long long*)(sync + kPulledRowsWord);
+            struct { std::string name; int local; } items[] = {
+                {std::string("prim_surface_map_") + prv, kSpatialReach}, {std::string("prim_gbuffer_d0_") + prv, kSpatialReach}, {std::string("prim_gbuffer_d1_") + prv, kSpatialReach},
+                {"di_reservoirs_0", 0}, {"gi_reservoirs_0", 0}, {"di_diff_prev_colors", 0}, {"gi_diff_prev_colors", 0},
+                {std::string("di_diff_moments_") + prv, 0}, {std::string("gi_diff_moments_") + prv, 0}};
+            for (auto& it : items) {
+                size_t kk = 0; float4* base = camera_buffer(cs, it.name, &kk);
+                if (!base) return fail(ST_ERR_NOT_FOUND, "pull list names unknown buffer " + it.name);
+                pl.items[pl.nitems++] = StripPullItem{(size_t)((char*)base - (char*)cs->arena.p), (int)kk, it.local};
+            }
+            e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_pull(pl, s); });
+            break;
+        }
         }
     }
-    // frame start: the primary pass needs nobody; then wait until every rank has finished the previous frame, pull, tell everybody
-    size_t k = 0;
-    if (!pre.empty() && pre[0]->pass == P_PRIM_GBUFFER) { emit(*pre[0]); k = 1; }
-    wait(SLOT_FRAME_DONE, all, seq - 1u);
-    {
-        StripPull pl; std::memset(&pl, 0, sizeof pl);
-        for (int r = 0; r < N; r++) { pl.arena[r] = cs->peer.arena[r]; pl.bounds[r] = bounds[r].first; }
-        pl.bounds[N] = H; pl.n_ranks = N; pl.rank = R; pl.w = (int)cs->desc.width; pl.h = H; pl.own_y0 = d.own_y0; pl.own_y1 = d.own_y1;
-        pl.need_rows = (const int*)(sync + kNeedRowsWord); pl.pulled_rows = (unsigned long long*)(sync + kPulledRowsWord);
-        const char* prv = (cs->frame % 2u == 1u) ? "a" : "b";
-        struct { std::string name; int local; } items[] = {
-            {std::string("prim_surface_map_") + prv, kSpatialReach}, {std::string("prim_gbuffer_d0_") + prv, kSpatialReach}, {std::string("prim_gbuffer_d1_") + prv, kSpatialReach},
-            {"di_reservoirs_0", 0}, {"gi_reservoirs_0", 0}, {"di_diff_prev_colors", 0}, {"gi_diff_prev_colors", 0},
-            {std::string("di_diff_moments_") + prv, 0}, {std::string("gi_diff_moments_") + prv, 0}};
-        for (auto& it : items) {
-            size_t kk = 0; float4* base = camera_buffer(cs, it.name, &kk);
-            if (!base) return fail(ST_ERR_NOT_FOUND, "pull list names unknown buffer " + it.name);
-            pl.items[pl.nitems++] = StripPullItem{(size_t)((char*)base - (char*)cs->arena.p), (int)kk, it.local};
-        }
-        e->run_timed(P_HALO_EXCHANGE, [=](cudaStream_t s) { launch_strip_pull(pl, s); });
-    }
-    signal(SLOT_PULL_DONE, all, true);
-    for (; k < pre.size(); k++) emit(*pre[k]);
-    // DI and GI up to their first gathering pass
-    for (auto* st : di1) emit(*st);
-    if (!di1.empty()) signal(SLOT_DI1, nb);
-    for (auto* st : gi1) emit(*st);
-    if (dma) {   // the flags of the GI halos are raised by the side streams, behind their copies
-        if (!gi1.empty()) push_rows("gi_reservoirs_1", kSpatialReach, SLOT_GI1);
-        if (!di_pick.empty()) wait(SLOT_DI1, nb, seq);
-    } else if (!gi1.empty() && !di_pick.empty()) signal_wait(SLOT_GI1, nb, SLOT_DI1, nb, seq);
-    else if (!gi1.empty()) signal(SLOT_GI1, nb);
-    else if (!di_pick.empty()) wait(SLOT_DI1, nb, seq);
-    for (auto* st : di_pick) emit(*st);
-    if (!gi1.empty()) wait(SLOT_GI1, nb, seq);
-    for (auto* st : gi_sp) emit(*st);
-    // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
-    if (!gi_sp.empty() && dma) { push_rows("gi_reservoirs_2", kSpatialReach, SLOT_GI2); wait(SLOT_PULL_DONE, all, seq); }
-    else if (!gi_sp.empty()) signal_wait(SLOT_GI2, nb, SLOT_PULL_DONE, all, seq);
-    else wait(SLOT_PULL_DONE, all, seq);
-    if (!di_rest.empty()) emit(*di_rest[0]);
-    if (!gi_sp.empty()) wait(SLOT_GI2, nb, seq);
-    for (auto* st : pv1) emit(*st);
-    if (!pv1.empty()) signal(SLOT_GI3, nb);
-    for (size_t i = 1; i < di_rest.size(); i++) emit(*di_rest[i]);
-    if (!pv1.empty()) wait(SLOT_GI3, nb, seq);
-    for (auto* st : gi_tail) emit(*st);
-    // SVGF: K20 mirrors its rows, then everything downstream is recomputed locally
-    bool svgf_waited = false;
-    for (auto* st : post) {
-        if ((st->pass == P_DENOISE_VARIANCE) && !svgf_waited) { signal_wait(SLOT_SVGF, nb, SLOT_SVGF, nb, seq); svgf_waited = true; }
-        emit(*st);
-    }
-    signal(SLOT_FRAME_DONE, all);
     d.y0 = d.own_y0; d.y1 = d.own_y1;
     if (push_rc) return push_rc;
     CK(cudaGetLastError());
@@ -1711,6 +1744,27 @@ static int enqueue_strip_frame(st_engine* e, CameraSlot* cs, int temporal_reach)
 // `gather`: 0 = render only; 1 = assemble the composed frame on rank 0 (strips travel in `format`; rank 0 copies it to `host_out`);
 // 2 = every rank converts its OWN rows and copies them into rows [y0, y1) of `host_out`, a full-frame host buffer that the ranks
 // share (one buffer in a single-process host, a shared-memory segment between processes): no funnel through rank 0.
+int st_plan_strip_order(const int* schedule, int n, int dma, char* out, size_t cap) {
+    if (!schedule || !out || cap == 0) return fail(ST_ERR_INVALID, "null argument");
+    static const char* kSlot[SLOT_COUNT] = {"FRAME_DONE", "PULL_DONE", "DI1", "GI1", "GI2", "GI3", "SVGF", "OUTPUT"};
+    std::vector<int> ids(schedule, schedule + n);
+    std::vector<StripOp> ops; plan_strip_order(ids, dma != 0, &ops);
+    std::string text;
+    for (const StripOp& op : ops) {
+        switch (op.kind) {
+        case StripOp::STEP: text += "step:" + std::to_string(op.step); break;
+        case StripOp::SIGNAL: text += std::string("signal:") + kSlot[op.sig_slot] + (op.sig_all ? ":all" : ":nb"); break;
+        case StripOp::WAIT: text += std::string("wait:") + kSlot[op.wait_slot] + (op.wait_all ? ":all" : ":nb") + (op.wait_prev_frame ? ":prev" : ""); break;
+        case StripOp::SIGNAL_WAIT: text += std::string("signal:") + kSlot[op.sig_slot] + ":nb;wait:" + kSlot[op.wait_slot] + (op.wait_all ? ":all" : ":nb"); break;
+        case StripOp::PULL: text += "pull"; break;
+        case StripOp::PUSH: text += std::string("push:") + op.buffer + ":" + kSlot[op.sig_slot]; break;
+        }
+        text += ";";
+    }
+    if (text.size() + 1 > cap) return fail(ST_ERR_LIMIT, "plan text buffer too small");
+    std::memcpy(out, text.c_str(), text.size() + 1);
+    return ST_OK;
+}
 int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int format, int temporal_reach, int gather) {
     CameraSlot* cs = e ? get_camera(e, h) : nullptr;
     if (!cs) return fail(ST_ERR_NOT_FOUND, "unknown camera");

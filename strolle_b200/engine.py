@@ -98,6 +98,7 @@ def load_library():
         "st_count_rays": [P, C.c_int], "st_ray_count": [P, C.POINTER(C.c_uint64), C.c_int],
         "st_nccl_unique_id": [C.c_void_p], "st_nccl_init": [P, C.c_void_p, C.c_int, C.c_int],
         "st_plan_frame": [C.POINTER(C.c_int), C.c_int, u32, C.c_int, C.c_char_p, C.c_size_t],
+        "st_plan_strip_order": [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_char_p, C.c_size_t],
         "st_render_strips": [P, i32, P, C.c_int, C.c_int, C.c_int], "st_halo_bytes": [P, C.POINTER(C.c_uint64)],
         "st_peer_export": [P, i32, C.c_void_p], "st_peer_import": [P, i32, C.c_void_p, C.c_int, C.c_int],
         "st_peer_errors": [P, i32, C.POINTER(u32)],
@@ -587,6 +588,17 @@ def nccl_unique_id():
     if rc != 0:
         raise StrolleError(lib.st_last_error().decode())
     return bytes(buf)
+
+
+def plan_strip_order(schedule, dma=True):
+    """The fused strip transport's op order for a pass schedule, as a list of strings (st_plan_strip_order; no GPU needed)."""
+    lib = load_library()
+    arr = (C.c_int * len(schedule))(*schedule)
+    out = C.create_string_buffer(8192)
+    rc = lib.st_plan_strip_order(arr, len(schedule), int(dma), out, 8192)
+    if rc != 0:
+        raise StrolleError(lib.st_last_error().decode())
+    return [x for x in out.value.decode().split(";") if x]
 
 
 def plan_frame_native(schedule, frame, temporal_reach=16):

@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 
 from strolle_b200 import multigpu as mg
 
@@ -122,3 +123,79 @@ def test_native_plan_matches_python_plan():
     b = [(ex.before_step, tuple(ex.buffers)) for ex in mg.plan_frame(fused, 1, 16)]
     cut = full.index(mg.P_DENOISE_REPROJECT)
     assert [(s - 1 if s > cut else s, bufs) for s, bufs in a] == b
+
+
+# ---- fused strip transport: the order of one frame (engine.cu plan_strip_order, exported through st_plan_strip_order) --------------------
+
+def _schedules():
+    """Pass-id schedules as build_schedule (engine.cu) emits them: reference order and fused-pass order, the three GI cadences, DI-only,
+    GI-only, denoise off, no instances."""
+    P = mg
+    svgf = [P.P_DENOISE_REPROJECT, P.P_DENOISE_VARIANCE] + [P.P_DENOISE_WAVELET] * 5
+    di_ref = [P.P_DI_SAMPLING, P.P_DI_TEMPORAL, P.P_DI_SPATIAL_PICK, P.P_DI_SPATIAL_TRACE, P.P_DI_SPATIAL_SAMPLE, P.P_DI_RESOLVING]
+    di_fused = [P.P_DI_TEMPORAL, P.P_DI_SPATIAL_PICK, P.P_DI_RESOLVING]
+    def gi(kind, fused):
+        samp = [P.P_GI_SAMPLING_B] if fused else [P.P_GI_SAMPLING_A, P.P_GI_SAMPLING_B]
+        spat = [P.P_GI_SPATIAL_PICK] if fused else [P.P_GI_SPATIAL_PICK, P.P_GI_SPATIAL_TRACE, P.P_GI_SPATIAL_SAMPLE]
+        tail = [P.P_GI_PREVIEW, P.P_GI_PREVIEW] + ([] if fused else [P.P_GI_RESOLVING])
+        head = [] if (fused and kind != "validate") else [P.P_GI_REPROJECTION]
+        body = {"even": samp + [P.P_GI_TEMPORAL], "odd": [P.P_GI_TEMPORAL] + spat, "validate": samp + [P.P_GI_TEMPORAL]}[kind]
+        return head + body + tail
+    out = {}
+    for fused in (False, True):
+        di = di_fused if fused else di_ref
+        for kind in ("even", "odd", "validate"):
+            out[f"image-{kind}-{'fused' if fused else 'ref'}"] = [P.P_PRIM_GBUFFER, P.P_FRAME_REPROJECTION] + di + gi(kind, fused) + svgf + [P.P_COMPOSITION]
+        out[f"di-only-{'fused' if fused else 'ref'}"] = [P.P_PRIM_GBUFFER, P.P_FRAME_REPROJECTION] + di + svgf + [P.P_COMPOSITION]
+        out[f"gi-only-nodenoise-{'fused' if fused else 'ref'}"] = [P.P_PRIM_GBUFFER, P.P_FRAME_REPROJECTION] + gi("odd", fused) + [P.P_COMPOSITION]
+    out["no-instances"] = [P.P_PRIM_GBUFFER] + svgf + [P.P_COMPOSITION]
+    return out
+
+
+@pytest.mark.parametrize("dma", [True, False])
+def test_fused_strip_order_invariants(dma):
+    """Every pass runs exactly once and chains keep their internal order; every pass that gathers from a neighbouring strip is preceded
+    by a wait on the flag that its producer's signal (or copy-engine push) raises; nothing a neighbour may still pull is overwritten before
+    every rank signalled PULL_DONE; the frame opens with the previous frame's FRAME_DONE and closes with this frame's."""
+    from strolle_b200.engine import plan_strip_order
+    P = mg
+    producer_slot = {P.P_DI_TEMPORAL: "DI1", P.P_GI_TEMPORAL: "GI1", P.P_DENOISE_REPROJECT: "SVGF"}
+    for name, sched in _schedules().items():
+        ops = plan_strip_order(sched, dma)
+        steps = [int(o.split(":")[1]) for o in ops if o.startswith("step:")]
+        assert sorted(steps) == list(range(len(sched))), name
+        for chain in ([P.P_DI_SAMPLING, P.P_DI_TEMPORAL, P.P_DI_SPATIAL_PICK, P.P_DI_SPATIAL_TRACE, P.P_DI_SPATIAL_SAMPLE, P.P_DI_RESOLVING],
+                      [P.P_GI_REPROJECTION, P.P_GI_SAMPLING_A, P.P_GI_SAMPLING_B, P.P_GI_TEMPORAL, P.P_GI_SPATIAL_PICK, P.P_GI_SPATIAL_TRACE, P.P_GI_SPATIAL_SAMPLE, P.P_GI_PREVIEW, P.P_GI_RESOLVING],
+                      [P.P_DENOISE_REPROJECT, P.P_DENOISE_VARIANCE, P.P_DENOISE_WAVELET, P.P_COMPOSITION]):
+            inside = [i for i in steps if sched[i] in chain]
+            assert inside == sorted(inside), f"{name}: chain order"
+        assert ops[0] == "step:0" and ops[1] == "wait:FRAME_DONE:all:prev" and ops[2] == "pull" and ops[3] == "signal:PULL_DONE:all" and ops[-1] == "signal:FRAME_DONE:all", name
+        raised, waited = set(), set()
+        previews = 0
+        for o in ops:
+            f = o.split(":")
+            if f[0] == "signal":
+                raised.add(f[1])
+            elif f[0] == "push":
+                assert dma and f[1] in ("gi_reservoirs_1", "gi_reservoirs_2")
+                raised.add(f[2])
+            elif f[0] == "wait" and len(f) == 3:
+                assert f[1] in raised, f"{name}: waits for {f[1]} before this rank raised it itself (ranks run the same order: nobody would)"
+                waited.add(f[1])
+            elif f[0] == "step":
+                p = sched[int(f[1])]
+                need = None
+                if p == P.P_DI_SPATIAL_PICK: need = "DI1"
+                elif p == P.P_GI_SPATIAL_PICK: need = "GI1"
+                elif p == P.P_GI_PREVIEW:
+                    previews += 1
+                    need = ("GI2" if any(q == P.P_GI_SPATIAL_PICK for q in sched) else "GI1") if previews == 1 else "GI3"
+                elif p == P.P_DENOISE_VARIANCE: need = "SVGF"
+                if need:
+                    assert need in waited, f"{name}: pass {p} gathers before wait:{need}"
+                if p in (P.P_DI_RESOLVING, P.P_GI_RESOLVING, P.P_DENOISE_WAVELET) or (p == P.P_GI_PREVIEW and previews == 2):
+                    assert "PULL_DONE" in waited, f"{name}: pass {p} overwrites pulled buffers before every rank pulled"
+                if p in producer_slot and producer_slot[p] not in raised:
+                    pass   # raised right after the producer (checked through the waits above)
+        if any(q == P.P_GI_PREVIEW for q in sched):
+            assert "GI3" in raised and "GI3" in waited, name
