@@ -306,186 +306,6 @@ __global__ void ST_LB_DI_SAMPLING k_di_sample_temporal(KPARAMS, int cur, u32 see
     di_store_m(cam, di_temporal_px(cam, sc, cur, seed_temporal, p, hit, fresh), cam.di_reservoirs[1], screen_idx(cam, p.x, p.y), p.y, ST_REACH_SPATIAL);
 }
 
-// The four scratch texels of one checkerboard pair: (d0, d1) of texel a = (2gx, gy) and texel b = (2gx + 1, gy).
-// state 0: the pair has no left-hand pixel on the screen, nothing is written; 1: only the two d1 texels are cleared; 2: all four.
-struct PairTexels { float4 a0, a1, b0, b1; int state; };
-
-// K7 di_spatial_resampling::pick (di_spatial_resampling.rs:4-147); scratch buf_d0 = di_diff_samples,
-// buf_d1 = di_diff_curr_colors (passes/di_spatial_resampling.rs:24-28).  Sky pixels clear buf_d1
-// (the reference leaves stale texels there and later reads out of bounds — SURVEY Appendix C-15).
-ST_DEV PairTexels di_spatial_pick_pair(const CameraDev& cam, const SceneDev& sc, int cur, u32 seed, u32 frame, Px g) {
-    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
-    uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
-    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return o;
-    o.state = 1;
-    size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
-    Rng rng = rng_make(seed, lp.x, lp.y);
-    const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
-    Hit lhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, lp.x, lp.y);
-    if (!hit_some(lhs_hit)) return o;
-    DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
-    DiRes rhs = di_zero();
-    size_t rhs_idx = 0;
-    Hit rhs_hit = hit_zero();
-    float max_radius = 128.0f;
-    for (u32 nth = 0u; nth < 8u; nth++) {
-        float2 off = rng_disk(rng) * max_radius;
-        float2 fp = f2((float)lp.x, (float)lp.y) + off;
-        uint2 rpos = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
-        if (rpos.x == lp.x && rpos.y == lp.y) continue;
-        // the rejection tests only need the neighbour's depth and normal: one (normal, depth) float4
-        float4 nd = tex_or_zero(cam.surface_nd, cam, rpos.x, rpos.y);
-        if (nd.w == 0.0f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
-        if (fabs_(nd.w - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
-        if (dot(xyz(nd), lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
-        rhs_idx = screen_idx(cam, rpos.x, rpos.y);
-        rhs = di_load(cam.di_reservoirs[1], rhs_idx);
-        if (rhs.m != 0.0f) { rhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, rpos.x, rpos.y); break; }
-    }
-    if (rhs.m == 0.0f) return o;
-    float lhs_rhs_pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), rhs_hit);
-    float rhs_lhs_pdf = di_pdf_with(rhs, light_load(sc, rhs.light_id), lhs_hit);
-    Ray ra = (lhs_rhs_pdf > 0.0f) ? di_ray(lhs, rhs_hit.point) : ray_zero();
-    Ray rb = (rhs_lhs_pdf > 0.0f) ? di_ray(rhs, lhs_hit.point) : ray_zero();
-    float2 na = oct_encode(ra.d), nb = oct_encode(rb.d);
-    o.a0 = f4(ra.o, ra.len); o.a1 = f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), 0.0f);
-    o.b0 = f4(rb.o, rb.len); o.b1 = f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf);
-    o.state = 2;
-    return o;
-}
-ST_DEV void store_pair_texels(const CameraDev& cam, const PairTexels& o, float4* buf_d0, float4* buf_d1, Px g) {
-    if (o.state == 0) return;
-    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
-    if (o.state == 2) { tex_store(buf_d0, cam, ax, g.y, o.a0); tex_store(buf_d0, cam, bx, g.y, o.b0); }
-    tex_store(buf_d1, cam, ax, g.y, o.a1); tex_store(buf_d1, cam, bx, g.y, o.b1);
-}
-__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
-    Px g = pixel_half(cam);
-    if (!g.in) return;
-    store_pair_texels(cam, di_spatial_pick_pair(cam, sc, cur, seed, frame, g), cam.di_diff_samples, cam.di_diff_curr_colors, g);
-}
-
-// K8 / K16 *_spatial_resampling::trace (di_spatial_resampling.rs:150-209, gi_spatial_resampling.rs:163-222): one scratch texel
-ST_DEV float4 spatial_trace_texel(const SceneDev& sc, const TraceStack& stk, float4 d0, float4 d1) {
-    if (all_zero(d1)) return f4zero();
-    Ray ray = ray_make(xyz(d0), oct_decode(f2(d1.x, d1.y)), d0.w);
-    bool occ = trace_any(ray, sc, stk);
-    return f4(occ ? 0.0f : 1.0f, d1.z, d1.w, 0.0f);
-}
-__global__ void ST_LB_SPATIAL_TRACE k_spatial_trace(KPARAMS, const float4* __restrict__ buf_d0, const float4* __restrict__ buf_d1, float4* __restrict__ buf_d2) {
-    ST_TRACE_STACK();
-    Px p = pixel_full(cam);
-    if (!p.in) return;
-    size_t i = pix(cam, p.x, p.y);
-    buf_d2[i] = spatial_trace_texel(sc, stk, buf_d0[i], buf_d1[i]);
-}
-// the two visibility texels of a pair as K8 / K16 would leave them for K9 / K17 (a texel outside the texture reads as zero)
-ST_DEV void trace_pair_texels(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, const PairTexels& o, Px g, float4* d2a, float4* d2b) {
-    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
-    *d2a = (o.state == 2 && in_tex(cam, ax, g.y)) ? spatial_trace_texel(sc, stk, o.a0, o.a1) : f4zero();
-    *d2b = (o.state == 2 && in_tex(cam, bx, g.y)) ? spatial_trace_texel(sc, stk, o.b0, o.b1) : f4zero();
-}
-
-// K9 di_spatial_resampling::sample (di_spatial_resampling.rs:212-297); d0 / d1 = the pair's two visibility texels
-ST_DEV void di_spatial_sample_pair(const CameraDev& cam, u32 seed, u32 frame, Px g, float4 d0, float4 d1) {
-    uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
-    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
-    size_t npx = (size_t)cam.w * cam.h;
-    size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
-    Rng rng = rng_make(seed, lp.x, lp.y);
-    const float4* in = cam.di_reservoirs[1]; float4* out = cam.di_reservoirs[2];
-    float lhs_rhs_vis = d0.x; u32 rhs_idx = fbits(d0.y);
-    float rhs_lhs_vis = d1.x, lhs_rhs_pdf = d1.y, rhs_lhs_pdf = d1.z;
-    DiRes lhs = di_load(in, lhs_idx);
-    if (rhs_idx > 0u && (size_t)rhs_idx - 1 < npx) {
-        DiRes rhs = di_load(in, (size_t)rhs_idx - 1);
-        MisIn mi;
-        mi.lhs_m = lhs.m; mi.rhs_m = rhs.m; mi.rhs_jacobian = 1.0f; mi.lhs_lhs_pdf = lhs.pdf;
-        mi.lhs_rhs_pdf = lhs_rhs_pdf * lhs_rhs_vis; mi.rhs_lhs_pdf = rhs_lhs_pdf * rhs_lhs_vis; mi.rhs_rhs_pdf = rhs.pdf;
-        MisOut mo = mis_eval(mi);
-        DiRes main_ = di_zero();
-        float main_pdf = 0.0f;
-        if (di_update(main_, rng, lhs, mo.lhs_mis * mo.lhs_pdf * lhs.w)) main_pdf = mo.lhs_pdf;
-        if (di_update(main_, rng, rhs, mo.rhs_mis * mo.rhs_pdf * rhs.w)) { main_pdf = mo.rhs_pdf; main_.occluded = lhs_rhs_vis == 0.0f; }
-        main_.m = lhs.m + mo.m;
-        main_.pdf = main_pdf;
-        main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
-        di_store(main_, out, lhs_idx);
-    } else di_store(lhs, out, lhs_idx);
-    uint2 op = checker(g.x, g.y, frame / 2u);
-    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); di_store(di_load(in, oi), out, oi); }
-}
-__global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 seed, u32 frame) {
-    Px g = pixel_half(cam);
-    if (!g.in) return;
-    di_spatial_sample_pair(cam, seed, frame, g, tex_or_zero(cam.di_diff_stash, cam, g.x * 2u, g.y), tex_or_zero(cam.di_diff_stash, cam, g.x * 2u + 1u, g.y));
-}
-// K7 + K8 + K9 in one launch (ST_OPT_FUSED_PASSES): one thread per checkerboard pair picks the neighbour, traces the pair's two shadow
-// rays and merges — the three scratch textures (48 B per pixel written and read back) never leave the registers.  Same draws, same rays
-// (direction through the same octahedral round trip), same merge as the three-launch sequence.
-__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_fused(KPARAMS, int cur, u32 seed_pick, u32 seed_sample, u32 frame) {
-    ST_TRACE_STACK();
-    Px g = pixel_half(cam);
-    if (!g.in) return;
-    PairTexels o = di_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
-    if (o.state == 0) return;
-    float4 d2a, d2b; trace_pair_texels(cam, sc, stk, o, g, &d2a, &d2b);
-    di_spatial_sample_pair(cam, seed_sample, frame, g, d2a, d2b);
-}
-
-// K10 di_resolving::main (di_resolving.rs:4-119)
-__global__ void ST_LB_DI_RESOLVING k_di_resolving(KPARAMS, int cur) {
-    ST_TRACE_STACK();
-    Px p = pixel_full(cam);
-    if (!p.in) return;
-    size_t idx = screen_idx(cam, p.x, p.y);
-    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    DiRes res = di_load(cam.di_reservoirs[2], idx);
-    float confidence;
-    LightRad rad;
-    if (hit_some(hit)) {
-        bool occ = trace_any(di_ray(res, hit.point), sc, stk);
-        confidence = (res.occluded == occ) ? res.confidence : 0.0f;
-        res.confidence = 1.0f;
-        res.occluded = occ;
-        if (occ) rad = lightrad_zero();
-        else { rad = light_radiance(light_load(sc, res.light_id), hit); rad.radiance = rad.radiance * res.w; }
-    } else {
-        confidence = 1.0f;
-        rad.radiance = atmosphere_sample(sc, world_sun_dir(sc.world), hit.dir);
-        rad.diff = f3s(1.0f); rad.spec = f3s(0.0f);
-    }
-    float diff_brdf = (1.0f - hit.g.metallic) / kPi;
-    size_t i = pix(cam, p.x, p.y);
-    cam.di_diff_samples[i] = f4(rad.radiance * diff_brdf, confidence);
-    cam.di_spec_samples[i] = f4(rad.radiance * rad.spec, confidence);
-    di_store(res, cam.di_reservoirs[0], idx);
-}
-
-// K11 gi_reprojection::main (gi_reprojection.rs:4-51)
-ST_DEV GiRes gi_reprojection_px(const CameraDev& cam, const Hit& hit, const Reproj& rp) {
-    size_t npx = (size_t)cam.w * cam.h;
-    GiRes res = gi_zero();
-    if (reproj_some(rp)) {
-        uint2 rpos = reproj_round(rp);
-        size_t ridx = screen_idx(cam, rpos.x, rpos.y);
-        if (ridx < npx) res = gi_load(cam.gi_reservoirs[0], ridx);
-    }
-    res.confidence = 1.0f;
-    res.v1 = hit.point;
-    return res;
-}
-__global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) {
-    Px p = pixel_full(cam);
-    if (!p.in) return;
-    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
-    if (!hit_some(hit)) return;
-    // strips: the columns the checkerboard passes do not cover (widths whose (W + 7) / 8 is odd) keep this entry as the spatial pass's
-    // output, so there it is one of the rows a neighbouring strip's preview pass gathers
-    gi_store_m(cam, gi_reprojection_px(cam, hit, reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)])), cam.gi_reservoirs[2], screen_idx(cam, p.x, p.y), p.y,
-               (int)p.x >= 2 * half_grid_w(cam.w) ? cam.gi_mirror_reach : 0);
-}
-
 // ---- how a kernel traces the rays of its CTA ---------------------------------------------------------------------------------------
 // DirectTracer: every thread walks the BVH for its own ray (what every kernel did so far).
 // BinnedTracer: the CTA's rays are first sorted by direction octant through shared memory (counting sort over warp ballots), thread i
@@ -560,6 +380,206 @@ struct BinnedTracer {
 #define ST_BINNED_TRACER(name)                                                                                   \
     __shared__ float4 s_bin_ray[2 * ST_BLOCK]; __shared__ float4 s_bin_hit[3 * ST_BLOCK]; __shared__ u32 s_bin_cnt[36]; \
     BinnedTracer name{sc, stk, s_bin_ray, s_bin_hit, s_bin_cnt};
+
+// The four scratch texels of one checkerboard pair: (d0, d1) of texel a = (2gx, gy) and texel b = (2gx + 1, gy).
+// state 0: the pair has no left-hand pixel on the screen, nothing is written; 1: only the two d1 texels are cleared; 2: all four.
+struct PairTexels { float4 a0, a1, b0, b1; int state; };
+
+// K7 di_spatial_resampling::pick (di_spatial_resampling.rs:4-147); scratch buf_d0 = di_diff_samples,
+// buf_d1 = di_diff_curr_colors (passes/di_spatial_resampling.rs:24-28).  Sky pixels clear buf_d1
+// (the reference leaves stale texels there and later reads out of bounds — SURVEY Appendix C-15).
+ST_DEV PairTexels di_spatial_pick_pair(const CameraDev& cam, const SceneDev& sc, int cur, u32 seed, u32 frame, Px g) {
+    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
+    uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
+    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return o;
+    o.state = 1;
+    size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
+    Rng rng = rng_make(seed, lp.x, lp.y);
+    const float4* gd0 = cam.prim_gbuffer_d0[cur]; const float4* gd1 = cam.prim_gbuffer_d1[cur];
+    Hit lhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, lp.x, lp.y);
+    if (!hit_some(lhs_hit)) return o;
+    DiRes lhs = di_load(cam.di_reservoirs[1], lhs_idx);
+    DiRes rhs = di_zero();
+    size_t rhs_idx = 0;
+    Hit rhs_hit = hit_zero();
+    float max_radius = 128.0f;
+    for (u32 nth = 0u; nth < 8u; nth++) {
+        float2 off = rng_disk(rng) * max_radius;
+        float2 fp = f2((float)lp.x, (float)lp.y) + off;
+        uint2 rpos = cam_contain(cam.curr, to_i32_sat(fp.x), to_i32_sat(fp.y));
+        if (rpos.x == lp.x && rpos.y == lp.y) continue;
+        // the rejection tests only need the neighbour's depth and normal: one (normal, depth) float4
+        float4 nd = tex_or_zero(cam.surface_nd, cam, rpos.x, rpos.y);
+        if (nd.w == 0.0f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (fabs_(nd.w - lhs_hit.g.depth) > 0.33f * lhs_hit.g.depth) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        if (dot(xyz(nd), lhs_hit.g.normal) < 0.33f) { max_radius = rmax(max_radius * 0.5f, 5.0f); continue; }
+        rhs_idx = screen_idx(cam, rpos.x, rpos.y);
+        rhs = di_load(cam.di_reservoirs[1], rhs_idx);
+        if (rhs.m != 0.0f) { rhs_hit = load_hit_lut(sc, cam.curr, gd0, gd1, cam, rpos.x, rpos.y); break; }
+    }
+    if (rhs.m == 0.0f) return o;
+    float lhs_rhs_pdf = di_pdf_with(lhs, light_load(sc, lhs.light_id), rhs_hit);
+    float rhs_lhs_pdf = di_pdf_with(rhs, light_load(sc, rhs.light_id), lhs_hit);
+    Ray ra = (lhs_rhs_pdf > 0.0f) ? di_ray(lhs, rhs_hit.point) : ray_zero();
+    Ray rb = (rhs_lhs_pdf > 0.0f) ? di_ray(rhs, lhs_hit.point) : ray_zero();
+    float2 na = oct_encode(ra.d), nb = oct_encode(rb.d);
+    o.a0 = f4(ra.o, ra.len); o.a1 = f4(na.x, na.y, bitsf((u32)rhs_idx + 1u), 0.0f);
+    o.b0 = f4(rb.o, rb.len); o.b1 = f4(nb.x, nb.y, lhs_rhs_pdf, rhs_lhs_pdf);
+    o.state = 2;
+    return o;
+}
+ST_DEV void store_pair_texels(const CameraDev& cam, const PairTexels& o, float4* buf_d0, float4* buf_d1, Px g) {
+    if (o.state == 0) return;
+    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
+    if (o.state == 2) { tex_store(buf_d0, cam, ax, g.y, o.a0); tex_store(buf_d0, cam, bx, g.y, o.b0); }
+    tex_store(buf_d1, cam, ax, g.y, o.a1); tex_store(buf_d1, cam, bx, g.y, o.b1);
+}
+__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_pick(KPARAMS, int cur, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    store_pair_texels(cam, di_spatial_pick_pair(cam, sc, cur, seed, frame, g), cam.di_diff_samples, cam.di_diff_curr_colors, g);
+}
+
+// K8 / K16 *_spatial_resampling::trace (di_spatial_resampling.rs:150-209, gi_spatial_resampling.rs:163-222): one scratch texel
+ST_DEV float4 spatial_trace_texel(const SceneDev& sc, const TraceStack& stk, float4 d0, float4 d1) {
+    if (all_zero(d1)) return f4zero();
+    Ray ray = ray_make(xyz(d0), oct_decode(f2(d1.x, d1.y)), d0.w);
+    bool occ = trace_any(ray, sc, stk);
+    return f4(occ ? 0.0f : 1.0f, d1.z, d1.w, 0.0f);
+}
+__global__ void ST_LB_SPATIAL_TRACE k_spatial_trace(KPARAMS, const float4* __restrict__ buf_d0, const float4* __restrict__ buf_d1, float4* __restrict__ buf_d2) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t i = pix(cam, p.x, p.y);
+    buf_d2[i] = spatial_trace_texel(sc, stk, buf_d0[i], buf_d1[i]);
+}
+// the two visibility texels of a pair as K8 / K16 would leave them for K9 / K17 (a texel outside the texture reads as zero); collective
+// when the tracer is (every thread of the CTA calls it, `o.state` = 0 for threads without a pair)
+template <class Tracer>
+ST_DEV float4 spatial_trace_texel_t(Tracer& tr, float4 d0, float4 d1, bool present) {
+    const bool active = present && !all_zero(d1);
+    Ray ray = active ? ray_make(xyz(d0), oct_decode(f2(d1.x, d1.y)), d0.w) : ray_zero();
+    bool occ = tr.any(ray, active);
+    return active ? f4(occ ? 0.0f : 1.0f, d1.z, d1.w, 0.0f) : f4zero();
+}
+template <class Tracer>
+ST_DEV void trace_pair_texels(const CameraDev& cam, Tracer& tr, const PairTexels& o, Px g, float4* d2a, float4* d2b) {
+    u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
+    *d2a = spatial_trace_texel_t(tr, o.a0, o.a1, o.state == 2 && in_tex(cam, ax, g.y));
+    *d2b = spatial_trace_texel_t(tr, o.b0, o.b1, o.state == 2 && in_tex(cam, bx, g.y));
+}
+
+// K9 di_spatial_resampling::sample (di_spatial_resampling.rs:212-297); d0 / d1 = the pair's two visibility texels
+ST_DEV void di_spatial_sample_pair(const CameraDev& cam, u32 seed, u32 frame, Px g, float4 d0, float4 d1) {
+    uint2 lp = checker(g.x, g.y, frame / 2u + 1u);
+    if (!cam_contains_u(cam.curr, lp.x, lp.y)) return;
+    size_t npx = (size_t)cam.w * cam.h;
+    size_t lhs_idx = screen_idx(cam, lp.x, lp.y);
+    Rng rng = rng_make(seed, lp.x, lp.y);
+    const float4* in = cam.di_reservoirs[1]; float4* out = cam.di_reservoirs[2];
+    float lhs_rhs_vis = d0.x; u32 rhs_idx = fbits(d0.y);
+    float rhs_lhs_vis = d1.x, lhs_rhs_pdf = d1.y, rhs_lhs_pdf = d1.z;
+    DiRes lhs = di_load(in, lhs_idx);
+    if (rhs_idx > 0u && (size_t)rhs_idx - 1 < npx) {
+        DiRes rhs = di_load(in, (size_t)rhs_idx - 1);
+        MisIn mi;
+        mi.lhs_m = lhs.m; mi.rhs_m = rhs.m; mi.rhs_jacobian = 1.0f; mi.lhs_lhs_pdf = lhs.pdf;
+        mi.lhs_rhs_pdf = lhs_rhs_pdf * lhs_rhs_vis; mi.rhs_lhs_pdf = rhs_lhs_pdf * rhs_lhs_vis; mi.rhs_rhs_pdf = rhs.pdf;
+        MisOut mo = mis_eval(mi);
+        DiRes main_ = di_zero();
+        float main_pdf = 0.0f;
+        if (di_update(main_, rng, lhs, mo.lhs_mis * mo.lhs_pdf * lhs.w)) main_pdf = mo.lhs_pdf;
+        if (di_update(main_, rng, rhs, mo.rhs_mis * mo.rhs_pdf * rhs.w)) { main_pdf = mo.rhs_pdf; main_.occluded = lhs_rhs_vis == 0.0f; }
+        main_.m = lhs.m + mo.m;
+        main_.pdf = main_pdf;
+        main_.w = res_norm(main_.w, main_pdf, 1.0f, 1.0f);
+        di_store(main_, out, lhs_idx);
+    } else di_store(lhs, out, lhs_idx);
+    uint2 op = checker(g.x, g.y, frame / 2u);
+    if (cam_contains_u(cam.curr, op.x, op.y)) { size_t oi = screen_idx(cam, op.x, op.y); di_store(di_load(in, oi), out, oi); }
+}
+__global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 seed, u32 frame) {
+    Px g = pixel_half(cam);
+    if (!g.in) return;
+    di_spatial_sample_pair(cam, seed, frame, g, tex_or_zero(cam.di_diff_stash, cam, g.x * 2u, g.y), tex_or_zero(cam.di_diff_stash, cam, g.x * 2u + 1u, g.y));
+}
+// K7 + K8 + K9 in one launch (ST_OPT_FUSED_PASSES): one thread per checkerboard pair picks the neighbour, traces the pair's two shadow
+// rays and merges — the three scratch textures (48 B per pixel written and read back) never leave the registers.  Same draws, same rays
+// (direction through the same octahedral round trip), same merge as the three-launch sequence.
+template <bool BINNED>
+__global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_fused(KPARAMS, int cur, u32 seed_pick, u32 seed_sample, u32 frame) {
+    ST_TRACE_STACK();
+    Px g = pixel_half(cam);
+    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
+    float4 d2a, d2b;
+    if (BINNED) {
+        ST_BINNED_TRACER(tr);
+        if (g.in) o = di_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
+    } else {
+        if (!g.in) return;
+        DirectTracer tr{sc, stk};
+        o = di_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+        if (o.state == 0) return;
+        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
+    }
+    if (!g.in || o.state == 0) return;
+    di_spatial_sample_pair(cam, seed_sample, frame, g, d2a, d2b);
+}
+
+// K10 di_resolving::main (di_resolving.rs:4-119)
+__global__ void ST_LB_DI_RESOLVING k_di_resolving(KPARAMS, int cur) {
+    ST_TRACE_STACK();
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    size_t idx = screen_idx(cam, p.x, p.y);
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    DiRes res = di_load(cam.di_reservoirs[2], idx);
+    float confidence;
+    LightRad rad;
+    if (hit_some(hit)) {
+        bool occ = trace_any(di_ray(res, hit.point), sc, stk);
+        confidence = (res.occluded == occ) ? res.confidence : 0.0f;
+        res.confidence = 1.0f;
+        res.occluded = occ;
+        if (occ) rad = lightrad_zero();
+        else { rad = light_radiance(light_load(sc, res.light_id), hit); rad.radiance = rad.radiance * res.w; }
+    } else {
+        confidence = 1.0f;
+        rad.radiance = atmosphere_sample(sc, world_sun_dir(sc.world), hit.dir);
+        rad.diff = f3s(1.0f); rad.spec = f3s(0.0f);
+    }
+    float diff_brdf = (1.0f - hit.g.metallic) / kPi;
+    size_t i = pix(cam, p.x, p.y);
+    cam.di_diff_samples[i] = f4(rad.radiance * diff_brdf, confidence);
+    cam.di_spec_samples[i] = f4(rad.radiance * rad.spec, confidence);
+    di_store(res, cam.di_reservoirs[0], idx);
+}
+
+// K11 gi_reprojection::main (gi_reprojection.rs:4-51)
+ST_DEV GiRes gi_reprojection_px(const CameraDev& cam, const Hit& hit, const Reproj& rp) {
+    size_t npx = (size_t)cam.w * cam.h;
+    GiRes res = gi_zero();
+    if (reproj_some(rp)) {
+        uint2 rpos = reproj_round(rp);
+        size_t ridx = screen_idx(cam, rpos.x, rpos.y);
+        if (ridx < npx) res = gi_load(cam.gi_reservoirs[0], ridx);
+    }
+    res.confidence = 1.0f;
+    res.v1 = hit.point;
+    return res;
+}
+__global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) {
+    Px p = pixel_full(cam);
+    if (!p.in) return;
+    Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
+    if (!hit_some(hit)) return;
+    // strips: the columns the checkerboard passes do not cover (widths whose (W + 7) / 8 is odd) keep this entry as the spatial pass's
+    // output, so there it is one of the rows a neighbouring strip's preview pass gathers
+    gi_store_m(cam, gi_reprojection_px(cam, hit, reproj_decode(cam.reprojection_map[pix(cam, p.x, p.y)])), cam.gi_reservoirs[2], screen_idx(cam, p.x, p.y), p.y,
+               (int)p.x >= 2 * half_grid_w(cam.w) ? cam.gi_mirror_reach : 0);
+}
 
 // K12 gi_sampling_a::main (gi_sampling_a.rs:4-122).  `live` = this thread has a checkerboard cell to work on; returns false where the
 // kernel leaves without writing its three scratch texels (gi_d0: ray direction + pdf, gi_d1/gi_d2: the packed G-buffer entry of what the
@@ -864,13 +884,24 @@ __global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u
     gi_spatial_sample_pair(cam, seed, frame, g, tex_or_zero(cam.gi_d2, cam, g.x * 2u, g.y), tex_or_zero(cam.gi_d2, cam, g.x * 2u + 1u, g.y));
 }
 // K15 + K16 + K17 in one launch (ST_OPT_FUSED_PASSES), like k_di_spatial_fused
+template <bool BINNED>
 __global__ void ST_LB_GI_SPATIAL_PICK k_gi_spatial_fused(KPARAMS, int cur, u32 seed_pick, u32 seed_sample, u32 frame) {
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
-    if (!g.in) return;
-    PairTexels o = gi_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
-    if (o.state == 0) return;
-    float4 d2a, d2b; trace_pair_texels(cam, sc, stk, o, g, &d2a, &d2b);
+    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
+    float4 d2a, d2b;
+    if (BINNED) {
+        ST_BINNED_TRACER(tr);
+        if (g.in) o = gi_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
+    } else {
+        if (!g.in) return;
+        DirectTracer tr{sc, stk};
+        o = gi_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+        if (o.state == 0) return;
+        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
+    }
+    if (!g.in || o.state == 0) return;
     gi_spatial_sample_pair(cam, seed_sample, frame, g, d2a, d2b);
 }
 
@@ -1647,11 +1678,15 @@ void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u
 void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, int mirror_reach, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out, mirror_reach); }
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
 void launch_di_sample_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed_sampling, u32 seed_temporal, u32 frame, cudaStream_t st) { k_di_sample_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed_sampling, seed_temporal, frame); }
-void launch_di_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_di_spatial_fused, c, st, c, s, cur, seed_pick, seed_sample, frame); }
+void launch_di_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, bool binned, cudaStream_t st) {
+    if (binned) HALF_LAUNCH(k_di_spatial_fused<true>, c, st, c, s, cur, seed_pick, seed_sample, frame); else HALF_LAUNCH(k_di_spatial_fused<false>, c, st, c, s, cur, seed_pick, seed_sample, frame);
+}
 void launch_gi_sampling_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_a, u32 seed_b, u32 frame, bool binned, cudaStream_t st) {
     if (binned) HALF_LAUNCH(k_gi_sampling_fused<true>, c, st, c, s, cur, seed_a, seed_b, frame); else HALF_LAUNCH(k_gi_sampling_fused<false>, c, st, c, s, cur, seed_a, seed_b, frame);
 }
-void launch_gi_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_fused, c, st, c, s, cur, seed_pick, seed_sample, frame); }
+void launch_gi_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, bool binned, cudaStream_t st) {
+    if (binned) HALF_LAUNCH(k_gi_spatial_fused<true>, c, st, c, s, cur, seed_pick, seed_sample, frame); else HALF_LAUNCH(k_gi_spatial_fused<false>, c, st, c, s, cur, seed_pick, seed_sample, frame);
+}
 void launch_gi_preview_resolve(const CameraDev& c, const SceneDev& s, int cur, u32 seed, const float4* in, const float4* source, cudaStream_t st) { k_gi_preview_resolve<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, in, source); }
 #if ST_EXACT_ONLY
 void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, int with_reprojection, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, with_reprojection); }

@@ -812,7 +812,7 @@ def test_fused_passes_bit_exact(gpu, oracle, blue_noise, scene_name, size):
     scene = {"cornell": scenes.cornell, "demo_level": scenes.demo_level, "textured_room": scenes.textured_room}[scene_name](*size)
     eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
     eg.set_option(OPT_FUSED_PASSES, 1)
-    eg.set_option(OPT_BINNED_TRACE, 0 if size == (121, 67) else 1)   # the fused GI sampling launch with and without its direction-sorted tracer
+    eg.set_option(OPT_BINNED_TRACE, 0 if size == (121, 67) else 7)   # the fused launches with and without their direction-sorted CTA tracer
     c = scene["camera"]
     base = np.asarray(c["transform"], np.float32).copy()
     names = [n for n in CAMERA_BUFFERS if n not in NOT_WRITTEN_WHEN_FUSED]
