@@ -172,11 +172,7 @@ int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset);
  * GPU's SFU approximations (ex2/sqrt/rcp.approx, <= 2 ulp) and fused multiply-adds, like a GLSL compiler
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
-enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9, ST_OPT_STRIP_FUSED = 10, ST_OPT_FUSED_PASSES = 11, ST_OPT_STRIP_DMA = 12, ST_OPT_BINNED_TRACE = 13 };
-/* ST_OPT_BINNED_TRACE (with ST_OPT_FUSED_PASSES), bit mask: the fused launch sorts its CTA's rays by direction octant through shared
- * memory before tracing them (a warp then walks the BVH coherently); every ray's hit is unchanged.  bit 0: gi_sampling (bounce rays, then
- * their shadow rays), bit 1: gi_spatial_resampling, bit 2: di_spatial_resampling (the pairs' two visibility rays). */
-#define ST_BINNED_TRACE_DEFAULT 1
+enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9, ST_OPT_STRIP_FUSED = 10, ST_OPT_FUSED_PASSES = 11, ST_OPT_STRIP_DMA = 12 };
 /* ST_OPT_STRIP_DMA (default 1; fused strip transport only): the 128-row halos of gi_reservoirs[1] / [2] (64 B per pixel, the bulk of what
  * travels) are pushed by the copy engines on one side stream per neighbour right after the kernel that produced them, overlapping the DI
  * passes that follow, instead of being mirrored by that kernel's own stores; 0 = every halo is mirrored in-kernel. */

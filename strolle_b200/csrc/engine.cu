@@ -429,7 +429,6 @@ struct st_engine {
     bool svgf_fast = true;   // ST_OPT_SVGF_FAST_MATH
     bool shading_fast = ST_SHADING_FAST_DEFAULT != 0;   // ST_OPT_SHADING_FAST_MATH
     bool fused_passes = ST_FUSED_PASSES_DEFAULT != 0;   // ST_OPT_FUSED_PASSES
-    int binned_trace = ST_BINNED_TRACE_DEFAULT;   // ST_OPT_BINNED_TRACE (bit mask)
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
     bool strip_dma = ST_STRIP_DMA_DEFAULT != 0;   // ST_OPT_STRIP_DMA: gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores
@@ -679,14 +678,13 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
     // ST_OPT_FUSED_PASSES: passes whose hand-over is private to a pixel (or to a checkerboard pair) run as one launch; the step keeps
     // the pass id of the member that gathers from other pixels, which is what the strip plans key on.
     const bool fp = e->fused_passes;
-    const int binned_mask = e->binned_trace;   // bit 0 gi_sampling, 1 gi_spatial, 2 di_spatial
     if (!e->instances.empty()) {
         if (!k4_in_k0) add(P_FRAME_REPROJECTION, [=](cudaStream_t s) { launch_frame_reprojection(cam, sc, cur, s); });
         if (needs_di) {
             uint32_t s1 = seed(P_DI_SAMPLING), s2 = seed(P_DI_TEMPORAL), s3 = seed(P_DI_SPATIAL_PICK), s5 = seed(P_DI_SPATIAL_SAMPLE);
             if (fp) {
                 add(P_DI_TEMPORAL, [=](cudaStream_t s) { (fs ? stf::launch_di_sample_temporal : st::launch_di_sample_temporal)(cam, sc, cur, s1, s2, f, s); });
-                add(P_DI_SPATIAL_PICK, [=](cudaStream_t s) { (fs ? stf::launch_di_spatial_fused : st::launch_di_spatial_fused)(cam, sc, cur, s3, s5, f, (binned_mask & 4) != 0, s); });
+                add(P_DI_SPATIAL_PICK, [=](cudaStream_t s) { (fs ? stf::launch_di_spatial_fused : st::launch_di_spatial_fused)(cam, sc, cur, s3, s5, f, s); });
             } else {
                 add(P_DI_SAMPLING, [=](cudaStream_t s) { (fs ? stf::launch_di_sampling : st::launch_di_sampling)(cam, sc, cur, s1, f, s); });
                 add(P_DI_TEMPORAL, [=](cudaStream_t s) { (fs ? stf::launch_di_temporal : st::launch_di_temporal)(cam, sc, cur, s2, s); });
@@ -703,7 +701,7 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
             const int inline_rp = (fp && tracing) ? 1 : 0;   // K11 inside K14; validation frames keep K11 (K12 / K13 read its output)
             if (!inline_rp) add(P_GI_REPROJECTION, [=](cudaStream_t s) { (fs ? stf::launch_gi_reprojection : st::launch_gi_reprojection)(cam, sc, cur, s); });
             auto sampling = [&]() {
-                if (fp) { add(P_GI_SAMPLING_B, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_fused : st::launch_gi_sampling_fused)(cam, sc, cur, sa, sb, f, (binned_mask & 1) != 0, s); }); return; }
+                if (fp) { add(P_GI_SAMPLING_B, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_fused : st::launch_gi_sampling_fused)(cam, sc, cur, sa, sb, f, s); }); return; }
                 add(P_GI_SAMPLING_A, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_a : st::launch_gi_sampling_a)(cam, sc, cur, sa, f, s); });
                 add(P_GI_SAMPLING_B, [=](cudaStream_t s) { (fs ? stf::launch_gi_sampling_b : st::launch_gi_sampling_b)(cam, sc, cur, sb, f, s); });
             };
@@ -711,7 +709,7 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
                 if (f % 2u == 0u) sampling();
                 add(P_GI_TEMPORAL, [=](cudaStream_t s) { (fs ? stf::launch_gi_temporal : st::launch_gi_temporal)(cam, sc, cur, st_, f, inline_rp, s); });
                 if (f % 2u == 1u) {
-                    if (fp) add(P_GI_SPATIAL_PICK, [=](cudaStream_t s) { (fs ? stf::launch_gi_spatial_fused : st::launch_gi_spatial_fused)(cam, sc, cur, sp, ss, f, (binned_mask & 2) != 0, s); });
+                    if (fp) add(P_GI_SPATIAL_PICK, [=](cudaStream_t s) { (fs ? stf::launch_gi_spatial_fused : st::launch_gi_spatial_fused)(cam, sc, cur, sp, ss, f, s); });
                     else {
                         add(P_GI_SPATIAL_PICK, [=](cudaStream_t s) { (fs ? stf::launch_gi_spatial_pick : st::launch_gi_spatial_pick)(cam, sc, cur, sp, f, s); });
                         add(P_GI_SPATIAL_TRACE, [=](cudaStream_t s) { (fs ? stf::launch_spatial_trace : st::launch_spatial_trace)(cam, sc, cam.gi_d0, cam.gi_d1, cam.gi_d2, s); });
@@ -1534,7 +1532,6 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
     if (option == ST_OPT_STRIP_DMA) { e->strip_dma = value != 0; return ST_OK; }
     if (option == ST_OPT_FUSED_PASSES) { e->fused_passes = value != 0; return ST_OK; }
-    if (option == ST_OPT_BINNED_TRACE) { e->binned_trace = value & 7; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
     if (option == ST_OPT_VARIANCE_TILED) { e->variance_tiled = value != 0; return ST_OK; }
     if (option == ST_OPT_BVH_REUSE) { e->bvh_reuse = value != 0; return ST_OK; }

@@ -306,81 +306,6 @@ __global__ void ST_LB_DI_SAMPLING k_di_sample_temporal(KPARAMS, int cur, u32 see
     di_store_m(cam, di_temporal_px(cam, sc, cur, seed_temporal, p, hit, fresh), cam.di_reservoirs[1], screen_idx(cam, p.x, p.y), p.y, ST_REACH_SPATIAL);
 }
 
-// ---- how a kernel traces the rays of its CTA ---------------------------------------------------------------------------------------
-// DirectTracer: every thread walks the BVH for its own ray (what every kernel did so far).
-// BinnedTracer: the CTA's rays are first sorted by direction octant through shared memory (counting sort over warp ballots), thread i
-// traces the i-th ray of that order and hands the hit back to the ray's owner.  Bounce rays of neighbouring pixels point anywhere
-// in a hemisphere (12-15 of 32 lanes active in the traversal loop on the dungeon); after the sort a warp's rays share a direction
-// octant and visit the BVH in a similar order.  Which thread walks a ray does not change its hit, so results are bit-identical.
-// Both are CTA-collective: EVERY thread of the CTA calls closest() / any() (with active = false when it has no ray).
-struct DirectTracer {
-    const SceneDev& sc; const TraceStack& stk;
-    ST_DEV TriHit closest(const Ray& r, bool active) { return active ? trace_closest(r, sc, stk) : trihit_none(); }
-    ST_DEV bool any(const Ray& r, bool active) { return active ? trace_any(r, sc, stk) : false; }
-};
-struct BinnedTracer {
-    const SceneDev& sc; const TraceStack& stk;
-    float4* s_ray;    // [2 * ST_BLOCK]: (origin, len), (direction, owner thread)
-    float4* s_hit;    // [3 * ST_BLOCK]: the owner's TriHit; any(): word 0 of the owner's first float4
-    u32* s_cnt;       // [4 warps][9 keys]
-    // slot of this thread's ray in the octant order (inactive threads last); *n_active = rays in the CTA
-    ST_DEV u32 sort_slot(const Ray& r, bool active, u32* n_active) {
-        const u32 lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-        const u32 key = active ? ((r.d.x < 0.0f ? 1u : 0u) | (r.d.y < 0.0f ? 2u : 0u) | (r.d.z < 0.0f ? 4u : 0u)) : 8u;
-        u32 rank = 0u;
-#pragma unroll
-        for (u32 k = 0; k < 9u; k++) {
-            u32 m = __ballot_sync(0xffffffffu, key == k);
-            if (lane == 0u) s_cnt[warp * 9u + k] = (u32)__popc(m);
-            if (key == k) rank = (u32)__popc(m & ((1u << lane) - 1u));
-        }
-        __syncthreads();
-        u32 pos = rank, total = 0u;
-#pragma unroll
-        for (u32 k = 0; k < 9u; k++) {
-            u32 ck = s_cnt[k] + s_cnt[9u + k] + s_cnt[18u + k] + s_cnt[27u + k];
-            if (k < key) pos += ck;
-            if (k < 8u) total += ck;
-        }
-        for (u32 w = 0; w < warp; w++) pos += s_cnt[w * 9u + key];
-        *n_active = total;
-        return pos;
-    }
-    ST_DEV TriHit closest(const Ray& r, bool active) {
-        u32 n; u32 pos = sort_slot(r, active, &n);
-        s_ray[2u * pos] = f4(r.o, r.len); s_ray[2u * pos + 1u] = f4(r.d, bitsf(threadIdx.x));
-        __syncthreads();
-        if (threadIdx.x < n) {
-            float4 a = s_ray[2u * threadIdx.x], b = s_ray[2u * threadIdx.x + 1u];
-            TriHit h = trace_closest(ray_make(xyz(a), xyz(b), a.w), sc, stk);
-            u32 owner = fbits(b.w);
-            s_hit[3u * owner] = f4(h.t, h.point.x, h.point.y, h.point.z);
-            s_hit[3u * owner + 1u] = f4(h.normal, h.uv.x);
-            s_hit[3u * owner + 2u] = f4(h.uv.y, bitsf(h.material_id), bitsf(h.triangle_id), 0.0f);
-        }
-        __syncthreads();
-        if (!active) return trihit_none();
-        float4 h0 = s_hit[3u * threadIdx.x], h1 = s_hit[3u * threadIdx.x + 1u], h2 = s_hit[3u * threadIdx.x + 2u];
-        TriHit h; h.t = h0.x; h.point = f3(h0.y, h0.z, h0.w); h.normal = xyz(h1); h.uv = f2(h1.w, h2.x); h.material_id = fbits(h2.y); h.triangle_id = fbits(h2.z);
-        return h;
-    }
-    ST_DEV bool any(const Ray& r, bool active) {
-        u32 n; u32 pos = sort_slot(r, active, &n);
-        s_ray[2u * pos] = f4(r.o, r.len); s_ray[2u * pos + 1u] = f4(r.d, bitsf(threadIdx.x));
-        __syncthreads();
-        if (threadIdx.x < n) {
-            float4 a = s_ray[2u * threadIdx.x], b = s_ray[2u * threadIdx.x + 1u];
-            bool occ = trace_any(ray_make(xyz(a), xyz(b), a.w), sc, stk);
-            s_hit[3u * fbits(b.w)].x = occ ? 1.0f : 0.0f;
-        }
-        __syncthreads();
-        return active && s_hit[3u * threadIdx.x].x != 0.0f;
-    }
-};
-#define ST_BINNED_TRACER(name)                                                                                   \
-    __shared__ float4 s_bin_ray[2 * ST_BLOCK]; __shared__ float4 s_bin_hit[3 * ST_BLOCK]; __shared__ u32 s_bin_cnt[36]; \
-    BinnedTracer name{sc, stk, s_bin_ray, s_bin_hit, s_bin_cnt};
-
 // The four scratch texels of one checkerboard pair: (d0, d1) of texel a = (2gx, gy) and texel b = (2gx + 1, gy).
 // state 0: the pair has no left-hand pixel on the screen, nothing is written; 1: only the two d1 texels are cleared; 2: all four.
 struct PairTexels { float4 a0, a1, b0, b1; int state; };
@@ -454,20 +379,11 @@ __global__ void ST_LB_SPATIAL_TRACE k_spatial_trace(KPARAMS, const float4* __res
     size_t i = pix(cam, p.x, p.y);
     buf_d2[i] = spatial_trace_texel(sc, stk, buf_d0[i], buf_d1[i]);
 }
-// the two visibility texels of a pair as K8 / K16 would leave them for K9 / K17 (a texel outside the texture reads as zero); collective
-// when the tracer is (every thread of the CTA calls it, `o.state` = 0 for threads without a pair)
-template <class Tracer>
-ST_DEV float4 spatial_trace_texel_t(Tracer& tr, float4 d0, float4 d1, bool present) {
-    const bool active = present && !all_zero(d1);
-    Ray ray = active ? ray_make(xyz(d0), oct_decode(f2(d1.x, d1.y)), d0.w) : ray_zero();
-    bool occ = tr.any(ray, active);
-    return active ? f4(occ ? 0.0f : 1.0f, d1.z, d1.w, 0.0f) : f4zero();
-}
-template <class Tracer>
-ST_DEV void trace_pair_texels(const CameraDev& cam, Tracer& tr, const PairTexels& o, Px g, float4* d2a, float4* d2b) {
+// the two visibility texels of a pair as K8 / K16 would leave them for K9 / K17 (a texel outside the texture reads as zero)
+ST_DEV void trace_pair_texels(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, const PairTexels& o, Px g, float4* d2a, float4* d2b) {
     u32 ax = g.x * 2u, bx = g.x * 2u + 1u;
-    *d2a = spatial_trace_texel_t(tr, o.a0, o.a1, o.state == 2 && in_tex(cam, ax, g.y));
-    *d2b = spatial_trace_texel_t(tr, o.b0, o.b1, o.state == 2 && in_tex(cam, bx, g.y));
+    *d2a = (o.state == 2 && in_tex(cam, ax, g.y)) ? spatial_trace_texel(sc, stk, o.a0, o.a1) : f4zero();
+    *d2b = (o.state == 2 && in_tex(cam, bx, g.y)) ? spatial_trace_texel(sc, stk, o.b0, o.b1) : f4zero();
 }
 
 // K9 di_spatial_resampling::sample (di_spatial_resampling.rs:212-297); d0 / d1 = the pair's two visibility texels
@@ -507,24 +423,13 @@ __global__ void __launch_bounds__(ST_BLOCK) k_di_spatial_sample(KPARAMS, u32 see
 // K7 + K8 + K9 in one launch (ST_OPT_FUSED_PASSES): one thread per checkerboard pair picks the neighbour, traces the pair's two shadow
 // rays and merges — the three scratch textures (48 B per pixel written and read back) never leave the registers.  Same draws, same rays
 // (direction through the same octahedral round trip), same merge as the three-launch sequence.
-template <bool BINNED>
 __global__ void ST_LB_DI_SPATIAL_PICK k_di_spatial_fused(KPARAMS, int cur, u32 seed_pick, u32 seed_sample, u32 frame) {
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
-    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
-    float4 d2a, d2b;
-    if (BINNED) {
-        ST_BINNED_TRACER(tr);
-        if (g.in) o = di_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
-        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
-    } else {
-        if (!g.in) return;
-        DirectTracer tr{sc, stk};
-        o = di_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
-        if (o.state == 0) return;
-        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
-    }
-    if (!g.in || o.state == 0) return;
+    if (!g.in) return;
+    PairTexels o = di_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+    if (o.state == 0) return;
+    float4 d2a, d2b; trace_pair_texels(cam, sc, stk, o, g, &d2a, &d2b);
     di_spatial_sample_pair(cam, seed_sample, frame, g, d2a, d2b);
 }
 
@@ -581,34 +486,29 @@ __global__ void __launch_bounds__(ST_BLOCK) k_gi_reprojection(KPARAMS, int cur) 
                (int)p.x >= 2 * half_grid_w(cam.w) ? cam.gi_mirror_reach : 0);
 }
 
-// K12 gi_sampling_a::main (gi_sampling_a.rs:4-122).  `live` = this thread has a checkerboard cell to work on; returns false where the
-// kernel leaves without writing its three scratch texels (gi_d0: ray direction + pdf, gi_d1/gi_d2: the packed G-buffer entry of what the
-// ray hit).  No thread returns before the trace: the tracer may be CTA-collective.
-template <class Tracer>
-ST_DEV bool gi_sampling_a_pair(const CameraDev& cam, const SceneDev& sc, Tracer& tr, int cur, u32 seed, u32 frame, Px g, bool live, float4* t0, float4* t1, float4* t2) {
+// K12 gi_sampling_a::main (gi_sampling_a.rs:4-122)
+// returns false where the kernel leaves without writing its three scratch texels (gi_d0: ray direction + pdf, gi_d1/gi_d2: the packed
+// G-buffer entry of what the ray hit)
+ST_DEV bool gi_sampling_a_pair(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, int cur, u32 seed, u32 frame, Px g, float4* t0, float4* t1, float4* t2) {
     bool tracing = gi_tracing_frame(frame);
     uint2 sp = tracing ? checker(g.x, g.y, frame / 2u) : checker(g.x, g.y, frame);
-    live = live && cam_contains_u(cam.curr, sp.x, sp.y);
-    Ray gi_r = ray_zero(); float gi_pdf_ = 0.0f;
-    if (live) {
-        size_t idx = screen_idx(cam, sp.x, sp.y);
-        if (tracing) {
-            Rng rng = rng_make(seed, sp.x, sp.y);
-            Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
-            if (!hit_some(hit)) live = false;
-            else {
-                BrdfS s = brdf_layered_sample(hit.g, rng, -hit.dir);
-                gi_r = ray_make(hit.point, s.dir);
-                gi_pdf_ = s.pdf;
-            }
-        } else {
-            GiRes res = gi_load(cam.gi_reservoirs[2], idx);
-            if (res.m == 0.0f) live = false;
-            else { gi_r = ray_make(res.v1, gi_dir(res, res.v1)); gi_pdf_ = 1.0f; }
-        }
+    if (!cam_contains_u(cam.curr, sp.x, sp.y)) return false;
+    size_t idx = screen_idx(cam, sp.x, sp.y);
+    Ray gi_r; float gi_pdf_;
+    if (tracing) {
+        Rng rng = rng_make(seed, sp.x, sp.y);
+        Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
+        if (!hit_some(hit)) return false;
+        BrdfS s = brdf_layered_sample(hit.g, rng, -hit.dir);
+        gi_r = ray_make(hit.point, s.dir);
+        gi_pdf_ = s.pdf;
+    } else {
+        GiRes res = gi_load(cam.gi_reservoirs[2], idx);
+        if (res.m == 0.0f) return false;
+        gi_r = ray_make(res.v1, gi_dir(res, res.v1));
+        gi_pdf_ = 1.0f;
     }
-    TriHit gh = tr.closest(gi_r, live);
-    if (!live) return false;
+    TriHit gh = trace_closest(gi_r, sc, stk);
     GBuf gg = gbuf_zero();
     u32 gi_color_bits = 0u;
     if (trihit_some(gh)) {
@@ -626,71 +526,56 @@ __global__ void ST_LB_GI_SAMPLING_A k_gi_sampling_a(KPARAMS, int cur, u32 seed, 
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
     if (!g.in) return;
-    DirectTracer tr{sc, stk};
     float4 t0, t1, t2;
-    if (!gi_sampling_a_pair(cam, sc, tr, cur, seed, frame, g, true, &t0, &t1, &t2)) return;
+    if (!gi_sampling_a_pair(cam, sc, stk, cur, seed, frame, g, &t0, &t1, &t2)) return;
     size_t gi = pix(cam, g.x, g.y);
     cam.gi_d0[gi] = t0; cam.gi_d1[gi] = t1; cam.gi_d2[gi] = t2;
 }
 
 // K13 gi_sampling_b::main (gi_sampling_b.rs:4-235)
-template <class Tracer>
-ST_DEV void gi_sampling_b_pair(const CameraDev& cam, const SceneDev& sc, Tracer& tr, int cur, u32 seed, u32 frame, Px g, bool live, float4 d0, float4 d1, float4 d2) {
+ST_DEV void gi_sampling_b_pair(const CameraDev& cam, const SceneDev& sc, const TraceStack& stk, int cur, u32 seed, u32 frame, Px g, float4 d0, float4 d1, float4 d2) {
     bool tracing = gi_tracing_frame(frame);
     uint2 sp = tracing ? checker(g.x, g.y, frame / 2u) : checker(g.x, g.y, frame);
-    live = live && cam_contains_u(cam.curr, sp.x, sp.y);
-    size_t idx = 0;
-    Hit prim = hit_zero();
-    Rng rng; rng.s = 0u; Hit gh = hit_zero(); float gi_pdf_ = 0.0f;
-    if (live) {
-        idx = screen_idx(cam, sp.x, sp.y);
-        prim = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
-        if (!hit_some(prim)) live = false;
-    }
-    if (live) {
-        if (tracing) {
-            rng = rng_make(seed, sp.x, sp.y);
-            gh = hit_make(ray_make(prim.point, xyz(d0)), gbuf_unpack(sc, d1, d2));
-            gi_pdf_ = d0.w;
-        } else {
-            GiRes res = gi_load(cam.gi_reservoirs[2], idx);
-            if (res.m == 0.0f) live = false;
-            else {
-                rng.s = res.rng;
-                gh = hit_make(ray_make(res.v1, xyz(d0)), gbuf_unpack(sc, d1, d2));
-                gi_pdf_ = 1.0f;
-            }
-        }
+    if (!cam_contains_u(cam.curr, sp.x, sp.y)) return;
+    size_t idx = screen_idx(cam, sp.x, sp.y);
+    Hit prim = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, sp.x, sp.y);
+    if (!hit_some(prim)) return;
+    Rng rng; Hit gh; float gi_pdf_;
+    if (tracing) {
+        rng = rng_make(seed, sp.x, sp.y);
+        gh = hit_make(ray_make(prim.point, xyz(d0)), gbuf_unpack(sc, d1, d2));
+        gi_pdf_ = d0.w;
+    } else {
+        GiRes res = gi_load(cam.gi_reservoirs[2], idx);
+        if (res.m == 0.0f) return;
+        rng.s = res.rng;
+        gh = hit_make(ray_make(res.v1, xyz(d0)), gbuf_unpack(sc, d1, d2));
+        gi_pdf_ = 1.0f;
     }
     u32 rng_state = rng.s;
     const u32 SKY = 0xffffffffu;
-    u32 light_id = 0u; float light_pdf = 0.0f; float3 light_rad = f3s(0.f); float3 light_dir = f3s(0.f);
-    bool shadow = false; Ray shadow_ray = ray_zero();
-    if (live) {
-        float3 sun_dir = world_sun_dir(sc.world);
-        if (!hit_some(gh)) { light_id = SKY; light_pdf = 1.0f; light_rad = atmosphere_sample(sc, sun_dir, gh.dir); }
-        else {
-            float atm_pdf = (sc.world.sun_altitude <= -1.0f) ? 0.0f : 0.25f;
-            if (sc.world.light_count == 0u || rng_f(rng) < atm_pdf) {
-                light_id = SKY; light_pdf = atm_pdf;
-                light_dir = rng_hemisphere(rng, gh.g.normal);
-                light_rad = atmosphere_sample(sc, sun_dir, light_dir) * dot(gh.g.normal, light_dir);
-            } else {
-                EphRes er = ephemeral_build(rng, sc, gh);
-                if (er.w > 0.0f) { light_id = er.light_id; light_pdf = (1.0f / er.w) * (1.0f - atm_pdf); light_rad = er.rad.radiance * (f3s(1.0f) + er.rad.spec); }
-                else { light_id = 0u; light_pdf = 1.0f; light_rad = f3s(0.f); }
-            }
-        }
-        if (light_pdf > 0.0f && hit_some(gh)) {
-            shadow = true;
-            shadow_ray = (light_id == SKY) ? ray_make(gh.point, light_dir) : light_ray_wnoise(light_load(sc, light_id), rng, gh.point);
+    float3 sun_dir = world_sun_dir(sc.world);
+    u32 light_id; float light_pdf; float3 light_rad; float3 light_dir = f3s(0.f);
+    if (!hit_some(gh)) { light_id = SKY; light_pdf = 1.0f; light_rad = atmosphere_sample(sc, sun_dir, gh.dir); }
+    else {
+        float atm_pdf = (sc.world.sun_altitude <= -1.0f) ? 0.0f : 0.25f;
+        if (sc.world.light_count == 0u || rng_f(rng) < atm_pdf) {
+            light_id = SKY; light_pdf = atm_pdf;
+            light_dir = rng_hemisphere(rng, gh.g.normal);
+            light_rad = atmosphere_sample(sc, sun_dir, light_dir) * dot(gh.g.normal, light_dir);
+        } else {
+            EphRes er = ephemeral_build(rng, sc, gh);
+            if (er.w > 0.0f) { light_id = er.light_id; light_pdf = (1.0f / er.w) * (1.0f - atm_pdf); light_rad = er.rad.radiance * (f3s(1.0f) + er.rad.spec); }
+            else { light_id = 0u; light_pdf = 1.0f; light_rad = f3s(0.f); }
         }
     }
-    bool occluded = tr.any(shadow_ray, shadow);
-    if (!live) return;
     float3 radiance;
     if (light_pdf > 0.0f) {
-        float vis = shadow ? (occluded ? 0.0f : 1.0f) : 1.0f;
+        float vis;
+        if (hit_some(gh)) {
+            Ray r = (light_id == SKY) ? ray_make(gh.point, light_dir) : light_ray_wnoise(light_load(sc, light_id), rng, gh.point);
+            vis = trace_any(r, sc, stk) ? 0.0f : 1.0f;
+        } else vis = 1.0f;
         radiance = light_rad * vis / light_pdf;
     } else radiance = f3s(0.f);
     if (hit_some(gh)) { radiance = radiance * (xyz(gh.g.base_color) / kPi); radiance = radiance + gh.g.emissive; }
@@ -709,28 +594,18 @@ __global__ void ST_LB_GI_SAMPLING_B k_gi_sampling_b(KPARAMS, int cur, u32 seed, 
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
     if (!g.in) return;
-    DirectTracer tr{sc, stk};
     size_t gi = pix(cam, g.x, g.y);
-    gi_sampling_b_pair(cam, sc, tr, cur, seed, frame, g, true, cam.gi_d0[gi], cam.gi_d1[gi], cam.gi_d2[gi]);
+    gi_sampling_b_pair(cam, sc, stk, cur, seed, frame, g, cam.gi_d0[gi], cam.gi_d1[gi], cam.gi_d2[gi]);
 }
 // K12 + K13 in one launch (ST_OPT_FUSED_PASSES): the bounce ray is traced and shaded by the same thread; the hit still goes through
-// GBufferEntry's pack / unpack (its 8-bit quantisation is part of the result), just not through memory.  BINNED (ST_OPT_BINNED_TRACE):
-// the CTA's bounce rays and then its shadow rays are traced in direction-octant order (BinnedTracer).
-template <bool BINNED>
+// GBufferEntry's pack / unpack (its 8-bit quantisation is part of the result), just not through memory.
 __global__ void ST_LB_GI_SAMPLING_B k_gi_sampling_fused(KPARAMS, int cur, u32 seed_a, u32 seed_b, u32 frame) {
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
-    float4 t0 = f4zero(), t1 = f4zero(), t2 = f4zero();
-    if (BINNED) {
-        ST_BINNED_TRACER(tr);
-        bool live = gi_sampling_a_pair(cam, sc, tr, cur, seed_a, frame, g, g.in, &t0, &t1, &t2);
-        gi_sampling_b_pair(cam, sc, tr, cur, seed_b, frame, g, live, t0, t1, t2);
-    } else {
-        if (!g.in) return;
-        DirectTracer tr{sc, stk};
-        if (!gi_sampling_a_pair(cam, sc, tr, cur, seed_a, frame, g, true, &t0, &t1, &t2)) return;
-        gi_sampling_b_pair(cam, sc, tr, cur, seed_b, frame, g, true, t0, t1, t2);
-    }
+    if (!g.in) return;
+    float4 t0, t1, t2;
+    if (!gi_sampling_a_pair(cam, sc, stk, cur, seed_a, frame, g, &t0, &t1, &t2)) return;
+    gi_sampling_b_pair(cam, sc, stk, cur, seed_b, frame, g, t0, t1, t2);
 }
 
 // K14 gi_temporal_resampling::main (gi_temporal_resampling.rs:4-156)
@@ -884,24 +759,13 @@ __global__ void ST_LB_GI_SPATIAL_SAMPLE k_gi_spatial_sample(KPARAMS, u32 seed, u
     gi_spatial_sample_pair(cam, seed, frame, g, tex_or_zero(cam.gi_d2, cam, g.x * 2u, g.y), tex_or_zero(cam.gi_d2, cam, g.x * 2u + 1u, g.y));
 }
 // K15 + K16 + K17 in one launch (ST_OPT_FUSED_PASSES), like k_di_spatial_fused
-template <bool BINNED>
 __global__ void ST_LB_GI_SPATIAL_PICK k_gi_spatial_fused(KPARAMS, int cur, u32 seed_pick, u32 seed_sample, u32 frame) {
     ST_TRACE_STACK();
     Px g = pixel_half(cam);
-    PairTexels o; o.a0 = o.a1 = o.b0 = o.b1 = f4zero(); o.state = 0;
-    float4 d2a, d2b;
-    if (BINNED) {
-        ST_BINNED_TRACER(tr);
-        if (g.in) o = gi_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
-        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
-    } else {
-        if (!g.in) return;
-        DirectTracer tr{sc, stk};
-        o = gi_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
-        if (o.state == 0) return;
-        trace_pair_texels(cam, tr, o, g, &d2a, &d2b);
-    }
-    if (!g.in || o.state == 0) return;
+    if (!g.in) return;
+    PairTexels o = gi_spatial_pick_pair(cam, sc, cur, seed_pick, frame, g);
+    if (o.state == 0) return;
+    float4 d2a, d2b; trace_pair_texels(cam, sc, stk, o, g, &d2a, &d2b);
     gi_spatial_sample_pair(cam, seed_sample, frame, g, d2a, d2b);
 }
 
@@ -1678,15 +1542,9 @@ void launch_gi_spatial_sample(const CameraDev& c, const SceneDev& s, u32 seed, u
 void launch_gi_preview(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 nth, const float4* in, float4* out, int mirror_reach, cudaStream_t st) { k_gi_preview<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, nth, in, out, mirror_reach); }
 void launch_gi_resolving(const CameraDev& c, const SceneDev& s, int cur, const float4* in, cudaStream_t st) { k_gi_resolving<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, in); }
 void launch_di_sample_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed_sampling, u32 seed_temporal, u32 frame, cudaStream_t st) { k_di_sample_temporal<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed_sampling, seed_temporal, frame); }
-void launch_di_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, bool binned, cudaStream_t st) {
-    if (binned) HALF_LAUNCH(k_di_spatial_fused<true>, c, st, c, s, cur, seed_pick, seed_sample, frame); else HALF_LAUNCH(k_di_spatial_fused<false>, c, st, c, s, cur, seed_pick, seed_sample, frame);
-}
-void launch_gi_sampling_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_a, u32 seed_b, u32 frame, bool binned, cudaStream_t st) {
-    if (binned) HALF_LAUNCH(k_gi_sampling_fused<true>, c, st, c, s, cur, seed_a, seed_b, frame); else HALF_LAUNCH(k_gi_sampling_fused<false>, c, st, c, s, cur, seed_a, seed_b, frame);
-}
-void launch_gi_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, bool binned, cudaStream_t st) {
-    if (binned) HALF_LAUNCH(k_gi_spatial_fused<true>, c, st, c, s, cur, seed_pick, seed_sample, frame); else HALF_LAUNCH(k_gi_spatial_fused<false>, c, st, c, s, cur, seed_pick, seed_sample, frame);
-}
+void launch_di_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_di_spatial_fused, c, st, c, s, cur, seed_pick, seed_sample, frame); }
+void launch_gi_sampling_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_a, u32 seed_b, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_sampling_fused, c, st, c, s, cur, seed_a, seed_b, frame); }
+void launch_gi_spatial_fused(const CameraDev& c, const SceneDev& s, int cur, u32 seed_pick, u32 seed_sample, u32 frame, cudaStream_t st) { HALF_LAUNCH(k_gi_spatial_fused, c, st, c, s, cur, seed_pick, seed_sample, frame); }
 void launch_gi_preview_resolve(const CameraDev& c, const SceneDev& s, int cur, u32 seed, const float4* in, const float4* source, cudaStream_t st) { k_gi_preview_resolve<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, seed, in, source); }
 #if ST_EXACT_ONLY
 void launch_prim_gbuffer(const CameraDev& c, const SceneDev& s, int cur, int with_reprojection, cudaStream_t st) { k_prim_gbuffer<<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, with_reprojection); }

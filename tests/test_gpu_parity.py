@@ -255,9 +255,9 @@ def test_default_fast_svgf_mode_within_tolerance(gpu, oracle, blue_noise):
     """The product default evaluates the SVGF edge-stopping weights with SFU approximations (ST_OPT_SVGF_FAST_MATH).
     Everything that is not a denoiser colour buffer stays bit-exact; the denoised colours and the composed image stay
     inside north_star's tolerance: 1e-3 relative per-channel L2, after 13 frames of temporal feedback."""
-    from strolle_b200.engine import OPT_SHADING_FAST_MATH
+    from strolle_b200.engine import OPT_SHADING_FAST_MATH, OPT_FUSED_PASSES
     eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scenes.cornell(192, 108), exact=False)
-    eg.set_option(OPT_SHADING_FAST_MATH, 0)   # only the denoiser's weights are approximate here; test_fast_shading_* covers the product default
+    eg.set_option(OPT_SHADING_FAST_MATH, 0); eg.set_option(OPT_FUSED_PASSES, 0)   # only the denoiser's weights are approximate here; test_fast_shading_* covers the product default
     for f in range(13):
         eg.tick(); eo.tick(); eg.render_camera(cg); eo.render_camera(co)
         for name in CAMERA_BUFFERS:
@@ -808,11 +808,10 @@ def test_fused_passes_bit_exact(gpu, oracle, blue_noise, scene_name, size):
     leave every reservoir, sample, colour, moment and the composed frame bit-identical to the oracle's one-dispatch-per-pass frame, over
     two GI cycles with a moving camera (widths 200 and 121 have columns the checkerboard passes do not cover; the textured room has
     alpha-tested and metallic surfaces)."""
-    from strolle_b200.engine import OPT_FUSED_PASSES, OPT_BINNED_TRACE
+    from strolle_b200.engine import OPT_FUSED_PASSES
     scene = {"cornell": scenes.cornell, "demo_level": scenes.demo_level, "textured_room": scenes.textured_room}[scene_name](*size)
     eg, cg, eo, co = make_pair(gpu, oracle, blue_noise, scene)
     eg.set_option(OPT_FUSED_PASSES, 1)
-    eg.set_option(OPT_BINNED_TRACE, 0 if size == (121, 67) else 7)   # the fused launches with and without their direction-sorted CTA tracer
     c = scene["camera"]
     base = np.asarray(c["transform"], np.float32).copy()
     names = [n for n in CAMERA_BUFFERS if n not in NOT_WRITTEN_WHEN_FUSED]

@@ -8,7 +8,7 @@ from strolle_b200 import scenes
 w, h = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (1920, 1080)
 name = sys.argv[3] if len(sys.argv) > 3 else "cornell"
 e = strolle_b200.Engine(exact=bool(int(os.environ.get('ST_EXACT', '0'))))
-for env, opt in (('ST_BINNED', 13), ('ST_FUSED', 11), ('ST_FAST', 9)):   # development switches: ST_OPT_BINNED_TRACE / _FUSED_PASSES / _SHADING_FAST_MATH
+for env, opt in (('ST_FUSED', 11), ('ST_FAST', 9)):   # development switches: ST_OPT_FUSED_PASSES / ST_OPT_SHADING_FAST_MATH
     if env in os.environ:
         e.set_option(opt, int(os.environ[env]))
 sc = {"cornell": scenes.cornell, "dungeon": scenes.dungeon, "demo": scenes.demo_level}[name](w, h)
