@@ -30,6 +30,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")   # one hardware queue per stream (strolle_b200/__init__.py); must precede CUDA initialisation
 
 CPU_THREADS = 1
 METRIC = "Mrays/s (+ frames/s) at 1080p-per-GPU Cornell, ReSTIR DI+GI + SVGF; B200 vs CPU restatement of the reference"

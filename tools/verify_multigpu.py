@@ -8,6 +8,8 @@ reduces to the single-GPU accumulation.  Prints one OK/FAIL line per check on ra
 import os
 import sys
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
