@@ -982,10 +982,7 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     d.need_rows = (int*)(sync + kNeedRowsWord);
     const bool dma = e->strip_dma;
     d.gi_mirror_reach = dma ? 0 : kSpatialReach;
-    if (dma && !cs->ev_produced) {
-        CK(cudaEventCreateWithFlags(&cs->ev_produced, cudaEventDisableTiming));
-        for (int k = 0; k < 2; k++) { CK(cudaStreamCreateWithFlags(&cs->side[k], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&cs->ev_pushed[k], cudaEventDisableTiming)); }
-    }
+    if (dma && !cs->ev_produced) return fail(ST_ERR_INVALID, "strip side streams missing: link the camera first (st_link_local / st_peer_import)");
     // the copy engines of last frame have long finished; this orders this frame's writes of the pushed rows after them formally
     for (int k = 0; k < 2; k++) if (cs->pushed_pending[k]) { CK(cudaStreamWaitEvent(e->stream, cs->ev_pushed[k], 0)); cs->pushed_pending[k] = false; }
     StripExt ext; ext.gbuffer = kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
@@ -1669,7 +1666,7 @@ int st_peer_import(st_engine* e, st_camera_handle h, const uint8_t* all, int ran
         CK(cudaIpcOpenMemHandle(&p, hs[2], cudaIpcMemLazyEnablePeerAccess)); cs->peer.rgba8[r] = (char*)p;
     }
     e->rank = rank; e->n_ranks = world; cs->peer.seq = 0; cs->peer.fseq = 0; cs->peer.ready = true; cs->peer.ipc = true;
-    return ST_OK;
+    return strip_streams_prepare(e, cs);
 }
 int st_peer_errors(st_engine* e, st_camera_handle h, uint32_t* count) {
     CameraSlot* cs = e ? get_camera(e, h) : nullptr;
@@ -1815,6 +1812,23 @@ int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int forma
 // Links engines that live in THIS process into a strip group (rank = index): enables peer access between their devices and hands every
 // engine the others' buffers directly (the multi-process route is st_peer_export / st_peer_import over CUDA IPC).  Two ranks may share
 // a device, which is how a single-GPU box exercises the whole protocol.
+// Side streams and events of the copy-engine halo pushes, created when the camera is linked — and the device-to-device copy path is
+// exercised once here: the first such copy may load a driver-internal module, which synchronises the device, and inside a frame that
+// would stall this thread while another rank's stream spins on a flag only this thread's later launches can raise.
+static int strip_streams_prepare(st_engine* e, CameraSlot* cs) {
+    if (cs->ev_produced) return ST_OK;
+    CK(cudaEventCreateWithFlags(&cs->ev_produced, cudaEventDisableTiming));
+    for (int k = 0; k < 2; k++) { CK(cudaStreamCreateWithFlags(&cs->side[k], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&cs->ev_pushed[k], cudaEventDisableTiming)); }
+    uint32_t* sync = (uint32_t*)cs->peer.sync.p;
+    for (int k = 0; k < 2; k++) {
+        CK(cudaMemcpyAsync(sync + 512 + 8 * k, sync + 528 + 8 * k, 16, cudaMemcpyDefault, cs->side[k]));   // unused words of the sync buffer
+        CK(cudaEventRecord(cs->ev_pushed[k], cs->side[k]));
+        CK(cudaStreamSynchronize(cs->side[k]));
+    }
+    CK(cudaEventRecord(cs->ev_produced, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return ST_OK;
+}
 static int link_prepare(st_engine* e, CameraSlot* cs) {
     CK(cudaSetDevice(e->device));
     size_t n = (size_t)cs->desc.width * cs->desc.height;
@@ -1822,7 +1836,7 @@ static int link_prepare(st_engine* e, CameraSlot* cs) {
     if ((rc = cs->peer.sync.ensure(kSyncBytes))) return rc;
     const int need0[2] = {(int)cs->desc.height, -1};
     CK(cudaMemcpy((uint32_t*)cs->peer.sync.p + kNeedRowsWord, need0, 8, cudaMemcpyHostToDevice));
-    return ST_OK;
+    return strip_streams_prepare(e, cs);
 }
 int st_link_local(st_engine* const* engines, const st_camera_handle* cameras, int n) {
     if (!engines || !cameras || n < 1 || n > ST_PEER_MAX_RANKS) return fail(ST_ERR_LIMIT, "1..16 engines");
