@@ -846,7 +846,7 @@ static int halo_exchange(st_engine* e, CameraSlot* cs, const HaloExchange& ex) {
     return ST_OK;
 }
 
-static const int kLegacyFlagWord = 128, kNeedRowsWord = 200, kStripErrorWord = 202, kPulledRowsWord = 204, kSyncBytes = 4096;
+static const int kLegacyFlagWord = 128, kNeedRowsWord = 200, kStripErrorWord = 202, kPulledRowsWord = 204, kWarmupWord = 512, kSyncBytes = 4096;
 // the same exchange over mapped peer memory: one kernel stores my rows into every neighbour and runs the barrier
 static void peer_fill(st_engine* e, CameraSlot* cs, PeerExchange* x) {
     uint32_t* sync = (uint32_t*)cs->peer.sync.p + kLegacyFlagWord;   // [0..16) flags, [16] completion counter, [17] time-outs
@@ -1650,6 +1650,27 @@ int st_peer_export(st_engine* e, st_camera_handle h, uint8_t* out192) {
     std::memcpy(out192, hs, ST_PEER_HANDLE_BYTES);
     return ST_OK;
 }
+// Side streams and events of the copy-engine halo pushes, created when the camera is linked (peer pointers known) — and the copy path
+// to each neighbour is exercised once here: the first such copy may load a driver-internal module, which synchronises the device, and
+// inside a frame that would stall this thread while another rank's stream spins on a flag only this thread's later launches can raise.
+static int strip_streams_prepare(st_engine* e, CameraSlot* cs) {
+    CK(cudaSetDevice(e->device));
+    if (!cs->ev_produced) {
+        CK(cudaEventCreateWithFlags(&cs->ev_produced, cudaEventDisableTiming));
+        for (int k = 0; k < 2; k++) { CK(cudaStreamCreateWithFlags(&cs->side[k], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&cs->ev_pushed[k], cudaEventDisableTiming)); }
+    }
+    const uint32_t* mine = (const uint32_t*)cs->peer.sync.p;
+    for (int k = 0; k < 2; k++) {
+        const int nbr = k == 0 ? e->rank - 1 : e->rank + 1;
+        if (nbr < 0 || nbr >= e->n_ranks || !cs->peer.flags[nbr]) continue;
+        CK(cudaMemcpyAsync(cs->peer.flags[nbr] + kWarmupWord + 8 * k, mine + kWarmupWord + 16, 16, cudaMemcpyDefault, cs->side[k]));
+        CK(cudaEventRecord(cs->ev_pushed[k], cs->side[k]));
+        CK(cudaStreamSynchronize(cs->side[k]));
+    }
+    CK(cudaEventRecord(cs->ev_produced, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return ST_OK;
+}
 int st_peer_import(st_engine* e, st_camera_handle h, const uint8_t* all, int rank, int world) {
     CameraSlot* cs = e ? get_camera(e, h) : nullptr;
     if (!cs || !all) return fail(ST_ERR_NOT_FOUND, "unknown camera");
@@ -1812,23 +1833,6 @@ int st_render_strips(st_engine* e, st_camera_handle h, void* host_out, int forma
 // Links engines that live in THIS process into a strip group (rank = index): enables peer access between their devices and hands every
 // engine the others' buffers directly (the multi-process route is st_peer_export / st_peer_import over CUDA IPC).  Two ranks may share
 // a device, which is how a single-GPU box exercises the whole protocol.
-// Side streams and events of the copy-engine halo pushes, created when the camera is linked — and the device-to-device copy path is
-// exercised once here: the first such copy may load a driver-internal module, which synchronises the device, and inside a frame that
-// would stall this thread while another rank's stream spins on a flag only this thread's later launches can raise.
-static int strip_streams_prepare(st_engine* e, CameraSlot* cs) {
-    if (cs->ev_produced) return ST_OK;
-    CK(cudaEventCreateWithFlags(&cs->ev_produced, cudaEventDisableTiming));
-    for (int k = 0; k < 2; k++) { CK(cudaStreamCreateWithFlags(&cs->side[k], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&cs->ev_pushed[k], cudaEventDisableTiming)); }
-    uint32_t* sync = (uint32_t*)cs->peer.sync.p;
-    for (int k = 0; k < 2; k++) {
-        CK(cudaMemcpyAsync(sync + 512 + 8 * k, sync + 528 + 8 * k, 16, cudaMemcpyDefault, cs->side[k]));   // unused words of the sync buffer
-        CK(cudaEventRecord(cs->ev_pushed[k], cs->side[k]));
-        CK(cudaStreamSynchronize(cs->side[k]));
-    }
-    CK(cudaEventRecord(cs->ev_produced, e->stream));
-    CK(cudaStreamSynchronize(e->stream));
-    return ST_OK;
-}
 static int link_prepare(st_engine* e, CameraSlot* cs) {
     CK(cudaSetDevice(e->device));
     size_t n = (size_t)cs->desc.width * cs->desc.height;
@@ -1836,7 +1840,7 @@ static int link_prepare(st_engine* e, CameraSlot* cs) {
     if ((rc = cs->peer.sync.ensure(kSyncBytes))) return rc;
     const int need0[2] = {(int)cs->desc.height, -1};
     CK(cudaMemcpy((uint32_t*)cs->peer.sync.p + kNeedRowsWord, need0, 8, cudaMemcpyHostToDevice));
-    return strip_streams_prepare(e, cs);
+    return ST_OK;
 }
 int st_link_local(st_engine* const* engines, const st_camera_handle* cameras, int n) {
     if (!engines || !cameras || n < 1 || n > ST_PEER_MAX_RANKS) return fail(ST_ERR_LIMIT, "1..16 engines");
@@ -1862,6 +1866,7 @@ int st_link_local(st_engine* const* engines, const st_camera_handle* cameras, in
         for (int q = 0; q < n; q++) { cs->peer.arena[q] = (char*)cams[q]->arena.p; cs->peer.flags[q] = (uint32_t*)cams[q]->peer.sync.p; cs->peer.rgba8[q] = (char*)cams[q]->rgba8.p; }
         engines[r]->rank = r; engines[r]->n_ranks = n; cs->peer.seq = 0; cs->peer.fseq = 0; cs->peer.ready = true; cs->peer.ipc = false;
     }
+    for (int r = 0; r < n; r++) { int rc = strip_streams_prepare(engines[r], cams[r]); if (rc) return rc; }
     return ST_OK;
 }
 int st_halo_bytes(st_engine* e, uint64_t* bytes) { if (!e || !bytes) return fail(ST_ERR_INVALID, "null argument"); *bytes = e->halo_bytes_last_frame; return ST_OK; }
