@@ -1580,6 +1580,12 @@ int st_get_stat(st_engine* e, int stat, uint64_t* value) {
         for (CameraSlot* c : e->cameras) if (c->alive && c->peer.sync.p) { uint64_t v = 0; CK(cudaMemcpy(&v, (uint32_t*)c->peer.sync.p + kPulledRowsWord, 8, cudaMemcpyDeviceToHost)); total += v; }
         *value = total; return ST_OK;
     }
+    if (stat == ST_STAT_STRIP_FIRST_TIMEOUT) {   // 0, or 0x80000000 | slot << 16 | awaited rank << 8 | low byte of the sequence value: the first flag wait that gave up
+        CK(cudaSetDevice(e->device)); CK(cudaStreamSynchronize(e->stream));
+        *value = 0;
+        for (CameraSlot* c : e->cameras) if (c->alive && c->peer.sync.p && !*value) { uint32_t v = 0; CK(cudaMemcpy(&v, (uint32_t*)c->peer.sync.p + kStripErrorWord + 1, 4, cudaMemcpyDeviceToHost)); *value = v; }
+        return ST_OK;
+    }
     if (stat == ST_STAT_LAST_FRAME_FUSED_STRIPS) { *value = e->last_frame_fused ? 1 : 0; return ST_OK; }
     if (stat == ST_STAT_WAVELET_TILED_ERRORS) {
         CK(cudaSetDevice(e->device));

@@ -1772,7 +1772,9 @@ __global__ void __launch_bounds__(32) k_strip_wait(const __grid_constant__ Strip
         const u32* f = s.my_flags + slot * ST_PEER_MAX_RANKS + r;
         long long t0 = clock64();
         while ((int)(ld_acquire_sys(f) - seq) < 0) {
-            if (clock64() - t0 > 20000000000ll) { atomicAdd(s.errors, 1u); break; }   // ~10 s: a peer died; do not hang the GPU
+            if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer died; do not hang the GPU.  errors[1] keeps the first wait that gave up
+                atomicAdd(s.errors, 1u); atomicCAS(s.errors + 1, 0u, 0x80000000u | ((u32)slot << 16) | ((u32)r << 8) | (seq & 0xffu)); break;
+            }
             __nanosleep(64);
         }
     }

@@ -31,6 +31,7 @@ STAT_BVH_GRAFTED_SUBTREES = 3
 STAT_VARIANCE_TILED_LAUNCHES = 4
 STAT_STRIP_PULLED_ROWS = 5
 STAT_LAST_FRAME_FUSED_STRIPS = 6
+STAT_STRIP_FIRST_TIMEOUT = 7
 
 
 class StrolleError(RuntimeError):

@@ -20,7 +20,8 @@ c1, cn = scenes.apply(one, scene), scenes.apply(grp, scene)
 bounds = [(h * r // n, h * (r + 1) // n) for r in range(n)]
 for f in range(frames):
     one.tick(); grp.tick(); one.render_camera(c1); grp.render_camera(cn)
-    print(f"frame {f + 1}: peer errors {grp.peer_errors(cn)}")
+    print(f"frame {f + 1}: peer errors {grp.peer_errors(cn)}; first wait that gave up per rank (slot << 16 | awaited rank << 8 | seq): "
+          + ", ".join(hex(grp.member(r).get_stat(7)) for r in range(n)))
     for name in CAMERA_BUFFERS:
         want = one.read_buffer(c1, name).reshape(h, -1)
         for r in range(n):
