@@ -1661,6 +1661,11 @@ int st_peer_export(st_engine* e, st_camera_handle h, uint8_t* out192) {
 // inside a frame that would stall this thread while another rank's stream spins on a flag only this thread's later launches can raise.
 static int strip_streams_prepare(st_engine* e, CameraSlot* cs) {
     CK(cudaSetDevice(e->device));
+    {   // no kernel may be loaded lazily once streams wait on each other's flags (see preload_kernels)
+        const int a = st::preload_kernels(), b = stf::preload_kernels();
+        static bool warned = false;
+        if ((a || b) && !warned) { warned = true; std::fprintf(stderr, "strolle_b200: this driver cannot enumerate the library's kernels (%d/%d); set CUDA_MODULE_LOADING=EAGER when several strips share one host thread\n", a, b); }
+    }
     if (!cs->ev_produced) {
         CK(cudaEventCreateWithFlags(&cs->ev_produced, cudaEventDisableTiming));
         for (int k = 0; k < 2; k++) { CK(cudaStreamCreateWithFlags(&cs->side[k], cudaStreamNonBlocking)); CK(cudaEventCreateWithFlags(&cs->ev_pushed[k], cudaEventDisableTiming)); }

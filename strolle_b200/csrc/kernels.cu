@@ -14,6 +14,7 @@
 #include <map>
 #include <mutex>
 #include <tuple>
+#include <vector>
 #include "st_device.cuh"
 #include "kernels.h"
 
@@ -1867,4 +1868,34 @@ void launch_atm_sky(const float4* tl, const float4* sl, float sun_altitude, floa
 void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st) { k_atm_sun_color<<<1, 1, 0, st>>>(out2, world); }
 
 #endif   // ST_EXACT_ONLY
+
+// Load every kernel of this translation unit's module now.  CUDA loads kernels lazily, at their first launch, and that load can
+// synchronise the whole context; the strip transport lets one stream spin on a flag that a kernel launched later (by the same host
+// thread, for another member of a device group) raises, so a load at that moment would stall the thread until the wait gives up.
+// The module is found through one of its kernels; every function it holds is then loaded (cuFuncLoad, CUDA >= 12.4).
+int preload_kernels() {
+    static int state = -1;   // per flavour (this function is compiled into st:: and stf::)
+    if (state >= 0) return state;
+    auto entry = [](const char* name) -> void* {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+        return p;
+    };
+    typedef CUresult (*GetModule)(CUmodule*, CUfunction);
+    typedef CUresult (*GetCount)(unsigned int*, CUmodule);
+    typedef CUresult (*Enumerate)(CUfunction*, unsigned int, CUmodule);
+    typedef CUresult (*Load)(CUfunction);
+    GetModule get_module = (GetModule)entry("cuFuncGetModule"); GetCount get_count = (GetCount)entry("cuModuleGetFunctionCount");
+    Enumerate enumerate = (Enumerate)entry("cuModuleEnumerateFunctions"); Load load = (Load)entry("cuFuncLoad");
+    cudaGetLastError();
+    if (!get_module || !get_count || !enumerate || !load) return state = 1;
+    cudaFunction_t anchor = nullptr;
+    if (cudaGetFuncBySymbol(&anchor, (const void*)k_di_sample_temporal) != cudaSuccess) { cudaGetLastError(); return state = 2; }
+    CUmodule mod = nullptr; unsigned int n = 0;
+    if (get_module(&mod, (CUfunction)anchor) != CUDA_SUCCESS || get_count(&n, mod) != CUDA_SUCCESS || n == 0u) return state = 3;
+    std::vector<CUfunction> fns(n);
+    if (enumerate(fns.data(), n, mod) != CUDA_SUCCESS) return state = 4;
+    for (CUfunction f : fns) if (load(f) != CUDA_SUCCESS) return state = 5;
+    return state = 0;
+}
 }  // namespace ST_NS

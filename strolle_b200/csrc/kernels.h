@@ -76,6 +76,7 @@ struct StripPull {
     const int* need_rows; unsigned long long* pulled_rows;
     StripPullItem items[12]; int nitems;
 };
+int preload_kernels();   // 0 = every kernel of the strict build is loaded; > 0 = the driver cannot enumerate them (kernels then load at first launch)
 void launch_strip_signal(const StripSync& s, int slot, u32 seq, u32 dst_mask, int* reset_need, int h, cudaStream_t st);
 void launch_strip_wait(const StripSync& s, int slot, u32 seq, u32 src_mask, cudaStream_t st);
 void launch_strip_signal_wait(const StripSync& s, int sig_slot, u32 seq, u32 dst_mask, int wait_slot, u32 wait_seq, u32 src_mask, cudaStream_t st);
@@ -88,6 +89,7 @@ void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st);
 // -DST_FAST=1, see st_math.cuh): same launch interface, selected by ST_OPT_SHADING_FAST_MATH.
 namespace stf {
 using st::CameraDev; using st::SceneDev; using st::u32;
+int preload_kernels();   // the fast-shading build's kernels
 void launch_di_sampling(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
 void launch_di_temporal(const CameraDev& c, const SceneDev& s, int cur, u32 seed, cudaStream_t st);
 void launch_di_spatial_pick(const CameraDev& c, const SceneDev& s, int cur, u32 seed, u32 frame, cudaStream_t st);
