@@ -198,7 +198,8 @@ class StripRunner:
         if self.world == 1:
             return "single GPU"
         if self.native and self.peer:
-            return ("fused peer-memory transport over NVLink (CUDA IPC): producer kernels store boundary rows into the neighbours' buffers, neighbour-only "
+            return ("fused peer-memory transport over NVLink (CUDA IPC): DI / preview / SVGF boundary rows stored into the neighbours' buffers by "
+                    "the kernels that produce them, the 128-row GI reservoir halos pushed by the copy engines on side streams, neighbour-only "
                     "sequence flags, G-buffer / SVGF halo rows recomputed, temporal rows pulled on demand; no NCCL on the data path")
         return "engine-owned NCCL send/recv per exchange point" if self.native else "torch.distributed P2P between st_render_range calls"
 
