@@ -374,6 +374,7 @@ struct CameraSlot {
     std::vector<std::pair<std::string, float4**>> named;   // buffer name -> pointer slot in `dev`
     std::vector<std::pair<std::string, size_t>> sizes;      // float4 count per named buffer
     DevMem arena;
+    DevMem svgf_pairs; float4* pair[2] = {nullptr, nullptr};   // interleaved {DI, GI} records of the wide-stride à-trous iterations (ST_OPT_WAVELET_PAIRED); private scratch, never exchanged
     DevMem rgba8; int rgba8_slot = 0;
     // asynchronous RGBA8 read-back: slot k of the staging buffer is converted on the engine stream (ev_ready[k]) and copied to
     // the host on the copy stream (ev_copied[k]); the engine stream only waits for ev_copied[k] before reusing slot k
@@ -431,6 +432,7 @@ struct st_engine {
     bool fused_passes = ST_FUSED_PASSES_DEFAULT != 0;   // ST_OPT_FUSED_PASSES
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
+    int wavelet_paired = ST_WAVELET_PAIRED_DEFAULT;   // ST_OPT_WAVELET_PAIRED
     bool strip_dma = ST_STRIP_DMA_DEFAULT != 0;   // ST_OPT_STRIP_DMA: gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores
     bool strip_fused = true;     // ST_OPT_STRIP_FUSED: mirror stores + neighbour flags + recompute instead of stand-alone exchanges
     bool last_frame_fused = false;
@@ -628,6 +630,11 @@ static int allocate_camera(st_engine* e, CameraSlot* cs) {
     cs->arena.release();
     int rc = cs->arena.ensure(total); if (rc) return rc;
     CK(cudaMemsetAsync(cs->arena.p, 0, total, e->stream));
+    const size_t pair_bytes = (2 * n * 16 + 255) / 256 * 256;
+    cs->svgf_pairs.release();
+    if ((rc = cs->svgf_pairs.ensure(2 * pair_bytes))) return rc;
+    CK(cudaMemsetAsync(cs->svgf_pairs.p, 0, 2 * pair_bytes, e->stream));
+    cs->pair[0] = (float4*)cs->svgf_pairs.p; cs->pair[1] = (float4*)((char*)cs->svgf_pairs.p + pair_bytes);
     size_t off = 0;
     for (size_t i = 0; i < cs->named.size(); i++) { *cs->named[i].second = (float4*)((char*)cs->arena.p + off); off += (cs->sizes[i].second * 16 + 255) / 256 * 256; }
     d.w = (int)cs->desc.width; d.h = (int)cs->desc.height; d.y0 = 0; d.y1 = d.h;
@@ -748,14 +755,19 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
                                {cam.di_diff_curr_colors, cam.di_diff_stash}, {cam.di_diff_stash, cam.di_diff_curr_colors}};
         float4* gi_io[5][2] = {{cam.gi_diff_stash, cam.gi_diff_prev_colors}, {cam.gi_diff_prev_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors},
                                {cam.gi_diff_curr_colors, cam.gi_diff_stash}, {cam.gi_diff_stash, cam.gi_diff_curr_colors}};
+        // ST_OPT_WAVELET_PAIRED: from which iteration on the signals travel as interleaved records (5 = never)
+        const bool whole_or_fused = ext != nullptr || (cam.y0 == 0 && cam.y1 == cam.h);
+        const int first_paired_read = (fast && whole_or_fused && cs->pair[0]) ? (e->wavelet_paired == 2 ? 3 : e->wavelet_paired == 1 ? 4 : 5) : 5;
         for (uint32_t nth = 0; nth < 5; nth++) {
             float4 *a = di_io[nth][0], *b = di_io[nth][1], *c = gi_io[nth][0], *g = gi_io[nth][1];
-            const bool tiled = ((e->wavelet_tiled >> nth) & 1) != 0; const int cfg = (e->wavelet_cfg >> (4 * nth)) & 15;
+            const bool reads_pair = (int)nth >= first_paired_read, writes_pair = (int)nth + 1 >= first_paired_read && nth < 4;
+            const float4* pin = reads_pair ? cs->pair[nth & 1] : nullptr; float4* pout = writes_pair ? cs->pair[(nth + 1) & 1] : nullptr;
+            const bool tiled = !reads_pair && ((e->wavelet_tiled >> nth) & 1) != 0; const int cfg = (e->wavelet_cfg >> (4 * nth)) & 15;
             uint32_t* terr = (uint32_t*)e->d_tile_errors.p;
             const CameraDev camW = grown(cam, x.wavelet[nth]);
             add(P_DENOISE_WAVELET, [=](cudaStream_t s) {
-                if (tiled && launch_denoise_wavelet_tiled(camW, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, cfg, terr, s)) { e->wavelet_tiled_launches++; return; }
-                launch_denoise_wavelet(camW, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, fast, s);
+                if (tiled && launch_denoise_wavelet_tiled(camW, sc, f, 1u << nth, (float)(1 + nth), a, b, c, g, pout, fast, cfg, terr, s)) { e->wavelet_tiled_launches++; return; }
+                launch_denoise_wavelet(camW, sc, cur, f, 1u << nth, (float)(1 + nth), a, b, c, g, pin, pout, fast, s);
             });
             steps->back().sub = (int)nth;
         }
@@ -1100,7 +1112,7 @@ void st_engine_destroy(st_engine* e) {
     cudaStreamSynchronize(e->stream);
     if (e->copy_stream) cudaStreamSynchronize(e->copy_stream);
     for (CameraSlot* c : e->cameras) { for (int k = 0; k < 2; k++) { if (c->side[k]) { cudaStreamSynchronize(c->side[k]); cudaStreamDestroy(c->side[k]); } if (c->ev_pushed[k]) cudaEventDestroy(c->ev_pushed[k]); } if (c->ev_produced) cudaEventDestroy(c->ev_produced);
-        c->arena.release(); c->rgba8.release(); for (int k = 0; k < 2; k++) { if (c->ev_ready[k]) cudaEventDestroy(c->ev_ready[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); } delete c; }
+        c->arena.release(); c->svgf_pairs.release(); c->rgba8.release(); for (int k = 0; k < 2; k++) { if (c->ev_ready[k]) cudaEventDestroy(c->ev_ready[k]); if (c->ev_copied[k]) cudaEventDestroy(c->ev_copied[k]); } delete c; }
     DevMem* all[] = {&e->d_triangles, &e->d_bvh, &e->d_materials, &e->d_lights, &e->d_noise, &e->d_tlut, &e->d_slut, &e->d_skylut, &e->d_scratch, &e->d_raycount, &e->d_matpacked, &e->d_unpacklut, &e->d_atlas, &e->d_srgb, &e->d_tri_instance, &e->d_instance_xforms, &e->d_tile_errors};
     for (DevMem* d : all) d->release();
     for (auto& t : e->pending) { cudaEventDestroy(t.a); cudaEventDestroy(t.b); }
@@ -1274,7 +1286,7 @@ int st_delete_camera(st_engine* e, st_camera_handle h) {
     CK(cudaStreamSynchronize(e->stream));
     if (e->copy_stream) CK(cudaStreamSynchronize(e->copy_stream));
     for (int k = 0; k < 2; k++) if (cs->side[k]) CK(cudaStreamSynchronize(cs->side[k]));
-    cs->alive = false; cs->arena.release(); cs->rgba8.release();
+    cs->alive = false; cs->arena.release(); cs->svgf_pairs.release(); cs->pair[0] = cs->pair[1] = nullptr; cs->rgba8.release();
     return ST_OK;
 }
 int st_camera_set_strip(st_engine* e, st_camera_handle h, int y0, int y1) {
@@ -1528,6 +1540,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
     if (option == ST_OPT_STRIP_DMA) { e->strip_dma = value != 0; return ST_OK; }
+    if (option == ST_OPT_WAVELET_PAIRED) { if (value < 0 || value > 2) return fail(ST_ERR_INVALID, "ST_OPT_WAVELET_PAIRED: 0, 1 or 2"); e->wavelet_paired = value; return ST_OK; }
     if (option == ST_OPT_FUSED_PASSES) { e->fused_passes = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
     if (option == ST_OPT_VARIANCE_TILED) { e->variance_tiled = value != 0; return ST_OK; }

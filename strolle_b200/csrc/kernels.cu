@@ -984,20 +984,25 @@ __global__ void __launch_bounds__(ST_BLOCK) k_denoise_variance(KPARAMS, int cur)
 #ifndef ST_WAVELET_MIN_BLOCKS
 #define ST_WAVELET_MIN_BLOCKS 10
 #endif
-template <bool FAST>
+// PAIR_IN: the two signals arrive interleaved, {DI, GI} = one 32-byte record per pixel (`pair_in`, written by the previous iteration
+// through `pair_out`), so that a jittered tap of the wide strides is one full sector and one 256-bit load instead of two half-used
+// sectors; `pair_out` != nullptr writes that layout.  Values and arithmetic are those of the planar layout.
+template <bool FAST, bool PAIR_IN>
 __global__ void __launch_bounds__(ST_BLOCK, ST_WAVELET_MIN_BLOCKS) k_denoise_wavelet(KPARAMS, int cur, u32 frame, u32 stride, float strength,
                                                               const float4* __restrict__ di_in, float4* __restrict__ di_out,
-                                                              const float4* __restrict__ gi_in, float4* __restrict__ gi_out) {
+                                                              const float4* __restrict__ gi_in, float4* __restrict__ gi_out,
+                                                              const float4* __restrict__ pair_in, float4* __restrict__ pair_out) {
     Px p = pixel_full(cam);
     if (!p.in) return;
     size_t i = pix(cam, p.x, p.y);
     const float4* __restrict__ snd = cam.surface_nd;
     float4 cnd = snd[i];
-    float4 cdi = di_in[i];
+    float4 cdi, cgi;
+    if (PAIR_IN) { F8 c = ld8(pair_in + 2 * i); cdi = c.a; cgi = c.b; } else cdi = di_in[i];
     float3 cdc = xyz(cdi); float cdv = cdi.w;
-    if (cnd.w == 0.0f) { di_out[i] = f4(cdc, cdv); return; }
+    if (cnd.w == 0.0f) { if (pair_out) pair_out[2 * i] = f4(cdc, cdv); else di_out[i] = f4(cdc, cdv); return; }
     float4 bn = blue_noise(sc, p.x, p.y, frame);
-    float4 cgi = gi_in[i];
+    if (!PAIR_IN) cgi = gi_in[i];
     float3 cgc = xyz(cgi); float cgv = cgi.w;
     float3 cn = xyz(cnd);
     float scdl = sv_sqrt<FAST>(sv_luma<FAST>(cdc)), scgl = sv_sqrt<FAST>(sv_luma<FAST>(cgc));
@@ -1022,8 +1027,8 @@ __global__ void __launch_bounds__(ST_BLOCK, ST_WAVELET_MIN_BLOCKS) k_denoise_wav
             float nw = svgf_normal_weight<FAST>(cn, xyz(nds));
             if (dw == 0.0f || nw == 0.0f) continue;
             float dnw = dw * nw;
-            float4 sdi = di_in[si];
-            float4 sgi = gi_in[si];
+            float4 sdi, sgi;
+            if (PAIR_IN) { F8 t = ld8(pair_in + 2 * si); sdi = t.a; sgi = t.b; } else { sdi = di_in[si]; sgi = gi_in[si]; }
             if (FAST) {
                 float wd = svgf_luma_weight<true>(scdl, sv_luma<true>(xyz(sdi)), ls_di) * dnw;
                 if (wd > 0.0f) { sdw += wd; sdc = f3(__fmaf_rn(wd, sdi.x, sdc.x), __fmaf_rn(wd, sdi.y, sdc.y), __fmaf_rn(wd, sdi.z, sdc.z)); sdv = __fmaf_rn(wd * wd, sdi.w, sdv); }
@@ -1037,14 +1042,17 @@ __global__ void __launch_bounds__(ST_BLOCK, ST_WAVELET_MIN_BLOCKS) k_denoise_wav
             }
         }
     }
+    float4 odi, ogi;
     if (FAST) {
         float rd = sfu_rcp(sdw), rg = sfu_rcp(sgw);
-        di_out[i] = f4(sdc * rd, sdv * (rd * rd));
-        gi_out[i] = f4(sgc * rg, sgv * (rg * rg));
+        odi = f4(sdc * rd, sdv * (rd * rd));
+        ogi = f4(sgc * rg, sgv * (rg * rg));
     } else {
-        di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
-        gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
+        odi = f4(sdc / sdw, sdv / (sdw * sdw));
+        ogi = f4(sgc / sgw, sgv / (sgw * sgw));
     }
+    if (pair_out) st8(pair_out + 2 * i, odi, ogi);
+    else { di_out[i] = odi; gi_out[i] = ogi; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1106,15 +1114,18 @@ template <bool FAST> struct WaveletCentre {
             if (wg > 0.0f) { sgw += wg; sgc = sgc + wg * xyz(sgi); sgv += sq(wg) * sgi.w; }
         }
     }
-    ST_DEV void store(float4* __restrict__ di_out, float4* __restrict__ gi_out, size_t i) const {
+    ST_DEV void store(float4* __restrict__ di_out, float4* __restrict__ gi_out, float4* __restrict__ pair_out, size_t i) const {
+        float4 odi, ogi;
         if (FAST) {
             float rd = sfu_rcp(sdw), rg = sfu_rcp(sgw);
-            di_out[i] = f4(sdc * rd, sdv * (rd * rd));
-            gi_out[i] = f4(sgc * rg, sgv * (rg * rg));
+            odi = f4(sdc * rd, sdv * (rd * rd));
+            ogi = f4(sgc * rg, sgv * (rg * rg));
         } else {
-            di_out[i] = f4(sdc / sdw, sdv / (sdw * sdw));
-            gi_out[i] = f4(sgc / sgw, sgv / (sgw * sgw));
+            odi = f4(sdc / sdw, sdv / (sdw * sdw));
+            ogi = f4(sgc / sgw, sgv / (sgw * sgw));
         }
+        if (pair_out) st8(pair_out + 2 * i, odi, ogi);   // interleaved {DI, GI} record for the wide-stride iterations (see k_denoise_wavelet)
+        else { di_out[i] = odi; gi_out[i] = ogi; }
     }
 };
 
@@ -1132,7 +1143,8 @@ template <bool FAST, int S, int J, int TW, int TH>
 __global__ void __launch_bounds__(TW * TH, (TW * TH <= 256 && S <= 8) ? ST_WAVELET_TILED_MINB : 1) k_denoise_wavelet_tiled(KPARAMS, u32 frame, float strength,
                                                                    const __grid_constant__ CUtensorMap tm_nd, const __grid_constant__ CUtensorMap tm_di,
                                                                    const __grid_constant__ CUtensorMap tm_gi,
-                                                                   float4* __restrict__ di_out, float4* __restrict__ gi_out, u32* __restrict__ errors) {
+                                                                   float4* __restrict__ di_out, float4* __restrict__ gi_out, float4* __restrict__ pair_out,
+                                                                   u32* __restrict__ errors) {
     typedef WaveletTile<S, J, TW, TH> T;
     extern __shared__ unsigned char s_raw[];
     __shared__ __align__(8) unsigned long long s_bar;
@@ -1170,7 +1182,7 @@ __global__ void __launch_bounds__(TW * TH, (TW * TH <= 256 && S <= 8) ? ST_WAVEL
     const size_t i = pix(cam, px, py);
     float4 cnd = t_nd[c];
     float4 cdi = t_di[c];
-    if (cnd.w == 0.0f) { di_out[i] = f4(xyz(cdi), cdi.w); return; }   // sky: DI passes through, GI is not written (frame_denoising.rs:248-254)
+    if (cnd.w == 0.0f) { if (pair_out) pair_out[2 * i] = f4(xyz(cdi), cdi.w); else di_out[i] = f4(xyz(cdi), cdi.w); return; }   // sky: DI passes through, GI is not written (frame_denoising.rs:248-254)
     WaveletCentre<FAST> ctr;
     ctr.init(cnd, cdi, t_gi[c], 0.33f / strength);   // depth sigma is the same for DI and GI (frame_denoising.rs:264,267)
     const int cj = c + jo;
@@ -1187,7 +1199,7 @@ __global__ void __launch_bounds__(TW * TH, (TW * TH <= 256 && S <= 8) ? ST_WAVEL
             ctr.add(dw, nw, t_di[k], t_gi[k]);
         }
     }
-    ctr.store(di_out, gi_out, i);
+    ctr.store(di_out, gi_out, pair_out, i);
 }
 
 // R2 frame_composition::fs (frame_composition.rs:19-82), linear HDR out
@@ -1559,9 +1571,12 @@ void launch_denoise_reproject_pair(const CameraDev& c, const SceneDev& s, int cu
 void launch_denoise_variance(const CameraDev& c, const SceneDev& s, int cur, bool fast, cudaStream_t st) {
     if (fast) k_denoise_variance<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur); else k_denoise_variance<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur);
 }
-void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out, bool fast, cudaStream_t st) {
-    if (fast) k_denoise_wavelet<true><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
-    else k_denoise_wavelet<false><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out);
+void launch_denoise_wavelet(const CameraDev& c, const SceneDev& s, int cur, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out,
+                            const float4* pair_in, float4* pair_out, bool fast, cudaStream_t st) {
+#define ST_WG(F_, P_) k_denoise_wavelet<F_, P_><<<grid_full(c), ST_BLOCK, 0, st>>>(c, s, cur, frame, stride, strength, di_in, di_out, gi_in, gi_out, pair_in, pair_out)
+    if (pair_in) { if (fast) ST_WG(true, true); else ST_WG(false, true); }
+    else { if (fast) ST_WG(true, false); else ST_WG(false, false); }
+#undef ST_WG
 }
 // K21, tile-staged: the 6x5 window of frame_denoising::estimate_variance (quirk C-3: row -2 spans x in [-2,2], rows -1..2 span
 // x in [-3,2]) is only walked by pixels whose history is shorter than 4 frames, but a warp pays for it as soon as one of its
@@ -1684,7 +1699,7 @@ static bool wavelet_tensor_map(const float4* plane, int w, int h, int bw, int bh
 }
 template <bool FAST, int S, int J, int TW, int TH>
 static bool wavelet_tiled_go(const CameraDev& c, const SceneDev& s, u32 frame, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out,
-                             u32* errors, cudaStream_t st) {
+                             float4* pair_out, u32* errors, cudaStream_t st) {
     typedef WaveletTile<S, J, TW, TH> T;
     if (T::BW * 2 > 256 || T::BH > 256) return false;
     CUtensorMap tn, td, tg;
@@ -1695,27 +1710,27 @@ static bool wavelet_tiled_go(const CameraDev& c, const SceneDev& s, u32 frame, f
     int dev = 0; cudaGetDevice(&dev); dev &= 63;
     if (!attr_set[dev]) { if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM) != cudaSuccess) { cudaGetLastError(); return false; } attr_set[dev] = true; }
     dim3 grid((c.w + TW - 1) / TW, (c.y1 - c.y0 + TH - 1) / TH);
-    kern<<<grid, TW * TH, T::SMEM, st>>>(c, s, frame, strength, tn, td, tg, di_out, gi_out, errors);
+    kern<<<grid, TW * TH, T::SMEM, st>>>(c, s, frame, strength, tn, td, tg, di_out, gi_out, pair_out, errors);
     return true;
 }
 template <bool FAST, int S, int J>
 static bool wavelet_tiled_cfg(int cfg, const CameraDev& c, const SceneDev& s, u32 frame, float strength, const float4* di_in, float4* di_out, const float4* gi_in, float4* gi_out,
-                              u32* errors, cudaStream_t st) {
+                              float4* pair_out, u32* errors, cudaStream_t st) {
     switch (cfg) {
-    case 0: return wavelet_tiled_go<FAST, S, J, 32, 8>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
-    case 1: return wavelet_tiled_go<FAST, S, J, 32, 16>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
-    case 2: return wavelet_tiled_go<FAST, S, J, 64, 4>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
-    case 3: return wavelet_tiled_go<FAST, S, J, 64, 8>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st);
+    case 0: return wavelet_tiled_go<FAST, S, J, 32, 8>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, pair_out, errors, st);
+    case 1: return wavelet_tiled_go<FAST, S, J, 32, 16>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, pair_out, errors, st);
+    case 2: return wavelet_tiled_go<FAST, S, J, 64, 4>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, pair_out, errors, st);
+    case 3: return wavelet_tiled_go<FAST, S, J, 64, 8>(c, s, frame, strength, di_in, di_out, gi_in, gi_out, pair_out, errors, st);
     default: return false;
     }
 }
 // Returns false when the tile-staged kernel cannot be used for this launch (the caller then runs the gather kernel):
 // the camera's screen is not the buffer size, no tensor-map encoder, or an unknown configuration.
 bool launch_denoise_wavelet_tiled(const CameraDev& c, const SceneDev& s, u32 frame, u32 stride, float strength, const float4* di_in, float4* di_out, const float4* gi_in,
-                                  float4* gi_out, bool fast, int cfg, u32* errors, cudaStream_t st) {
+                                  float4* gi_out, float4* pair_out, bool fast, int cfg, u32* errors, cudaStream_t st) {
     if (c.curr.screen.x != (float)c.w || c.curr.screen.y != (float)c.h) return false;   // zero fill == Camera::contains only then
-#define ST_WT(S_, J_) (fast ? wavelet_tiled_cfg<true, S_, J_>(cfg, c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st) \
-                            : wavelet_tiled_cfg<false, S_, J_>(cfg, c, s, frame, strength, di_in, di_out, gi_in, gi_out, errors, st))
+#define ST_WT(S_, J_) (fast ? wavelet_tiled_cfg<true, S_, J_>(cfg, c, s, frame, strength, di_in, di_out, gi_in, gi_out, pair_out, errors, st) \
+                            : wavelet_tiled_cfg<false, S_, J_>(cfg, c, s, frame, strength, di_in, di_out, gi_in, gi_out, pair_out, errors, st))
     switch (stride) {
     case 1: return ST_WT(1, 0);
     case 2: return ST_WT(2, 0);

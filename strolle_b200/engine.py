@@ -21,6 +21,7 @@ OPT_FUSE_REPROJECT = 6     # K20 for DI and GI in one launch
 OPT_BVH_REUSE = 7          # graft unchanged subtrees of the previous BVH (reference behaviour)
 OPT_VARIANCE_TILED = 8     # K21 window from a TMA-filled shared-memory tile
 OPT_FUSED_PASSES = 11        # K5+K6, K7+K8+K9, K12+K13, K11 in K14, K15+K16+K17, preview#2+K19 as single launches
+OPT_WAVELET_PAIRED = 13      # wide-stride a-trous iterations read {DI, GI} as interleaved 32-byte records (0 / 1 / 2)
 OPT_STRIP_DMA = 12           # strips: gi_reservoirs[1]/[2] halos by copy engine on side streams instead of in-kernel mirror stores
 OPT_STRIP_FUSED = 10         # strips: fused transport (mirror stores, neighbour flags, recompute) instead of push+barrier exchanges
 OPT_SHADING_FAST_MATH = 9  # ReSTIR kernels K5-K19 from the fast-shading build (FMA + SFU approximations; traversal unchanged)

@@ -395,10 +395,11 @@ def test_tiled_wavelet_matches_gather(gpu, blue_noise, cfg, exact):
     """K22 staged through shared memory by TMA tensor copies (all five strides, every tile shape) produces the same
     bits as the per-tap gather kernel, in the strict-IEEE and in the fast-SVGF flavour, on frame sizes that are
     not multiples of the tile (zero-filled borders) and smaller than the largest stride's reach."""
-    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_WAVELET_TILE_CFG, STAT_WAVELET_TILED_LAUNCHES, STAT_WAVELET_TILED_ERRORS
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_WAVELET_TILE_CFG, OPT_WAVELET_PAIRED, STAT_WAVELET_TILED_LAUNCHES, STAT_WAVELET_TILED_ERRORS
     for size in [(200, 120), (67, 45)]:
         scene = scenes.cornell(*size)
         ea, eb = gpu.Engine(blue_noise=blue_noise, exact=exact), gpu.Engine(blue_noise=blue_noise, exact=exact)
+        ea.set_option(OPT_WAVELET_PAIRED, 0); eb.set_option(OPT_WAVELET_PAIRED, 0)   # planar buffers: every stride can run tile-staged
         ea.set_option(OPT_WAVELET_TILED, 0)
         eb.set_option(OPT_WAVELET_TILED, 31); eb.set_option(OPT_WAVELET_TILE_CFG, cfg * 0x11111)
         ca, cb = scenes.apply(ea, scene), scenes.apply(eb, scene)
@@ -409,6 +410,30 @@ def test_tiled_wavelet_matches_gather(gpu, blue_noise, cfg, exact):
         assert ea.get_stat(STAT_WAVELET_TILED_LAUNCHES) == 0
         assert eb.get_stat(STAT_WAVELET_TILED_LAUNCHES) == 20, "the tile-staged kernel must be the one that ran"
         assert eb.get_stat(STAT_WAVELET_TILED_ERRORS) == 0
+
+
+@pytest.mark.parametrize("tiled", [0, 31])
+def test_paired_wavelet_records_match_planar(gpu, blue_noise, tiled):
+    """ST_OPT_WAVELET_PAIRED: the wide-stride à-trous iterations reading the two signals as interleaved 32-byte records (written by the
+    iteration before them, gather or tile-staged) give the same bits as the planar buffers — denoised colours, history, output — on
+    frame sizes that are not multiples of the tile and with sky pixels (whose GI half of a record is never written)."""
+    from strolle_b200.engine import OPT_WAVELET_TILED, OPT_WAVELET_PAIRED, STAT_WAVELET_TILED_ERRORS
+    keep = [n for n in DENOISER_BUFFERS if not n.endswith("_stash")]   # the stash keeps the last planar iteration's output
+    for scene in [scenes.cornell(200, 120), scenes.cornell(67, 45), scenes.demo_level(160, 96)]:
+        engines = []
+        for paired in (0, 1, 2):
+            e = gpu.Engine(blue_noise=blue_noise)
+            e.set_option(OPT_WAVELET_PAIRED, paired); e.set_option(OPT_WAVELET_TILED, tiled)
+            engines.append((e, scenes.apply(e, scene)))
+        for f in range(5):
+            for e, c in engines:
+                e.tick(); e.render_camera(c)
+            for name in keep:
+                want = engines[0][0].read_buffer(engines[0][1], name)
+                for k in (1, 2):
+                    assert_bits_equal(engines[k][0].read_buffer(engines[k][1], name), want, f"paired {k} tiled {tiled} frame {f + 1} {name}")
+        for e, _ in engines:
+            assert e.get_stat(STAT_WAVELET_TILED_ERRORS) == 0
 
 
 @pytest.mark.parametrize("exact", [True, False])
