@@ -173,13 +173,14 @@ int st_wavelet_times(st_engine* e, float* ms5, uint32_t* launches5, int reset);
  * does for the reference's shaders; 0 selects strict IEEE arithmetic with polynomial exp, which makes the
  * denoiser bit-identical to the CPU oracle (everything else is bit-identical in both modes). */
 enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3, ST_OPT_WAVELET_TILED = 4, ST_OPT_WAVELET_TILE_CFG = 5, ST_OPT_FUSE_REPROJECT = 6, ST_OPT_BVH_REUSE = 7, ST_OPT_VARIANCE_TILED = 8, ST_OPT_SHADING_FAST_MATH = 9, ST_OPT_STRIP_FUSED = 10, ST_OPT_FUSED_PASSES = 11, ST_OPT_STRIP_DMA = 12, ST_OPT_WAVELET_PAIRED = 13 };
-/* ST_OPT_WAVELET_PAIRED (default 2; only with ST_OPT_SVGF_FAST_MATH, and never under the exchange-point strip transports, which ship the
+/* ST_OPT_WAVELET_PAIRED (default 1; only with ST_OPT_SVGF_FAST_MATH, and never under the exchange-point strip transports, which ship the
  * named buffers between iterations): the wide-stride à-trous iterations, whose taps are scattered by the per-pixel jitter, read the DI and
  * GI signal as one interleaved 32-byte record per pixel (private scratch; one full sector and one 256-bit load per tap instead of two
  * half-used sectors).  1 = the stride-16 iteration reads records written by the stride-8 iteration; 2 = strides 8 and 16 both do (the
- * stride-4 iteration writes the records, the stride-8 iteration runs the gather kernel); 0 = planar buffers throughout.  Same values in
+ * stride-4 iteration writes the records, the stride-8 iteration runs the gather kernel, which measured slower than the tile-staged one:
+ * 65.6 vs 61.8 us at 1080p); 0 = planar buffers throughout.  Stride 16: 78.1 -> 70.0 us (Cornell), 113.5 -> 98.7 us (dungeon).  Same values in
  * every layout; `*_diff_stash` then keeps the output of the last planar iteration. */
-#define ST_WAVELET_PAIRED_DEFAULT 2
+#define ST_WAVELET_PAIRED_DEFAULT 1
 /* ST_OPT_STRIP_DMA (default 1; fused strip transport only): the 128-row halos of gi_reservoirs[1] / [2] (64 B per pixel, the bulk of what
  * travels) are pushed by the copy engines on one side stream per neighbour right after the kernel that produced them, overlapping the DI
  * passes that follow, instead of being mirrored by that kernel's own stores; 0 = every halo is mirrored in-kernel. */
