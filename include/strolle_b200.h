@@ -264,6 +264,10 @@ int st_render_strips(st_engine* e, st_camera_handle camera, void* host_out, int 
 /* The fused strip transport's order of one frame for a given pass schedule (st_frame_schedule), as text for tests:
  * "step:i;signal:SLOT:nb|all;wait:SLOT:nb|all[:prev];pull;push:buffer:SLOT;..." (no device needed). */
 int st_plan_strip_order(const int* schedule, int n, int dma, char* out, size_t cap);
+/* The row partition st_render_strips / st_multi_* use for a frame of `height` rows over `world` ranks: rows_out[2r], rows_out[2r+1] = rank r's
+ * [y0, y1).  Equal strips for one or two ranks; from three on the outer strips (one neighbour) get a few rows more than the inner ones
+ * (two neighbours' worth of recomputed and mirrored halo rows).  No device needed. */
+int st_strip_bounds(int height, int world, int* rows_out);
 int st_halo_bytes(st_engine* e, uint64_t* bytes);
 /* Peer-memory halo transport (default once linked): every rank exports CUDA IPC handles of the camera's buffers
  * (st_peer_export, ST_PEER_HANDLE_BYTES bytes), the host runtime all-gathers them, st_peer_import maps the other

@@ -100,6 +100,7 @@ def load_library():
         "st_nccl_unique_id": [C.c_void_p], "st_nccl_init": [P, C.c_void_p, C.c_int, C.c_int],
         "st_plan_frame": [C.POINTER(C.c_int), C.c_int, u32, C.c_int, C.c_char_p, C.c_size_t],
         "st_plan_strip_order": [C.POINTER(C.c_int), C.c_int, C.c_int, C.c_char_p, C.c_size_t],
+        "st_strip_bounds": [C.c_int, C.c_int, C.POINTER(C.c_int)],
         "st_render_strips": [P, i32, P, C.c_int, C.c_int, C.c_int], "st_halo_bytes": [P, C.POINTER(C.c_uint64)],
         "st_peer_export": [P, i32, C.c_void_p], "st_peer_import": [P, i32, C.c_void_p, C.c_int, C.c_int],
         "st_peer_errors": [P, i32, C.POINTER(u32)],
@@ -589,6 +590,15 @@ def nccl_unique_id():
     if rc != 0:
         raise StrolleError(lib.st_last_error().decode())
     return bytes(buf)
+
+
+def strip_bounds_native(height, world):
+    """The engine's row partition [(y0, y1), ...] (st_strip_bounds; no GPU needed) — multigpu.strip_bounds must agree."""
+    lib = load_library()
+    out = (C.c_int * (2 * world))()
+    if lib.st_strip_bounds(int(height), int(world), out) != 0:
+        raise StrolleError(lib.st_last_error().decode())
+    return [(out[2 * r], out[2 * r + 1]) for r in range(world)]
 
 
 def plan_strip_order(schedule, dma=True):

@@ -30,9 +30,18 @@ VEC4_PER_PIXEL = {"di_reservoirs_0": 2, "di_reservoirs_1": 2, "di_reservoirs_2":
                   "gi_reservoirs_0": 4, "gi_reservoirs_1": 4, "gi_reservoirs_2": 4, "gi_reservoirs_3": 4}
 
 
+STRIP_SIDE_ROWS = 36   # what one neighbour costs a strip, in rows of its own (engine.cu::kStripSideRows)
+
+
 def strip_bounds(height: int, world: int) -> List[Tuple[int, int]]:
-    """Rows [y0, y1) of every rank: contiguous, near-equal, multiples of 8 where possible."""
-    edges = [(height * r // world) for r in range(world + 1)]
+    """Rows [y0, y1) of every rank, contiguous.  From three ranks on the two outer strips (one neighbour each) get STRIP_SIDE_ROWS rows
+    more than the inner ones (two neighbours: twice the recomputed / mirrored halo rows), unless the inner strips would get shorter
+    than 160 rows; equal strips otherwise.  Same arithmetic as engine.cu::strip_bounds (st_strip_bounds)."""
+    k = STRIP_SIDE_ROWS
+    if world < 3 or (height + k * (2 * world - 2)) // world - 2 * k < 160:
+        k = 0
+    total = height + k * (2 * world - 2)
+    edges = [0] + [total * r // world - k * (2 * r - 1) for r in range(1, world)] + [height]
     return [(edges[r], edges[r + 1]) for r in range(world)]
 
 

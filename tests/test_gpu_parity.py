@@ -770,7 +770,8 @@ def _devices(n):
 
 
 @pytest.mark.parametrize("n,size,exact,fused", [(2, (320, 288), True, True), (3, (256, 400), True, True), (2, (320, 288), False, True),
-                                                (4, (200, 520), False, True), (2, (320, 288), True, False), (3, (200, 400), False, "mirror")])
+                                                (4, (200, 520), False, True), (2, (320, 288), True, False), (3, (200, 400), False, "mirror"),
+                                                (3, (128, 720), False, True)])   # 720 rows over 3: outer strips 252 rows, inner 216 (weighted partition)
 def test_multi_device_group_matches_single_gpu(gpu, blue_noise, n, size, exact, fused):
     """st_multi_* (one process, n devices): the frame rendered as n row strips — producer kernels mirroring their
     boundary rows into the neighbours, neighbour-only sequence flags, G-buffer / SVGF halo rows recomputed, temporal rows pulled on

@@ -14,11 +14,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def test_strip_bounds_cover_frame():
-    for h, n in [(1080, 1), (1080, 2), (2160, 8), (4320, 8), (67, 3)]:
+    from strolle_b200.engine import strip_bounds_native
+    for h, n in [(1080, 1), (1080, 2), (2160, 8), (4320, 8), (67, 3), (1528, 2), (2160, 4), (3056, 8), (720, 3), (400, 3), (5000, 16), (161, 16)]:
         b = mg.strip_bounds(h, n)
         assert b[0][0] == 0 and b[-1][1] == h
         assert all(b[i][1] == b[i + 1][0] for i in range(n - 1))
         assert all(y1 > y0 for y0, y1 in b)
+        assert b == strip_bounds_native(h, n), "multigpu.strip_bounds and the engine's partition must be one function"
+
+
+def test_strip_bounds_weigh_the_neighbours():
+    """Outer strips (one neighbour) are STRIP_SIDE_ROWS taller than inner ones (two), when the strips are tall enough; equal otherwise."""
+    rows = [y1 - y0 for y0, y1 in mg.strip_bounds(3056, 8)]
+    assert rows[0] - rows[1] in (mg.STRIP_SIDE_ROWS - 1, mg.STRIP_SIDE_ROWS, mg.STRIP_SIDE_ROWS + 1) and rows[-1] - rows[-2] in (mg.STRIP_SIDE_ROWS - 1, mg.STRIP_SIDE_ROWS, mg.STRIP_SIDE_ROWS + 1)
+    assert max(rows[1:-1]) - min(rows[1:-1]) <= 1 and min(rows) >= 160
+    for h, n in [(1528, 2), (1080, 1), (400, 3), (1080, 8)]:
+        rows = [y1 - y0 for y0, y1 in mg.strip_bounds(h, n)]
+        assert max(rows) - min(rows) <= 1
 
 
 def test_halo_transfers_cover_reach():

@@ -17,7 +17,8 @@ one = strolle_b200.Engine(exact=exact)
 grp = strolle_b200.MultiEngine([0] * n, exact=exact)
 grp.set_option(OPT_STRIP_DMA, dma)
 c1, cn = scenes.apply(one, scene), scenes.apply(grp, scene)
-bounds = [(h * r // n, h * (r + 1) // n) for r in range(n)]
+from strolle_b200.multigpu import strip_bounds
+bounds = strip_bounds(h, n)
 for f in range(frames):
     one.tick(); grp.tick(); one.render_camera(c1); grp.render_camera(cn)
     print(f"frame {f + 1}: peer errors {grp.peer_errors(cn)}; first wait that gave up per rank (slot << 16 | awaited rank << 8 | seq): "
