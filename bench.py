@@ -407,6 +407,7 @@ def main():
     import numpy as np
     import strolle_b200
     from strolle_b200 import scenes
+    from strolle_b200.multigpu import strip_bounds
     ctx = Ctx()
     rank, world = ctx.rank, ctx.world
     W, H = frame_size(args)
@@ -515,7 +516,7 @@ def main():
     line = {
         "metric": METRIC, "value": main_m["mrays"], "unit": "Mrays/s", "fps": main_m["fps"], "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": main_m["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args), "partition": f"{world} row strip(s) of {W}x{rows} px", "transport": main_m["transport"], "ranks": world,
+        "config": {"workload": workload_name(args), "partition": f"{world} row strip(s) of {W} px x {[y1 - y0 for y0, y1 in strip_bounds(H, world)]} rows (outer strips, with one neighbour, are taller than inner ones from 3 ranks on)", "transport": main_m["transport"], "ranks": world,
                    "l2": "per-frame working set (~1.8 GB of per-camera buffers per 1080p strip) exceeds the 126 MB L2; no explicit flush", "seed_base": "0xC0FFEE",
                    "timing": "value: CUDA events around K frames on the engine stream, max over ranks; rays and per-pass events from a replay of the same frame ids"},
         "exact_ms_per_step": main_m.get("exact_ms_per_step"),
