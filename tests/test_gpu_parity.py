@@ -261,6 +261,8 @@ def test_default_fast_svgf_mode_within_tolerance(gpu, oracle, blue_noise):
     for f in range(13):
         eg.tick(); eo.tick(); eg.render_camera(cg); eo.render_camera(co)
         for name in CAMERA_BUFFERS:
+            if name.endswith("_stash"):
+                continue   # scratch: with ST_OPT_WAVELET_PAIRED the stride-8 iteration's output goes to interleaved records instead (test_paired_wavelet_records_match_planar)
             a, b = eg.read_buffer(cg, name), eo.read_buffer(co, name)
             if name in SVGF_BUFFERS:
                 a3, b3 = a.reshape(-1, 4)[:, :3], b.reshape(-1, 4)[:, :3]

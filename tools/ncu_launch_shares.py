@@ -36,9 +36,27 @@ for name, v in sorted(t.items(), key=lambda kv: -sum(kv[1])):
         share = f"{100.0 * bench['pass_ms_per_frame'].get(KERNEL_PASS[base], 0.0) / inrun_total:12.1f}%"
     print(f"{name:52s} {len(v):8d} {sum(v) / len(v):8.1f} {100.0 * sum(v) / total:9.1f}% {share:>13s}")
 if bench:
-    grp = {"wavelet (all variants)": ("k_denoise_wavelet", "frame_denoising_wavelet"), "variance (all variants)": ("k_denoise_variance", "frame_denoising_estimate_variance"),
-           "spatial trace (DI + GI)": ("k_spatial_trace", None)}
-    for label, (prefix, p) in grp.items():
-        s = sum(sum(v) for n, v in t.items() if n.startswith(prefix))
-        inrun = bench["pass_ms_per_frame"].get(p, 0.0) if p else bench["pass_ms_per_frame"].get("di_spatial_resampling_trace", 0.0) + bench["pass_ms_per_frame"].get("gi_spatial_resampling_trace", 0.0)
-        print(f"{label:52s} {'':8s} {'':8s} {100.0 * s / total:9.1f}% {100.0 * inrun / inrun_total:12.1f}%")
+    # Product-default frames only (the bench also renders strict-tier frames, whose kernels carry other names): per-frame time of
+    # every pass under ncu = mean launch time x launches per frame, next to the in-run CUDA-event time of the same pass.
+    frames = len(t.get("stf::k_di_sample_temporal", [])) or 1
+    PASS_OF = [("prim_gbuffer", ["k_prim_gbuffer"], 1), ("di_temporal_resampling", ["stf::k_di_sample_temporal"], None), ("di_spatial_resampling_pick", ["stf::k_di_spatial_fused"], None),
+               ("di_resolving", ["stf::k_di_resolving"], None), ("gi_reprojection", ["stf::k_gi_reprojection"], None), ("gi_sampling_b", ["stf::k_gi_sampling_fused"], None),
+               ("gi_temporal_resampling", ["stf::k_gi_temporal"], None), ("gi_spatial_resampling_pick", ["stf::k_gi_spatial_fused"], None),
+               ("gi_preview_resampling", ["stf::k_gi_preview", "stf::k_gi_preview_resolve"], None), ("frame_denoising_reproject", ["k_denoise_reproject_pair"], 1),
+               ("frame_denoising_estimate_variance", [n for n in t if n.startswith("k_denoise_variance") and "<1" in n], None),
+               ("frame_denoising_wavelet", [n for n in t if n.startswith("k_denoise_wavelet") and "<1" in n], None), ("frame_composition", ["k_composition"], 1)]
+    per = {}
+    for pname, kernels, fixed in PASS_OF:
+        us = 0.0
+        for k in kernels:
+            v = t.get(k, [])
+            if v:
+                us += (sum(v) / len(v)) * (fixed if fixed else len(v) / frames)
+        per[pname] = us
+    tot_ncu = sum(per.values()); tot_run = sum(bench["pass_ms_per_frame"].get(pn, 0.0) for pn in per) * 1000.0
+    print(f"\n# product-default frames ({frames} captured): per-frame time of each pass, ncu (cold caches, serialised) vs in-run CUDA events")
+    print(f"{'pass':40s} {'ncu us':>9s} {'ncu share':>10s} {'in-run us':>10s} {'in-run share':>13s}")
+    for pname, us in sorted(per.items(), key=lambda kv: -kv[1]):
+        run = bench["pass_ms_per_frame"].get(pname, 0.0) * 1000.0
+        print(f"{pname:40s} {us:9.1f} {100.0 * us / tot_ncu:9.1f}% {run:10.1f} {100.0 * run / tot_run:12.1f}%")
+    print(f"{'total':40s} {tot_ncu:9.1f} {'':10s} {tot_run:10.1f}")
