@@ -262,7 +262,8 @@ int st_nccl_init(st_engine* e, const uint8_t* id128, int rank, int world);
 int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap);
 int st_render_strips(st_engine* e, st_camera_handle camera, void* host_out, int format, int temporal_reach, int gather);
 /* The fused strip transport's order of one frame for a given pass schedule (st_frame_schedule), as text for tests:
- * "step:i;signal:SLOT:nb|all;wait:SLOT:nb|all[:prev];pull;push:buffer:SLOT;..." (no device needed). */
+ * "step:i;signal:SLOT:nb|all;wait:SLOT:nb|all[:prev];pull;push:buffer:SLOT;..." (no device needed).  `dma`: bit 0 = ST_OPT_STRIP_DMA,
+ * bit 1 = a frame on which nothing moved (no temporal pull, no wait for PULL_DONE). */
 int st_plan_strip_order(const int* schedule, int n, int dma, char* out, size_t cap);
 /* The row partition st_render_strips / st_multi_* use for a frame of `height` rows over `world` ranks: rows_out[2r], rows_out[2r+1] = rank r's
  * [y0, y1).  Equal strips for one or two ranks; from three on the outer strips (one neighbour) get a few rows more than the inner ones

@@ -646,7 +646,7 @@ static int allocate_camera(st_engine* e, CameraSlot* cs) {
 // Rows a pass computes beyond the owned strip [y0, y1) in a strip-partitioned frame (fused transport): the G-buffer pass recomputes the
 // rows its neighbours' spatial taps reach, K21 / K22 recompute the rows the following à-trous iterations read, so that none of
 // those buffers has to travel.  All zero = every pass runs on [y0, y1).
-struct StripExt { int gbuffer = 0, variance = 0, wavelet[5] = {0, 0, 0, 0, 0}; int preview_mirror[2] = {0, 0}; };
+struct StripExt { int gbuffer = 0, variance = 0, wavelet[5] = {0, 0, 0, 0, 0}; int preview_mirror[2] = {0, 0}; bool still = false; /* nothing moved: no rows of last frame are pulled */ };
 static CameraDev grown(const CameraDev& c, int rows) { CameraDev g = c; g.y0 = std::max(0, c.y0 - rows); g.y1 = std::min(c.h, c.y1 + rows); return g; }
 static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* steps, const StripExt* ext = nullptr) {
     const CameraDev cam = cs->dev;   // snapshot (pointers + cameras)
@@ -679,8 +679,9 @@ static void build_schedule(st_engine* e, CameraSlot* cs, std::vector<Step>* step
     }
     const bool needs_di = d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_DI_DIFFUSE || d.mode == ST_MODE_DI_SPECULAR;
     const bool needs_gi = d.mode == ST_MODE_IMAGE || d.mode == ST_MODE_GI_DIFFUSE || d.mode == ST_MODE_GI_SPECULAR;
-    // K4 inside the G-buffer launch: only where nothing has to happen between the two (a strip pulls last frame's rows in between)
-    const int k4_in_k0 = (e->fused_passes && ext == nullptr && !e->instances.empty()) ? 1 : 0;
+    // K4 inside the G-buffer launch: only where nothing has to happen between the two (a strip pulls last frame's rows in between,
+    // unless nothing moved: then every reprojected read is the pixel itself)
+    const int k4_in_k0 = (e->fused_passes && (ext == nullptr || ext->still) && !e->instances.empty()) ? 1 : 0;
     add(P_PRIM_GBUFFER, [=](cudaStream_t s) { launch_prim_gbuffer(camG, sc, cur, k4_in_k0, s); });
     // ST_OPT_FUSED_PASSES: passes whose hand-over is private to a pixel (or to a checkerboard pair) run as one launch; the step keeps
     // the pass id of the member that gathers from other pixels, which is what the strip plans key on.
@@ -916,7 +917,7 @@ struct StripOp {
     bool wait_prev_frame = false, reset_need = false;
     const char* buffer = nullptr;                    // PUSH: rows of this buffer go to the neighbours by copy engine, then sig_slot is raised there
 };
-static void plan_strip_order(const std::vector<int>& pass, bool dma, std::vector<StripOp>* out) {
+static void plan_strip_order(const std::vector<int>& pass, bool dma, bool still, std::vector<StripOp>* out) {
     auto step = [&](int i) { StripOp o; o.kind = StripOp::STEP; o.step = i; out->push_back(o); };
     auto signal = [&](int slot, bool all_ranks = false, bool reset_need = false) { StripOp o; o.kind = StripOp::SIGNAL; o.sig_slot = slot; o.sig_all = all_ranks; o.reset_need = reset_need; out->push_back(o); };
     auto wait = [&](int slot, bool all_ranks = false, bool prev = false) { StripOp o; o.kind = StripOp::WAIT; o.wait_slot = slot; o.wait_all = all_ranks; o.wait_prev_frame = prev; out->push_back(o); };
@@ -941,9 +942,11 @@ static void plan_strip_order(const std::vector<int>& pass, bool dma, std::vector
     // frame start: the primary pass needs nobody; then wait until every rank has finished the previous frame, pull, tell everybody
     size_t k = 0;
     if (!pre.empty() && pass[pre[0]] == P_PRIM_GBUFFER) { step(pre[0]); k = 1; }
+    // (`still`: neither the camera nor an instance moved, so every temporal read is the pixel itself: nothing to pull, nobody to wait
+    // for before history is overwritten; PULL_DONE is still raised so that a rank that does pull never waits for one that does not)
     wait(SLOT_FRAME_DONE, true, true);
-    { StripOp o; o.kind = StripOp::PULL; out->push_back(o); }
-    signal(SLOT_PULL_DONE, true, true);
+    if (!still) { StripOp o; o.kind = StripOp::PULL; out->push_back(o); }
+    signal(SLOT_PULL_DONE, true, !still);
     for (; k < pre.size(); k++) step(pre[k]);
     // DI and GI up to their first gathering pass
     for (int i : di1) step(i);
@@ -959,9 +962,10 @@ static void plan_strip_order(const std::vector<int>& pass, bool dma, std::vector
     if (!gi1.empty()) wait(SLOT_GI1);
     for (int i : gi_sp) step(i);
     // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
-    if (!gi_sp.empty() && dma) { push("gi_reservoirs_2", SLOT_GI2); wait(SLOT_PULL_DONE, true); }
+    if (!gi_sp.empty() && dma) { push("gi_reservoirs_2", SLOT_GI2); if (!still) wait(SLOT_PULL_DONE, true); }
+    else if (!gi_sp.empty() && still) signal(SLOT_GI2);
     else if (!gi_sp.empty()) signal_wait(SLOT_GI2, SLOT_PULL_DONE, true);
-    else wait(SLOT_PULL_DONE, true);
+    else if (!still) wait(SLOT_PULL_DONE, true);
     if (!di_rest.empty()) step(di_rest[0]);
     if (!gi_sp.empty()) wait(SLOT_GI2);
     for (int i : pv1) step(i);
@@ -1009,6 +1013,10 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     StripExt ext; ext.gbuffer = kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
     for (int i = 0; i < 5; i++) ext.wavelet[i] = wext[i];
     ext.preview_mirror[0] = kPreview2Reach; ext.preview_mirror[1] = 0;
+    // Nothing moved since the last frame (same camera bytes, no instance touched): velocities are zero, so K4 / K6 / K14 / K20 read last
+    // frame at the pixel itself — no rows to pull, K4 can run inside the G-buffer launch.  Every rank sees the same updates, hence decides alike.
+    ext.still = cs->frame > 1 && !e->moved_last_tick && std::memcmp(&cs->dev.curr, &cs->dev.prev, sizeof(GpuCamera)) == 0;
+    if (ext.still) d.need_rows = nullptr;
     std::vector<Step> steps; build_schedule(e, cs, &steps, &ext);
 
     StripSync ss; ss.my_flags = sync; ss.errors = sync + kStripErrorWord; ss.n_ranks = N; ss.rank = R;
@@ -1046,7 +1054,7 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
 
     // the order of passes, flags, pulls and pushes is planned by a pure function (CPU-testable: st_plan_strip_order); execute it
     std::vector<int> ids; for (const Step& st : steps) ids.push_back(st.pass);
-    std::vector<StripOp> ops; plan_strip_order(ids, dma, &ops);
+    std::vector<StripOp> ops; plan_strip_order(ids, dma, ext.still, &ops);
     const char* prv = (cs->frame % 2u == 1u) ? "a" : "b";
     for (const StripOp& op : ops) {
         const uint32_t smask = op.sig_all ? all : nb, wmask = op.wait_all ? all : nb;
@@ -1802,7 +1810,7 @@ int st_plan_strip_order(const int* schedule, int n, int dma, char* out, size_t c
     if (!schedule || !out || cap == 0) return fail(ST_ERR_INVALID, "null argument");
     static const char* kSlot[SLOT_COUNT] = {"FRAME_DONE", "PULL_DONE", "DI1", "GI1", "GI2", "GI3", "SVGF", "OUTPUT"};
     std::vector<int> ids(schedule, schedule + n);
-    std::vector<StripOp> ops; plan_strip_order(ids, dma != 0, &ops);
+    std::vector<StripOp> ops; plan_strip_order(ids, (dma & 1) != 0, (dma & 2) != 0, &ops);
     std::string text;
     for (const StripOp& op : ops) {
         switch (op.kind) {

@@ -150,7 +150,7 @@ template <int ALL, int ONE> struct LbMin { static constexpr int value = ALL > 0 
 // Primary-visibility G-buffer (stands in for strolle-shaders/src/prim_raster.rs:41-128)
 // ---------------------------------------------------------------------------------------------
 ST_DEV float4 frame_reprojection_px(const CameraDev& cam, int cur, Px p, float4 surface_texel, float4 vel);
-// `with_reprojection` (ST_OPT_FUSED_PASSES, single GPU): K4 runs in this launch too — its inputs for the pixel are still in registers
+// `with_reprojection` (ST_OPT_FUSED_PASSES; single GPU, or a strip on a frame where nothing moved): K4 runs in this launch too — its inputs for the pixel are still in registers
 __global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur, int with_reprojection) {
     ST_TRACE_STACK();
     Px p = pixel_full(cam);
@@ -190,7 +190,7 @@ __global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur, int with_rep
     size_t i = pix(cam, p.x, p.y);
     cam.prim_gbuffer_d0[cur][i] = g0; cam.prim_gbuffer_d1[cur][i] = g1; cam.prim_surface_map[cur][i] = surf;
     cam.velocity_map[i] = vel; cam.prim_triangle_ids[i] = tid; cam.surface_nd[i] = nd;
-    if (with_reprojection) cam.reprojection_map[i] = frame_reprojection_px(cam, cur, p, surf, vel);
+    if (with_reprojection && (int)p.y >= cam.own_y0 && (int)p.y < cam.own_y1) cam.reprojection_map[i] = frame_reprojection_px(cam, cur, p, surf, vel);   // not for the rows a strip recomputes beyond its own
 }
 
 // K4 frame_reprojection::main (frame_reprojection.rs:7-95): where the pixel was last frame and how far that can be trusted

@@ -164,16 +164,18 @@ def _schedules():
     return out
 
 
+@pytest.mark.parametrize("still", [False, True])
 @pytest.mark.parametrize("dma", [True, False])
-def test_fused_strip_order_invariants(dma):
+def test_fused_strip_order_invariants(dma, still):
     """Every pass runs exactly once and chains keep their internal order; every pass that gathers from a neighbouring strip is preceded
     by a wait on the flag that its producer's signal (or copy-engine push) raises; nothing a neighbour may still pull is overwritten before
-    every rank signalled PULL_DONE; the frame opens with the previous frame's FRAME_DONE and closes with this frame's."""
+    every rank signalled PULL_DONE; the frame opens with the previous frame's FRAME_DONE and closes with this frame's.  On a frame where
+    nothing moved (`still`) there is no pull and no wait for PULL_DONE (it is still raised, for ranks that might pull)."""
     from strolle_b200.engine import plan_strip_order
     P = mg
     producer_slot = {P.P_DI_TEMPORAL: "DI1", P.P_GI_TEMPORAL: "GI1", P.P_DENOISE_REPROJECT: "SVGF"}
     for name, sched in _schedules().items():
-        ops = plan_strip_order(sched, dma)
+        ops = plan_strip_order(sched, dma, still)
         steps = [int(o.split(":")[1]) for o in ops if o.startswith("step:")]
         assert sorted(steps) == list(range(len(sched))), name
         for chain in ([P.P_DI_SAMPLING, P.P_DI_TEMPORAL, P.P_DI_SPATIAL_PICK, P.P_DI_SPATIAL_TRACE, P.P_DI_SPATIAL_SAMPLE, P.P_DI_RESOLVING],
@@ -181,7 +183,11 @@ def test_fused_strip_order_invariants(dma):
                       [P.P_DENOISE_REPROJECT, P.P_DENOISE_VARIANCE, P.P_DENOISE_WAVELET, P.P_COMPOSITION]):
             inside = [i for i in steps if sched[i] in chain]
             assert inside == sorted(inside), f"{name}: chain order"
-        assert ops[0] == "step:0" and ops[1] == "wait:FRAME_DONE:all:prev" and ops[2] == "pull" and ops[3] == "signal:PULL_DONE:all" and ops[-1] == "signal:FRAME_DONE:all", name
+        assert ops[0] == "step:0" and ops[1] == "wait:FRAME_DONE:all:prev" and ops[-1] == "signal:FRAME_DONE:all", name
+        if still:
+            assert "pull" not in ops and ops[2] == "signal:PULL_DONE:all" and not any(o.startswith("wait:PULL_DONE") for o in ops), name
+        else:
+            assert ops[2] == "pull" and ops[3] == "signal:PULL_DONE:all", name
         raised, waited = set(), set()
         previews = 0
         for o in ops:
@@ -206,7 +212,7 @@ def test_fused_strip_order_invariants(dma):
                 if need:
                     assert need in waited, f"{name}: pass {p} gathers before wait:{need}"
                 if p in (P.P_DI_RESOLVING, P.P_GI_RESOLVING, P.P_DENOISE_WAVELET) or (p == P.P_GI_PREVIEW and previews == 2):
-                    assert "PULL_DONE" in waited, f"{name}: pass {p} overwrites pulled buffers before every rank pulled"
+                    assert still or "PULL_DONE" in waited, f"{name}: pass {p} overwrites pulled buffers before every rank pulled"
                 if p in producer_slot and producer_slot[p] not in raised:
                     pass   # raised right after the producer (checked through the waits above)
         if any(q == P.P_GI_PREVIEW for q in sched):
