@@ -181,10 +181,13 @@ enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3,
  * 65.6 vs 61.8 us at 1080p); 0 = planar buffers throughout.  Stride 16: 78.1 -> 70.0 us (Cornell), 113.5 -> 98.7 us (dungeon).  Same values in
  * every layout; `*_diff_stash` then keeps the output of the last planar iteration. */
 #define ST_WAVELET_PAIRED_DEFAULT 1
-/* ST_OPT_STRIP_DMA (default 1; fused strip transport only): the 128-row halos of gi_reservoirs[1] / [2] (64 B per pixel, the bulk of what
+/* ST_OPT_STRIP_DMA (default 2; fused strip transport only): 1 = the 128-row halos of gi_reservoirs[1] / [2] (64 B per pixel, the bulk of what
  * travels) are pushed by the copy engines on one side stream per neighbour right after the kernel that produced them, overlapping the DI
- * passes that follow, instead of being mirrored by that kernel's own stores; 0 = every halo is mirrored in-kernel. */
-#define ST_STRIP_DMA_DEFAULT 1
+ * passes that follow, instead of being mirrored by that kernel's own stores; 2 = the copy engines also push the 128 G-buffer rows
+ * (prim_gbuffer_d0 / d1, surface map, surface_nd: 64 B per pixel) next to each strip edge right after the primary pass, instead of every
+ * strip recomputing its neighbours' rows (which costs an inner strip of an 8-GPU frame two thirds of a G-buffer pass); 0 = every halo is
+ * mirrored in-kernel and the G-buffer rows are recomputed. */
+#define ST_STRIP_DMA_DEFAULT 2
 /* ST_OPT_FUSED_PASSES (default 1): reference passes whose hand-over is private to a pixel or to a checkerboard pair run as ONE launch:
  * K5+K6 (di_sampling + di_temporal_resampling), K7+K8+K9 (di_spatial_resampling pick / trace / sample), K12+K13 (gi_sampling a + b),
  * K11 inside K14 on tracing frames (gi_reprojection + gi_temporal_resampling), K15+K16+K17 (gi_spatial_resampling) and the second
@@ -262,8 +265,8 @@ int st_nccl_init(st_engine* e, const uint8_t* id128, int rank, int world);
 int st_plan_frame(const int* schedule, int n, uint32_t frame, int temporal_reach, char* out, size_t cap);
 int st_render_strips(st_engine* e, st_camera_handle camera, void* host_out, int format, int temporal_reach, int gather);
 /* The fused strip transport's order of one frame for a given pass schedule (st_frame_schedule), as text for tests:
- * "step:i;signal:SLOT:nb|all;wait:SLOT:nb|all[:prev];pull;push:buffer:SLOT;..." (no device needed).  `dma`: bit 0 = ST_OPT_STRIP_DMA,
- * bit 1 = a frame on which nothing moved (no temporal pull, no wait for PULL_DONE). */
+ * "step:i;signal:SLOT:nb|all;wait:SLOT:nb|all[:prev];pull;push:buffer:SLOT;..." (no device needed).  `dma`: bits 0-1 = ST_OPT_STRIP_DMA (0, 1, 2),
+ * bit 2 = a frame on which nothing moved (no temporal pull, no wait for PULL_DONE). */
 int st_plan_strip_order(const int* schedule, int n, int dma, char* out, size_t cap);
 /* The row partition st_render_strips / st_multi_* use for a frame of `height` rows over `world` ranks: rows_out[2r], rows_out[2r+1] = rank r's
  * [y0, y1).  Equal strips for one or two ranks; from three on the outer strips (one neighbour) get a few rows more than the inner ones

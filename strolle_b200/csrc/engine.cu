@@ -433,7 +433,7 @@ struct st_engine {
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
     int wavelet_paired = ST_WAVELET_PAIRED_DEFAULT;   // ST_OPT_WAVELET_PAIRED
-    bool strip_dma = ST_STRIP_DMA_DEFAULT != 0;   // ST_OPT_STRIP_DMA: gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores
+    int strip_dma = ST_STRIP_DMA_DEFAULT;   // ST_OPT_STRIP_DMA: 1 = gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores; 2 = also the G-buffer halo rows (instead of recomputing them)
     bool strip_fused = true;     // ST_OPT_STRIP_FUSED: mirror stores + neighbour flags + recompute instead of stand-alone exchanges
     bool last_frame_fused = false;
     int wavelet_tiled = ST_WAVELET_TILED_DEFAULT;   // ST_OPT_WAVELET_TILED: bit i = à-trous iteration i (stride 2^i) runs the tile-staged (TMA) kernel
@@ -917,7 +917,8 @@ struct StripOp {
     bool wait_prev_frame = false, reset_need = false;
     const char* buffer = nullptr;                    // PUSH: rows of this buffer go to the neighbours by copy engine, then sig_slot is raised there
 };
-static void plan_strip_order(const std::vector<int>& pass, bool dma, bool still, std::vector<StripOp>* out) {
+static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool still, std::vector<StripOp>* out) {
+    const bool dma = dma_level >= 1, dma_gbuffer = dma_level >= 2;
     auto step = [&](int i) { StripOp o; o.kind = StripOp::STEP; o.step = i; out->push_back(o); };
     auto signal = [&](int slot, bool all_ranks = false, bool reset_need = false) { StripOp o; o.kind = StripOp::SIGNAL; o.sig_slot = slot; o.sig_all = all_ranks; o.reset_need = reset_need; out->push_back(o); };
     auto wait = [&](int slot, bool all_ranks = false, bool prev = false) { StripOp o; o.kind = StripOp::WAIT; o.wait_slot = slot; o.wait_all = all_ranks; o.wait_prev_frame = prev; out->push_back(o); };
@@ -947,6 +948,11 @@ static void plan_strip_order(const std::vector<int>& pass, bool dma, bool still,
     wait(SLOT_FRAME_DONE, true, true);
     if (!still) { StripOp o; o.kind = StripOp::PULL; out->push_back(o); }
     signal(SLOT_PULL_DONE, true, !still);
+    // the G-buffer rows the neighbours' spatial taps and SVGF windows reach: pushed by copy engine (instead of each neighbour
+    // recomputing them), with everything up to the first gathering pass to hide behind
+    bool gbuf_waited = !dma_gbuffer;
+    if (dma_gbuffer && !pre.empty() && pass[pre[0]] == P_PRIM_GBUFFER) push("@gbuffer", SLOT_GBUF); else gbuf_waited = true;
+    auto need_gbuffer = [&]() { if (!gbuf_waited) { wait(SLOT_GBUF); gbuf_waited = true; } };
     for (; k < pre.size(); k++) step(pre[k]);
     // DI and GI up to their first gathering pass
     for (int i : di1) step(i);
@@ -958,8 +964,10 @@ static void plan_strip_order(const std::vector<int>& pass, bool dma, bool still,
     } else if (!gi1.empty() && !di_pick.empty()) signal_wait(SLOT_GI1, SLOT_DI1);
     else if (!gi1.empty()) signal(SLOT_GI1);
     else if (!di_pick.empty()) wait(SLOT_DI1);
+    if (!di_pick.empty()) need_gbuffer();
     for (int i : di_pick) step(i);
     if (!gi1.empty()) wait(SLOT_GI1);
+    if (!gi_sp.empty()) need_gbuffer();
     for (int i : gi_sp) step(i);
     // from here on this rank overwrites buffers others pull from (di[0], gi[0], prev colours)
     if (!gi_sp.empty() && dma) { push("gi_reservoirs_2", SLOT_GI2); if (!still) wait(SLOT_PULL_DONE, true); }
@@ -968,6 +976,7 @@ static void plan_strip_order(const std::vector<int>& pass, bool dma, bool still,
     else if (!still) wait(SLOT_PULL_DONE, true);
     if (!di_rest.empty()) step(di_rest[0]);
     if (!gi_sp.empty()) wait(SLOT_GI2);
+    if (!pv1.empty()) need_gbuffer();
     for (int i : pv1) step(i);
     if (!pv1.empty()) signal(SLOT_GI3);
     for (size_t i = 1; i < di_rest.size(); i++) step(di_rest[i]);
@@ -976,9 +985,10 @@ static void plan_strip_order(const std::vector<int>& pass, bool dma, bool still,
     // SVGF: K20 mirrors its rows, then everything downstream is recomputed locally
     bool svgf_waited = false;
     for (int i : post) {
-        if (pass[i] == P_DENOISE_VARIANCE && !svgf_waited) { signal_wait(SLOT_SVGF, SLOT_SVGF); svgf_waited = true; }
+        if (pass[i] == P_DENOISE_VARIANCE && !svgf_waited) { signal_wait(SLOT_SVGF, SLOT_SVGF); svgf_waited = true; need_gbuffer(); }
         step(i);
     }
+    need_gbuffer();   // (a mode without any gathering pass: the flag is still consumed, so that sequence numbers stay in step)
     signal(SLOT_FRAME_DONE, true);
 }
 
@@ -1005,12 +1015,12 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     d.mirror_up = R > 0 ? (long long)(cs->peer.arena[R - 1] - cs->peer.arena[R]) : 0;
     d.mirror_dn = R + 1 < N ? (long long)(cs->peer.arena[R + 1] - cs->peer.arena[R]) : 0;
     d.need_rows = (int*)(sync + kNeedRowsWord);
-    const bool dma = e->strip_dma;
+    const bool dma = e->strip_dma >= 1, dma_gbuffer = e->strip_dma >= 2;
     d.gi_mirror_reach = dma ? 0 : kSpatialReach;
     if (dma && !cs->ev_produced) return fail(ST_ERR_INVALID, "strip side streams missing: link the camera first (st_link_local / st_peer_import)");
     // the copy engines of last frame have long finished; this orders this frame's writes of the pushed rows after them formally
     for (int k = 0; k < 2; k++) if (cs->pushed_pending[k]) { CK(cudaStreamWaitEvent(e->stream, cs->ev_pushed[k], 0)); cs->pushed_pending[k] = false; }
-    StripExt ext; ext.gbuffer = kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
+    StripExt ext; ext.gbuffer = dma_gbuffer ? 0 : kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
     for (int i = 0; i < 5; i++) ext.wavelet[i] = wext[i];
     ext.preview_mirror[0] = kPreview2Reach; ext.preview_mirror[1] = 0;
     // Nothing moved since the last frame (same camera bytes, no instance touched): velocities are zero, so K4 / K6 / K14 / K20 read last
@@ -1036,17 +1046,19 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     // mirrored by the producing kernel (whose own time they would stretch) but pushed by the copy engines right after it, one side
     // stream per neighbour, while this stream goes on with the other chain's passes; the flag is raised on the side stream behind the copy.
     int push_rc = ST_OK;
-    auto push_rows = [&](const char* name, int reach, int slot) {
-        size_t kk = 0; float4* base = camera_buffer(cs, name, &kk);
-        if (!base) { push_rc = fail(ST_ERR_NOT_FOUND, std::string("unknown buffer ") + name); return; }
-        const size_t W = cs->desc.width, row_bytes = W * kk * 16, off = (size_t)((char*)base - (char*)cs->arena.p);
+    auto push_rows = [&](const std::vector<std::string>& names, int reach, int slot) {
         cudaEventRecord(cs->ev_produced, e->stream);
         for (int k = 0; k < 2; k++) {
             const int nbr = k == 0 ? R - 1 : R + 1;
             if (nbr < 0 || nbr >= N) continue;
             const int r0 = k == 0 ? d.own_y0 : std::max(d.own_y0, d.own_y1 - reach), r1 = k == 0 ? std::min(d.own_y1, d.own_y0 + reach) : d.own_y1;
             cudaStreamWaitEvent(cs->side[k], cs->ev_produced, 0);
-            cudaMemcpyAsync(cs->peer.arena[nbr] + off + (size_t)r0 * row_bytes, (char*)base + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDefault, cs->side[k]);
+            for (const std::string& name : names) {
+                size_t kk = 0; float4* base = camera_buffer(cs, name, &kk);
+                if (!base) { push_rc = fail(ST_ERR_NOT_FOUND, std::string("unknown buffer ") + name); return; }
+                const size_t W = cs->desc.width, row_bytes = W * kk * 16, off = (size_t)((char*)base - (char*)cs->arena.p);
+                cudaMemcpyAsync(cs->peer.arena[nbr] + off + (size_t)r0 * row_bytes, (char*)base + (size_t)r0 * row_bytes, (size_t)(r1 - r0) * row_bytes, cudaMemcpyDefault, cs->side[k]);
+            }
             launch_strip_signal(ss, slot, seq, 1u << nbr, nullptr, H, cs->side[k]);
             cudaEventRecord(cs->ev_pushed[k], cs->side[k]); cs->pushed_pending[k] = true;
         }
@@ -1054,7 +1066,7 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
 
     // the order of passes, flags, pulls and pushes is planned by a pure function (CPU-testable: st_plan_strip_order); execute it
     std::vector<int> ids; for (const Step& st : steps) ids.push_back(st.pass);
-    std::vector<StripOp> ops; plan_strip_order(ids, dma, ext.still, &ops);
+    std::vector<StripOp> ops; plan_strip_order(ids, e->strip_dma, ext.still, &ops);
     const char* prv = (cs->frame % 2u == 1u) ? "a" : "b";
     for (const StripOp& op : ops) {
         const uint32_t smask = op.sig_all ? all : nb, wmask = op.wait_all ? all : nb;
@@ -1064,7 +1076,12 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
         case StripOp::SIGNAL: signal(op.sig_slot, smask, op.reset_need); break;
         case StripOp::WAIT: wait(op.wait_slot, wmask, wseq); break;
         case StripOp::SIGNAL_WAIT: signal_wait(op.sig_slot, smask, op.wait_slot, wmask, wseq); break;
-        case StripOp::PUSH: push_rows(op.buffer, kSpatialReach, op.sig_slot); break;
+        case StripOp::PUSH:
+            if (!std::strcmp(op.buffer, "@gbuffer")) {   // what the primary pass wrote for this frame and other strips read at their taps
+                const std::string c = (cs->frame % 2u == 1u) ? "b" : "a";
+                push_rows({"prim_gbuffer_d0_" + c, "prim_gbuffer_d1_" + c, "prim_surface_map_" + c, "surface_nd"}, kSpatialReach, op.sig_slot);
+            } else push_rows({op.buffer}, kSpatialReach, op.sig_slot);
+            break;
         case StripOp::PULL: {
             StripPull pl; std::memset(&pl, 0, sizeof pl);
             for (int r = 0; r < N; r++) { pl.arena[r] = cs->peer.arena[r]; pl.bounds[r] = bounds[r].first; }
@@ -1556,7 +1573,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
-    if (option == ST_OPT_STRIP_DMA) { e->strip_dma = value != 0; return ST_OK; }
+    if (option == ST_OPT_STRIP_DMA) { if (value < 0 || value > 2) return fail(ST_ERR_INVALID, "ST_OPT_STRIP_DMA: 0, 1 or 2"); e->strip_dma = value; return ST_OK; }
     if (option == ST_OPT_WAVELET_PAIRED) { if (value < 0 || value > 2) return fail(ST_ERR_INVALID, "ST_OPT_WAVELET_PAIRED: 0, 1 or 2"); e->wavelet_paired = value; return ST_OK; }
     if (option == ST_OPT_FUSED_PASSES) { e->fused_passes = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }
@@ -1808,9 +1825,9 @@ int st_strip_bounds(int height, int world, int* rows_out) {
 }
 int st_plan_strip_order(const int* schedule, int n, int dma, char* out, size_t cap) {
     if (!schedule || !out || cap == 0) return fail(ST_ERR_INVALID, "null argument");
-    static const char* kSlot[SLOT_COUNT] = {"FRAME_DONE", "PULL_DONE", "DI1", "GI1", "GI2", "GI3", "SVGF", "OUTPUT"};
+    static const char* kSlot[SLOT_COUNT] = {"FRAME_DONE", "PULL_DONE", "DI1", "GI1", "GI2", "GI3", "SVGF", "GBUF"};
     std::vector<int> ids(schedule, schedule + n);
-    std::vector<StripOp> ops; plan_strip_order(ids, (dma & 1) != 0, (dma & 2) != 0, &ops);
+    std::vector<StripOp> ops; plan_strip_order(ids, dma & 3, (dma & 4) != 0, &ops);
     std::string text;
     for (const StripOp& op : ops) {
         switch (op.kind) {

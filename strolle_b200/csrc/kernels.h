@@ -62,7 +62,7 @@ struct PeerExchange {
 void launch_peer_exchange(const PeerExchange& x, cudaStream_t st);
 
 // Fused strip transport (engine.cu render_strips_fused): sequence flags between ranks and the temporal pull
-enum StripSlot { SLOT_FRAME_DONE = 0, SLOT_PULL_DONE = 1, SLOT_DI1 = 2, SLOT_GI1 = 3, SLOT_GI2 = 4, SLOT_GI3 = 5, SLOT_SVGF = 6, SLOT_OUTPUT = 7, SLOT_COUNT = 8 };
+enum StripSlot { SLOT_FRAME_DONE = 0, SLOT_PULL_DONE = 1, SLOT_DI1 = 2, SLOT_GI1 = 3, SLOT_GI2 = 4, SLOT_GI3 = 5, SLOT_SVGF = 6, SLOT_GBUF = 7, SLOT_COUNT = 8 };
 struct StripSync {
     const u32* my_flags;                  // this rank's flag words, [slot * ST_PEER_MAX_RANKS + source rank]
     u32* peer_flags[ST_PEER_MAX_RANKS];   // every other rank's flag array (mapped peer memory); null for self

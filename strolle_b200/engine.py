@@ -603,11 +603,11 @@ def strip_bounds_native(height, world):
 
 def plan_strip_order(schedule, dma=True, still=False):
     """The fused strip transport's op order for a pass schedule, as a list of strings (st_plan_strip_order; no GPU needed).
-    `still`: the order of a frame on which neither the camera nor an instance moved."""
+    `dma`: ST_OPT_STRIP_DMA (0 / False, 1 / True, 2); `still`: the order of a frame on which neither the camera nor an instance moved."""
     lib = load_library()
     arr = (C.c_int * len(schedule))(*schedule)
     out = C.create_string_buffer(8192)
-    rc = lib.st_plan_strip_order(arr, len(schedule), int(bool(dma)) | (2 if still else 0), out, 8192)
+    rc = lib.st_plan_strip_order(arr, len(schedule), (int(dma) & 3) | (4 if still else 0), out, 8192)
     if rc != 0:
         raise StrolleError(lib.st_last_error().decode())
     return [x for x in out.value.decode().split(";") if x]

@@ -165,7 +165,7 @@ def _schedules():
 
 
 @pytest.mark.parametrize("still", [False, True])
-@pytest.mark.parametrize("dma", [True, False])
+@pytest.mark.parametrize("dma", [2, 1, 0])
 def test_fused_strip_order_invariants(dma, still):
     """Every pass runs exactly once and chains keep their internal order; every pass that gathers from a neighbouring strip is preceded
     by a wait on the flag that its producer's signal (or copy-engine push) raises; nothing a neighbour may still pull is overwritten before
@@ -195,7 +195,7 @@ def test_fused_strip_order_invariants(dma, still):
             if f[0] == "signal":
                 raised.add(f[1])
             elif f[0] == "push":
-                assert dma and f[1] in ("gi_reservoirs_1", "gi_reservoirs_2")
+                assert dma and f[1] in ("gi_reservoirs_1", "gi_reservoirs_2", "@gbuffer") and (f[1] != "@gbuffer" or dma == 2)
                 raised.add(f[2])
             elif f[0] == "wait" and len(f) == 3:
                 assert f[1] in raised, f"{name}: waits for {f[1]} before this rank raised it itself (ranks run the same order: nobody would)"
@@ -211,9 +211,11 @@ def test_fused_strip_order_invariants(dma, still):
                 elif p == P.P_DENOISE_VARIANCE: need = "SVGF"
                 if need:
                     assert need in waited, f"{name}: pass {p} gathers before wait:{need}"
+                    assert dma < 2 or "GBUF" in waited, f"{name}: pass {p} reads the neighbours' G-buffer rows before wait:GBUF"
                 if p in (P.P_DI_RESOLVING, P.P_GI_RESOLVING, P.P_DENOISE_WAVELET) or (p == P.P_GI_PREVIEW and previews == 2):
                     assert still or "PULL_DONE" in waited, f"{name}: pass {p} overwrites pulled buffers before every rank pulled"
                 if p in producer_slot and producer_slot[p] not in raised:
                     pass   # raised right after the producer (checked through the waits above)
         if any(q == P.P_GI_PREVIEW for q in sched):
             assert "GI3" in raised and "GI3" in waited, name
+        assert ("GBUF" in raised) == (dma == 2) and ("GBUF" in waited) == (dma == 2), f"{name}: the G-buffer flag is raised and consumed every frame, or never"
