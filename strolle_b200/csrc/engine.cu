@@ -638,7 +638,7 @@ static int allocate_camera(st_engine* e, CameraSlot* cs) {
     size_t off = 0;
     for (size_t i = 0; i < cs->named.size(); i++) { *cs->named[i].second = (float4*)((char*)cs->arena.p + off); off += (cs->sizes[i].second * 16 + 255) / 256 * 256; }
     d.w = (int)cs->desc.width; d.h = (int)cs->desc.height; d.y0 = 0; d.y1 = d.h;
-    d.own_y0 = 0; d.own_y1 = d.h; d.mirror_up = 0; d.mirror_dn = 0; d.need_rows = nullptr; d.gi_mirror_reach = 128;
+    d.own_y0 = 0; d.own_y1 = d.h; d.mirror_up = 0; d.mirror_dn = 0; d.need_rows = nullptr; d.gi_mirror_reach = 128; d.di_mirror_reach = 128;
     return ST_OK;
 }
 
@@ -916,6 +916,7 @@ struct StripOp {
     bool sig_all = false, wait_all = false;          // every rank instead of the two neighbours
     bool wait_prev_frame = false, reset_need = false;
     const char* buffer = nullptr;                    // PUSH: rows of this buffer go to the neighbours by copy engine, then sig_slot is raised there
+    int reach = 0;                                   // PUSH: rows next to each strip edge (0 = the spatial reach)
 };
 static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool still, std::vector<StripOp>* out) {
     const bool dma = dma_level >= 1, dma_gbuffer = dma_level >= 2;
@@ -923,7 +924,7 @@ static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool s
     auto signal = [&](int slot, bool all_ranks = false, bool reset_need = false) { StripOp o; o.kind = StripOp::SIGNAL; o.sig_slot = slot; o.sig_all = all_ranks; o.reset_need = reset_need; out->push_back(o); };
     auto wait = [&](int slot, bool all_ranks = false, bool prev = false) { StripOp o; o.kind = StripOp::WAIT; o.wait_slot = slot; o.wait_all = all_ranks; o.wait_prev_frame = prev; out->push_back(o); };
     auto signal_wait = [&](int sslot, int wslot, bool wall = false) { StripOp o; o.kind = StripOp::SIGNAL_WAIT; o.sig_slot = sslot; o.wait_slot = wslot; o.wait_all = wall; out->push_back(o); };
-    auto push = [&](const char* buffer, int slot) { StripOp o; o.kind = StripOp::PUSH; o.buffer = buffer; o.sig_slot = slot; out->push_back(o); };
+    auto push = [&](const char* buffer, int slot, int reach = 0) { StripOp o; o.kind = StripOp::PUSH; o.buffer = buffer; o.sig_slot = slot; o.reach = reach; out->push_back(o); };
     // split the reference order into the blocks the interleaving moves around
     std::vector<int> pre, di1, di_pick, di_rest, gi1, gi_sp, pv1, gi_tail, post;
     int nth_preview = 0;
@@ -956,7 +957,7 @@ static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool s
     for (; k < pre.size(); k++) step(pre[k]);
     // DI and GI up to their first gathering pass
     for (int i : di1) step(i);
-    if (!di1.empty()) signal(SLOT_DI1);
+    if (!di1.empty()) { if (dma_gbuffer) push("di_reservoirs_1", SLOT_DI1); else signal(SLOT_DI1); }   // level 2: every halo with slack before its reader goes by copy engine
     for (int i : gi1) step(i);
     if (dma) {   // the flags of the GI halos are raised by the side streams, behind their copies
         if (!gi1.empty()) push("gi_reservoirs_1", SLOT_GI1);
@@ -978,7 +979,7 @@ static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool s
     if (!gi_sp.empty()) wait(SLOT_GI2);
     if (!pv1.empty()) need_gbuffer();
     for (int i : pv1) step(i);
-    if (!pv1.empty()) signal(SLOT_GI3);
+    if (!pv1.empty()) { if (dma_gbuffer) push("gi_reservoirs_3", SLOT_GI3, kPreview2Reach); else signal(SLOT_GI3); }
     for (size_t i = 1; i < di_rest.size(); i++) step(di_rest[i]);
     if (!pv1.empty()) wait(SLOT_GI3);
     for (int i : gi_tail) step(i);
@@ -1016,13 +1017,13 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     d.mirror_dn = R + 1 < N ? (long long)(cs->peer.arena[R + 1] - cs->peer.arena[R]) : 0;
     d.need_rows = (int*)(sync + kNeedRowsWord);
     const bool dma = e->strip_dma >= 1, dma_gbuffer = e->strip_dma >= 2;
-    d.gi_mirror_reach = dma ? 0 : kSpatialReach;
+    d.gi_mirror_reach = dma ? 0 : kSpatialReach; d.di_mirror_reach = dma_gbuffer ? 0 : kSpatialReach;
     if (dma && !cs->ev_produced) return fail(ST_ERR_INVALID, "strip side streams missing: link the camera first (st_link_local / st_peer_import)");
     // the copy engines of last frame have long finished; this orders this frame's writes of the pushed rows after them formally
     for (int k = 0; k < 2; k++) if (cs->pushed_pending[k]) { CK(cudaStreamWaitEvent(e->stream, cs->ev_pushed[k], 0)); cs->pushed_pending[k] = false; }
     StripExt ext; ext.gbuffer = dma_gbuffer ? 0 : kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
     for (int i = 0; i < 5; i++) ext.wavelet[i] = wext[i];
-    ext.preview_mirror[0] = kPreview2Reach; ext.preview_mirror[1] = 0;
+    ext.preview_mirror[0] = dma_gbuffer ? 0 : kPreview2Reach; ext.preview_mirror[1] = 0;
     // Nothing moved since the last frame (same camera bytes, no instance touched): velocities are zero, so K4 / K6 / K14 / K20 read last
     // frame at the pixel itself — no rows to pull, K4 can run inside the G-buffer launch.  Every rank sees the same updates, hence decides alike.
     ext.still = cs->frame > 1 && !e->moved_last_tick && std::memcmp(&cs->dev.curr, &cs->dev.prev, sizeof(GpuCamera)) == 0;
@@ -1080,7 +1081,7 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
             if (!std::strcmp(op.buffer, "@gbuffer")) {   // what the primary pass wrote for this frame and other strips read at their taps
                 const std::string c = (cs->frame % 2u == 1u) ? "b" : "a";
                 push_rows({"prim_gbuffer_d0_" + c, "prim_gbuffer_d1_" + c, "prim_surface_map_" + c, "surface_nd"}, kSpatialReach, op.sig_slot);
-            } else push_rows({op.buffer}, kSpatialReach, op.sig_slot);
+            } else push_rows({op.buffer}, op.reach ? op.reach : kSpatialReach, op.sig_slot);
             break;
         case StripOp::PULL: {
             StripPull pl; std::memset(&pl, 0, sizeof pl);

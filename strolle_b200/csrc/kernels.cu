@@ -292,7 +292,7 @@ __global__ void ST_LB_DI_TEMPORAL k_di_temporal(KPARAMS, int cur, u32 seed) {
     size_t lhs_idx = screen_idx(cam, p.x, p.y);
     Hit lhs_hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     if (!hit_some(lhs_hit)) return;
-    di_store_m(cam, di_temporal_px(cam, sc, cur, seed, p, lhs_hit, di_load(cam.di_reservoirs[1], lhs_idx)), cam.di_reservoirs[1], lhs_idx, p.y, ST_REACH_SPATIAL);
+    di_store_m(cam, di_temporal_px(cam, sc, cur, seed, p, lhs_hit, di_load(cam.di_reservoirs[1], lhs_idx)), cam.di_reservoirs[1], lhs_idx, p.y, cam.di_mirror_reach);
 }
 // K5 + K6 in one launch (ST_OPT_FUSED_PASSES): the pixel's fresh sample goes from K5 to K6 in registers instead of through di_reservoirs[1]
 // (the hit is decoded once).  What di_store / di_load would do to the sample on the way (confidence -> byte) is the identity for K5's
@@ -304,7 +304,7 @@ __global__ void ST_LB_DI_SAMPLING k_di_sample_temporal(KPARAMS, int cur, u32 see
     Hit hit = load_hit_lut(sc, cam.curr, cam.prim_gbuffer_d0[cur], cam.prim_gbuffer_d1[cur], cam, p.x, p.y);
     if (!hit_some(hit)) return;
     DiRes fresh = di_sampling_px(cam, sc, stk, hit, seed_sampling, frame, p);
-    di_store_m(cam, di_temporal_px(cam, sc, cur, seed_temporal, p, hit, fresh), cam.di_reservoirs[1], screen_idx(cam, p.x, p.y), p.y, ST_REACH_SPATIAL);
+    di_store_m(cam, di_temporal_px(cam, sc, cur, seed_temporal, p, hit, fresh), cam.di_reservoirs[1], screen_idx(cam, p.x, p.y), p.y, cam.di_mirror_reach);
 }
 
 // The four scratch texels of one checkerboard pair: (d0, d1) of texel a = (2gx, gy) and texel b = (2gx + 1, gy).

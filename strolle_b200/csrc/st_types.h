@@ -72,6 +72,7 @@ struct CameraDev {
     // layout on every rank, so the remote address is the local one plus a constant byte offset.  0 = no neighbour there.
     long long mirror_up, mirror_dn;
     int gi_mirror_reach;         // rows of gi_reservoirs[1] / [2] the GI kernels mirror themselves (ST_REACH_SPATIAL), or 0 when those rows travel by copy engine after the kernel
+    int di_mirror_reach;         // the same for di_reservoirs[1] (K6)
     int own_y0, own_y1;          // the rows this rank owns (mirror decisions); [y0, y1) may be wider when a pass recomputes halo rows
     int* need_rows;              // device: {min, max} previous-frame row the reprojection of the owned rows reaches (K0 -> temporal pull); null = off
 };

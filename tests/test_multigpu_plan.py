@@ -195,7 +195,7 @@ def test_fused_strip_order_invariants(dma, still):
             if f[0] == "signal":
                 raised.add(f[1])
             elif f[0] == "push":
-                assert dma and f[1] in ("gi_reservoirs_1", "gi_reservoirs_2", "@gbuffer") and (f[1] != "@gbuffer" or dma == 2)
+                assert dma and f[1] in ("gi_reservoirs_1", "gi_reservoirs_2", "@gbuffer", "di_reservoirs_1", "gi_reservoirs_3") and (f[1] in ("gi_reservoirs_1", "gi_reservoirs_2") or dma == 2)
                 raised.add(f[2])
             elif f[0] == "wait" and len(f) == 3:
                 assert f[1] in raised, f"{name}: waits for {f[1]} before this rank raised it itself (ranks run the same order: nobody would)"
