@@ -181,13 +181,15 @@ enum { ST_OPT_SVGF_FAST_MATH = 1, ST_OPT_ASYNC_OUTPUT = 2, ST_OPT_HALO_NCCL = 3,
  * 65.6 vs 61.8 us at 1080p); 0 = planar buffers throughout.  Stride 16: 78.1 -> 70.0 us (Cornell), 113.5 -> 98.7 us (dungeon).  Same values in
  * every layout; `*_diff_stash` then keeps the output of the last planar iteration. */
 #define ST_WAVELET_PAIRED_DEFAULT 1
-/* ST_OPT_STRIP_DMA (default 2; fused strip transport only): 1 = the 128-row halos of gi_reservoirs[1] / [2] (64 B per pixel, the bulk of what
- * travels) are pushed by the copy engines on one side stream per neighbour right after the kernel that produced them, overlapping the DI
- * passes that follow, instead of being mirrored by that kernel's own stores; 2 = the copy engines also push the 128 G-buffer rows
+/* ST_OPT_STRIP_DMA (fused strip transport only): which halos travel by copy engine (one side stream per neighbour, flag raised behind the
+ * copy) instead of the producing kernel's own mirror stores.  1 = the 128-row halos of gi_reservoirs[1] / [2] (64 B per pixel, the bulk of
+ * what travels), pushed right after the kernel that produced them and overlapping the DI passes that follow; 2 = also the 128 G-buffer rows
  * (prim_gbuffer_d0 / d1, surface map, surface_nd: 64 B per pixel) next to each strip edge right after the primary pass, instead of every
- * strip recomputing its neighbours' rows (which costs an inner strip of an 8-GPU frame two thirds of a G-buffer pass); 0 = every halo is
- * mirrored in-kernel and the G-buffer rows are recomputed. */
-#define ST_STRIP_DMA_DEFAULT 2
+ * strip recomputing its neighbours' rows (which costs an inner strip of an 8-GPU frame two thirds of a G-buffer pass); 3 = also
+ * di_reservoirs[1] and the preview pass's gi_reservoirs[3] (measured slower at 2 GPUs: 1.398 vs 1.351 ms — the flags behind the copies
+ * arrive later than the in-kernel stores did); 0 = every halo is mirrored in-kernel and the G-buffer rows are recomputed.
+ * Default -1: level 1 for two strips, level 2 from three strips on (the configurations measured at 2 and at 8 GPUs). */
+#define ST_STRIP_DMA_DEFAULT (-1)
 /* ST_OPT_FUSED_PASSES (default 1): reference passes whose hand-over is private to a pixel or to a checkerboard pair run as ONE launch:
  * K5+K6 (di_sampling + di_temporal_resampling), K7+K8+K9 (di_spatial_resampling pick / trace / sample), K12+K13 (gi_sampling a + b),
  * K11 inside K14 on tracing frames (gi_reprojection + gi_temporal_resampling), K15+K16+K17 (gi_spatial_resampling) and the second

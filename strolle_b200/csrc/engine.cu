@@ -433,7 +433,7 @@ struct st_engine {
     bool async_output = false;   // ST_OPT_ASYNC_OUTPUT
     bool halo_nccl = false;      // ST_OPT_HALO_NCCL
     int wavelet_paired = ST_WAVELET_PAIRED_DEFAULT;   // ST_OPT_WAVELET_PAIRED
-    int strip_dma = ST_STRIP_DMA_DEFAULT;   // ST_OPT_STRIP_DMA: 1 = gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores; 2 = also the G-buffer halo rows (instead of recomputing them)
+    int strip_dma = ST_STRIP_DMA_DEFAULT;   // ST_OPT_STRIP_DMA: 1 = gi_reservoirs[1] / [2] halo rows by copy engine on side streams instead of in-kernel mirror stores; 2 = also the G-buffer halo rows (instead of recomputing them); 3 = also di_reservoirs[1] and gi_reservoirs[3]; -1 = 1 for two strips, 2 from three on
     bool strip_fused = true;     // ST_OPT_STRIP_FUSED: mirror stores + neighbour flags + recompute instead of stand-alone exchanges
     bool last_frame_fused = false;
     int wavelet_tiled = ST_WAVELET_TILED_DEFAULT;   // ST_OPT_WAVELET_TILED: bit i = à-trous iteration i (stride 2^i) runs the tile-staged (TMA) kernel
@@ -919,7 +919,7 @@ struct StripOp {
     int reach = 0;                                   // PUSH: rows next to each strip edge (0 = the spatial reach)
 };
 static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool still, std::vector<StripOp>* out) {
-    const bool dma = dma_level >= 1, dma_gbuffer = dma_level >= 2;
+    const bool dma = dma_level >= 1, dma_gbuffer = dma_level >= 2, dma_all = dma_level >= 3;
     auto step = [&](int i) { StripOp o; o.kind = StripOp::STEP; o.step = i; out->push_back(o); };
     auto signal = [&](int slot, bool all_ranks = false, bool reset_need = false) { StripOp o; o.kind = StripOp::SIGNAL; o.sig_slot = slot; o.sig_all = all_ranks; o.reset_need = reset_need; out->push_back(o); };
     auto wait = [&](int slot, bool all_ranks = false, bool prev = false) { StripOp o; o.kind = StripOp::WAIT; o.wait_slot = slot; o.wait_all = all_ranks; o.wait_prev_frame = prev; out->push_back(o); };
@@ -957,7 +957,7 @@ static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool s
     for (; k < pre.size(); k++) step(pre[k]);
     // DI and GI up to their first gathering pass
     for (int i : di1) step(i);
-    if (!di1.empty()) { if (dma_gbuffer) push("di_reservoirs_1", SLOT_DI1); else signal(SLOT_DI1); }   // level 2: every halo with slack before its reader goes by copy engine
+    if (!di1.empty()) { if (dma_all) push("di_reservoirs_1", SLOT_DI1); else signal(SLOT_DI1); }   // level 3: every halo with slack before its reader goes by copy engine
     for (int i : gi1) step(i);
     if (dma) {   // the flags of the GI halos are raised by the side streams, behind their copies
         if (!gi1.empty()) push("gi_reservoirs_1", SLOT_GI1);
@@ -979,7 +979,7 @@ static void plan_strip_order(const std::vector<int>& pass, int dma_level, bool s
     if (!gi_sp.empty()) wait(SLOT_GI2);
     if (!pv1.empty()) need_gbuffer();
     for (int i : pv1) step(i);
-    if (!pv1.empty()) { if (dma_gbuffer) push("gi_reservoirs_3", SLOT_GI3, kPreview2Reach); else signal(SLOT_GI3); }
+    if (!pv1.empty()) { if (dma_all) push("gi_reservoirs_3", SLOT_GI3, kPreview2Reach); else signal(SLOT_GI3); }
     for (size_t i = 1; i < di_rest.size(); i++) step(di_rest[i]);
     if (!pv1.empty()) wait(SLOT_GI3);
     for (int i : gi_tail) step(i);
@@ -1016,14 +1016,17 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
     d.mirror_up = R > 0 ? (long long)(cs->peer.arena[R - 1] - cs->peer.arena[R]) : 0;
     d.mirror_dn = R + 1 < N ? (long long)(cs->peer.arena[R + 1] - cs->peer.arena[R]) : 0;
     d.need_rows = (int*)(sync + kNeedRowsWord);
-    const bool dma = e->strip_dma >= 1, dma_gbuffer = e->strip_dma >= 2;
-    d.gi_mirror_reach = dma ? 0 : kSpatialReach; d.di_mirror_reach = dma_gbuffer ? 0 : kSpatialReach;
+    // ST_OPT_STRIP_DMA; -1 = by rank count: with inner strips (two neighbours each) recomputing both neighbours' G-buffer rows costs more than
+    // pushing them, with two strips it does not (measured: N=2 1.351 ms at level 1, 1.398 at level 3; N=8 1.685 ms at level 2)
+    const int dma_level = e->strip_dma < 0 ? (N >= 3 ? 2 : 1) : e->strip_dma;
+    const bool dma = dma_level >= 1, dma_gbuffer = dma_level >= 2, dma_all = dma_level >= 3;
+    d.gi_mirror_reach = dma ? 0 : kSpatialReach; d.di_mirror_reach = dma_all ? 0 : kSpatialReach;
     if (dma && !cs->ev_produced) return fail(ST_ERR_INVALID, "strip side streams missing: link the camera first (st_link_local / st_peer_import)");
     // the copy engines of last frame have long finished; this orders this frame's writes of the pushed rows after them formally
     for (int k = 0; k < 2; k++) if (cs->pushed_pending[k]) { CK(cudaStreamWaitEvent(e->stream, cs->ev_pushed[k], 0)); cs->pushed_pending[k] = false; }
     StripExt ext; ext.gbuffer = dma_gbuffer ? 0 : kSpatialReach; ext.variance = 35; const int wext[5] = {34, 32, 28, 19, 0};
     for (int i = 0; i < 5; i++) ext.wavelet[i] = wext[i];
-    ext.preview_mirror[0] = dma_gbuffer ? 0 : kPreview2Reach; ext.preview_mirror[1] = 0;
+    ext.preview_mirror[0] = dma_all ? 0 : kPreview2Reach; ext.preview_mirror[1] = 0;
     // Nothing moved since the last frame (same camera bytes, no instance touched): velocities are zero, so K4 / K6 / K14 / K20 read last
     // frame at the pixel itself — no rows to pull, K4 can run inside the G-buffer launch.  Every rank sees the same updates, hence decides alike.
     ext.still = cs->frame > 1 && !e->moved_last_tick && std::memcmp(&cs->dev.curr, &cs->dev.prev, sizeof(GpuCamera)) == 0;
@@ -1067,7 +1070,7 @@ static int render_strips_fused(st_engine* e, CameraSlot* cs, const std::vector<s
 
     // the order of passes, flags, pulls and pushes is planned by a pure function (CPU-testable: st_plan_strip_order); execute it
     std::vector<int> ids; for (const Step& st : steps) ids.push_back(st.pass);
-    std::vector<StripOp> ops; plan_strip_order(ids, e->strip_dma, ext.still, &ops);
+    std::vector<StripOp> ops; plan_strip_order(ids, dma_level, ext.still, &ops);
     const char* prv = (cs->frame % 2u == 1u) ? "a" : "b";
     for (const StripOp& op : ops) {
         const uint32_t smask = op.sig_all ? all : nb, wmask = op.wait_all ? all : nb;
@@ -1574,7 +1577,7 @@ int st_set_option(st_engine* e, int option, int value) {
     if (option == ST_OPT_ASYNC_OUTPUT) { e->async_output = value != 0; return ST_OK; }
     if (option == ST_OPT_HALO_NCCL) { e->halo_nccl = value != 0; return ST_OK; }
     if (option == ST_OPT_STRIP_FUSED) { e->strip_fused = value != 0; return ST_OK; }
-    if (option == ST_OPT_STRIP_DMA) { if (value < 0 || value > 2) return fail(ST_ERR_INVALID, "ST_OPT_STRIP_DMA: 0, 1 or 2"); e->strip_dma = value; return ST_OK; }
+    if (option == ST_OPT_STRIP_DMA) { if (value < -1 || value > 3) return fail(ST_ERR_INVALID, "ST_OPT_STRIP_DMA: -1 .. 3"); e->strip_dma = value; return ST_OK; }
     if (option == ST_OPT_WAVELET_PAIRED) { if (value < 0 || value > 2) return fail(ST_ERR_INVALID, "ST_OPT_WAVELET_PAIRED: 0, 1 or 2"); e->wavelet_paired = value; return ST_OK; }
     if (option == ST_OPT_FUSED_PASSES) { e->fused_passes = value != 0; return ST_OK; }
     if (option == ST_OPT_WAVELET_TILED) { e->wavelet_tiled = value & 31; return ST_OK; }

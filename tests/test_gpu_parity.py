@@ -773,7 +773,7 @@ def _devices(n):
 
 @pytest.mark.parametrize("n,size,exact,fused", [(2, (320, 288), True, True), (3, (256, 400), True, True), (2, (320, 288), False, True),
                                                 (4, (200, 520), False, True), (2, (320, 288), True, False), (3, (200, 400), False, "mirror"),
-                                                (3, (128, 720), False, True), (2, (320, 288), False, "dma1"), (3, (256, 400), True, "dma1")])   # 720 rows over 3: outer strips 252 rows, inner 216 (weighted partition)
+                                                (3, (128, 720), False, True), (2, (320, 288), False, "dma3"), (3, (256, 400), True, "dma3")])   # 720 rows over 3: outer strips 252 rows, inner 216 (weighted partition)
 def test_multi_device_group_matches_single_gpu(gpu, blue_noise, n, size, exact, fused):
     """st_multi_* (one process, n devices): the frame rendered as n row strips — producer kernels mirroring their
     boundary rows into the neighbours, neighbour-only sequence flags, G-buffer / SVGF halo rows recomputed, temporal rows pulled on
@@ -785,8 +785,10 @@ def test_multi_device_group_matches_single_gpu(gpu, blue_noise, n, size, exact, 
     one = gpu.Engine(blue_noise=blue_noise, exact=exact)
     grp = gpu.MultiEngine(_devices(n), blue_noise=blue_noise, exact=exact)
     grp.set_option(OPT_STRIP_FUSED, int(bool(fused)))
-    if fused in ("mirror", "dma1"):   # "mirror": every halo by in-kernel stores, G-buffer rows recomputed; "dma1": GI halos by copy engine, G-buffer rows recomputed
-        grp.set_option(OPT_STRIP_DMA, 0 if fused == "mirror" else 1)   # default (2): the copy engines also push the G-buffer rows
+    # ST_OPT_STRIP_DMA: "mirror" = every halo by in-kernel stores, G-buffer rows recomputed; "dma3" = every halo with slack by copy engine;
+    # default = GI halos by copy engine, and from three strips on the G-buffer rows too
+    if fused in ("mirror", "dma3"):
+        grp.set_option(OPT_STRIP_DMA, 0 if fused == "mirror" else 3)
     c1, cn = scenes.apply(one, scene), scenes.apply(grp, scene)
     c = scene["camera"]
     for f in range(13):
