@@ -157,6 +157,7 @@ __global__ void ST_LB_PRIM_GBUFFER k_prim_gbuffer(KPARAMS, int cur, int with_rep
     if (!p.in) return;
     Ray ray = cam_ray(cam.curr, p.x, p.y);
     TriHit th = trace_closest(ray, sc, stk);
+    if ((int)p.y < cam.own_y0 || (int)p.y >= cam.own_y1) uncount_ray(sc);   // a neighbour's row, recomputed here: not counted as a ray of the frame
     float4 g0 = f4zero(), g1 = f4zero(), surf = f4zero(), vel = f4zero(), tid = f4(bitsf(0xffffffffu), 0.f, 0.f, 0.f), nd = f4zero();
     if (trihit_some(th)) {
         const GpuMaterial m = sc.materials[th.material_id];

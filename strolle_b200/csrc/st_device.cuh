@@ -157,6 +157,14 @@ ST_DEV void count_ray(const SceneDev& sc) {
         if ((threadIdx.x & 31u) == (unsigned)(__ffs(m) - 1)) atomicAdd(sc.ray_counter, (unsigned long long)__popc(m));
     }
 }
+// takes a ray back out of the statistics: the primary rays a strip traces for rows it does not own (recomputed halo rows) are not work
+// the frame asked for, and would flatter the strip-parallel Mrays/s
+ST_DEV void uncount_ray(const SceneDev& sc) {
+    if (sc.ray_counter) {
+        unsigned m = __activemask();
+        if ((threadIdx.x & 31u) == (unsigned)(__ffs(m) - 1)) atomicAdd(sc.ray_counter, 0ull - (unsigned long long)__popc(m));
+    }
+}
 // Both traversals are written "while-while": a lane first walks internal nodes until it stands on a leaf entry (or runs out of
 // work), then the whole run of leaf entries, then pops.  Per lane this is exactly the node sequence of the reference's single
 // loop; across a warp it lets lanes that are still descending catch up before anyone starts triangle tests, so the expensive
