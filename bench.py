@@ -45,7 +45,7 @@ def parse():
     p.add_argument("--scene", default="cornell", choices=["cornell", "dungeon"])
     p.add_argument("--width", type=int, default=1920)
     p.add_argument("--height", type=int, default=1080)
-    p.add_argument("--cpu-sample-frames", type=int, default=3)
+    p.add_argument("--cpu-sample-frames", type=int, default=12)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-extras", action="store_true", help="skip the c3 / c4 / c5 / small blocks")
     p.add_argument("--c5-spp", type=int, default=1024)
