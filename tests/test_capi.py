@@ -83,3 +83,22 @@ def test_rust_engine_forwards_every_reference_method():
     sys_src = open(os.path.join(ROOT, "rust", "strolle-b200-sys", "src", "lib.rs")).read()
     for ffi in set(re.findall(r"sys::(st_\w+)\(", src)):
         assert f"pub fn {ffi}(" in sys_src, f"{ffi} used by the safe crate but not declared by the sys crate"
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores; no GPU involved) prints ONE JSON line with the keys the
+    bench contract names, its own cpu_baseline and an e2e block that repeats the line's value with zero copy bytes."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--width", "160", "--height", "90"],
+                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=300, cwd=ROOT).stdout
+    lines = [l for l in out.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mrays/s" and d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1
+    for key in ("metric", "value", "ms_per_step", "scaling", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert d["value"] > 0 and "160x90" in d["config"]["workload"]
