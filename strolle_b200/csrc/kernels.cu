@@ -1890,7 +1890,11 @@ void launch_atm_sun_color(float4* out2, const GpuWorld& world, cudaStream_t st) 
 // thread, for another member of a device group) raises, so a load at that moment would stall the thread until the wait gives up.
 // The module is found through one of its kernels; every function it holds is then loaded (cuFuncLoad, CUDA >= 12.4).
 int preload_kernels() {
-    static int state = -1;   // per flavour (this function is compiled into st:: and stf::)
+    static int states[64];   // per flavour (this function is compiled into st:: and stf::) and per device: every context holds its own copy of the module
+    static bool init = false;
+    if (!init) { for (int& v : states) v = -1; init = true; }
+    int dev = 0; cudaGetDevice(&dev);
+    int& state = states[dev & 63];
     if (state >= 0) return state;
     auto entry = [](const char* name) -> void* {
         void* p = nullptr; cudaDriverEntryPointQueryResult q;
