@@ -25,6 +25,8 @@ CASES = {
     "cornell_ref_64x48_f4": dict(scene=("cornell", dict(width=64, height=48, mode=scenes.MODE_REFERENCE, ref_depth=1)), frames=4),   # config C5 shape
     "dungeon_96x54_f7": dict(scene=("dungeon", dict(width=96, height=54, cells=6)), frames=7),        # config C3 stand-in
     "cornell_spots_80x56_f5": dict(scene=("cornell_spots", dict(width=80, height=56)), frames=5),     # Light::Spot cone (glam acos_approx)
+    "demo_level_96x54_f5": dict(scene=("demo_level", dict(width=96, height=54)), frames=5),          # config C3: the reference's dungeon asset, textures, sun + atmosphere
+    "textured_room_80x44_f4": dict(scene=("textured_room", dict(width=80, height=44)), frames=4),     # texture atlas, alpha cut-outs, normal maps
 }
 
 
@@ -39,7 +41,7 @@ def digest(a):
 
 def run_case(engine, case):
     kind, kw = case["scene"]
-    sc = {"cornell": scenes.cornell, "dungeon": scenes.dungeon, "cornell_spots": scenes.cornell_spots}[kind](**kw)
+    sc = {"cornell": scenes.cornell, "dungeon": scenes.dungeon, "cornell_spots": scenes.cornell_spots, "demo_level": scenes.demo_level, "textured_room": scenes.textured_room}[kind](**kw)
     cam = scenes.apply(engine, sc)
     for _ in range(case["frames"]):
         engine.tick(); engine.render_camera(cam)
