@@ -227,3 +227,34 @@ def test_primary_visibility_matches_textbook_float64(oracle, blue_noise):
     cos = -dv[..., 2] / np.linalg.norm(dv, axis=-1)
     err = np.abs(depth[hit] - (best[hit] - near / cos[hit]))
     assert err.max() < 2e-5, err.max()
+
+
+def test_ray_stream_matches_float64_brute_force(cornell_oracle):
+    """Ray::trace on random rays against a float64 Möller–Trumbore over all triangles (written from the textbook definition, two-sided,
+    no BVH): same closest triangle except at distance ties, hit distance within f32 rounding of the f64 one."""
+    e, _ = cornell_oracle
+    rays = random_rays(6000, 3, (-1.0, 0.0, -1.0), (1.0, 2.0, 3.0))
+    hits = e.trace_closest(rays)
+    tris = e.read_scene("triangles").reshape(-1, 9, 4).astype(np.float64)
+    o, d = rays[:, 0:3].astype(np.float64), rays[:, 4:7].astype(np.float64)
+    best = np.full(len(rays), np.inf); who = np.full(len(rays), 0xFFFFFFFF, dtype=np.uint32)
+    for i, t3 in enumerate(tris):
+        p0, e1, e2 = t3[0, :3], t3[3, :3] - t3[0, :3], t3[6, :3] - t3[0, :3]
+        pv = np.cross(d, e2); det = pv @ e1
+        with np.errstate(divide="ignore", invalid="ignore"):
+            inv = 1.0 / det
+            tv = o - p0
+            u = (pv * tv).sum(-1) * inv
+            qv = np.cross(tv, e1)
+            v = (d * qv).sum(-1) * inv
+            t = (qv @ e2) * inv
+        ok = (np.abs(det) > 1e-12) & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 1e-9) & (t < best)
+        best = np.where(ok, t, best); who = np.where(ok, np.uint32(i), who)
+    got_tri = hits[:, 9].copy().view(np.uint32)
+    got_t = hits[:, 8].astype(np.float64)
+    miss = np.isinf(best)
+    assert ((got_tri == 0xFFFFFFFF) == miss).mean() > 0.999
+    both = ~miss & (got_tri != 0xFFFFFFFF)
+    assert (got_tri[both] == who[both]).mean() > 0.995
+    same = both & (got_tri == who)
+    assert (np.abs(got_t[same] - best[same]) <= 4e-6 * np.maximum(1.0, best[same])).all()
