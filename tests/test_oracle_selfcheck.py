@@ -198,7 +198,8 @@ def test_primary_visibility_matches_textbook_float64(oracle, blue_noise):
     cam = scenes.apply(e, sc)
     e.tick(); e.render_camera(cam)
     tid = e.read_buffer(cam, "prim_triangle_ids").reshape(H, W, 4)[..., 0].copy().view(np.uint32)
-    depth = e.read_buffer(cam, "prim_surface_map_b").reshape(H, W, 4)[..., 2]          # frame 1 writes the "b" half
+    surface = e.read_buffer(cam, "prim_surface_map_b").reshape(H, W, 4)                # frame 1 writes the "b" half
+    depth = surface[..., 2]
     tris = e.read_scene("triangles").reshape(-1, 9, 4).astype(np.float64)               # positions in vec4 0, 3, 6 (triangle.rs:8-21)
     P = sc["camera"]["projection"].reshape(4, 4).astype(np.float64)                     # [column][row]
     T = sc["camera"]["transform"].reshape(4, 4).astype(np.float64)
@@ -208,6 +209,7 @@ def test_primary_visibility_matches_textbook_float64(oracle, blue_noise):
     dw = dv[..., 0:1] * R[0] + dv[..., 1:2] * R[1] + dv[..., 2:3] * R[2]
     dw /= np.linalg.norm(dw, axis=-1, keepdims=True)
     best = np.full((H, W), np.inf); who = np.full((H, W), 0xFFFFFFFF, dtype=np.uint32)
+    normal = np.zeros((H, W, 3))
     for i, t3 in enumerate(tris):
         p0, e1, e2 = t3[0, :3], t3[3, :3] - t3[0, :3], t3[6, :3] - t3[0, :3]
         pv = np.cross(dw, e2); det = (pv * e1).sum(-1)
@@ -220,6 +222,10 @@ def test_primary_visibility_matches_textbook_float64(oracle, blue_noise):
             t = (qv * e2).sum(-1) * inv
         ok = (np.abs(det) > 1e-12) & (u >= 0) & (v >= 0) & (u + v <= 1) & (t > 1e-9) & (t < best)
         best = np.where(ok, t, best); who = np.where(ok, np.uint32(i), who)
+        with np.errstate(invalid="ignore"):
+            n = t3[4, :3] * u[..., None] + t3[7, :3] * v[..., None] + t3[1, :3] * (1 - u - v)[..., None]    # vertex normals in vec4 1, 4, 7
+            n = n / np.linalg.norm(n, axis=-1, keepdims=True) * np.sign(det)[..., None]                    # two-sided: faces the ray
+        normal = np.where(ok[..., None], n, normal)
     same = who == tid
     assert same.mean() > 0.995, f"triangle under the pixel: {same.mean():.4f} agree"      # the rest sit on shared edges
     assert ((tid == 0xFFFFFFFF) == np.isinf(best))[same].all()
@@ -227,6 +233,13 @@ def test_primary_visibility_matches_textbook_float64(oracle, blue_noise):
     cos = -dv[..., 2] / np.linalg.norm(dv, axis=-1)
     err = np.abs(depth[hit] - (best[hit] - near / cos[hit]))
     assert err.max() < 2e-5, err.max()
+    # the surface map's normal: standard octahedral decode of its first two components == the interpolated vertex normal
+    m = surface[..., 0:2].astype(np.float64) * 2 - 1
+    dec = np.stack([m[..., 0], m[..., 1], 1 - np.abs(m[..., 0]) - np.abs(m[..., 1])], -1)
+    fold = np.maximum(-dec[..., 2], 0)
+    dec[..., 0] -= np.copysign(fold, dec[..., 0]); dec[..., 1] -= np.copysign(fold, dec[..., 1])
+    dec /= np.linalg.norm(dec, axis=-1, keepdims=True)
+    assert np.abs(dec[hit] - normal[hit]).max() < 1e-5
 
 
 def test_ray_stream_matches_float64_brute_force(cornell_oracle):
