@@ -271,3 +271,20 @@ def test_ray_stream_matches_float64_brute_force(cornell_oracle):
     assert (got_tri[both] == who[both]).mean() > 0.995
     same = both & (got_tri == who)
     assert (np.abs(got_t[same] - best[same]) <= 4e-6 * np.maximum(1.0, best[same])).all()
+
+
+def test_transmittance_lut_is_physically_plausible(oracle, blue_noise):
+    """The atmosphere's transmittance LUT against closed-form physics with the published constants of the model the reference implements
+    (Hillaire 2020: Rayleigh 5.802 / 13.558 / 33.1 e-6 per m with an 8 km scale height, Mie extinction 8.396e-6 with 1.2 km, ozone
+    0.650 / 1.881 / 0.085 e-6 over a 30 km tent): looking straight up from the ground the optical depth is sum(beta_i * column_i).
+    The LUT is a fixed-step numerical integral, so the match is loose (5 %); it also has to be 1 at the top of the atmosphere, 0 below
+    the horizon at ground level, and grow with the elevation of the view direction."""
+    e = oracle.OracleEngine(blue_noise=blue_noise)
+    cam = scenes.apply(e, scenes.demo_level(64, 36))
+    e.tick(); e.render_camera(cam)
+    t = e.read_scene("transmittance_lut").reshape(64, 256, 4)[..., :3].astype(np.float64)   # [height][cos zenith -1..1]
+    tau = np.array([5.802, 13.558, 33.1]) * 1e-6 * 8000.0 + 8.396e-6 * 1200.0 + np.array([0.650, 1.881, 0.085]) * 1e-6 * 15000.0
+    assert np.abs(t[0, 255] - np.exp(-tau)).max() < 0.05, (t[0, 255], np.exp(-tau))
+    assert (t[63, 128:] > 0.999).all() and (t[0, :100] == 0).all()
+    assert (np.diff(t[0, 128:], axis=0) >= -2e-3).all(), "transmittance grows towards the zenith"
+    assert (t >= 0).all() and (t <= 1).all()
